@@ -1,0 +1,236 @@
+/*
+ * eg3d.h — C-ABI of libeg3d.so: the B200-native replacement for EdgeGraph3D's
+ * epipolar polyline-matching + Gauss-Newton triangulation hot path.
+ *
+ * The reference (abignoli/EdgeGraph3D) has no FFI layer: it is one statically
+ * linked C++ executable.  The seams this library sits behind are the free
+ * functions / abstract classes listed in SURVEY.md §8(b); every entry point
+ * below cites the reference interface it replaces (paths relative to the
+ * reference root).  include/eg3d_ref_api.hpp is the thin C++ shim that keeps
+ * the reference's own signatures on top of this ABI.
+ *
+ * Conventions: plain C structs, caller-owned inputs (copied during the call),
+ * library-owned outputs released with the matching *_free / *_destroy, int
+ * status codes, no exceptions across the boundary.  A scene handle is bound to
+ * the CUDA device that was current when it was created.  Thread-compatible,
+ * not thread-safe.  All entry points fail with EG3D_ERR_NO_DEVICE when no CUDA
+ * device is usable: there is no CPU fallback in this library.
+ */
+#ifndef EG3D_H_
+#define EG3D_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum eg3d_status {
+  EG3D_OK = 0,
+  EG3D_ERR_INVALID_ARG = 1,
+  EG3D_ERR_NO_DEVICE = 2,   /* no usable CUDA device: the product path never falls back to the CPU */
+  EG3D_ERR_CUDA = 3,        /* a CUDA runtime call failed; see eg3d_last_error() */
+  EG3D_ERR_CAPACITY = 4,    /* a fixed per-seed capacity (chain length, hits) was exceeded; see eg3d_params */
+  EG3D_ERR_OOM = 5
+} eg3d_status;
+
+/* ------------------------------------------------------------------------- */
+/* Flat scene: what SfMData + vector<PolyLineGraph2DHMapImpl> + Mat** F hold.  */
+/* ------------------------------------------------------------------------- */
+/*
+ * Replaces, as inputs of every entry point of the path:
+ *   SfMData                     external/manifoldReconstructor/include/SfMData.h:16-30
+ *   CameraType::cameraMatrix    external/manifoldReconstructor/include/types_reconstructor.hpp:68-82
+ *   PolyLineGraph2D::polyline   include/edgegraph3d/plgs/polyline_graph_2d.hpp:85-119
+ *   const Mat** all_fundamental_matrices   src/edgegraph3d/utils/edge_graph_3d_utilities.cpp:581-589
+ */
+typedef struct eg3d_scene_desc {
+  int32_t n_views;
+  int32_t width, height;            /* image size (all views), SfMData::imageWidth_/imageHeight_ */
+  const float*   cameras;           /* [V][12] rows 0..2 of cameraMatrix read as [row][col]: P = K[R|t] */
+  const double*  fundamental;       /* [V][V][9] row-major; F[a][b] maps a point of view a to its line in view b */
+  const uint8_t* fundamental_valid; /* [V][V] 0 = the reference's 1x1 dummy Mat (geometric_utilities.cpp:780) */
+  /* polyline graphs, CSR.  Polyline id inside a view = global index - view_poly_off[view].               */
+  const int64_t*  view_poly_off;    /* [V+1] */
+  const int64_t*  poly_vert_off;    /* [NP+1]; an empty range is an invalidated polyline (polyline_graph_2d.cpp:1035-1038) */
+  const float*    verts;            /* [NVERT][2] polyline_coords */
+  const uint32_t* poly_start;       /* [NP] polyline::start node id */
+  const uint32_t* poly_end;         /* [NP] polyline::end node id */
+  /* SfM tracks: only needed by eg3d_match_refpoints and eg3d_filter (may be NULL with n_tracks = 0).     */
+  int64_t        n_tracks;
+  const float*   track_xyz;         /* [NT][3] SfMData::points_ */
+  const int64_t* track_off;         /* [NT+1] */
+  const int32_t* track_view;        /* [NOBS] SfMData::camViewingPointN_ */
+  const float*   track_xy;          /* [NOBS][2] SfMData::point2DoncamViewingPoint_ */
+} eg3d_scene_desc;
+
+/* Every compile-time constant of the path, defaulted by eg3d_params_default(). */
+typedef struct eg3d_params {
+  float  split_interval_distance;     /* 20    polyline_matching.hpp:51 */
+  float  follow_first_image_distance; /* 10    plg_matching.hpp:39 */
+  float  follow_corr_min;             /* 5     plg_matching.hpp:40 */
+  float  follow_corr_max;             /* 20    plg_matching.hpp:41 */
+  float  quasiparallel_cos;           /* 0.965 polyline_graph_2d.hpp:73 */
+  float  quasiparallel_dist;          /* 5     polyline_graph_2d.hpp:74 */
+  float  max_proj_distsq_expand;      /* 16    triangulation.hpp:46 */
+  float  expand_grid_cell;            /* 4     edge_matcher.cpp:103 */
+  float  detection_starting_radius;   /* 10    global_defines.hpp:35 */
+  float  detection_mult;              /* 3     global_defines.hpp:37 */
+  int32_t gn_max_iters;               /* 30    triangulation.cpp:122, gauss_newton.cpp:97 */
+  double gn_stop;                     /* 5e-7  triangulation.cpp:150 */
+  double gn_det_min;                  /* 1e-5  triangulation.cpp:97 */
+  double gn_accept_mse;               /* 9     triangulation.cpp:168 */
+  double filter_gn_stop;              /* 5e-10 gauss_newton.cpp:114 (double literal; the float |diff| is promoted) */
+  double filter_gn_det_min;           /* 1e-10 gauss_newton.cpp:70 */
+  float  filter_gn_max_mse;           /* 2.25  gauss_newton.hpp:18 */
+  int32_t filter_3views_amount;       /* 3     outliers_filtering.hpp:16 */
+  float  dedup_cell;                  /* 3     filtering_close_plgps.cpp:75 */
+  /* 1 (default): when get_min_max's "last index" quirk selects the same camera twice for the 2-view DLT
+   * initialiser (edge_graph_3d_utilities.hpp:86-88), use the last list entry whose view differs instead
+   * (SURVEY A.2.1).  0: keep the rank-deficient DLT (result is implementation-defined noise).             */
+  int32_t dlt_wellposed;
+  /* 0 (default): `abs(mse/(2n) - last_mse)` in gauss_newton.cpp:114 is the float overload (GCC >= 6).
+   * 1: emulate the truncating `int abs(int)` binding of the author's GCC 5 toolchain.         */
+  int32_t filter_abs_int;
+  /* capacities of the device path (not reference constants) */
+  int32_t max_chain_points;           /* per seed; default 96 */
+  int32_t max_follow_points;          /* per direction during 3-view following; default 160 */
+} eg3d_params;
+
+void eg3d_params_default(eg3d_params* p);
+
+/* Seeds: the (view, plg_point) pairs the matching loop starts from
+ * (polyline_matching.cpp:168-190 produces them; plg_edge_manager.cpp:272-288 for pipeline 3). */
+typedef struct eg3d_seeds {
+  int64_t         n;
+  const int32_t*  view;      /* [n] starting_plg_id */
+  const uint32_t* polyline;  /* [n] plg_point::polyline_id */
+  const uint32_t* segment;   /* [n] pl_point::segment_index */
+  const float*    xy;        /* [n][2] pl_point::coords */
+  const int32_t*  cand_set;  /* [n] index into eg3d_candidates, or NULL / -1 = sweep all segments of every view */
+} eg3d_seeds;
+
+/* Candidate polyline sets: `vector<set<ulong>> potentially_compatible_polylines`, one per polyline match
+ * (pipelines.cpp:92-100).  CSR over (set, view) -> ascending polyline ids.                                   */
+typedef struct eg3d_candidates {
+  int32_t         n_sets;
+  const int64_t*  off;       /* [n_sets*V + 1] */
+  const uint32_t* polyline;  /* ids, ascending inside each (set, view) range */
+} eg3d_candidates;
+
+/* One epipolar hit = PolyLineGraph2D::plg_point (polyline_graph_2d.hpp:278-294) narrowed to 16 bytes. */
+typedef struct eg3d_hit {
+  uint32_t polyline;
+  uint32_t segment;
+  float    x, y;
+} eg3d_hit;
+
+/* Accepted 3D edge-points: flattened vector<new_3dpoint_plgp_matches> (polyline_graph_2d.hpp:451). */
+typedef struct eg3d_points_view {
+  int64_t n_points, n_obs;
+  const float*    xyz;        /* [n_points][3] */
+  const int32_t*  seed;       /* [n_points] ordinal of the producing seed in the call's seed order */
+  const int32_t*  chain_pos;  /* [n_points] position inside that seed's chain */
+  const int64_t*  obs_off;    /* [n_points+1] */
+  const int32_t*  obs_view;   /* [n_obs] */
+  const uint32_t* obs_poly;   /* [n_obs] */
+  const uint32_t* obs_seg;    /* [n_obs] */
+  const float*    obs_xy;     /* [n_obs][2] */
+} eg3d_points_view;
+
+/* Per-call device timings (CUDA events on the library's stream), in milliseconds. */
+typedef struct eg3d_timing {
+  float total_ms;             /* first kernel launch .. last kernel end (no H2D of the scene, no D2H of results) */
+  float k1_count_ms;          /* epipolar intersection, counting pass */
+  float k1_fill_ms;           /* epipolar intersection, fill pass */
+  float scan_ms;              /* prefix sums */
+  float k3_ms;                /* triple enumeration + PLG following + view expansion */
+  float pack_ms;              /* ordered compaction of accepted points */
+  float gn_ms;                /* stand-alone GN kernel (eg3d_gn_*) */
+  int64_t n_seeds, n_hits, n_segment_tests, n_points, n_obs;
+  int64_t k1_algorithmic_bytes; /* 16 B x segments swept per (seed, view) + 72 + 8 + 16 B x hits */
+  int32_t kernel_launches;
+  int32_t n_capacity_overflows; /* seeds dropped because a capacity in eg3d_params was exceeded */
+} eg3d_timing;
+
+typedef struct eg3d_scene  eg3d_scene;   /* opaque, device resident */
+typedef struct eg3d_points eg3d_points;  /* opaque, host+device resident result */
+typedef struct eg3d_hits   eg3d_hits;    /* opaque */
+
+const char* eg3d_last_error(void);
+int         eg3d_device_count(void);
+
+/* Copies the scene to the current CUDA device and builds the derived structures the path reads:
+ * per-view segment arrays in the reference's (P[i], P[i-1]) orientation (plg_edge_manager.hpp:92-93,
+ * polyline_graph_2d.cpp:318-323) and the uniform polyline grids (polyLine_2d_map.cpp:40-58) for the
+ * 4 px expansion lookups and the 30 px refpoint lookups. */
+eg3d_status eg3d_scene_create(const eg3d_scene_desc* desc, const eg3d_params* params, eg3d_scene** out);
+void        eg3d_scene_destroy(eg3d_scene*);
+
+/* Seed sampler: polyline::next_pl_point_by_distance walked from get_start_plp() towards `end`
+ * (polyline_matching.cpp:168-190, polyline_graph_2d.cpp:391-447).  Host code.
+ * Writes up to `capacity` seeds for the given (view, polyline) list; returns the count in *n_out. */
+eg3d_status eg3d_sample_seeds(const eg3d_scene_desc* desc, const int32_t* views, const uint32_t* polylines,
+                              int64_t n_polylines, float spacing, int64_t capacity,
+                              int32_t* out_view, uint32_t* out_polyline, uint32_t* out_segment, float* out_xy,
+                              int32_t* out_src /* index of the source (view,polyline) pair, may be NULL */,
+                              int64_t* n_out);
+
+/* K1 alone: find_epipolar_correspondences (polyline_matching.cpp:45-73) for a batch of seeds.
+ * Result: CSR over (seed, view) of eg3d_hit, in the reference's order (polyline id asc, segment asc). */
+eg3d_status eg3d_epipolar_intersect(eg3d_scene*, const eg3d_seeds*, const eg3d_candidates* /* may be NULL */,
+                                    eg3d_hits** out, eg3d_timing* timing /* may be NULL */);
+/* host pointers valid until eg3d_hits_free; off has n_seeds*V+1 entries */
+eg3d_status eg3d_hits_get(const eg3d_hits*, int64_t* n_seeds, int32_t* n_views, const int64_t** off, const eg3d_hit** hits);
+void        eg3d_hits_free(eg3d_hits*);
+
+/* B1/B4: find_new_3d_points_from_compatible_polylines_starting_plgp_expandallviews for a batch of seeds
+ * (polyline_matching.cpp:134-144 -> triangulation.cpp:1027-1088): K1 + triple enumeration + PLG following +
+ * view expansion.  Output order = seed order, chain order inside a seed. */
+eg3d_status eg3d_match_seeds(eg3d_scene*, const eg3d_seeds*, const eg3d_candidates* /* may be NULL */,
+                             eg3d_points** out, eg3d_timing* timing);
+
+/* B1 batched over polyline matches: find_new_3d_points_from_compatible_polylines_expandallviews[_parallel]
+ * (polyline_matching.hpp:55-56) called once per candidate set as pipelines.cpp:92-100 does; seeds are
+ * sampled internally (views ascending, candidate polylines ascending, 20 px steps).
+ * view_begin/view_end restrict the STARTING views (multi-GPU shard axis, polyline_matching.cpp:162). */
+eg3d_status eg3d_match_polyline_sets(eg3d_scene*, const eg3d_candidates*, int32_t view_begin, int32_t view_end,
+                                     eg3d_points** out, eg3d_timing* timing);
+
+/* B2: plg_matching_from_refpoints[_parallel] (plg_matching_from_refpoints.hpp:53-55) over tracks
+ * [track_begin, track_end) of the scene (multi-GPU shard axis, plg_matching_from_refpoints.cpp:90). */
+eg3d_status eg3d_match_refpoints(eg3d_scene*, int64_t track_begin, int64_t track_end,
+                                 eg3d_points** out, eg3d_timing* timing);
+
+eg3d_status eg3d_points_get(const eg3d_points*, eg3d_points_view* view);
+void        eg3d_points_free(eg3d_points*);
+
+/* K2 alone (B5/B6 primitives).  Hypotheses: CSR of (view, xy) observations + initial X.
+ * fp64 = 1: em_GaussNewton semantics (triangulation.cpp:105-176), inputs f32, arithmetic f64.
+ * fp64 = 0: GaussNewton of the outlier filter (filtering/gauss_newton.cpp:83-134), arithmetic f32.
+ * Host-buffer call: copies in, runs, copies out.  out_xyz [n][3], out_mse [n] (last_mse), out_ok [n]. */
+eg3d_status eg3d_gn_triangulate(eg3d_scene*, int64_t n_hyp, const int64_t* obs_off, const int32_t* obs_view,
+                                const float* obs_xy, const float* init_xyz, int fp64,
+                                float* out_xyz, float* out_mse, uint8_t* out_ok, eg3d_timing* timing);
+
+/* Device-resident variant used by the microbenchmark: all pointers are device pointers on the scene's
+ * device; fixed `obs_per_hyp` observations per hypothesis (obs arrays are [n][obs_per_hyp]). */
+eg3d_status eg3d_gn_triangulate_device(eg3d_scene*, int64_t n_hyp, int32_t obs_per_hyp, const int32_t* d_obs_view,
+                                       const float* d_obs_xy, const float* d_init_xyz, int fp64,
+                                       float* d_out_xyz, float* d_out_mse, uint8_t* d_out_ok, eg3d_timing* timing);
+
+/* a13: filter_3d_points_close_2d_array (filtering_close_plgps.cpp:75-124).  keep[n_points] on host.
+ * Order dependent: points are visited in the order given. */
+eg3d_status eg3d_dedup_close_points(eg3d_scene*, const eg3d_points_view* pts, uint8_t* keep);
+
+/* a14 / B6: filter(sfmd, first_edgepoint, gn_max_mse, forced_min_filter) (outliers_filtering.hpp:18-21).
+ * Points are tracks given as CSR; xyz is updated in place for GN inliers (gauss_newton.cpp:168-173);
+ * inliers[n] receives compute_inliers' bitmap (outliers_filtering.cpp:37-64). forced_min_filter < 0 = off. */
+eg3d_status eg3d_filter(eg3d_scene*, int64_t n, float* xyz, const int64_t* obs_off, const int32_t* obs_view,
+                        const float* obs_xy, int64_t first_edgepoint, float gn_max_mse, int32_t forced_min_filter,
+                        uint8_t* inliers, eg3d_timing* timing);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EG3D_H_ */
