@@ -1,0 +1,63 @@
+"""Oracle vs the cv2-generated known-answer vectors (tests/golden/make_golden_cv2.py): pins the oracle at the
+OpenCV boundary — the only third-party arithmetic on the hot path."""
+import ctypes as C
+import numpy as np
+from edgegraph3d_b200 import _abi as A
+from edgegraph3d_b200.scene import FlatScene
+from tests import oracle_lib as O
+
+
+def _scene_with_cameras(cams):
+    V = cams.shape[0]
+    # one dummy 2-vertex polyline per view: the GN / DLT entry points only read the cameras
+    return FlatScene(640, 480, cams, np.zeros((V, V, 9)), np.zeros((V, V), np.uint8), np.arange(V + 1), np.arange(V + 1) * 2,
+                     np.tile(np.array([[10, 10], [20, 20]], np.float32), (V, 1)), np.zeros(V, np.uint32), np.ones(V, np.uint32))
+
+
+def test_epiline_bit_exact(golden):
+    L = O.lib()
+    out = np.zeros(3, np.float32)
+    for F, p, ref in zip(golden["epi_F"], golden["epi_pts"], golden["epi_lines"]):
+        F = np.ascontiguousarray(F)
+        assert L.eg3d_oracle_epiline(A.ptr(F, A.c_f64p), float(p[0]), float(p[1]), A.ptr(out, A.c_f32p))
+        assert out.tobytes() == ref.tobytes()
+
+
+def test_dlt_matches_triangulatePoints(golden):
+    L = O.lib()
+    cams = golden["dlt_cams"]
+    out = np.zeros(4, np.float32)
+    worst = 0.0
+    for va, vb, x1, x2, ref in zip(golden["dlt_va"], golden["dlt_vb"], golden["dlt_x1"], golden["dlt_x2"], golden["dlt_X4"]):
+        P1, P2 = np.ascontiguousarray(cams[va]), np.ascontiguousarray(cams[vb])
+        x1, x2 = np.ascontiguousarray(x1), np.ascontiguousarray(x2)
+        L.eg3d_oracle_triangulate_dlt(A.ptr(P1, A.c_f32p), A.ptr(P2, A.c_f32p), A.ptr(x1, A.c_f32p), A.ptr(x2, A.c_f32p), A.ptr(out, A.c_f32p))
+        a = out[:3].astype(np.float64) / float(out[3])
+        b = ref[:3].astype(np.float64) / float(ref[3])
+        worst = max(worst, np.abs(a - b).max() / max(1e-3, np.abs(b).max()))
+    # only a GN initialiser: float32-cast agreement
+    assert worst < 5e-6, worst
+
+
+def _run_gn(golden, name, fp64):
+    sc = _scene_with_cameras(golden["cams"])
+    osc = O.OracleScene(sc)
+    init = golden[f"{name}_init"].astype(np.float32)
+    return osc.gn_triangulate(golden[f"{name}_off"], golden[f"{name}_view"], golden[f"{name}_xy"], init, fp64)
+
+
+def test_gn64_matches_cv2_rebuild(golden):
+    xyz, mse, ok = _run_gn(golden, "gn64", True)
+    assert np.array_equal(ok, golden["gn64_ok"])
+    sel = golden["gn64_ok"] == 1
+    # same operations in the same order on CV_64F: expect bit-level agreement after the float32 narrowing
+    assert np.array_equal(xyz[sel], golden["gn64_X"][sel].astype(np.float32))
+    assert np.array_equal(mse, golden["gn64_mse"].astype(np.float32))
+
+
+def test_gn32_matches_cv2_rebuild(golden):
+    xyz, mse, ok = _run_gn(golden, "gn32", False)
+    assert np.array_equal(ok, golden["gn32_ok"])
+    sel = golden["gn32_ok"] == 1
+    assert np.array_equal(xyz[sel], golden["gn32_X"][sel].astype(np.float32))
+    assert np.array_equal(mse, golden["gn32_mse"].astype(np.float32))
