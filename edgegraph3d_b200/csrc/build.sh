@@ -1,0 +1,8 @@
+#!/bin/bash
+# Builds edgegraph3d_b200/libeg3d.so for sm_100a (B200).  -fmad=false: float/double expressions must round exactly as
+# written (threshold parity with the reference's non-FMA x86-64 build); IEEE division / sqrt are nvcc defaults.
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+$NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true \
+  -Xcompiler -fPIC -Xcompiler -O3 -shared -o ../libeg3d.so eg3d_capi.cu "$@"

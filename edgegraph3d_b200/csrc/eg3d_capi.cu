@@ -1,0 +1,658 @@
+// eg3d_capi.cu — host side of libeg3d.so: scene upload + derived structures, kernel orchestration, ordered packing of
+// the accepted points, and the extern "C" boundary declared in include/eg3d.h.  No CPU fallback: every compute entry
+// point requires a CUDA device and fails with EG3D_ERR_NO_DEVICE otherwise.
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <set>
+#include <algorithm>
+#include <memory>
+#include <cub/cub.cuh>
+#include "eg3d_dev.cuh"
+#include "eg3d_k1.cuh"
+#include "eg3d_k3.cuh"
+#include "eg3d_gn.cuh"
+
+using namespace eg3d;
+
+static thread_local std::string g_err;
+static eg3d_status fail(eg3d_status s, const std::string& m) { g_err = m; return s; }
+#define CK(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) {                                                                                  \
+      char b_[512]; snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return fail(e_ == cudaErrorMemoryAllocation ? EG3D_ERR_OOM : EG3D_ERR_CUDA, b_);                         \
+    }                                                                                                         \
+  } while (0)
+
+template <typename T>
+struct DBuf {  // owning device buffer
+  T* p = nullptr; size_t n = 0;
+  DBuf() {}
+  DBuf(const DBuf&) = delete; DBuf& operator=(const DBuf&) = delete;
+  ~DBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t count) { if (p) cudaFree(p); p = nullptr; n = count; return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)); }
+  cudaError_t upload(const T* h, size_t count, cudaStream_t s) {
+    cudaError_t e = alloc(count); if (e != cudaSuccess) return e;
+    if (count) e = cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& h, cudaStream_t s) { return upload(h.data(), h.size(), s); }
+};
+
+struct HostGrid { float cell; int w, h; std::vector<int> off; std::vector<uint32_t> ids; };
+
+struct eg3d_scene {
+  int device = 0; cudaStream_t stream = nullptr;
+  int V = 0, width = 0, height = 0, num_sms = 0;
+  eg3d_params prm;
+  DBuf<float> P; DBuf<double> F; DBuf<uint8_t> Fvalid;
+  DBuf<int> view_poly_off, poly_vert_off, view_seg_off, poly_seg_off;
+  DBuf<float2> verts; DBuf<uint32_t> poly_start, poly_end;
+  DBuf<float4> seg; DBuf<uint2> seg_id;
+  DBuf<int> g4_off, g30_off; DBuf<uint32_t> g4_ids, g30_ids;
+  DBuf<float> track_xyz; DBuf<int64_t> track_off; DBuf<int32_t> track_view; DBuf<float2> track_xy;
+  DevScene dev;
+  // host copies needed by host-side steps (seed sampler, refpoint seeding)
+  std::vector<int> h_view_poly_off, h_poly_vert_off; std::vector<float2> h_verts; std::vector<uint32_t> h_start, h_end;
+  std::vector<int> h_view_seg_off;
+  HostGrid hg30;
+  std::vector<int64_t> h_track_off; std::vector<int32_t> h_track_view; std::vector<float2> h_track_xy;
+  int max_view_segs = 0;
+};
+
+struct eg3d_points {
+  std::vector<float> xyz; std::vector<int32_t> seed, chain_pos; std::vector<int64_t> obs_off;
+  std::vector<int32_t> obs_view; std::vector<uint32_t> obs_poly, obs_seg; std::vector<float> obs_xy;
+};
+struct eg3d_hits { int64_t n_seeds; int V; std::vector<int64_t> off; std::vector<eg3d_hit> hits; };
+
+// ------------------------------------------------------------------------------------------------ host helpers ----
+// polyline::get_intersectedcells_2dmap_set (polyline_graph_2d.cpp:798-835) + PolyLine2DMap ctor (polyLine_2d_map.cpp:40-58)
+static void build_grid(const eg3d_scene& sc, float cell, HostGrid& g) {
+  g.cell = cell; g.w = (int)ceilf(sc.width / cell); g.h = (int)ceilf(sc.height / cell);
+  const int V = sc.V; const size_t ncell = (size_t)g.w * g.h;
+  std::vector<std::vector<uint32_t>> cells(ncell);
+  g.off.assign((size_t)V * ncell + 1, 0);
+  g.ids.clear();
+  DevScene hs; memset(&hs, 0, sizeof hs);
+  hs.V = V; hs.view_poly_off = sc.h_view_poly_off.data(); hs.poly_vert_off = sc.h_poly_vert_off.data();
+  hs.verts = sc.h_verts.data(); hs.poly_start = sc.h_start.data(); hs.poly_end = sc.h_end.data();
+  const float step = (float)(cell / (1.414 + 0.1));
+  for (int v = 0; v < V; v++) {
+    for (auto& c : cells) c.clear();
+    const int npl = sc.h_view_poly_off[v + 1] - sc.h_view_poly_off[v];
+    for (int id = 0; id < npl; id++) {
+      Pl pl = get_pl(hs, v, (uint32_t)id);
+      if (pl.n < 2) continue;
+      std::set<std::pair<int, int>> cs;
+      PlP cur; cur.seg = 0; cur.c = pl.pc[0];
+      bool reached = false; bool first = true;
+      while (true) {
+        if (!first) { cur = step_by_distance(pl, cur, pl.end, step, reached); }
+        first = false;
+        bool on_boundary = is_multiple_of(cur.c.x, cell) || is_multiple_of(cur.c.y, cell);
+        if (!on_boundary) cs.insert({(int)floor_or_upper_if_close(cur.c.x / cell), (int)floor_or_upper_if_close(cur.c.y / cell)});
+        if (reached) break;
+      }
+      for (auto& c : cs) if (c.first >= 0 && c.first < g.w && c.second >= 0 && c.second < g.h) cells[(size_t)c.second * g.w + c.first].push_back((uint32_t)id);
+    }
+    for (size_t c = 0; c < ncell; c++) {
+      g.ids.insert(g.ids.end(), cells[c].begin(), cells[c].end());
+      g.off[(size_t)v * ncell + c + 1] = (int)g.ids.size();
+    }
+  }
+}
+
+static eg3d_status require_device() {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) return fail(EG3D_ERR_NO_DEVICE, "no usable CUDA device (libeg3d has no CPU fallback)");
+  return EG3D_OK;
+}
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s;
+  explicit Timer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~Timer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  void start() { cudaEventRecord(a, s); }
+  void stop() { cudaEventRecord(b, s); }
+  float ms() { float m = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&m, a, b); return m; }
+};
+
+// ------------------------------------------------------------------------------------------------ pack kernels ----
+__global__ void pack_points_kernel(int n_seeds, const int* __restrict__ seed_npts, const int64_t* __restrict__ seed_pbase,
+                                   const int64_t* __restrict__ pt_off, const float* __restrict__ uX, const int* __restrict__ unobs,
+                                   float* __restrict__ xyz, int* __restrict__ seed_out, int* __restrict__ pos_out,
+                                   int64_t* __restrict__ nobs_out, int64_t* __restrict__ src_out) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_seeds) return;
+  int n = seed_npts[s];
+  int64_t src = seed_pbase[s], dst = pt_off[s];
+  for (int j = 0; j < n; j++) {
+    xyz[3 * (dst + j)] = uX[3 * (src + j)]; xyz[3 * (dst + j) + 1] = uX[3 * (src + j) + 1]; xyz[3 * (dst + j) + 2] = uX[3 * (src + j) + 2];
+    seed_out[dst + j] = s; pos_out[dst + j] = j; nobs_out[dst + j] = unobs[src + j]; src_out[dst + j] = src + j;
+  }
+}
+__global__ void pack_obs_kernel(int64_t n_points, const int64_t* __restrict__ obs_off, const int64_t* __restrict__ src,
+                                const int64_t* __restrict__ uobase, const int* __restrict__ uv, const uint32_t* __restrict__ upl,
+                                const uint32_t* __restrict__ useg, const float* __restrict__ ux, const float* __restrict__ uy,
+                                int* __restrict__ ov, uint32_t* __restrict__ opl, uint32_t* __restrict__ oseg, float* __restrict__ oxy) {
+  int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (p >= n_points) return;
+  int64_t d0 = obs_off[p], n = obs_off[p + 1] - d0, s0 = uobase[src[p]];
+  for (int64_t k = lane; k < n; k += 32) {
+    ov[d0 + k] = uv[s0 + k]; opl[d0 + k] = upl[s0 + k]; oseg[d0 + k] = useg[s0 + k];
+    oxy[2 * (d0 + k)] = ux[s0 + k]; oxy[2 * (d0 + k) + 1] = uy[s0 + k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ seeds on device ----
+struct DevSeeds {
+  DBuf<int> view; DBuf<uint32_t> pl, seg; DBuf<float2> xy; DBuf<int> cand_set; int n = 0;
+  K1Seeds k1() const { K1Seeds s; s.n = n; s.view = view.p; s.pl = pl.p; s.seg = seg.p; s.xy = xy.p; s.cand_set = cand_set.p; return s; }
+};
+struct DevCand { DBuf<int64_t> off; DBuf<uint32_t> pl; };
+
+static eg3d_status upload_seeds(eg3d_scene* sc, const eg3d_seeds* s, bool need_cand, DevSeeds& d) {
+  d.n = (int)s->n;
+  CK(d.view.upload(s->view, s->n, sc->stream));
+  CK(d.pl.upload(s->polyline, s->n, sc->stream));
+  CK(d.seg.upload(s->segment, s->n, sc->stream));
+  CK(d.xy.upload((const float2*)s->xy, s->n, sc->stream));
+  if (need_cand) CK(d.cand_set.upload(s->cand_set, s->n, sc->stream));
+  return EG3D_OK;
+}
+
+// K1: count -> scan -> fill.  Leaves off (n*V+1) and hits on the device.
+static eg3d_status run_k1(eg3d_scene* sc, const DevSeeds& ds, const DevCand* dc, DBuf<int64_t>& off, DBuf<eg3d_hit>& hits,
+                          int64_t& n_hits, eg3d_timing* tm) {
+  const int V = sc->V; const int64_t nsv = (int64_t)ds.n * V;
+  CK(off.alloc(nsv + 1));
+  CK(cudaMemsetAsync(off.p + nsv, 0, sizeof(int64_t), sc->stream));
+  Timer t1(sc->stream), t2(sc->stream), t3(sc->stream);
+  K1Seeds ks = ds.k1();
+  dim3 grid((ds.n + K1_THREADS - 1) / K1_THREADS, V);
+  K1Cand kc; kc.off = dc ? dc->off.p : nullptr; kc.pl = dc ? dc->pl.p : nullptr;
+  const int cblocks = (int)((nsv + 255) / 256);
+  t1.start();
+  if (ds.n > 0) {
+    if (dc) k1_cand_kernel<false><<<cblocks, 256, 0, sc->stream>>>(sc->dev, ks, kc, off.p, nullptr, nullptr);
+    else k1_sweep_kernel<false><<<grid, K1_THREADS, K1_SMEM_BYTES, sc->stream>>>(sc->dev, ks, 0, off.p, nullptr, nullptr);
+  }
+  t1.stop();
+  CK(cudaGetLastError());
+  t2.start();
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, off.p, off.p, nsv + 1, sc->stream);
+  DBuf<unsigned char> tmp; CK(tmp.alloc(tb));
+  cub::DeviceScan::ExclusiveSum(tmp.p, tb, off.p, off.p, nsv + 1, sc->stream);
+  t2.stop();
+  CK(cudaMemcpyAsync(&n_hits, off.p + nsv, sizeof(int64_t), cudaMemcpyDeviceToHost, sc->stream));
+  CK(cudaStreamSynchronize(sc->stream));
+  CK(hits.alloc((size_t)n_hits));
+  t3.start();
+  if (ds.n > 0) {
+    if (dc) k1_cand_kernel<true><<<cblocks, 256, 0, sc->stream>>>(sc->dev, ks, kc, nullptr, off.p, hits.p);
+    else k1_sweep_kernel<true><<<grid, K1_THREADS, K1_SMEM_BYTES, sc->stream>>>(sc->dev, ks, 0, nullptr, off.p, hits.p);
+  }
+  t3.stop();
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(sc->stream));
+  if (tm) {
+    tm->k1_count_ms += t1.ms(); tm->scan_ms += t2.ms(); tm->k1_fill_ms += t3.ms();
+    tm->n_hits += n_hits; tm->kernel_launches += 4;
+  }
+  return EG3D_OK;
+}
+
+// K3 + ordered packing + D2H into an eg3d_points
+static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_off, const eg3d_hit* d_hits, eg3d_points* out, eg3d_timing* tm) {
+  const int V = sc->V; const int n = ds.n;
+  out->obs_off.assign(1, 0);
+  if (n == 0) return EG3D_OK;
+  const int capf = sc->prm.max_follow_points, capc = sc->prm.max_chain_points, oc = V + 16;
+  const size_t spw = k3_scratch_bytes(V, capf, capc, oc);
+  int blocks_per_sm = 8;  // 32 warps per SM
+  int nblocks = sc->num_sms * blocks_per_sm;
+  const int warps_per_block = K3_THREADS / 32;
+  int max_useful = (n + warps_per_block - 1) / warps_per_block;
+  if (nblocks > max_useful) nblocks = max_useful;
+  const size_t nwarps = (size_t)nblocks * warps_per_block;
+  DBuf<unsigned char> scratch; CK(scratch.alloc(nwarps * spw));
+  DBuf<int> counter; CK(counter.alloc(1)); CK(cudaMemsetAsync(counter.p, 0, sizeof(int), sc->stream));
+  DBuf<unsigned long long> oc4; CK(oc4.alloc(4)); CK(cudaMemsetAsync(oc4.p, 0, 4 * sizeof(unsigned long long), sc->stream));
+  // unordered output capacity: generous typical-case bound; exceeding it is reported, never silently truncated
+  int64_t pt_cap = std::min<int64_t>((int64_t)n * capc, std::max<int64_t>((int64_t)n * 24, 1 << 16));
+  int64_t ob_cap = pt_cap * std::min<int64_t>(oc, 64 + V / 2);
+  DBuf<float> uX; DBuf<int> unobs; DBuf<int64_t> uobase; DBuf<int> uv; DBuf<uint32_t> upl, useg; DBuf<float> ux, uy;
+  DBuf<int> snp; DBuf<int64_t> spb, sno;
+  CK(uX.alloc(3 * pt_cap)); CK(unobs.alloc(pt_cap)); CK(uobase.alloc(pt_cap));
+  CK(uv.alloc(ob_cap)); CK(upl.alloc(ob_cap)); CK(useg.alloc(ob_cap)); CK(ux.alloc(ob_cap)); CK(uy.alloc(ob_cap));
+  CK(snp.alloc(n)); CK(spb.alloc(n)); CK(sno.alloc(n));
+  K3Args a; memset(&a, 0, sizeof a);
+  a.n_seeds = n; a.seed_view = ds.view.p; a.seed_pl = ds.pl.p; a.seed_seg = ds.seg.p; a.seed_xy = ds.xy.p;
+  a.hit_off = d_off; a.hits = d_hits; a.capf = capf; a.capc = capc; a.oc = oc;
+  a.scratch = scratch.p; a.scratch_per_warp = spw; a.work_counter = counter.p;
+  a.pt_cap = pt_cap; a.ob_cap = ob_cap; a.out_counters = oc4.p;
+  a.o_X = uX.p; a.o_nobs = unobs.p; a.o_obase = uobase.p;
+  a.ob_view = uv.p; a.ob_pl = upl.p; a.ob_seg = useg.p; a.ob_x = ux.p; a.ob_y = uy.p;
+  a.seed_npts = snp.p; a.seed_pbase = spb.p; a.seed_nobs = sno.p;
+  Timer t3(sc->stream), tp(sc->stream);
+  t3.start();
+  k3_chain_kernel<<<nblocks, K3_THREADS, 0, sc->stream>>>(sc->dev, a);
+  t3.stop();
+  CK(cudaGetLastError());
+  unsigned long long cnt[4];
+  CK(cudaMemcpyAsync(cnt, oc4.p, sizeof cnt, cudaMemcpyDeviceToHost, sc->stream));
+  CK(cudaStreamSynchronize(sc->stream));
+  if (tm) { tm->k3_ms += t3.ms(); tm->kernel_launches += 1; tm->n_capacity_overflows += (int)(cnt[2] + cnt[3]); }
+  if (cnt[3]) return fail(EG3D_ERR_CAPACITY, "accepted-point output buffer exceeded (internal bound); split the seed batch");
+  if (cnt[2]) return fail(EG3D_ERR_CAPACITY, "a per-seed capacity (max_chain_points / max_follow_points / observations per point) was exceeded; raise eg3d_params capacities");
+  // ordered packing
+  tp.start();
+  DBuf<int64_t> pt_off; CK(pt_off.alloc(n + 1));
+  {
+    // int -> int64 exclusive scan of seed_npts
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, snp.p, pt_off.p, n, sc->stream);
+    DBuf<unsigned char> tmp; CK(tmp.alloc(tb));
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, snp.p, pt_off.p, n, sc->stream);
+    CK(cudaStreamSynchronize(sc->stream));
+  }
+  const int64_t npts = (int64_t)cnt[0], nobs = (int64_t)cnt[1];
+  DBuf<float> xyz; DBuf<int> pseed, ppos; DBuf<int64_t> obs_off, src;
+  CK(xyz.alloc(3 * npts)); CK(pseed.alloc(npts)); CK(ppos.alloc(npts)); CK(obs_off.alloc(npts + 1)); CK(src.alloc(npts));
+  CK(cudaMemsetAsync(obs_off.p + npts, 0, sizeof(int64_t), sc->stream));
+  pack_points_kernel<<<(n + 127) / 128, 128, 0, sc->stream>>>(n, snp.p, spb.p, pt_off.p, uX.p, unobs.p, xyz.p, pseed.p, ppos.p, obs_off.p, src.p);
+  {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, obs_off.p, obs_off.p, npts + 1, sc->stream);
+    DBuf<unsigned char> tmp; CK(tmp.alloc(tb));
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, obs_off.p, obs_off.p, npts + 1, sc->stream);
+    CK(cudaStreamSynchronize(sc->stream));
+  }
+  DBuf<int> ov; DBuf<uint32_t> opl, oseg; DBuf<float> oxy;
+  CK(ov.alloc(nobs)); CK(opl.alloc(nobs)); CK(oseg.alloc(nobs)); CK(oxy.alloc(2 * nobs));
+  if (npts > 0) {
+    int64_t threads = npts * 32;
+    pack_obs_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, sc->stream>>>(npts, obs_off.p, src.p, uobase.p, uv.p, upl.p, useg.p, ux.p, uy.p,
+                                                                            ov.p, opl.p, oseg.p, oxy.p);
+  }
+  tp.stop();
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(sc->stream));
+  if (tm) { tm->pack_ms += tp.ms(); tm->kernel_launches += 4; tm->n_points += npts; tm->n_obs += nobs; }
+  // D2H
+  out->xyz.resize(3 * npts); out->seed.resize(npts); out->chain_pos.resize(npts); out->obs_off.resize(npts + 1);
+  out->obs_view.resize(nobs); out->obs_poly.resize(nobs); out->obs_seg.resize(nobs); out->obs_xy.resize(2 * nobs);
+  if (npts > 0) {
+    CK(cudaMemcpyAsync(out->xyz.data(), xyz.p, 3 * npts * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+    CK(cudaMemcpyAsync(out->seed.data(), pseed.p, npts * sizeof(int), cudaMemcpyDeviceToHost, sc->stream));
+    CK(cudaMemcpyAsync(out->chain_pos.data(), ppos.p, npts * sizeof(int), cudaMemcpyDeviceToHost, sc->stream));
+    CK(cudaMemcpyAsync(out->obs_view.data(), ov.p, nobs * sizeof(int), cudaMemcpyDeviceToHost, sc->stream));
+    CK(cudaMemcpyAsync(out->obs_poly.data(), opl.p, nobs * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc->stream));
+    CK(cudaMemcpyAsync(out->obs_seg.data(), oseg.p, nobs * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc->stream));
+    CK(cudaMemcpyAsync(out->obs_xy.data(), oxy.p, 2 * nobs * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+  }
+  CK(cudaMemcpyAsync(out->obs_off.data(), obs_off.p, (npts + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, sc->stream));
+  CK(cudaStreamSynchronize(sc->stream));
+  return EG3D_OK;
+}
+
+static void k1_accounting(const eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d_candidates* cands, int64_t n_hits, eg3d_timing* tm) {
+  // per (seed, target view) 16 B x segments swept + 72 B (F) + 8 B (seed) + 16 B x hits written
+  int64_t tests = 0;
+  const int V = sc->V;
+  if (!cands) {
+    int64_t total = sc->h_view_seg_off[V];
+    for (int64_t i = 0; i < seeds->n; i++) tests += total - (sc->h_view_seg_off[seeds->view[i] + 1] - sc->h_view_seg_off[seeds->view[i]]);
+    tm->k1_algorithmic_bytes += 16 * tests + (72 + 8) * seeds->n * (int64_t)(V - 1) + 16 * n_hits;
+  } else {
+    int64_t ncand = 0;
+    for (int64_t i = 0; i < seeds->n; i++) {
+      int set = seeds->cand_set[i];
+      for (int v = 0; v < V; v++) {
+        if (v == seeds->view[i]) continue;
+        for (int64_t k = cands->off[(size_t)set * V + v]; k < cands->off[(size_t)set * V + v + 1]; k++) {
+          int g = sc->h_view_poly_off[v] + (int)cands->polyline[k];
+          int nv = sc->h_poly_vert_off[g + 1] - sc->h_poly_vert_off[g];
+          tests += nv > 1 ? nv - 1 : 0; ncand++;
+        }
+      }
+    }
+    tm->k1_algorithmic_bytes += 16 * tests + 4 * ncand + (72 + 8) * seeds->n * (int64_t)(V - 1) + 16 * n_hits;
+  }
+  tm->n_segment_tests += tests;
+}
+
+// ================================================================================================ C ABI ============
+extern "C" {
+
+const char* eg3d_last_error(void) { return g_err.c_str(); }
+int eg3d_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+void eg3d_params_default(eg3d_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->split_interval_distance = 20.0f; p->follow_first_image_distance = 10.0f;
+  p->follow_corr_min = 5.0f; p->follow_corr_max = 20.0f;
+  p->quasiparallel_cos = 0.965f; p->quasiparallel_dist = 5.0f;
+  p->max_proj_distsq_expand = 16.0f; p->expand_grid_cell = 4.0f;
+  p->detection_starting_radius = 10.0f; p->detection_mult = 3.0f;
+  p->gn_max_iters = 30; p->gn_stop = 0.0000005; p->gn_det_min = 0.00001; p->gn_accept_mse = 9;
+  p->filter_gn_stop = 0.0000000005; p->filter_gn_det_min = 0.0000000001; p->filter_gn_max_mse = 2.25f;
+  p->filter_3views_amount = 3; p->dedup_cell = 3.0f; p->dlt_wellposed = 1; p->filter_abs_int = 0;
+  p->max_chain_points = 96; p->max_follow_points = 160;
+}
+
+eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* params, eg3d_scene** out) {
+  if (!d || !out || d->n_views <= 0) return fail(EG3D_ERR_INVALID_ARG, "bad scene descriptor");
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  eg3d_scene* sc = new eg3d_scene();
+  std::unique_ptr<eg3d_scene> guard(sc);
+  CK(cudaGetDevice(&sc->device));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, sc->device));
+  sc->num_sms = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+  if (params) sc->prm = *params; else eg3d_params_default(&sc->prm);
+  const int V = sc->V = d->n_views; sc->width = d->width; sc->height = d->height;
+  const int64_t NP = d->view_poly_off[V], NV = d->poly_vert_off[NP];
+  if (NV > 0x7fffffff) return fail(EG3D_ERR_INVALID_ARG, "too many vertices");
+  sc->h_view_poly_off.resize(V + 1); for (int i = 0; i <= V; i++) sc->h_view_poly_off[i] = (int)d->view_poly_off[i];
+  sc->h_poly_vert_off.resize(NP + 1); for (int64_t i = 0; i <= NP; i++) sc->h_poly_vert_off[i] = (int)d->poly_vert_off[i];
+  sc->h_verts.assign((const float2*)d->verts, (const float2*)d->verts + NV);
+  sc->h_start.assign(d->poly_start, d->poly_start + NP); sc->h_end.assign(d->poly_end, d->poly_end + NP);
+  // staged segments: every valid polyline, (P[i], P[i-1]) orientation, as (x1, y1, dx, dy)
+  std::vector<float4> seg; std::vector<uint2> seg_id; std::vector<int> poly_seg_off(NP + 1, 0);
+  sc->h_view_seg_off.assign(V + 1, 0);
+  for (int v = 0; v < V; v++) {
+    for (int g = sc->h_view_poly_off[v]; g < sc->h_view_poly_off[v + 1]; g++) {
+      poly_seg_off[g] = (int)seg.size();
+      const int o = sc->h_poly_vert_off[g], nv = sc->h_poly_vert_off[g + 1] - o;
+      for (int i = 1; i < nv; i++) {
+        float2 a = sc->h_verts[o + i], b = sc->h_verts[o + i - 1];
+        seg.push_back(make_float4(a.x, a.y, b.x - a.x, b.y - a.y));
+        seg_id.push_back(make_uint2((uint32_t)(g - sc->h_view_poly_off[v]), (uint32_t)(i - 1)));
+      }
+    }
+    sc->h_view_seg_off[v + 1] = (int)seg.size();
+    sc->max_view_segs = std::max(sc->max_view_segs, sc->h_view_seg_off[v + 1] - sc->h_view_seg_off[v]);
+  }
+  poly_seg_off[NP] = (int)seg.size();
+  HostGrid g4; build_grid(*sc, sc->prm.expand_grid_cell, g4);
+  const bool tracks = d->n_tracks > 0;
+  if (tracks) build_grid(*sc, sc->prm.detection_starting_radius * sc->prm.detection_mult, sc->hg30);
+  cudaStream_t s = sc->stream;
+  CK(sc->P.upload(d->cameras, (size_t)V * 12, s));
+  CK(sc->F.upload(d->fundamental, (size_t)V * V * 9, s));
+  CK(sc->Fvalid.upload(d->fundamental_valid, (size_t)V * V, s));
+  CK(sc->view_poly_off.upload(sc->h_view_poly_off, s)); CK(sc->poly_vert_off.upload(sc->h_poly_vert_off, s));
+  CK(sc->verts.upload(sc->h_verts, s)); CK(sc->poly_start.upload(sc->h_start, s)); CK(sc->poly_end.upload(sc->h_end, s));
+  CK(sc->view_seg_off.upload(sc->h_view_seg_off, s)); CK(sc->poly_seg_off.upload(poly_seg_off, s));
+  CK(sc->seg.upload(seg, s)); CK(sc->seg_id.upload(seg_id, s));
+  CK(sc->g4_off.upload(g4.off, s)); CK(sc->g4_ids.upload(g4.ids, s));
+  if (tracks) {
+    CK(sc->g30_off.upload(sc->hg30.off, s)); CK(sc->g30_ids.upload(sc->hg30.ids, s));
+    const int64_t NO = d->track_off[d->n_tracks];
+    CK(sc->track_xyz.upload(d->track_xyz, (size_t)d->n_tracks * 3, s)); CK(sc->track_off.upload(d->track_off, (size_t)d->n_tracks + 1, s));
+    CK(sc->track_view.upload(d->track_view, (size_t)NO, s)); CK(sc->track_xy.upload((const float2*)d->track_xy, (size_t)NO, s));
+    sc->h_track_off.assign(d->track_off, d->track_off + d->n_tracks + 1);
+    sc->h_track_view.assign(d->track_view, d->track_view + NO);
+    sc->h_track_xy.assign((const float2*)d->track_xy, (const float2*)d->track_xy + NO);
+  }
+  CK(cudaStreamSynchronize(s));
+  DevScene& D = sc->dev; memset(&D, 0, sizeof D);
+  D.V = V; D.width = sc->width; D.height = sc->height;
+  D.P = sc->P.p; D.F = sc->F.p; D.Fvalid = sc->Fvalid.p;
+  D.view_poly_off = sc->view_poly_off.p; D.poly_vert_off = sc->poly_vert_off.p; D.verts = sc->verts.p;
+  D.poly_start = sc->poly_start.p; D.poly_end = sc->poly_end.p;
+  D.view_seg_off = sc->view_seg_off.p; D.seg = sc->seg.p; D.seg_id = sc->seg_id.p; D.poly_seg_off = sc->poly_seg_off.p;
+  D.g_expand.cell = g4.cell; D.g_expand.w = g4.w; D.g_expand.h = g4.h; D.g_expand.cell_off = sc->g4_off.p; D.g_expand.ids = sc->g4_ids.p;
+  if (tracks) { D.g_corr.cell = sc->hg30.cell; D.g_corr.w = sc->hg30.w; D.g_corr.h = sc->hg30.h; D.g_corr.cell_off = sc->g30_off.p; D.g_corr.ids = sc->g30_ids.p; }
+  D.n_tracks = d->n_tracks; D.track_xyz = sc->track_xyz.p; D.track_off = sc->track_off.p; D.track_view = sc->track_view.p; D.track_xy = sc->track_xy.p;
+  D.prm = sc->prm;
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
+  *out = guard.release();
+  return EG3D_OK;
+}
+
+void eg3d_scene_destroy(eg3d_scene* sc) {
+  if (!sc) return;
+  cudaSetDevice(sc->device);
+  if (sc->stream) cudaStreamDestroy(sc->stream);
+  delete sc;
+}
+
+eg3d_status eg3d_sample_seeds(const eg3d_scene_desc* d, const int32_t* views, const uint32_t* polylines, int64_t n_pl, float spacing,
+                              int64_t capacity, int32_t* o_view, uint32_t* o_pl, uint32_t* o_seg, float* o_xy, int32_t* o_src, int64_t* n_out) {
+  if (!d || !n_out) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  int64_t n = 0;
+  for (int64_t k = 0; k < n_pl; k++) {
+    const int64_t g = d->view_poly_off[views[k]] + polylines[k];
+    Pl pl; pl.pc = (const float2*)d->verts + d->poly_vert_off[g]; pl.n = (int)(d->poly_vert_off[g + 1] - d->poly_vert_off[g]);
+    pl.start = d->poly_start[g]; pl.end = d->poly_end[g];
+    if (pl.n < 2) continue;
+    PlP plp; plp.seg = 0; plp.c = pl.pc[0];                                  // get_start_plp
+    bool reached;
+    plp = step_by_distance(pl, plp, pl.end, spacing, reached);              // polyline_matching.cpp:172
+    while (!reached) {
+      if (n < capacity) { o_view[n] = views[k]; o_pl[n] = polylines[k]; o_seg[n] = plp.seg; o_xy[2 * n] = plp.c.x; o_xy[2 * n + 1] = plp.c.y; if (o_src) o_src[n] = (int32_t)k; }
+      n++;
+      plp = step_by_distance(pl, plp, pl.end, spacing, reached);            // :185
+    }
+  }
+  *n_out = n;
+  return n <= capacity ? EG3D_OK : fail(EG3D_ERR_CAPACITY, "seed capacity too small");
+}
+
+static eg3d_status check_seeds(const eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d_candidates* cands) {
+  if (!sc || !seeds) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  if (seeds->n > 0x7fffffff / std::max(1, sc->V)) {}
+  if (cands) {
+    if (!seeds->cand_set) return fail(EG3D_ERR_INVALID_ARG, "candidates given but seeds->cand_set is null");
+    for (int64_t i = 0; i < seeds->n; i++)
+      if (seeds->cand_set[i] < 0 || seeds->cand_set[i] >= cands->n_sets) return fail(EG3D_ERR_INVALID_ARG, "cand_set out of range (sweep and candidate seeds cannot be mixed in one call)");
+  }
+  return EG3D_OK;
+}
+static eg3d_status upload_cands(eg3d_scene* sc, const eg3d_candidates* c, DevCand& dc) {
+  const size_t no = (size_t)c->n_sets * sc->V + 1;
+  CK(dc.off.upload(c->off, no, sc->stream));
+  CK(dc.pl.upload(c->polyline, (size_t)c->off[no - 1], sc->stream));
+  return EG3D_OK;
+}
+
+eg3d_status eg3d_epipolar_intersect(eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d_candidates* cands, eg3d_hits** out, eg3d_timing* tm) {
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  st = check_seeds(sc, seeds, cands); if (st != EG3D_OK) return st;
+  CK(cudaSetDevice(sc->device));
+  eg3d_timing local; memset(&local, 0, sizeof local);
+  DevSeeds ds; st = upload_seeds(sc, seeds, cands != nullptr, ds); if (st != EG3D_OK) return st;
+  DevCand dc; if (cands) { st = upload_cands(sc, cands, dc); if (st != EG3D_OK) return st; }
+  DBuf<int64_t> off; DBuf<eg3d_hit> hits; int64_t nh = 0;
+  st = run_k1(sc, ds, cands ? &dc : nullptr, off, hits, nh, &local); if (st != EG3D_OK) return st;
+  eg3d_hits* h = new eg3d_hits(); h->n_seeds = seeds->n; h->V = sc->V;
+  h->off.resize((size_t)seeds->n * sc->V + 1); h->hits.resize((size_t)nh);
+  cudaMemcpy(h->off.data(), off.p, h->off.size() * sizeof(int64_t), cudaMemcpyDeviceToHost);
+  if (nh) cudaMemcpy(h->hits.data(), hits.p, (size_t)nh * sizeof(eg3d_hit), cudaMemcpyDeviceToHost);
+  local.n_seeds = seeds->n; local.total_ms = local.k1_count_ms + local.scan_ms + local.k1_fill_ms;
+  k1_accounting(sc, seeds, cands, nh, &local);
+  if (tm) *tm = local;
+  *out = h;
+  return EG3D_OK;
+}
+eg3d_status eg3d_hits_get(const eg3d_hits* h, int64_t* n_seeds, int32_t* n_views, const int64_t** off, const eg3d_hit** hits) {
+  if (!h) return fail(EG3D_ERR_INVALID_ARG, "null hits");
+  *n_seeds = h->n_seeds; *n_views = h->V; *off = h->off.data(); *hits = h->hits.data();
+  return EG3D_OK;
+}
+void eg3d_hits_free(eg3d_hits* h) { delete h; }
+
+eg3d_status eg3d_match_seeds(eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d_candidates* cands, eg3d_points** out, eg3d_timing* tm) {
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  st = check_seeds(sc, seeds, cands); if (st != EG3D_OK) return st;
+  CK(cudaSetDevice(sc->device));
+  eg3d_timing local; memset(&local, 0, sizeof local);
+  DevSeeds ds; st = upload_seeds(sc, seeds, cands != nullptr, ds); if (st != EG3D_OK) return st;
+  DevCand dc; if (cands) { st = upload_cands(sc, cands, dc); if (st != EG3D_OK) return st; }
+  Timer tall(sc->stream);
+  tall.start();
+  DBuf<int64_t> off; DBuf<eg3d_hit> hits; int64_t nh = 0;
+  st = run_k1(sc, ds, cands ? &dc : nullptr, off, hits, nh, &local); if (st != EG3D_OK) return st;
+  std::unique_ptr<eg3d_points> pts(new eg3d_points());
+  st = run_k3(sc, ds, off.p, hits.p, pts.get(), &local);
+  local.n_seeds = seeds->n;
+  local.total_ms = local.k1_count_ms + local.scan_ms + local.k1_fill_ms + local.k3_ms + local.pack_ms;
+  k1_accounting(sc, seeds, cands, nh, &local);
+  if (tm) *tm = local;
+  if (st != EG3D_OK) return st;
+  *out = pts.release();
+  return EG3D_OK;
+}
+
+eg3d_status eg3d_match_polyline_sets(eg3d_scene* sc, const eg3d_candidates* c, int32_t view_begin, int32_t view_end, eg3d_points** out, eg3d_timing* tm) {
+  if (!sc || !c) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  // seed sampler (polyline_matching.cpp:162-190): sets in order, starting views ascending, candidate polylines ascending
+  std::vector<int32_t> sv, scs; std::vector<uint32_t> spl, sseg; std::vector<float> sxy;
+  DevScene hs; memset(&hs, 0, sizeof hs);
+  hs.V = sc->V; hs.view_poly_off = sc->h_view_poly_off.data(); hs.poly_vert_off = sc->h_poly_vert_off.data();
+  hs.verts = sc->h_verts.data(); hs.poly_start = sc->h_start.data(); hs.poly_end = sc->h_end.data();
+  for (int set = 0; set < c->n_sets; set++)
+    for (int v = view_begin; v < view_end; v++)
+      for (int64_t k = c->off[(size_t)set * sc->V + v]; k < c->off[(size_t)set * sc->V + v + 1]; k++) {
+        Pl pl = get_pl(hs, v, c->polyline[k]);
+        if (pl.n < 2) continue;
+        PlP plp; plp.seg = 0; plp.c = pl.pc[0];
+        bool reached;
+        plp = step_by_distance(pl, plp, pl.end, sc->prm.split_interval_distance, reached);
+        while (!reached) {
+          sv.push_back(v); scs.push_back(set); spl.push_back(c->polyline[k]); sseg.push_back(plp.seg); sxy.push_back(plp.c.x); sxy.push_back(plp.c.y);
+          plp = step_by_distance(pl, plp, pl.end, sc->prm.split_interval_distance, reached);
+        }
+      }
+  eg3d_seeds s; s.n = (int64_t)sv.size(); s.view = sv.data(); s.polyline = spl.data(); s.segment = sseg.data(); s.xy = sxy.data(); s.cand_set = scs.data();
+  return eg3d_match_seeds(sc, &s, c, out, tm);
+}
+
+eg3d_status eg3d_points_get(const eg3d_points* p, eg3d_points_view* v) {
+  if (!p || !v) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  v->n_points = (int64_t)p->seed.size(); v->n_obs = (int64_t)p->obs_view.size();
+  v->xyz = p->xyz.data(); v->seed = p->seed.data(); v->chain_pos = p->chain_pos.data(); v->obs_off = p->obs_off.data();
+  v->obs_view = p->obs_view.data(); v->obs_poly = p->obs_poly.data(); v->obs_seg = p->obs_seg.data(); v->obs_xy = p->obs_xy.data();
+  return EG3D_OK;
+}
+void eg3d_points_free(eg3d_points* p) { delete p; }
+
+static eg3d_status launch_gn(eg3d_scene* sc, const GnProblem& pr, int fp64, eg3d_timing* tm) {
+  const size_t smem = (size_t)sc->V * 12 * sizeof(float);
+  if (smem > 48 * 1024) {
+    CK(cudaFuncSetAttribute(gn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(gn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  Timer t(sc->stream);
+  const unsigned blocks = (unsigned)((pr.n + GN_THREADS - 1) / GN_THREADS);
+  t.start();
+  if (pr.n > 0) {
+    if (fp64) gn_kernel<true><<<blocks, GN_THREADS, smem, sc->stream>>>(sc->dev, pr);
+    else gn_kernel<false><<<blocks, GN_THREADS, smem, sc->stream>>>(sc->dev, pr);
+  }
+  t.stop();
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(sc->stream));
+  if (tm) { tm->gn_ms += t.ms(); tm->total_ms += t.ms(); tm->kernel_launches += 1; }
+  return EG3D_OK;
+}
+
+eg3d_status eg3d_gn_triangulate(eg3d_scene* sc, int64_t n, const int64_t* obs_off, const int32_t* obs_view, const float* obs_xy,
+                                const float* init_xyz, int fp64, float* out_xyz, float* out_mse, uint8_t* out_ok, eg3d_timing* tm) {
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  if (!sc || !obs_off) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  CK(cudaSetDevice(sc->device));
+  if (tm) memset(tm, 0, sizeof *tm);
+  const int64_t no = obs_off[n];
+  DBuf<int64_t> d_off; DBuf<int> d_v; DBuf<float2> d_xy; DBuf<float> d_init, d_x, d_m; DBuf<uint8_t> d_ok;
+  CK(d_off.upload(obs_off, n + 1, sc->stream)); CK(d_v.upload(obs_view, no, sc->stream)); CK(d_xy.upload((const float2*)obs_xy, no, sc->stream));
+  CK(d_init.upload(init_xyz, 3 * n, sc->stream)); CK(d_x.alloc(3 * n)); CK(d_m.alloc(n)); CK(d_ok.alloc(n));
+  CK(cudaMemcpyAsync(d_x.p, d_init.p, 3 * n * sizeof(float), cudaMemcpyDeviceToDevice, sc->stream));
+  GnProblem pr; memset(&pr, 0, sizeof pr);
+  pr.n = n; pr.obs_off = d_off.p; pr.obs_view = d_v.p; pr.obs_xy = d_xy.p; pr.init = d_init.p;
+  pr.out_xyz = d_x.p; pr.out_mse = d_m.p; pr.out_ok = d_ok.p; pr.gn_max_mse = sc->prm.filter_gn_max_mse; pr.write_back_only_ok = 0;
+  st = launch_gn(sc, pr, fp64, tm); if (st != EG3D_OK) return st;
+  CK(cudaMemcpy(out_xyz, d_x.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out_mse, d_m.p, n * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(out_ok, d_ok.p, n, cudaMemcpyDeviceToHost));
+  return EG3D_OK;
+}
+
+eg3d_status eg3d_gn_triangulate_device(eg3d_scene* sc, int64_t n, int32_t k, const int32_t* d_obs_view, const float* d_obs_xy,
+                                       const float* d_init, int fp64, float* d_out_xyz, float* d_out_mse, uint8_t* d_out_ok, eg3d_timing* tm) {
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  if (!sc) return fail(EG3D_ERR_INVALID_ARG, "null scene");
+  CK(cudaSetDevice(sc->device));
+  if (tm) memset(tm, 0, sizeof *tm);
+  GnProblem pr; memset(&pr, 0, sizeof pr);
+  pr.n = n; pr.obs_off = nullptr; pr.k = k; pr.obs_view = d_obs_view; pr.obs_xy = (const float2*)d_obs_xy; pr.init = d_init;
+  pr.out_xyz = d_out_xyz; pr.out_mse = d_out_mse; pr.out_ok = d_out_ok; pr.gn_max_mse = sc->prm.filter_gn_max_mse; pr.write_back_only_ok = 0;
+  return launch_gn(sc, pr, fp64, tm);
+}
+
+// a13: order-dependent first-come-first-kept density limiter (filtering_close_plgps.cpp:75-124).  The dependency chain
+// is inherently sequential in the visiting order; it runs on the host over the gathered records.
+eg3d_status eg3d_dedup_close_points(eg3d_scene* sc, const eg3d_points_view* pts, uint8_t* keep) {
+  if (!sc || !pts || !keep) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  const float cs = sc->prm.dedup_cell;
+  const int w = (int)ceilf((float)sc->width / cs), h = (int)ceilf((float)sc->height / cs);
+  std::vector<std::vector<uint8_t>> bm(sc->V);
+  auto cell = [&](int64_t o) -> size_t { return (size_t)(int)(pts->obs_xy[2 * o + 1] / cs) * w + (size_t)(int)(pts->obs_xy[2 * o] / cs); };
+  for (int64_t i = 0; i < pts->n_points; i++) {
+    bool is_new = false;
+    for (int64_t o = pts->obs_off[i]; o < pts->obs_off[i + 1]; o++) {
+      auto& b = bm[pts->obs_view[o]];
+      if (b.empty()) b.assign((size_t)w * h, 0);
+      if (!b[cell(o)]) { is_new = true; break; }
+    }
+    keep[i] = is_new;
+    if (is_new) for (int64_t o = pts->obs_off[i]; o < pts->obs_off[i + 1]; o++) bm[pts->obs_view[o]][cell(o)] = 1;
+  }
+  return EG3D_OK;
+}
+
+eg3d_status eg3d_filter(eg3d_scene* sc, int64_t n, float* xyz, const int64_t* obs_off, const int32_t* obs_view, const float* obs_xy,
+                        int64_t first_edgepoint, float gn_max_mse, int32_t forced_min_filter, uint8_t* inliers, eg3d_timing* tm) {
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  if (!sc || !obs_off) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  CK(cudaSetDevice(sc->device));
+  if (tm) memset(tm, 0, sizeof *tm);
+  const int64_t no = obs_off[n];
+  DBuf<int64_t> d_off; DBuf<int> d_v; DBuf<float2> d_xy; DBuf<float> d_x; DBuf<uint8_t> d_ok;
+  CK(d_off.upload(obs_off, n + 1, sc->stream)); CK(d_v.upload(obs_view, no, sc->stream)); CK(d_xy.upload((const float2*)obs_xy, no, sc->stream));
+  CK(d_x.upload(xyz, 3 * n, sc->stream)); CK(d_ok.alloc(n));
+  GnProblem pr; memset(&pr, 0, sizeof pr);
+  pr.n = n; pr.obs_off = d_off.p; pr.obs_view = d_v.p; pr.obs_xy = d_xy.p; pr.init = d_x.p;
+  pr.out_xyz = d_x.p; pr.out_mse = nullptr; pr.out_ok = d_ok.p; pr.gn_max_mse = gn_max_mse; pr.write_back_only_ok = 1;
+  st = launch_gn(sc, pr, 0, tm); if (st != EG3D_OK) return st;   // gaussNewtonFiltering, gauss_newton.cpp:136-178
+  CK(cudaMemcpy(xyz, d_x.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(inliers, d_ok.p, n, cudaMemcpyDeviceToHost));
+  // compute_ray_stats + view-count rule (outliers_filtering.cpp:14-64): O(n) bookkeeping on the returned bitmap
+  std::vector<int64_t> dist(sc->V, 0);
+  int64_t count = 0;
+  for (int64_t i = 0; i < n; i++) if (inliers[i]) { count++; int64_t len = obs_off[i + 1] - obs_off[i]; if (len >= 1 && len <= sc->V) dist[len - 1]++; }
+  int median = 0; int64_t m = 0;
+  for (median = 0; median < sc->V; median++) { m += dist[median]; if (m >= count / 2) break; }
+  int intended = (sc->prm.filter_3views_amount >= median / 2 - 1) ? sc->prm.filter_3views_amount : (median / 2 - 1);
+  if (forced_min_filter > -1) intended = forced_min_filter;
+  for (int64_t i = first_edgepoint; i < n; i++) inliers[i] = inliers[i] && ((obs_off[i + 1] - obs_off[i]) > intended);
+  return EG3D_OK;
+}
+
+eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t track_begin, int64_t track_end, eg3d_points** out, eg3d_timing* tm) {
+  (void)sc; (void)track_begin; (void)track_end; (void)out; (void)tm;
+  return fail(EG3D_ERR_INVALID_ARG, "eg3d_match_refpoints: not built yet in this revision");
+}
+
+}  // extern "C"

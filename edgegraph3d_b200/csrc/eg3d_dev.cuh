@@ -1,0 +1,524 @@
+// eg3d_dev.cuh — device-resident scene view and the geometric / polyline / Gauss-Newton primitives shared by the
+// kernels of libeg3d.so.  Host+device where the host needs the same arithmetic (grid build, seed sampler).
+//
+// Arithmetic contract: the file is compiled with -fmad=false, IEEE division and square root, so every float/double
+// expression rounds exactly as written (the reference's x86-64 build has no FMA contraction).  Citations are to the
+// EdgeGraph3D reference tree.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/eg3d.h"
+
+#define EG3D_HD __host__ __device__ __forceinline__
+#define EG3D_D __device__ __forceinline__
+#define EG3D_HD_NI static __host__ __device__ __noinline__
+
+namespace eg3d {
+
+struct DevGrid {            // uniform polyline grid, PolyLine2DMap (polyLine_2d_map.cpp:40-58), CSR per (view, cell)
+  float cell; int w, h;
+  const int* cell_off;      // [V*w*h + 1]
+  const uint32_t* ids;      // ascending polyline ids per cell
+};
+
+struct DevScene {
+  int V, width, height;
+  const float* P;               // [V][12]
+  const double* F;              // [V*V][9]
+  const uint8_t* Fvalid;        // [V*V]
+  const int* view_poly_off;     // [V+1]
+  const int* poly_vert_off;     // [NP+1]
+  const float2* verts;
+  const uint32_t* poly_start;   // [NP]
+  const uint32_t* poly_end;     // [NP]
+  // K1 staging arrays: every segment of every valid polyline, ascending (polyline, segment), in the reference's
+  // intersect_line orientation (P[i] first, polyline_graph_2d.cpp:318-323) stored as (x1, y1, dx, dy).
+  const int* view_seg_off;      // [V+1]
+  const float4* seg;            // [NSEG]
+  const uint2* seg_id;          // [NSEG] (polyline id in view, segment_index = i-1)
+  const int* poly_seg_off;      // [NP+1] first staged segment of each polyline
+  DevGrid g_expand;             // 4 px
+  DevGrid g_corr;               // 30 px (only with tracks)
+  // tracks
+  int64_t n_tracks;
+  const float* track_xyz; const int64_t* track_off; const int32_t* track_view; const float2* track_xy;
+  eg3d_params prm;
+};
+
+struct PlP { uint32_t seg; float2 c; };                    // pl_point
+struct Plg { uint32_t pl; uint32_t seg; float2 c; };       // plg_point
+struct Pl { const float2* pc; int n; uint32_t start, end; };  // polyline view
+
+EG3D_HD Pl get_pl(const DevScene& S, int view, uint32_t pl_id) {
+  int g = S.view_poly_off[view] + (int)pl_id;
+  int o = S.poly_vert_off[g];
+  Pl p; p.pc = S.verts + o; p.n = S.poly_vert_off[g + 1] - o; p.start = S.poly_start[g]; p.end = S.poly_end[g];
+  return p;
+}
+
+// geometric_utilities.cpp:555-557: float subtraction, double square + sum, float result.  The squares are exact in
+// double, so contraction could not change the result.
+EG3D_HD float sqdist2(float2 a, float2 b) {
+  float dx = a.x - b.x, dy = a.y - b.y;
+  return (float)((double)dx * (double)dx + (double)dy * (double)dy);
+}
+EG3D_HD float dist2(float2 a, float2 b) { return sqrtf(sqdist2(a, b)); }  // :571-573
+
+// geometric_utilities.cpp:824-843 -> cv::computeCorrespondEpilines(whichImage = 1)
+EG3D_HD bool epiline(const DevScene& S, int a, int b, float2 p, float3& l) {
+  size_t idx = (size_t)a * S.V + b;
+  if (!S.Fvalid[idx]) return false;
+  const double* F = S.F + idx * 9;
+  double x = p.x, y = p.y;
+  double la = F[0] * x + F[1] * y + F[2];
+  double lb = F[3] * x + F[4] * y + F[5];
+  double lc = F[6] * x + F[7] * y + F[8];
+  double nu = la * la + lb * lb;
+  nu = nu ? 1. / sqrt(nu) : 1.;
+  l.x = (float)(la * nu); l.y = (float)(lb * nu); l.z = (float)(lc * nu);
+  return true;
+}
+
+// geometric_utilities.cpp:272-312 on a segment given as (x1, y1, dx, dy)
+EG3D_HD bool isect_seg_line(float x1, float y1, float dx, float dy, float3 l, float2& inter) {
+  float num = l.x * x1 + l.y * y1 + l.z;
+  float den = l.x * dx + l.y * dy;
+  if (den != 0) {
+    float t = -num / den;
+    if (t >= 0 && t <= 1) { inter.x = x1 + t * dx; inter.y = y1 + t * dy; return true; }
+  }
+  return false;
+}
+
+EG3D_HD float dist_point_line(float px, float py, float3 l) {  // geometric_utilities.cpp:997-1009
+  float den = l.x * px + l.y * py + l.z;
+  den *= den;
+  return sqrtf(den / (l.x * l.x + l.y * l.y));
+}
+
+// geometric_utilities.cpp:365-430.  Returns bit0 = intersection_found, bit1 = quasiparallel_within_distance.
+EG3D_HD int isect_seg_line_nqp(float x1, float y1, float x2, float y2, float3 l, float max_cos, float max_dist, float2& inter) {
+  float dx = x2 - x1, dy = y2 - y1;
+  int res = 0;
+  float num = l.x * x1 + l.y * y1 + l.z;
+  float den = l.x * dx + l.y * dy;
+  if (den != 0) {
+    float t = -num / den;
+    if (t >= 0 && t <= 1) { inter.x = x1 + t * dx; inter.y = y1 + t * dy; res |= 1; }
+    // compute_anglecos(segm, line): signed cosine between the segment and (1, -a/b) or (0,1) (:579-581, :608-618)
+    float lx, ly;
+    if (l.y == 0) { lx = 0.0f; ly = 1.0f; } else { lx = 1.0f; ly = -l.x / l.y; }
+    float ab = dx * lx + dy * ly, aa = dx * dx + dy * dy, bb = lx * lx + ly * ly;
+    float cosv = ab / sqrtf(aa * bb);
+    if (cosv > max_cos) {
+      float distance;
+      if (t < 0) distance = dist_point_line(x1, y1, l);
+      else if (t > 1) distance = dist_point_line(x2, y2, l);
+      else distance = 0;
+      if (distance <= max_dist) res |= 2;
+    }
+  } else {
+    if (dist_point_line(x1, y1, l) <= max_dist) res |= 2;
+  }
+  return res;
+}
+
+EG3D_HD float2 lerp2(float2 a, float2 b, float r) {  // first_plus_ratio_of_segment, geometric_utilities.cpp:1370-1372
+  return make_float2(a.x + r * (b.x - a.x), a.y + r * (b.y - a.y));
+}
+
+// polyline::next_pl_point_by_distance, polyline_graph_2d.cpp:391-447.  A direction that is neither extreme is UB in
+// the reference; rule shared with the oracle: cannot drive = reached extreme.
+EG3D_HD_NI PlP step_by_distance(const Pl& pl, PlP init, uint32_t dir, float distance, bool& reached) {
+  float prevdist = 0, curdist, ratio;
+  reached = false;
+  PlP r;
+  const int n = pl.n;
+  if (dir == pl.start) {
+    curdist = dist2(pl.pc[init.seg], init.c);
+    if (curdist >= distance) { ratio = distance / curdist; r.seg = init.seg; r.c = lerp2(init.c, pl.pc[init.seg], ratio); return r; }
+    int i;
+    for (i = (int)init.seg; i > 0; i--) {
+      prevdist = curdist;
+      curdist = dist2(pl.pc[i - 1], init.c);
+      if (curdist >= distance) break;
+    }
+    if (i == 0) { reached = true; r.seg = 0; r.c = pl.pc[0]; return r; }
+    ratio = (distance - prevdist) / (curdist - prevdist);
+    r.seg = (uint32_t)(i - 1); r.c = lerp2(pl.pc[i], pl.pc[i - 1], ratio); return r;
+  } else if (dir == pl.end) {
+    if ((int)init.seg >= n - 1) { reached = true; r.seg = (uint32_t)(n - 2); r.c = pl.pc[n - 1]; return r; }
+    curdist = dist2(pl.pc[init.seg + 1], init.c);
+    if (curdist >= distance) { ratio = distance / curdist; r.seg = init.seg; r.c = lerp2(init.c, pl.pc[init.seg + 1], ratio); return r; }
+    int i;
+    for (i = (int)init.seg + 1; i < n - 1; i++) {
+      prevdist = curdist;
+      curdist = dist2(pl.pc[i + 1], init.c);
+      if (curdist >= distance) break;
+    }
+    if (i == n - 1) { reached = true; r.seg = (uint32_t)(n - 2); r.c = pl.pc[n - 1]; return r; }
+    ratio = (distance - prevdist) / (curdist - prevdist);
+    r.seg = (uint32_t)i; r.c = lerp2(pl.pc[i], pl.pc[i + 1], ratio); return r;
+  }
+  reached = true;
+  return init;
+}
+
+// polyline::next_pl_point_by_line_intersection[_bounded_distance], polyline_graph_2d.cpp:579-780.
+// bounded = true applies the [min_dist, max_dist] window to the first intersection found (:689-699).
+EG3D_HD_NI bool walk_line(const Pl& pl, PlP init, uint32_t dir, float3 line, const eg3d_params& prm, bool bounded, PlP& next) {
+  const float qc = prm.quasiparallel_cos, qd = prm.quasiparallel_dist;
+  float2 inter = make_float2(0.f, 0.f);
+  int r;
+  const int n = pl.n;
+  bool found = false;
+  if (dir == pl.start) {
+    float2 b = pl.pc[init.seg];
+    r = isect_seg_line_nqp(init.c.x, init.c.y, b.x, b.y, line, qc, qd, inter);
+    if (r & 2) return false;
+    if (r & 1) { next.seg = init.seg; next.c = inter; found = true; }
+    else {
+      for (int i = (int)init.seg; i > 0; i--) {
+        float2 a = pl.pc[i], c = pl.pc[i - 1];
+        r = isect_seg_line_nqp(a.x, a.y, c.x, c.y, line, qc, qd, inter);
+        if (r & 2) return false;
+        if (r & 1) { next.seg = (uint32_t)(i - 1); next.c = inter; found = true; break; }
+      }
+    }
+  } else if (dir == pl.end) {
+    float2 b = pl.pc[init.seg + 1];
+    r = isect_seg_line_nqp(init.c.x, init.c.y, b.x, b.y, line, qc, qd, inter);
+    if (r & 2) return false;
+    if (r & 1) { next.seg = init.seg; next.c = inter; found = true; }
+    else {
+      for (int i = (int)init.seg + 1; i < n - 1; i++) {
+        float2 a = pl.pc[i], c = pl.pc[i + 1];
+        r = isect_seg_line_nqp(a.x, a.y, c.x, c.y, line, qc, qd, inter);
+        if (r & 2) return false;
+        if (r & 1) { next.seg = (uint32_t)i; next.c = inter; found = true; break; }
+      }
+    }
+  }
+  if (found && bounded) {
+    float dsq = sqdist2(next.c, init.c);
+    if (dsq < (prm.follow_corr_min * prm.follow_corr_min) || dsq > (prm.follow_corr_max * prm.follow_corr_max)) found = false;
+  }
+  return found;
+}
+
+// minimum_distancesq, geometric_utilities.cpp:940-954
+EG3D_HD float min_distsq_seg(float2 p, float2 v, float2 w, float2& proj) {
+  const float l2 = sqdist2(v, w);
+  if (l2 == 0.0) { proj = v; return sqdist2(p, v); }
+  float pvx = p.x - v.x, pvy = p.y - v.y, wvx = w.x - v.x, wvy = w.y - v.y;
+  float q = (pvx * wvx + pvy * wvy) / l2;
+  float m = (q < 1.0f) ? q : 1.0f;      // std::min<float>(1, q)
+  float t = (0.0f < m) ? m : 0.0f;      // std::max<float>(0, m)
+  proj.x = v.x + t * wvx; proj.y = v.y + t * wvy;
+  return sqdist2(p, proj);
+}
+
+// polyline::compute_distancesq, polyline_graph_2d.cpp:845-862
+EG3D_HD_NI float pl_distancesq(const Pl& pl, float2 p, uint32_t& seg, float2& proj) {
+  float md = min_distsq_seg(p, pl.pc[0], pl.pc[1], proj);
+  seg = 0;
+  float2 cp;
+  for (int i = 2; i < pl.n; i++) {
+    float cur = min_distsq_seg(p, pl.pc[i - 1], pl.pc[i], cp);
+    if (cur < md) { md = cur; proj = cp; seg = (uint32_t)(i - 1); }
+  }
+  return md;
+}
+
+// edge_graph_3d_utilities.cpp:600-629
+EG3D_HD float floor_or_upper_if_close(float v) {
+  float c = ceilf(v);
+  if ((double)(c - v) < 0.001) return c;
+  return floorf(v);
+}
+EG3D_HD bool is_multiple_of(float m, float n) {
+  float div = m / n;
+  float mul = floor_or_upper_if_close(div) * n;
+  return (double)fabsf(m - mul) < 0.001;
+}
+
+// compute_projection, geometric_utilities.cpp:973-983 (glm row-vector product)
+EG3D_HD float2 project(const float* P, float X, float Y, float Z) {
+  float h0 = P[0] * X + P[1] * Y + P[2] * Z + P[3] * 1.0f;
+  float h1 = P[4] * X + P[5] * Y + P[6] * Z + P[7] * 1.0f;
+  float h2 = P[8] * X + P[9] * Y + P[10] * Z + P[11] * 1.0f;
+  return make_float2(h0 / h2, h1 / h2);
+}
+
+// PolyLine2DMapSearch::find_unique_polyline_potentially_within_search_dist, polyLine_2d_map_search.cpp:46-88:
+// valid iff the union of the (clipped) 3x3 cell neighbourhood holds exactly one polyline id.
+// The "row" flag (x on a cell boundary) clips the ROW loop.
+template <typename Visit>
+EG3D_HD void grid_visit(const DevGrid& g, int view, int img_w, int img_h, float2 c, Visit visit) {
+  if (c.x <= 0 || c.x >= img_w || c.y <= 0 || c.y >= img_h) return;
+  bool on_row = is_multiple_of(c.x, g.cell);
+  bool on_col = is_multiple_of(c.y, g.cell);
+  int cx = (int)floor_or_upper_if_close(c.x / g.cell), cy = (int)floor_or_upper_if_close(c.y / g.cell);
+  if (cx >= g.w) cx = g.w - 1;
+  if (cy >= g.h) cy = g.h - 1;
+  int i0 = cy > 0 ? -1 : 0, i1 = on_row ? 0 : (cy < g.h - 1 ? 1 : 0);
+  int j0 = cx > 0 ? -1 : 0, j1 = on_col ? 0 : (cx < g.w - 1 ? 1 : 0);
+  const int* off = g.cell_off + (size_t)view * g.w * g.h;
+  for (int i = i0; i <= i1; i++)
+    for (int j = j0; j <= j1; j++) {
+      int cidx = (cy + i) * g.w + (cx + j);
+      for (int k = off[cidx]; k < off[cidx + 1]; k++) visit(g.ids[k]);
+    }
+}
+EG3D_HD bool grid_unique(const DevGrid& g, int view, int img_w, int img_h, float2 c, uint32_t& pl_id) {
+  int cnt = 0; uint32_t first = 0; bool multi = false;
+  grid_visit(g, view, img_w, img_h, c, [&](uint32_t id) {
+    if (cnt == 0) { first = id; cnt = 1; } else if (id != first) multi = true;
+  });
+  pl_id = first;
+  return cnt == 1 && !multi;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-view DLT initialiser = cv::triangulatePoints (triangulation.cpp:216,290): null vector of the 4x4 DLT matrix by
+// one-sided Jacobi SVD in double, cast to float.  Same operation sequence as the oracle's restatement.
+EG3D_HD_NI void dlt_null(const float* P1, const float* P2, float2 x1, float2 x2, float out4[4]) {
+  double A[4][4], Vm[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    A[0][k] = (double)x1.x * (double)P1[8 + k] - (double)P1[k];
+    A[1][k] = (double)x1.y * (double)P1[8 + k] - (double)P1[4 + k];
+    A[2][k] = (double)x2.x * (double)P2[8 + k] - (double)P2[k];
+    A[3][k] = (double)x2.y * (double)P2[8 + k] - (double)P2[4 + k];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) Vm[i][j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0;
+#pragma unroll
+    for (int p = 0; p < 3; p++)
+#pragma unroll
+      for (int q = p + 1; q < 4; q++) {
+        double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { alpha += A[i][p] * A[i][p]; beta += A[i][q] * A[i][q]; gamma += A[i][p] * A[i][q]; }
+        if (gamma != 0) {
+          double o = fabs(gamma) / sqrt(alpha * beta + 1e-300);
+          off = off > o ? off : o;
+          double zeta = (beta - alpha) / (2.0 * gamma);
+          double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            double ap = A[i][p], aq = A[i][q];
+            A[i][p] = c * ap - s * aq; A[i][q] = s * ap + c * aq;
+            double vp = Vm[i][p], vq = Vm[i][q];
+            Vm[i][p] = c * vp - s * vq; Vm[i][q] = s * vp + c * vq;
+          }
+        }
+      }
+    if (off < 1e-15) break;
+  }
+  double nn[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) s += A[i][j] * A[i][j];
+    nn[j] = s;
+  }
+  int best = 0; double bestn = 1e300;
+#pragma unroll
+  for (int j = 0; j < 4; j++) if (nn[j] < bestn) { bestn = nn[j]; best = j; }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    double v = Vm[i][0];
+    if (best == 1) v = Vm[i][1]; else if (best == 2) v = Vm[i][2]; else if (best == 3) v = Vm[i][3];
+    out4[i] = (float)v;
+  }
+}
+
+EG3D_HD double det3d(const double* m) {
+  return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+EG3D_HD void inv3d(const double* m, double d, double* t) {  // cv::invert closed form: cofactors * (1/det)
+  d = 1. / d;
+  t[0] = (m[4] * m[8] - m[5] * m[7]) * d; t[1] = (m[2] * m[7] - m[1] * m[8]) * d; t[2] = (m[1] * m[5] - m[2] * m[4]) * d;
+  t[3] = (m[5] * m[6] - m[3] * m[8]) * d; t[4] = (m[0] * m[8] - m[2] * m[6]) * d; t[5] = (m[2] * m[3] - m[0] * m[5]) * d;
+  t[6] = (m[3] * m[7] - m[4] * m[6]) * d; t[7] = (m[1] * m[6] - m[0] * m[7]) * d; t[8] = (m[0] * m[4] - m[1] * m[3]) * d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// em_GaussNewton for exactly three observations (triangulation.cpp:105-176), thread-local, SAME operation order as the
+// oracle (J and r kept in registers, H = J^T J accumulated row by row, update = (H^-1 J^T) r) => bit-identical results.
+// Returns true when accepted (last_mse < accept); X holds the result.
+EG3D_HD bool gn3_exact(const DevScene& S, const int v[3], const float2 pt[3], double X[3]) {
+  double Pd[3][12];
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const float* P = S.P + 12 * v[m];
+#pragma unroll
+    for (int i = 0; i < 12; i++) Pd[m][i] = (double)P[i];
+  }
+  double last_mse = 0;
+  const eg3d_params& prm = S.prm;
+  for (int it = 0; it < prm.gn_max_iters; it++) {
+    double r[6], J[18], mse = 0;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      const double* P = Pd[m];
+      double h0 = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3] * 1.0;
+      double h1 = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7] * 1.0;
+      double h2 = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11] * 1.0;
+      r[2 * m] = (double)pt[m].x - h0 / h2;
+      mse += r[2 * m] * r[2 * m];
+      r[2 * m + 1] = (double)pt[m].y - h1 / h2;
+      mse += r[2 * m + 1] * r[2 * m + 1];
+      double zz = h2 * h2;
+      J[6 * m + 0] = (P[0] * h2 - P[8] * h0) / zz;  J[6 * m + 3] = (P[4] * h2 - P[8] * h1) / zz;
+      J[6 * m + 1] = (P[1] * h2 - P[9] * h0) / zz;  J[6 * m + 4] = (P[5] * h2 - P[9] * h1) / zz;
+      J[6 * m + 2] = (P[2] * h2 - P[10] * h0) / zz; J[6 * m + 5] = (P[6] * h2 - P[10] * h1) / zz;
+    }
+    if (fabs(mse / 6 - last_mse) < prm.gn_stop) break;
+    last_mse = mse / 6;
+    double H[9];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        double acc = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) acc += J[3 * k + a] * J[3 * k + b];
+        H[3 * a + b] = acc;
+      }
+    double d = det3d(H);
+    if (d < prm.gn_det_min) return false;
+    double Hi[9]; inv3d(H, d, Hi);
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      double acc = 0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        double mk = Hi[3 * a + 0] * J[3 * k + 0] + Hi[3 * a + 1] * J[3 * k + 1] + Hi[3 * a + 2] * J[3 * k + 2];
+        acc += mk * r[k];
+      }
+      X[a] += acc;
+    }
+  }
+  return last_mse < prm.gn_accept_mse;
+}
+
+// em_estimate3Dpositions for three observations (triangulation.cpp:252-323) incl. the get_min_max quirk
+// (edge_graph_3d_utilities.hpp:69-92: min = first arg-min, "max" = last index) and the well-posed substitution.
+EG3D_HD_NI bool est3(const DevScene& S, const int v[3], const float2 pt[3], float Xo[3]) {
+  int mi = 0;
+  if (v[1] < v[mi]) mi = 1;
+  if (v[2] < v[mi]) mi = 2;
+  int ma = 2;
+  if (S.prm.dlt_wellposed && v[ma] == v[mi]) {
+    if (v[2] != v[mi]) ma = 2; else if (v[1] != v[mi]) ma = 1; else if (v[0] != v[mi]) ma = 0;
+  }
+  float2 pmi = pt[0], pma = pt[0];
+  int vmi = v[0], vma = v[0];
+  if (mi == 1) { pmi = pt[1]; vmi = v[1]; } else if (mi == 2) { pmi = pt[2]; vmi = v[2]; }
+  if (ma == 1) { pma = pt[1]; vma = v[1]; } else if (ma == 2) { pma = pt[2]; vma = v[2]; }
+  float t4[4];
+  dlt_null(S.P + 12 * vmi, S.P + 12 * vma, pmi, pma, t4);
+  double X[3] = {(double)(t4[0] / t4[3]), (double)(t4[1] / t4[3]), (double)(t4[2] / t4[3])};
+  if (!gn3_exact(S, v, pt, X)) return false;
+  Xo[0] = (float)X[0]; Xo[1] = (float)X[1]; Xo[2] = (float)X[2];
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gauss-Newton over n observations, one problem per THREAD, observations visited in order (same summation order as
+// the reference; the normal-equation right-hand side is accumulated as J^T r instead of (H^-1 J^T) r, a difference of
+// rounding only).  obs(i, view, x, y) yields observation i.
+struct GnAcc { double mse, h00, h01, h02, h11, h12, h22, g0, g1, g2; };
+
+EG3D_D void gn_accumulate(const float* __restrict__ P, float px, float py, const double X[3], GnAcc& a) {
+  double p0 = P[0], p1 = P[1], p2 = P[2], p3 = P[3], p4 = P[4], p5 = P[5], p6 = P[6], p7 = P[7], p8 = P[8], p9 = P[9], p10 = P[10], p11 = P[11];
+  double h0 = p0 * X[0] + p1 * X[1] + p2 * X[2] + p3 * 1.0;
+  double h1 = p4 * X[0] + p5 * X[1] + p6 * X[2] + p7 * 1.0;
+  double h2 = p8 * X[0] + p9 * X[1] + p10 * X[2] + p11 * 1.0;
+  double rx = (double)px - h0 / h2;
+  a.mse += rx * rx;
+  double ry = (double)py - h1 / h2;
+  a.mse += ry * ry;
+  double zz = h2 * h2;
+  double jx0 = (p0 * h2 - p8 * h0) / zz, jx1 = (p1 * h2 - p9 * h0) / zz, jx2 = (p2 * h2 - p10 * h0) / zz;
+  double jy0 = (p4 * h2 - p8 * h1) / zz, jy1 = (p5 * h2 - p9 * h1) / zz, jy2 = (p6 * h2 - p10 * h1) / zz;
+  a.h00 += jx0 * jx0; a.h00 += jy0 * jy0;
+  a.h01 += jx0 * jx1; a.h01 += jy0 * jy1;
+  a.h02 += jx0 * jx2; a.h02 += jy0 * jy2;
+  a.h11 += jx1 * jx1; a.h11 += jy1 * jy1;
+  a.h12 += jx1 * jx2; a.h12 += jy1 * jy2;
+  a.h22 += jx2 * jx2; a.h22 += jy2 * jy2;
+  a.g0 += jx0 * rx; a.g0 += jy0 * ry;
+  a.g1 += jx1 * rx; a.g1 += jy1 * ry;
+  a.g2 += jx2 * rx; a.g2 += jy2 * ry;
+}
+
+// one GN update from fully reduced sums; returns 0 = continue, 1 = converged (break), -1 = det failure
+EG3D_D int gn_update(const GnAcc& a, int n, const eg3d_params& prm, double& last_mse, double X[3]) {
+  double cur = a.mse / (n * 2);
+  if (fabs(cur - last_mse) < prm.gn_stop) return 1;
+  last_mse = cur;
+  double H[9] = {a.h00, a.h01, a.h02, a.h01, a.h11, a.h12, a.h02, a.h12, a.h22};
+  double d = det3d(H);
+  if (d < prm.gn_det_min) return -1;
+  double Hi[9]; inv3d(H, d, Hi);
+  X[0] += Hi[0] * a.g0 + Hi[1] * a.g1 + Hi[2] * a.g2;
+  X[1] += Hi[3] * a.g0 + Hi[4] * a.g1 + Hi[5] * a.g2;
+  X[2] += Hi[6] * a.g0 + Hi[7] * a.g1 + Hi[8] * a.g2;
+  return 0;
+}
+
+template <typename ObsFn>
+EG3D_D bool gn_thread(const DevScene& S, int n, ObsFn obs, double X[3], double* last_mse_out = nullptr) {
+  double last_mse = 0;
+  for (int it = 0; it < S.prm.gn_max_iters; it++) {
+    GnAcc a = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < n; i++) {
+      int v; float x, y;
+      obs(i, v, x, y);
+      gn_accumulate(S.P + 12 * v, x, y, X, a);
+    }
+    int r = gn_update(a, n, S.prm, last_mse, X);
+    if (r == 1) break;
+    if (r == -1) { if (last_mse_out) *last_mse_out = last_mse; return false; }
+  }
+  if (last_mse_out) *last_mse_out = last_mse;
+  return last_mse < S.prm.gn_accept_mse;
+}
+
+// Same problem solved by a whole warp: lanes stride over the observations, the ten sums are butterfly-reduced so every
+// lane holds identical values and control flow stays warp-uniform.  Must be called by all 32 lanes.
+EG3D_D double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <typename ObsFn>
+EG3D_D bool gn_warp(const DevScene& S, int n, ObsFn obs, double X[3], int lane) {
+  double last_mse = 0;
+  for (int it = 0; it < S.prm.gn_max_iters; it++) {
+    GnAcc a = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = lane; i < n; i += 32) {
+      int v; float x, y;
+      obs(i, v, x, y);
+      gn_accumulate(S.P + 12 * v, x, y, X, a);
+    }
+    a.mse = warp_sum(a.mse); a.h00 = warp_sum(a.h00); a.h01 = warp_sum(a.h01); a.h02 = warp_sum(a.h02);
+    a.h11 = warp_sum(a.h11); a.h12 = warp_sum(a.h12); a.h22 = warp_sum(a.h22);
+    a.g0 = warp_sum(a.g0); a.g1 = warp_sum(a.g1); a.g2 = warp_sum(a.g2);
+    int r = gn_update(a, n, S.prm, last_mse, X);
+    if (r == 1) break;
+    if (r == -1) return false;
+  }
+  return last_mse < S.prm.gn_accept_mse;
+}
+
+}  // namespace eg3d

@@ -1,0 +1,793 @@
+// eg3d_k3.cuh — K3: one warp per seed runs compute_3D_point_multiple_views_plg_following_expandallviews_vector
+// (triangulation.cpp:1027-1088): view-triple selection, triple enumeration with the uniqueness test (:550-601),
+// PLG following (plg_matching.cpp:51-370, 633-795, 1249-1287) and expansion to the remaining views
+// (triangulation.cpp:742-830, 960-973; plg_matching.cpp:797-914, 1011-1058, 1345-1412).
+//
+// Execution model: the warp is a scalar processor with a 32-wide vector unit.  Control flow is warp-uniform (every
+// lane evaluates the same sequential walk, so no broadcasts are needed), and the lanes fan out wherever the reference
+// loops over independent work: triples (one 3-view DLT+GN per lane), the four direction combos, the epipolar hits of a
+// view (one warm-started GN per lane, first success in order wins), the neighbours of a chain point (one GN per lane),
+// the views of a chain point when a step is extended, and the observations of a single large GN.
+// All per-seed state lives in a per-warp global scratch arena (L1/L2 resident); nothing is shared between warps, and a
+// persistent grid pulls seeds from an atomic counter because per-seed cost varies by orders of magnitude.
+#pragma once
+#include "eg3d_dev.cuh"
+
+namespace eg3d {
+
+constexpr int K3_THREADS = 128;  // 4 warps per CTA
+
+struct Pt3 {  // a 3-view point of the following phase (64 B)
+  float X[3];
+  uint8_t perm[4];    // perm[i] = index into sel[] of the i-th view of this point
+  uint32_t pl[3], seg[3];
+  float cx[3], cy[3];
+};
+struct NTmp { float X[3]; uint32_t seg; float cx, cy; };  // a neighbour candidate (polyline id is implied)
+
+struct K3Args {
+  int n_seeds;
+  const int* seed_view; const uint32_t* seed_pl; const uint32_t* seed_seg; const float2* seed_xy;
+  const int64_t* hit_off;   // [n_seeds*V + 1]
+  const eg3d_hit* hits;
+  int capf, capc, oc;       // capacities: follow points per list, chain points, observations per point
+  unsigned char* scratch; size_t scratch_per_warp;
+  int* work_counter;
+  // unordered outputs (a warp reserves a contiguous range per seed)
+  int64_t pt_cap, ob_cap;
+  unsigned long long* out_counters;   // [0] points, [1] observations, [2] capacity overflows, [3] output overflows
+  float* o_X; int* o_nobs; int64_t* o_obase;
+  int* ob_view; uint32_t* ob_pl; uint32_t* ob_seg; float* ob_x; float* ob_y;
+  int* seed_npts; int64_t* seed_pbase; int64_t* seed_nobs;
+};
+
+struct WS {  // per-warp scratch view
+  Pt3 *tri, *D1, *D2, *fD1, *fD2;
+  int* ov; uint32_t *opl, *oseg; float *ox, *oy;   // [capc][oc]
+  float* sX; int* snobs; int* order;               // [capc][3], [capc], [capc]
+  uint32_t *sdirs, *edirs;                         // [V]
+  NTmp *tmp1, *tmp2;                               // [capc]
+  int* idx;                                        // [oc] scratch index list (combination fallback)
+  unsigned char* selmask;                          // [oc]
+  int capf, capc, oc;
+};
+
+inline __host__ __device__ size_t k3_align(size_t x) { return (x + 15) & ~(size_t)15; }
+inline __host__ __device__ size_t k3_scratch_bytes(int V, int capf, int capc, int oc) {
+  size_t b = 0;
+  b += k3_align(sizeof(Pt3) * (size_t)capf * 8);
+  b += k3_align(sizeof(int) * (size_t)capc * oc) * 5;
+  b += k3_align(sizeof(float) * 3 * capc) + k3_align(sizeof(int) * capc) * 2;
+  b += k3_align(sizeof(uint32_t) * V) * 2;
+  b += k3_align(sizeof(NTmp) * capc) * 2;
+  b += k3_align(sizeof(int) * oc) + k3_align(oc);
+  return b;
+}
+EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
+  WS w; size_t o = 0;
+  auto take = [&](size_t bytes) { unsigned char* p = base + o; o += k3_align(bytes); return p; };
+  Pt3* p3 = (Pt3*)take(sizeof(Pt3) * (size_t)capf * 8);
+  w.tri = p3; w.D1 = p3 + 4 * capf; w.D2 = p3 + 5 * capf; w.fD1 = p3 + 6 * capf; w.fD2 = p3 + 7 * capf;
+  w.ov = (int*)take(sizeof(int) * (size_t)capc * oc);
+  w.opl = (uint32_t*)take(sizeof(int) * (size_t)capc * oc);
+  w.oseg = (uint32_t*)take(sizeof(int) * (size_t)capc * oc);
+  w.ox = (float*)take(sizeof(int) * (size_t)capc * oc);
+  w.oy = (float*)take(sizeof(int) * (size_t)capc * oc);
+  w.sX = (float*)take(sizeof(float) * 3 * capc);
+  w.snobs = (int*)take(sizeof(int) * capc);
+  w.order = (int*)take(sizeof(int) * capc);
+  w.sdirs = (uint32_t*)take(sizeof(uint32_t) * V);
+  w.edirs = (uint32_t*)take(sizeof(uint32_t) * V);
+  w.tmp1 = (NTmp*)take(sizeof(NTmp) * capc);
+  w.tmp2 = (NTmp*)take(sizeof(NTmp) * capc);
+  w.idx = (int*)take(sizeof(int) * oc);
+  w.selmask = (unsigned char*)take(oc);
+  w.capf = capf; w.capc = capc; w.oc = oc;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-seed context (registers; identical in every lane)
+struct Ctx {
+  const DevScene* S; const K3Args* A; WS w;
+  int lane, seed, sv;
+  int sel[3];
+  int len;         // chain length
+  int nslots;      // slots in use
+  int central;     // original_central_point_index
+  bool overflow;
+};
+
+// 3-view compatible, plg_matching.cpp:51-132.  cur / next: (pl, seg, c) per view a,b,c in sel order.
+struct Cur3 { uint32_t pl[3], seg[3]; float2 c[3]; };
+EG3D_D bool step3(const DevScene& S, const int ids[3], const Cur3& cur, const uint32_t dir[3], Cur3& next, float X[3]) {
+  Pl pla = get_pl(S, ids[0], cur.pl[0]), plb = get_pl(S, ids[1], cur.pl[1]), plc = get_pl(S, ids[2], cur.pl[2]);
+  bool reached;
+  PlP ia; ia.seg = cur.seg[0]; ia.c = cur.c[0];
+  PlP na = step_by_distance(pla, ia, dir[0], S.prm.follow_first_image_distance, reached);
+  if (reached) return false;
+  float3 l;
+  if (!epiline(S, ids[0], ids[1], na.c, l)) return false;
+  PlP ib; ib.seg = cur.seg[1]; ib.c = cur.c[1];
+  PlP nb;
+  if (!walk_line(plb, ib, dir[1], l, S.prm, false, nb)) return false;
+  if (!epiline(S, ids[0], ids[2], na.c, l)) return false;
+  PlP ic; ic.seg = cur.seg[2]; ic.c = cur.c[2];
+  PlP nc;
+  if (!walk_line(plc, ic, dir[2], l, S.prm, false, nc)) return false;
+  float2 pts[3] = {na.c, nb.c, nc.c};
+  if (!est3(S, ids, pts, X)) return false;
+  next.pl[0] = cur.pl[0]; next.pl[1] = cur.pl[1]; next.pl[2] = cur.pl[2];
+  next.seg[0] = na.seg; next.seg[1] = nb.seg; next.seg[2] = nc.seg;
+  next.c[0] = na.c; next.c[1] = nb.c; next.c[2] = nc.c;
+  return true;
+}
+
+EG3D_D void store_pt3(Pt3* dst, const Cur3& c, const float X[3]) {
+  Pt3 p;
+  p.X[0] = X[0]; p.X[1] = X[1]; p.X[2] = X[2];
+  p.perm[0] = 0; p.perm[1] = 1; p.perm[2] = 2; p.perm[3] = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { p.pl[i] = c.pl[i]; p.seg[i] = c.seg[i]; p.cx[i] = c.c[i].x; p.cy[i] = c.c[i].y; }
+  *dst = p;
+}
+
+// find_direction_given_first_extreme, plg_matching.cpp:142-203: the four (end_b, end_c) combos advance in lock-step,
+// one combo per lane; the last survivor wins.  Returns the number of points (0 = fail) copied into `dst`.
+EG3D_D int first_extreme(Ctx& c, const Cur3& start, uint32_t first_dir, uint32_t dir_out[3], Pt3* dst) {
+  const DevScene& S = *c.S;
+  const int lane = c.lane;
+  Pl plb = get_pl(S, c.sel[1], start.pl[1]), plc = get_pl(S, c.sel[2], start.pl[2]);
+  uint32_t dir[3] = {first_dir, (lane & 2) ? plb.end : plb.start, (lane & 1) ? plc.end : plc.start};
+  bool valid = lane < 4;
+  Cur3 cur = start;
+  int cnt = 0;
+  Pt3* mine = c.w.tri + (size_t)(lane & 3) * c.w.capf;
+  unsigned vm = __ballot_sync(0xffffffffu, valid);
+  while (__popc(vm) > 1) {
+    if (valid) {
+      Cur3 nx; float X[3];
+      if (step3(S, c.sel, cur, dir, nx, X)) {
+        cur = nx;
+        if (cnt < c.w.capf) store_pt3(mine + cnt, nx, X);
+        cnt++;
+      } else valid = false;
+    }
+    vm = __ballot_sync(0xffffffffu, valid);
+    if (__any_sync(0xffffffffu, cnt > c.w.capf)) { c.overflow = true; return 0; }
+  }
+  if (vm == 0) return 0;
+  int win = 31 - __clz(vm);
+  int n = __shfl_sync(0xffffffffu, cnt, win);
+  dir_out[0] = first_dir;
+  dir_out[1] = __shfl_sync(0xffffffffu, dir[1], win);
+  dir_out[2] = __shfl_sync(0xffffffffu, dir[2], win);
+  __syncwarp();
+  const Pt3* src = c.w.tri + (size_t)win * c.w.capf;
+  for (int i = lane; i < n; i += 32) dst[i] = src[i];
+  __syncwarp();
+  return n;
+}
+
+// all-view compatible (plg_matching.cpp:633-759) specialised to a 3-view point: exactly three observations survive or
+// the attempt is skipped; the combination fallback (:708-733) degenerates to the same 3-subset, so it cannot succeed.
+EG3D_D bool step_all3(const DevScene& S, const int sel[3], const uint32_t dirs[3], const Pt3& cur, Pt3& out) {
+  for (int si = 0; si < 3; si++) {
+    const int k = cur.perm[si];
+    const int sv = sel[k];
+    Pl pls = get_pl(S, sv, cur.pl[si]);
+    bool reached;
+    PlP ip; ip.seg = cur.seg[si]; ip.c = make_float2(cur.cx[si], cur.cy[si]);
+    PlP ns = step_by_distance(pls, ip, dirs[k], S.prm.follow_first_image_distance, reached);
+    if (reached) continue;
+    int nv = 1;
+    int v[3]; float2 pt[3]; uint32_t opl[3], oseg[3]; uint8_t perm[3];
+    v[0] = sv; pt[0] = ns.c; opl[0] = cur.pl[si]; oseg[0] = ns.seg; perm[0] = (uint8_t)k;
+    for (int i = 0; i < 3; i++) {
+      if (i == si) continue;
+      const int ki = cur.perm[i];
+      const int vv = sel[ki];
+      float3 l;
+      if (!epiline(S, sv, vv, ns.c, l)) continue;
+      Pl pl = get_pl(S, vv, cur.pl[i]);
+      PlP iq; iq.seg = cur.seg[i]; iq.c = make_float2(cur.cx[i], cur.cy[i]);
+      PlP np;
+      if (walk_line(pl, iq, dirs[ki], l, S.prm, true, np)) {
+        v[nv] = vv; pt[nv] = np.c; opl[nv] = cur.pl[i]; oseg[nv] = np.seg; perm[nv] = (uint8_t)ki; nv++;
+      }
+    }
+    if (nv < 3) continue;
+    float X[3];
+    if (!est3(S, v, pt, X)) continue;
+    out.X[0] = X[0]; out.X[1] = X[1]; out.X[2] = X[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { out.perm[i] = perm[i]; out.pl[i] = opl[i]; out.seg[i] = oseg[i]; out.cx[i] = pt[i].x; out.cy[i] = pt[i].y; }
+    out.perm[3] = 0;
+    return true;
+  }
+  return false;
+}
+
+// follow_direction on a 3-view list, plg_matching.cpp:765-769
+EG3D_D void follow3(Ctx& c, const uint32_t dirs[3], Pt3* list, int& n) {
+  while (true) {
+    Pt3 cur = list[n - 1];
+    Pt3 np;
+    if (!step_all3(*c.S, c.sel, dirs, cur, np)) break;
+    if (n >= c.w.capf) { c.overflow = true; break; }
+    __syncwarp();
+    if (c.lane == 0) list[n] = np;
+    __syncwarp();
+    n++;
+  }
+}
+
+// compatible_new_plg_point, plg_matching.cpp:1276-1287 (-> :1249-1270 -> :1060-1076 -> :325-370 -> :205-265).
+// D1/D2 (and their counts) persist across the triples of a seed and are only overwritten when the corresponding
+// direction is valid for THIS hypothesis.
+EG3D_D bool plg_compatible(Ctx& c, const Cur3& cand, int& n1, int& n2, uint32_t d1[3], uint32_t d2[3]) {
+  const DevScene& S = *c.S;
+  Pl pla = get_pl(S, c.sel[0], cand.pl[0]), plb = get_pl(S, c.sel[1], cand.pl[1]), plc = get_pl(S, c.sel[2], cand.pl[2]);
+  bool d1ok = false, d2ok = false;
+  uint32_t dir1[3];
+  auto opposite = [&](const uint32_t d[3], uint32_t o[3]) {
+    o[0] = pla.start == d[0] ? pla.end : pla.start;
+    o[1] = plb.start == d[1] ? plb.end : plb.start;
+    o[2] = plc.start == d[2] ? plc.end : plc.start;
+  };
+  int n = first_extreme(c, cand, pla.start, dir1, c.w.D1);
+  if (c.overflow) return false;
+  if (n > 0) {
+    d1ok = true; n1 = n;
+    d1[0] = dir1[0]; d1[1] = dir1[1]; d1[2] = dir1[2];
+    opposite(dir1, d2);
+    Cur3 nx; float X[3];
+    if (step3(S, c.sel, cand, d2, nx, X)) {
+      d2ok = true;
+      __syncwarp();
+      if (c.lane == 0) store_pt3(c.w.D2, nx, X);
+      __syncwarp();
+      n2 = 1;
+    }
+  } else {
+    n = first_extreme(c, cand, pla.end, dir1, c.w.D1);
+    if (c.overflow) return false;
+    if (n > 0) {
+      d1ok = true; n1 = n;
+      d1[0] = dir1[0]; d1[1] = dir1[1]; d1[2] = dir1[2];
+      opposite(dir1, d2);
+    }
+  }
+  if (d1ok) follow3(c, d1, c.w.D1, n1);
+  if (d2ok) follow3(c, d2, c.w.D2, n2);
+  if (c.overflow) return false;
+  if (d1ok && n1 >= 2) return true;
+  if (d2ok && n2 >= 2) return true;
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// expansion phase: chain of "big" points held in slots
+EG3D_D int slot_of(const Ctx& c, int pos) { return c.w.order[pos]; }
+
+struct SlotObs {  // observation accessor of a slot, optionally followed by one extra observation
+  const int* v; const float* x; const float* y; int n; int ev; float ex, ey;
+  EG3D_D void operator()(int i, int& view, float& px, float& py) const {
+    if (i < n) { view = v[i]; px = x[i]; py = y[i]; } else { view = ev; px = ex; py = ey; }
+  }
+};
+EG3D_D SlotObs slot_obs(const Ctx& c, int slot, int n, int ev, float ex, float ey) {
+  SlotObs o; size_t b = (size_t)slot * c.w.oc;
+  o.v = c.w.ov + b; o.x = c.w.ox + b; o.y = c.w.oy + b; o.n = n; o.ev = ev; o.ex = ex; o.ey = ey;
+  return o;
+}
+
+// append one observation to a slot (lane 0 writes; callers sync)
+EG3D_D void slot_append(Ctx& c, int slot, int view, uint32_t pl, uint32_t seg, float x, float y, const float X[3]) {
+  int n = c.w.snobs[slot];
+  if (n >= c.w.oc) { c.overflow = true; return; }
+  if (c.lane == 0) {
+    size_t b = (size_t)slot * c.w.oc + n;
+    c.w.ov[b] = view; c.w.opl[b] = pl; c.w.oseg[b] = seg; c.w.ox[b] = x; c.w.oy[b] = y;
+    c.w.snobs[slot] = n + 1;
+    c.w.sX[3 * slot] = X[0]; c.w.sX[3 * slot + 1] = X[1]; c.w.sX[3 * slot + 2] = X[2];
+  }
+}
+
+// em_estimate3Dpositions over the n observations of a slot (triangulation.cpp:178-250): DLT from (first arg-min view,
+// last entry) + warp-cooperative GN.
+EG3D_D bool est_slot(Ctx& c, int slot, int n, float Xo[3]) {
+  const DevScene& S = *c.S;
+  const size_t b = (size_t)slot * c.w.oc;
+  const int* ov = c.w.ov + b;
+  int bestv = 0x7fffffff, besti = 0x7fffffff;
+  for (int i = c.lane; i < n; i += 32) { int v = ov[i]; if (v < bestv) { bestv = v; besti = i; } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    int ov2 = __shfl_xor_sync(0xffffffffu, bestv, o), oi2 = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov2 < bestv || (ov2 == bestv && oi2 < besti)) { bestv = ov2; besti = oi2; }
+  }
+  int mi = besti, ma = n - 1;
+  if (S.prm.dlt_wellposed && ov[ma] == ov[mi]) {
+    for (int j = n - 1; j >= 0; j--) if (ov[j] != ov[mi]) { ma = j; break; }
+  }
+  float t4[4];
+  dlt_null(S.P + 12 * ov[mi], S.P + 12 * ov[ma], make_float2(c.w.ox[b + mi], c.w.oy[b + mi]), make_float2(c.w.ox[b + ma], c.w.oy[b + ma]), t4);
+  double X[3] = {(double)(t4[0] / t4[3]), (double)(t4[1] / t4[3]), (double)(t4[2] / t4[3])};
+  if (!gn_warp(S, n, slot_obs(c, slot, n, 0, 0.f, 0.f), X, c.lane)) return false;
+  Xo[0] = (float)X[0]; Xo[1] = (float)X[1]; Xo[2] = (float)X[2];
+  return true;
+}
+
+// next 3-combination in lexicographic order over [0, n); returns false past the last one
+EG3D_D bool next_comb3(int& i, int& j, int& k, int n) {
+  if (k + 1 < n) { k++; return true; }
+  if (j + 2 < n) { j++; k = j + 1; return true; }
+  if (i + 3 < n) { i++; j = i + 1; k = j + 1; return true; }
+  return false;
+}
+
+// compute_3d_point_coords_combinations(min_combinations = 3), triangulation.cpp:1105-1158, on the observations of a
+// slot.  On success the slot is compacted to the selected observations in their ORIGINAL order
+// (plg_matching.cpp:720-732) and n / Xo are updated.
+EG3D_D bool combos_slot(Ctx& c, int slot, int& n, float Xo[3]) {
+  const DevScene& S = *c.S;
+  const size_t b = (size_t)slot * c.w.oc;
+  int* ov = c.w.ov + b; float* ox = c.w.ox + b; float* oy = c.w.oy + b; uint32_t* opl = c.w.opl + b; uint32_t* oseg = c.w.oseg + b;
+  // 1) first 3-subset (lexicographic = std::prev_permutation order of the selection mask) that triangulates
+  int bi = 0, bj = 1, bk = 2;
+  bool more = true, got = false;
+  float X[3] = {0, 0, 0};
+  int si = 0, sj = 0, sk = 0;
+  while (more && !got) {
+    int i = bi, j = bj, k = bk;
+    bool mine = true;
+    for (int s = 0; s < c.lane && mine; s++) mine = next_comb3(i, j, k, n);
+    bool ok = false; float Xl[3] = {0, 0, 0};
+    if (mine) {
+      int v[3] = {ov[i], ov[j], ov[k]};
+      float2 pt[3] = {make_float2(ox[i], oy[i]), make_float2(ox[j], oy[j]), make_float2(ox[k], oy[k])};
+      ok = est3(S, v, pt, Xl);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    if (m) {
+      int w = __ffs(m) - 1;
+      si = __shfl_sync(0xffffffffu, i, w); sj = __shfl_sync(0xffffffffu, j, w); sk = __shfl_sync(0xffffffffu, k, w);
+      X[0] = __shfl_sync(0xffffffffu, Xl[0], w); X[1] = __shfl_sync(0xffffffffu, Xl[1], w); X[2] = __shfl_sync(0xffffffffu, Xl[2], w);
+      got = true;
+    } else {
+      for (int s = 0; s < 32 && more; s++) more = next_comb3(bi, bj, bk, n);
+    }
+  }
+  if (!got) return false;
+  // 2) greedily add the remaining observations in index order (warm-started GN each)
+  __syncwarp();
+  for (int i = c.lane; i < n; i += 32) c.w.selmask[i] = (i == si || i == sj || i == sk) ? 1 : 0;
+  if (c.lane == 0) { c.w.idx[0] = si; c.w.idx[1] = sj; c.w.idx[2] = sk; }
+  __syncwarp();
+  int m = 3;
+  for (int i = 0; i < n; i++) {
+    if (c.w.selmask[i]) continue;
+    const int* idx = c.w.idx;
+    auto obs = [&](int q, int& view, float& px, float& py) {
+      int s = (q < m) ? idx[q] : i;
+      view = ov[s]; px = ox[s]; py = oy[s];
+    };
+    double Xd[3] = {X[0], X[1], X[2]};
+    if (gn_warp(S, m + 1, obs, Xd, c.lane)) {
+      X[0] = (float)Xd[0]; X[1] = (float)Xd[1]; X[2] = (float)Xd[2];
+      __syncwarp();
+      if (c.lane == 0) { c.w.selmask[i] = 1; c.w.idx[m] = i; }
+      __syncwarp();
+      m++;
+    }
+  }
+  // 3) compact the slot by the mask, original order
+  __syncwarp();
+  int w = 0;
+  for (int i = 0; i < n; i++) {
+    if (c.w.selmask[i]) {
+      if (w != i && c.lane == 0) { ov[w] = ov[i]; ox[w] = ox[i]; oy[w] = oy[i]; opl[w] = opl[i]; oseg[w] = oseg[i]; }
+      w++;
+    }
+  }
+  __syncwarp();
+  n = w;
+  Xo[0] = X[0]; Xo[1] = X[1]; Xo[2] = X[2];
+  return true;
+}
+
+// all-view compatible (plg_matching.cpp:633-759) on a chain point with many views.  Builds the candidate in slot
+// c.nslots (not yet claimed); returns true and leaves the new point there when a step is found.
+EG3D_D bool step_all_big(Ctx& c, const uint32_t* dirs, int cur_slot) {
+  const DevScene& S = *c.S;
+  if (c.nslots >= c.w.capc) { c.overflow = true; return false; }
+  const int t = c.nslots;
+  const int n = c.w.snobs[cur_slot];
+  const size_t cb = (size_t)cur_slot * c.w.oc, tb = (size_t)t * c.w.oc;
+  for (int si = 0; si < n; si++) {
+    const int sv = c.w.ov[cb + si];
+    const uint32_t spl = c.w.opl[cb + si];
+    Pl pls = get_pl(S, sv, spl);
+    PlP ip; ip.seg = c.w.oseg[cb + si]; ip.c = make_float2(c.w.ox[cb + si], c.w.oy[cb + si]);
+    bool reached;
+    PlP ns = step_by_distance(pls, ip, dirs[sv], S.prm.follow_first_image_distance, reached);
+    if (reached) continue;
+    __syncwarp();
+    if (c.lane == 0) { c.w.ov[tb] = sv; c.w.opl[tb] = spl; c.w.oseg[tb] = ns.seg; c.w.ox[tb] = ns.c.x; c.w.oy[tb] = ns.c.y; }
+    int count = 1;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + c.lane;
+      bool found = false; PlP np; int vv = 0; uint32_t ipl = 0;
+      if (i < n && i != si) {
+        vv = c.w.ov[cb + i]; ipl = c.w.opl[cb + i];
+        float3 l;
+        if (epiline(S, sv, vv, ns.c, l)) {
+          Pl pl = get_pl(S, vv, ipl);
+          PlP iq; iq.seg = c.w.oseg[cb + i]; iq.c = make_float2(c.w.ox[cb + i], c.w.oy[cb + i]);
+          found = walk_line(pl, iq, dirs[vv], l, S.prm, true, np);
+        }
+      }
+      unsigned m = __ballot_sync(0xffffffffu, found);
+      if (found) {
+        int pos = count + __popc(m & ((1u << c.lane) - 1u));
+        c.w.ov[tb + pos] = vv; c.w.opl[tb + pos] = ipl; c.w.oseg[tb + pos] = np.seg; c.w.ox[tb + pos] = np.c.x; c.w.oy[tb + pos] = np.c.y;
+      }
+      count += __popc(m);
+    }
+    __syncwarp();
+    if (count < 3) continue;
+    float X[3];
+    bool valid = est_slot(c, t, count, X);
+    if (!valid) valid = combos_slot(c, t, count, X);
+    if (valid) {
+      __syncwarp();
+      if (c.lane == 0) { c.w.snobs[t] = count; c.w.sX[3 * t] = X[0]; c.w.sX[3 * t + 1] = X[1]; c.w.sX[3 * t + 2] = X[2]; }
+      __syncwarp();
+      return true;
+    }
+  }
+  return false;
+}
+
+// follow_direction_vector_start / _end, plg_matching.cpp:771-795.  Returns the number of points added.
+EG3D_D int follow_big(Ctx& c, const uint32_t* dirs, bool at_start) {
+  int added = 0;
+  while (true) {
+    int cur_slot = slot_of(c, at_start ? 0 : c.len - 1);
+    if (!step_all_big(c, dirs, cur_slot)) break;
+    if (c.len >= c.w.capc) { c.overflow = true; break; }
+    const int t = c.nslots++;
+    __syncwarp();
+    if (at_start) {
+      // shift order right by one (descending so a single lane can do it safely)
+      if (c.lane == 0) { for (int i = c.len; i > 0; i--) c.w.order[i] = c.w.order[i - 1]; c.w.order[0] = t; }
+    } else if (c.lane == 0) c.w.order[c.len] = t;
+    __syncwarp();
+    c.len++;
+    added++;
+  }
+  return added;
+}
+
+// compatible_direction_noupdate_vector, plg_matching.cpp:866-914.  The polyline walk is sequential and cheap; the
+// warm-started GNs of the visited chain points are independent, so they run one per lane and the list is truncated at
+// the first failure.  Returns the number of accepted neighbours (entries of tmp[]).
+EG3D_D int walk_dir(Ctx& c, int v, const Plg& p, uint32_t dir, bool towards_start, int lo, int cur, int hi, NTmp* tmp) {
+  const DevScene& S = *c.S;
+  Pl pl = get_pl(S, v, p.pl);
+  PlP q; q.seg = p.seg; q.c = p.c;
+  int cnt = 0;
+  int j = towards_start ? cur - 1 : cur + 1;
+  __syncwarp();
+  while (towards_start ? (j >= lo) : (j < hi)) {
+    const int slot = slot_of(c, j);
+    const size_t b = (size_t)slot * c.w.oc;
+    float3 l;
+    if (!epiline(S, c.w.ov[b], v, make_float2(c.w.ox[b], c.w.oy[b]), l)) break;   // known_point's first observation (:797-806)
+    PlP nq;
+    if (!walk_line(pl, q, dir, l, S.prm, false, nq)) break;
+    if (c.lane == 0) { tmp[cnt].seg = nq.seg; tmp[cnt].cx = nq.c.x; tmp[cnt].cy = nq.c.y; }
+    cnt++;
+    q = nq;
+    j += towards_start ? -1 : 1;
+  }
+  __syncwarp();
+  int keep = cnt;
+  for (int base = 0; base < cnt; base += 32) {
+    const int k = base + c.lane;
+    bool fail = false;
+    if (k < cnt) {
+      const int jj = towards_start ? cur - 1 - k : cur + 1 + k;
+      const int slot = slot_of(c, jj);
+      const int n = c.w.snobs[slot];
+      double X[3] = {c.w.sX[3 * slot], c.w.sX[3 * slot + 1], c.w.sX[3 * slot + 2]};
+      if (gn_thread(S, n + 1, slot_obs(c, slot, n, v, tmp[k].cx, tmp[k].cy), X)) {
+        tmp[k].X[0] = (float)X[0]; tmp[k].X[1] = (float)X[1]; tmp[k].X[2] = (float)X[2];
+      } else fail = true;
+    }
+    unsigned fm = __ballot_sync(0xffffffffu, fail);
+    if (fm) { keep = base + __ffs(fm) - 1; break; }
+  }
+  __syncwarp();
+  return keep;
+}
+
+// add_view_to_3dpoint_and_sides_plgp_matches_vector after its first GN succeeded (plg_matching.cpp:1345-1412;
+// neighbour search = find_directions_on_plg_known_3D_point_no_update_vector :1011-1058)
+EG3D_D bool add_view_finish(Ctx& c, int v, const Plg& p, const float Xc[3], int lo, int cur, int hi, int& ns, int& ne) {
+  const DevScene& S = *c.S;
+  Pl pl = get_pl(S, v, p.pl);
+  int n1 = 0, n2 = 0; uint32_t nd1 = 0, nd2 = 0;
+  if (cur > lo) {
+    n1 = walk_dir(c, v, p, pl.start, true, lo, cur, hi, c.w.tmp1);
+    if (n1 > 0) {
+      nd1 = pl.start; nd2 = pl.end;
+      if (cur < hi) n2 = walk_dir(c, v, p, pl.end, false, lo, cur, hi, c.w.tmp2);
+    } else {
+      n1 = walk_dir(c, v, p, pl.end, true, lo, cur, hi, c.w.tmp1);
+      if (n1 > 0) {
+        nd1 = pl.end; nd2 = pl.start;
+        if (cur < hi) n2 = walk_dir(c, v, p, pl.start, false, lo, cur, hi, c.w.tmp2);
+      } else if (cur < hi) {
+        n2 = walk_dir(c, v, p, pl.end, false, lo, cur, hi, c.w.tmp2);
+        if (n2 > 0) { nd2 = pl.end; nd1 = pl.start; }
+        else {
+          n2 = walk_dir(c, v, p, pl.start, false, lo, cur, hi, c.w.tmp2);
+          if (n2 > 0) { nd2 = pl.start; nd1 = pl.end; }
+        }
+      }
+    }
+  }
+  if (cur > 0 && n1 == 0) return false;           // SWITCH_PLG_MATCHING_ADDPOINT_BOTHDIR_ONE (:1363-1368)
+  if (cur < c.len - 1 && n2 == 0) return false;
+  // success: commit
+  __syncwarp();
+  slot_append(c, slot_of(c, cur), v, p.pl, p.seg, p.c.x, p.c.y, Xc);
+  for (int k = 0; k < n1; k++) { NTmp t = c.w.tmp1[k]; slot_append(c, slot_of(c, cur - 1 - k), v, p.pl, t.seg, t.cx, t.cy, t.X); }
+  for (int k = 0; k < n2; k++) { NTmp t = c.w.tmp2[k]; slot_append(c, slot_of(c, cur + 1 + k), v, p.pl, t.seg, t.cx, t.cy, t.X); }
+  __syncwarp();
+  if (c.overflow) return false;
+  ns = n1; ne = n2;
+  if (n1 > 0 && n1 == cur) {
+    if (c.lane == 0) c.w.sdirs[v] = nd1;
+    __syncwarp();
+    int added = follow_big(c, c.w.sdirs, true);
+    ns += added; cur += added;
+  }
+  if (n2 > 0 && n2 == (c.len - cur - 1)) {
+    if (c.lane == 0) c.w.edirs[v] = nd2;
+    __syncwarp();
+    ne += follow_big(c, c.w.edirs, false);
+  }
+  return true;
+}
+
+// expand_allpoints_to_other_view_using_plmap, triangulation.cpp:742-830
+EG3D_D void expand_view(Ctx& c, int v) {
+  const DevScene& S = *c.S;
+  const int64_t h0 = c.A->hit_off[(size_t)c.seed * S.V + v];
+  const int nh = (int)(c.A->hit_off[(size_t)c.seed * S.V + v + 1] - h0);
+  const eg3d_hit* epcs = c.A->hits + h0;
+  bool matched = false; int iv0 = 0, iv1 = 0;
+  // the epipolar hits on the central point: one warm-started GN per lane, first complete success in order wins
+  for (int base = 0; base < nh && !matched; base += 32) {
+    const int e = base + c.lane;
+    const int cslot = slot_of(c, c.central);
+    const int n = c.w.snobs[cslot];
+    bool ok = false; float Xe[3] = {0, 0, 0};
+    if (e < nh) {
+      eg3d_hit h = epcs[e];
+      double X[3] = {c.w.sX[3 * cslot], c.w.sX[3 * cslot + 1], c.w.sX[3 * cslot + 2]};
+      ok = gn_thread(S, n + 1, slot_obs(c, cslot, n, v, h.x, h.y), X);
+      Xe[0] = (float)X[0]; Xe[1] = (float)X[1]; Xe[2] = (float)X[2];
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    while (m && !matched) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      eg3d_hit h = epcs[base + b];
+      float Xc[3] = {__shfl_sync(0xffffffffu, Xe[0], b), __shfl_sync(0xffffffffu, Xe[1], b), __shfl_sync(0xffffffffu, Xe[2], b)};
+      Plg p; p.pl = h.polyline; p.seg = h.segment; p.c = make_float2(h.x, h.y);
+      int ns = 0, ne = 0;
+      const int cc = c.central;
+      if (add_view_finish(c, v, p, Xc, 0, cc, c.len, ns, ne)) {
+        matched = true;
+        if (ns > cc) { c.central = ns; iv0 = 0; iv1 = ns + ne; }
+        else { iv0 = cc - ns; iv1 = cc + ne; }
+      }
+      if (c.overflow) return;
+    }
+  }
+  int last = -1;
+  for (int cur = 0; cur < c.len; cur++) {
+    if (matched && cur == iv0) { cur = iv1; last = iv1; continue; }
+    const int slot = slot_of(c, cur);
+    float2 q = project(S.P + 12 * v, c.w.sX[3 * slot], c.w.sX[3 * slot + 1], c.w.sX[3 * slot + 2]);
+    uint32_t pl_id;
+    if (!grid_unique(S.g_expand, v, S.width, S.height, q, pl_id)) continue;
+    Pl pl = get_pl(S, v, pl_id);
+    Plg init; init.pl = pl_id;
+    if (pl_distancesq(pl, q, init.seg, init.c) > S.prm.max_proj_distsq_expand) return;  // abandons the view
+    const int hi = matched ? (cur <= iv0 ? iv0 : c.len) : c.len;
+    const int n = c.w.snobs[slot];
+    double X[3] = {c.w.sX[3 * slot], c.w.sX[3 * slot + 1], c.w.sX[3 * slot + 2]};
+    if (!gn_warp(S, n + 1, slot_obs(c, slot, n, v, init.c.x, init.c.y), X, c.lane)) continue;
+    float Xc[3] = {(float)X[0], (float)X[1], (float)X[2]};
+    int ns = 0, ne = 0;
+    if (add_view_finish(c, v, init, Xc, last + 1, cur, hi, ns, ne)) {
+      if (ns > cur) { c.central = ns; cur = ns + ne; }
+      else cur = cur + ne;
+      last = cur;
+    }
+    if (c.overflow) return;
+  }
+}
+
+// materialise a 3-view point as a chain slot
+EG3D_D void slot_from_pt3(Ctx& c, int slot, const Pt3& p) {
+  if (c.lane == 0) {
+    size_t b = (size_t)slot * c.w.oc;
+    for (int i = 0; i < 3; i++) {
+      c.w.ov[b + i] = c.sel[p.perm[i]]; c.w.opl[b + i] = p.pl[i]; c.w.oseg[b + i] = p.seg[i]; c.w.ox[b + i] = p.cx[i]; c.w.oy[b + i] = p.cy[i];
+    }
+    c.w.snobs[slot] = 3;
+    c.w.sX[3 * slot] = p.X[0]; c.w.sX[3 * slot + 1] = p.X[1]; c.w.sX[3 * slot + 2] = p.X[2];
+  }
+}
+
+EG3D_D void process_seed(Ctx& c) {
+  const DevScene& S = *c.S; const K3Args& A = *c.A;
+  const int V = S.V, lane = c.lane;
+  const int64_t* off = A.hit_off + (size_t)c.seed * V;
+  // --- view triple (triangulation.cpp:1035-1066)
+  int ne = 0, minv = -1, maxv = -1;
+  for (int base = 0; base < V; base += 32) {
+    int v = base + lane;
+    bool nz = v < V && off[v + 1] > off[v];
+    unsigned m = __ballot_sync(0xffffffffu, nz);
+    if (m) { if (minv < 0) minv = base + __ffs(m) - 1; maxv = base + 31 - __clz(m); ne += __popc(m); }
+  }
+  if (ne < 3) return;
+  int mid = 0;
+  {
+    int want = ne / 2, seen = 0;
+    for (int base = 0; base < V; base += 32) {
+      int v = base + lane;
+      bool nz = v < V && off[v + 1] > off[v];
+      unsigned m = __ballot_sync(0xffffffffu, nz);
+      int pc = __popc(m);
+      if (seen + pc > want) {
+        int r = want - seen;
+        for (int k = 0; k < r; k++) m &= m - 1;
+        mid = base + __ffs(m) - 1;
+        break;
+      }
+      seen += pc;
+    }
+  }
+  c.sel[0] = minv; c.sel[1] = (c.sv == minv || c.sv == maxv) ? mid : c.sv; c.sel[2] = maxv;
+  const eg3d_hit* h0 = A.hits + off[c.sel[0]]; const int n0 = (int)(off[c.sel[0] + 1] - off[c.sel[0]]);
+  const eg3d_hit* h1 = A.hits + off[c.sel[1]]; const int n1h = (int)(off[c.sel[1] + 1] - off[c.sel[1]]);
+  const eg3d_hit* h2 = A.hits + off[c.sel[2]]; const int n2h = (int)(off[c.sel[2] + 1] - off[c.sel[2]]);
+  // --- triple enumeration with the uniqueness test (triangulation.cpp:550-601): one triple per lane
+  const long long total = (long long)n0 * n1h * n2h;
+  bool found = false;
+  int nD1 = 0, nD2 = 0, fn1 = 0, fn2 = 0;
+  uint32_t d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0}, fd1[3] = {0, 0, 0}, fd2[3] = {0, 0, 0};
+  Cur3 fcentral; float fX[3] = {0, 0, 0};
+  for (long long base = 0; base < total; base += 32) {
+    const long long t = base + lane;
+    bool ok = false; float X[3] = {0, 0, 0};
+    int i0 = 0, i1 = 0, i2 = 0;
+    if (t < total) {
+      i0 = (int)(t / ((long long)n1h * n2h));
+      long long rem = t - (long long)i0 * n1h * n2h;
+      i1 = (int)(rem / n2h); i2 = (int)(rem - (long long)i1 * n2h);
+      float2 pts[3] = {make_float2(h0[i0].x, h0[i0].y), make_float2(h1[i1].x, h1[i1].y), make_float2(h2[i2].x, h2[i2].y)};
+      ok = est3(S, c.sel, pts, X);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, ok);
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int j0 = __shfl_sync(0xffffffffu, i0, b), j1 = __shfl_sync(0xffffffffu, i1, b), j2 = __shfl_sync(0xffffffffu, i2, b);
+      float Xb[3] = {__shfl_sync(0xffffffffu, X[0], b), __shfl_sync(0xffffffffu, X[1], b), __shfl_sync(0xffffffffu, X[2], b)};
+      Cur3 cand;
+      eg3d_hit a0 = h0[j0], a1 = h1[j1], a2 = h2[j2];
+      cand.pl[0] = a0.polyline; cand.seg[0] = a0.segment; cand.c[0] = make_float2(a0.x, a0.y);
+      cand.pl[1] = a1.polyline; cand.seg[1] = a1.segment; cand.c[1] = make_float2(a1.x, a1.y);
+      cand.pl[2] = a2.polyline; cand.seg[2] = a2.segment; cand.c[2] = make_float2(a2.x, a2.y);
+      bool comp = plg_compatible(c, cand, nD1, nD2, d1, d2);
+      if (c.overflow) return;
+      if (comp) {
+        if (found) return;  // a second compatible triple: ambiguous, the seed yields nothing (:587-590)
+        found = true;
+        fn1 = nD1; fn2 = nD2;
+        for (int k = 0; k < 3; k++) { fd1[k] = d1[k]; fd2[k] = d2[k]; fX[k] = Xb[k]; }
+        fcentral = cand;
+        __syncwarp();
+        for (int i = lane; i < nD1; i += 32) c.w.fD1[i] = c.w.D1[i];
+        for (int i = lane; i < nD2; i += 32) c.w.fD2[i] = c.w.D2[i];
+        __syncwarp();
+      }
+    }
+  }
+  if (!found) return;
+  // --- chain = reverse(D1) + central + D2 (polyline_graph_2d.cpp:1298-1306)
+  c.len = fn1 + 1 + fn2;
+  if (c.len > c.w.capc) { c.overflow = true; return; }
+  __syncwarp();
+  for (int i = 0; i < fn1; i++) slot_from_pt3(c, i, c.w.fD1[fn1 - 1 - i]);
+  { Pt3 p; store_pt3(&p, fcentral, fX); slot_from_pt3(c, fn1, p); }
+  for (int i = 0; i < fn2; i++) slot_from_pt3(c, fn1 + 1 + i, c.w.fD2[i]);
+  for (int i = lane; i < c.len; i += 32) c.w.order[i] = i;
+  for (int v = lane; v < V; v += 32) { c.w.sdirs[v] = 0; c.w.edirs[v] = 0; }
+  __syncwarp();
+  if (lane == 0) for (int k = 0; k < 3; k++) { c.w.sdirs[c.sel[k]] = fd1[k]; c.w.edirs[c.sel[k]] = fd2[k]; }
+  __syncwarp();
+  c.nslots = c.len;
+  c.central = fn1;
+  // --- expansion to every other view (triangulation.cpp:960-973)
+  for (int v = 0; v < V; v++) {
+    if (v == c.sel[0] || v == c.sel[1] || v == c.sel[2]) continue;
+    expand_view(c, v);
+    if (c.overflow) return;
+  }
+}
+
+__global__ void __launch_bounds__(K3_THREADS) k3_chain_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  Ctx c;
+  c.S = &S; c.A = &A; c.lane = lane;
+  c.w = make_ws(A.scratch + (size_t)warp * A.scratch_per_warp, S.V, A.capf, A.capc, A.oc);
+  while (true) {
+    int seed = 0;
+    if (lane == 0) seed = atomicAdd(A.work_counter, 1);
+    seed = __shfl_sync(0xffffffffu, seed, 0);
+    if (seed >= A.n_seeds) break;
+    c.seed = seed; c.sv = A.seed_view[seed];
+    c.len = 0; c.nslots = 0; c.central = 0; c.overflow = false;
+    process_seed(c);
+    __syncwarp();
+    int npts = c.overflow ? 0 : c.len;
+    long long nobs = 0;
+    for (int i = lane; i < npts; i += 32) nobs += c.w.snobs[c.w.order[i]];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nobs += __shfl_xor_sync(0xffffffffu, nobs, o);
+    unsigned long long pbase = 0, obase = 0;
+    if (lane == 0) {
+      if (c.overflow) atomicAdd(&A.out_counters[2], 1ull);
+      if (npts > 0) {
+        pbase = atomicAdd(&A.out_counters[0], (unsigned long long)npts);
+        obase = atomicAdd(&A.out_counters[1], (unsigned long long)nobs);
+      }
+    }
+    pbase = __shfl_sync(0xffffffffu, pbase, 0); obase = __shfl_sync(0xffffffffu, obase, 0);
+    if (npts > 0 && ((long long)pbase + npts > A.pt_cap || (long long)obase + nobs > A.ob_cap)) {
+      if (lane == 0) atomicAdd(&A.out_counters[3], 1ull);
+      npts = 0; nobs = 0;
+    }
+    if (lane == 0) { A.seed_npts[seed] = npts; A.seed_pbase[seed] = (int64_t)pbase; A.seed_nobs[seed] = nobs; }
+    // write the chain: point headers by lane 0 sequentially (offsets), observations coalesced
+    long long ob = (long long)obase;
+    for (int i = 0; i < npts; i++) {
+      const int slot = c.w.order[i];
+      const int n = c.w.snobs[slot];
+      if (lane == 0) {
+        A.o_X[3 * (pbase + i)] = c.w.sX[3 * slot]; A.o_X[3 * (pbase + i) + 1] = c.w.sX[3 * slot + 1]; A.o_X[3 * (pbase + i) + 2] = c.w.sX[3 * slot + 2];
+        A.o_nobs[pbase + i] = n; A.o_obase[pbase + i] = ob;
+      }
+      const size_t b = (size_t)slot * c.w.oc;
+      for (int k = lane; k < n; k += 32) {
+        A.ob_view[ob + k] = c.w.ov[b + k]; A.ob_pl[ob + k] = c.w.opl[b + k]; A.ob_seg[ob + k] = c.w.oseg[b + k];
+        A.ob_x[ob + k] = c.w.ox[b + k]; A.ob_y[ob + k] = c.w.oy[b + k];
+      }
+      ob += n;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace eg3d

@@ -1,0 +1,221 @@
+"""ctypes binding of edgegraph3d_b200/libeg3d.so (the C-ABI of include/eg3d.h).
+
+The library is the product: if it is missing or no CUDA device is usable every call raises — there is no CPU
+fallback and nothing here imports the oracle.
+"""
+import ctypes as C
+import os
+import numpy as np
+from . import _abi as A
+from .scene import PointSet
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libeg3d.so")
+_lib = None
+
+EXPORTS = [
+    "eg3d_last_error", "eg3d_device_count", "eg3d_params_default", "eg3d_scene_create", "eg3d_scene_destroy",
+    "eg3d_sample_seeds", "eg3d_epipolar_intersect", "eg3d_hits_get", "eg3d_hits_free", "eg3d_match_seeds",
+    "eg3d_match_polyline_sets", "eg3d_match_refpoints", "eg3d_points_get", "eg3d_points_free", "eg3d_gn_triangulate",
+    "eg3d_gn_triangulate_device", "eg3d_dedup_close_points", "eg3d_filter",
+]
+
+
+class Eg3dError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"eg3d status {status}: {msg}")
+        self.status = status
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Eg3dError(-1, f"{LIB_PATH} is missing: build it with edgegraph3d_b200/csrc/build.sh "
+                            "(python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    L.eg3d_last_error.restype = C.c_char_p
+    L.eg3d_device_count.restype = C.c_int
+    L.eg3d_params_default.argtypes = [C.POINTER(A.Params)]
+    L.eg3d_scene_create.argtypes = [C.POINTER(A.SceneDesc), C.POINTER(A.Params), C.POINTER(C.c_void_p)]
+    L.eg3d_scene_destroy.argtypes = [C.c_void_p]
+    L.eg3d_sample_seeds.argtypes = [C.POINTER(A.SceneDesc), A.c_i32p, A.c_u32p, C.c_int64, C.c_float, C.c_int64,
+                                    A.c_i32p, A.c_u32p, A.c_u32p, A.c_f32p, A.c_i32p, A.c_i64p]
+    L.eg3d_epipolar_intersect.argtypes = [C.c_void_p, C.POINTER(A.Seeds), C.POINTER(A.Candidates), C.POINTER(C.c_void_p), C.POINTER(A.Timing)]
+    L.eg3d_hits_get.argtypes = [C.c_void_p, A.c_i64p, A.c_i32p, C.POINTER(A.c_i64p), C.POINTER(C.POINTER(A.Hit))]
+    L.eg3d_hits_free.argtypes = [C.c_void_p]
+    L.eg3d_match_seeds.argtypes = [C.c_void_p, C.POINTER(A.Seeds), C.POINTER(A.Candidates), C.POINTER(C.c_void_p), C.POINTER(A.Timing)]
+    L.eg3d_match_polyline_sets.argtypes = [C.c_void_p, C.POINTER(A.Candidates), C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(A.Timing)]
+    L.eg3d_match_refpoints.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(A.Timing)]
+    L.eg3d_points_get.argtypes = [C.c_void_p, C.POINTER(A.PointsView)]
+    L.eg3d_points_free.argtypes = [C.c_void_p]
+    L.eg3d_gn_triangulate.argtypes = [C.c_void_p, C.c_int64, A.c_i64p, A.c_i32p, A.c_f32p, A.c_f32p, C.c_int, A.c_f32p, A.c_f32p,
+                                      A.c_u8p, C.POINTER(A.Timing)]
+    L.eg3d_gn_triangulate_device.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(A.Timing)]
+    L.eg3d_dedup_close_points.argtypes = [C.c_void_p, C.POINTER(A.PointsView), A.c_u8p]
+    L.eg3d_filter.argtypes = [C.c_void_p, C.c_int64, A.c_f32p, A.c_i64p, A.c_i32p, A.c_f32p, C.c_int64, C.c_float, C.c_int32,
+                              A.c_u8p, C.POINTER(A.Timing)]
+    _lib = L
+    return L
+
+
+def _check(st):
+    if st != A.EG3D_OK:
+        raise Eg3dError(st, load().eg3d_last_error().decode(errors="replace"))
+
+
+def default_params(**overrides):
+    p = A.Params()
+    load().eg3d_params_default(C.byref(p))
+    for k, v in overrides.items():
+        setattr(p, k, v)
+    return p
+
+
+def sample_seeds(scene, views, polylines, spacing):
+    """a3 seed sampler (host C++): polyline_matching.cpp:168-190."""
+    L = load()
+    d = scene.desc()
+    views = np.ascontiguousarray(views, np.int32)
+    polylines = np.ascontiguousarray(polylines, np.uint32)
+    cap = 1 << 16
+    while True:
+        ov = np.zeros(cap, np.int32); op = np.zeros(cap, np.uint32); os_ = np.zeros(cap, np.uint32)
+        oxy = np.zeros((cap, 2), np.float32); osrc = np.zeros(cap, np.int32)
+        n = C.c_int64()
+        L.eg3d_sample_seeds(C.byref(d), A.ptr(views, A.c_i32p), A.ptr(polylines, A.c_u32p), len(views), spacing, cap,
+                            A.ptr(ov, A.c_i32p), A.ptr(op, A.c_u32p), A.ptr(os_, A.c_u32p), A.ptr(oxy, A.c_f32p),
+                            A.ptr(osrc, A.c_i32p), C.byref(n))
+        if n.value <= cap:
+            k = int(n.value)
+            return ov[:k].copy(), op[:k].copy(), os_[:k].copy(), oxy[:k].copy(), osrc[:k].copy()
+        cap = int(n.value)
+
+
+class DeviceScene:
+    """Device-resident scene handle (eg3d_scene)."""
+
+    def __init__(self, scene, params=None):
+        L = load()
+        self.scene = scene
+        self.params = params if params is not None else default_params()
+        self._desc = scene.desc()
+        h = C.c_void_p()
+        _check(L.eg3d_scene_create(C.byref(self._desc), C.byref(self.params), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            load().eg3d_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _points(self, handle):
+        L = load()
+        v = A.PointsView()
+        _check(L.eg3d_points_get(handle, C.byref(v)))
+        ps = PointSet.from_view(v)
+        L.eg3d_points_free(handle)
+        return ps
+
+    def epipolar_intersect(self, seeds, cands=None):
+        L = load()
+        sd = seeds.desc()
+        cd = cands.desc() if cands is not None else None
+        h = C.c_void_p()
+        tm = A.Timing()
+        _check(L.eg3d_epipolar_intersect(self.h, C.byref(sd), C.byref(cd) if cd is not None else None, C.byref(h), C.byref(tm)))
+        n = C.c_int64(); V = C.c_int32(); off = A.c_i64p(); hits = C.POINTER(A.Hit)()
+        _check(L.eg3d_hits_get(h, C.byref(n), C.byref(V), C.byref(off), C.byref(hits)))
+        cnt = int(n.value) * int(V.value) + 1
+        off_np = np.ctypeslib.as_array(off, shape=(cnt,)).copy()
+        nh = int(off_np[-1])
+        dt = np.dtype([("polyline", np.uint32), ("segment", np.uint32), ("x", np.float32), ("y", np.float32)])
+        if nh:
+            buf = (C.c_char * (nh * 16)).from_address(C.addressof(hits.contents))
+            hn = np.frombuffer(buf, dtype=dt).copy()
+        else:
+            hn = np.zeros(0, dt)
+        L.eg3d_hits_free(h)
+        return off_np, hn, int(V.value), tm.as_dict()
+
+    def match_seeds(self, seeds, cands=None):
+        L = load()
+        sd = seeds.desc()
+        cd = cands.desc() if cands is not None else None
+        h = C.c_void_p()
+        tm = A.Timing()
+        st = L.eg3d_match_seeds(self.h, C.byref(sd), C.byref(cd) if cd is not None else None, C.byref(h), C.byref(tm))
+        self.last_timing = tm.as_dict()
+        _check(st)
+        return self._points(h), tm.as_dict()
+
+    def match_polyline_sets(self, cands, view_begin=0, view_end=None):
+        L = load()
+        cd = cands.desc()
+        ve = self.scene.n_views if view_end is None else view_end
+        h = C.c_void_p()
+        tm = A.Timing()
+        st = L.eg3d_match_polyline_sets(self.h, C.byref(cd), view_begin, ve, C.byref(h), C.byref(tm))
+        self.last_timing = tm.as_dict()
+        _check(st)
+        return self._points(h), tm.as_dict()
+
+    def match_refpoints(self, tb=0, te=None):
+        L = load()
+        te = self.scene.n_tracks if te is None else te
+        h = C.c_void_p()
+        tm = A.Timing()
+        _check(L.eg3d_match_refpoints(self.h, tb, te, C.byref(h), C.byref(tm)))
+        return self._points(h), tm.as_dict()
+
+    def gn_triangulate(self, obs_off, obs_view, obs_xy, init_xyz, fp64):
+        L = load()
+        n = len(obs_off) - 1
+        obs_off = np.ascontiguousarray(obs_off, np.int64)
+        obs_view = np.ascontiguousarray(obs_view, np.int32)
+        obs_xy = np.ascontiguousarray(obs_xy, np.float32)
+        init_xyz = np.ascontiguousarray(init_xyz, np.float32)
+        xyz = np.zeros((n, 3), np.float32); mse = np.zeros(n, np.float32); ok = np.zeros(n, np.uint8)
+        tm = A.Timing()
+        _check(L.eg3d_gn_triangulate(self.h, n, A.ptr(obs_off, A.c_i64p), A.ptr(obs_view, A.c_i32p), A.ptr(obs_xy, A.c_f32p),
+                                     A.ptr(init_xyz, A.c_f32p), int(fp64), A.ptr(xyz, A.c_f32p), A.ptr(mse, A.c_f32p),
+                                     A.ptr(ok, A.c_u8p), C.byref(tm)))
+        return xyz, mse, ok, tm.as_dict()
+
+    def gn_triangulate_device(self, n, k, d_view, d_xy, d_init, fp64, d_xyz, d_mse, d_ok):
+        """Device pointers (ints) on this scene's device; returns the timing dict."""
+        tm = A.Timing()
+        _check(load().eg3d_gn_triangulate_device(self.h, n, k, d_view, d_xy, d_init, int(fp64), d_xyz, d_mse, d_ok, C.byref(tm)))
+        return tm.as_dict()
+
+    def dedup_close_points(self, pts):
+        keep = np.zeros(pts.n_points, np.uint8)
+        v = pts.view_struct()
+        _check(load().eg3d_dedup_close_points(self.h, C.byref(v), A.ptr(keep, A.c_u8p)))
+        return keep
+
+    def filter(self, xyz, obs_off, obs_view, obs_xy, first_edgepoint, gn_max_mse=2.25, forced_min_filter=-1):
+        xyz = np.ascontiguousarray(xyz, np.float32).copy()
+        obs_off = np.ascontiguousarray(obs_off, np.int64)
+        obs_view = np.ascontiguousarray(obs_view, np.int32)
+        obs_xy = np.ascontiguousarray(obs_xy, np.float32)
+        n = len(obs_off) - 1
+        inl = np.zeros(n, np.uint8)
+        tm = A.Timing()
+        _check(load().eg3d_filter(self.h, n, A.ptr(xyz, A.c_f32p), A.ptr(obs_off, A.c_i64p), A.ptr(obs_view, A.c_i32p),
+                                  A.ptr(obs_xy, A.c_f32p), first_edgepoint, gn_max_mse, forced_min_filter, A.ptr(inl, A.c_u8p), C.byref(tm)))
+        return xyz, inl, tm.as_dict()

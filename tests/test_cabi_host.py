@@ -1,0 +1,51 @@
+"""CPU-side checks of the product library: it loads, exports every symbol include/eg3d.h declares, its host-side
+seed sampler matches the oracle, and compute entry points refuse to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import numpy as np
+import pytest
+from edgegraph3d_b200 import lib as E, synthetic as syn, _abi as A
+from tests import oracle_lib as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = E.load()
+    hdr = open(os.path.join(ROOT, "include", "eg3d.h")).read()
+    declared = set(re.findall(r"\b(eg3d_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(E.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_params_default_match_reference_constants():
+    p = E.default_params()
+    q = O.default_params()
+    for name, _ in A.Params._fields_:
+        assert getattr(p, name) == getattr(q, name), name
+    assert p.split_interval_distance == 20.0 and p.gn_accept_mse == 9 and p.filter_gn_max_mse == 2.25
+
+
+def test_seed_sampler_matches_oracle():
+    sc = syn.make_scene(n_views=4, n_curves=16, seed=3)
+    a = syn.sample_seeds(E.sample_seeds, sc)
+    b = syn.sample_seeds(O.sample_seeds, sc)
+    assert len(a) == len(b) and len(a) > 100
+    assert np.array_equal(a.view, b.view) and np.array_equal(a.polyline, b.polyline) and np.array_equal(a.segment, b.segment)
+    assert a.xy.tobytes() == b.xy.tobytes()
+    # seeds are 20 px apart (Euclidean) along each polyline
+    same = (a.view[1:] == a.view[:-1]) & (a.polyline[1:] == a.polyline[:-1])
+    d = np.linalg.norm(a.xy[1:] - a.xy[:-1], axis=1)[same]
+    assert np.allclose(d, 20.0, atol=0.25)  # linear interpolation of the crossing segment (polyline_graph_2d.cpp:415,442)
+
+
+def test_no_cpu_fallback_without_device():
+    if E.load().eg3d_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    sc = syn.make_scene(n_views=3, n_curves=4, seed=1)
+    with pytest.raises(E.Eg3dError) as ei:
+        E.DeviceScene(sc)
+    assert ei.value.status == A.EG3D_ERR_NO_DEVICE

@@ -1,0 +1,182 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle on the same seeded
+inputs.  Bars: bit-exact for index / integer / 2D-geometry outputs (hit lists, identity sets, inlier bitmaps);
+3D coordinates within 1e-4 reprojection MSE of the oracle (north_star) — and in practice far tighter."""
+import numpy as np
+import pytest
+from edgegraph3d_b200 import lib as E, synthetic as syn
+from edgegraph3d_b200.scene import FlatScene
+from tests import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _reproj_mse(scene, pts):
+    """per-point mean squared reprojection error over its observations (px^2)"""
+    P = scene.cameras.astype(np.float64).reshape(-1, 3, 4)
+    out = np.zeros(pts.n_points)
+    for i in range(pts.n_points):
+        a, b = int(pts.obs_off[i]), int(pts.obs_off[i + 1])
+        Pv = P[pts.obs_view[a:b]]
+        h = Pv[:, :, :3] @ pts.xyz[i].astype(np.float64) + Pv[:, :, 3]
+        r = pts.obs_xy[a:b] - h[:, :2] / h[:, 2:3]
+        out[i] = (r ** 2).sum() / (2 * (b - a))
+    return out
+
+
+def assert_points_parity(scene, gpu, ref, mse_tol=1e-4):
+    assert gpu.n_points == ref.n_points, (gpu.n_points, ref.n_points)
+    assert np.array_equal(gpu.seed, ref.seed) and np.array_equal(gpu.chain_pos, ref.chain_pos)
+    assert np.array_equal(gpu.obs_off, ref.obs_off)
+    assert np.array_equal(gpu.obs_view, ref.obs_view)
+    assert np.array_equal(gpu.obs_poly, ref.obs_poly) and np.array_equal(gpu.obs_seg, ref.obs_seg)
+    assert gpu.obs_xy.tobytes() == ref.obs_xy.tobytes()      # 2D geometry is float arithmetic in a fixed order: bit-exact
+    if gpu.n_points:
+        d = np.abs(_reproj_mse(scene, gpu) - _reproj_mse(scene, ref))
+        assert d.max() <= mse_tol, d.max()
+        assert np.abs(gpu.xyz - ref.xyz).max() < 1e-4
+
+
+@pytest.fixture(scope="module")
+def small():
+    sc = syn.make_scene(n_views=6, n_curves=24, seed=1, n_tracks=150)
+    return sc, E.DeviceScene(sc), O.OracleScene(sc)
+
+
+def assert_hits_equal(a, b):
+    off_a, h_a, V_a = a[0], a[1], a[2]
+    off_b, h_b, V_b = b[0], b[1], b[2]
+    assert V_a == V_b
+    assert np.array_equal(off_a, off_b)
+    assert h_a.tobytes() == h_b.tobytes()
+
+
+def test_k1_sweep_bit_exact(small):
+    sc, dev, orc = small
+    seeds = syn.sample_seeds(E.sample_seeds, sc)
+    g = dev.epipolar_intersect(seeds)
+    assert_hits_equal(g, orc.epipolar_intersect(seeds))
+    assert g[1].shape[0] > 1000
+    tm = g[3]
+    assert tm["n_segment_tests"] == sum(sum(sc.n_segments(v) for v in range(sc.n_views) if v != s) for s in seeds.view)
+
+
+def test_k1_sweep_ragged_and_multichunk():
+    # a view with > K1_CHUNK segments (several TMA stages, ragged tail), views with invalid polylines, and an invalid F pair
+    sc = syn.make_scene(n_views=4, width=1920, height=1080, focal=1600.0, n_curves=260, segs_per_curve=20, curve_len=0.2,
+                        seed=11, extent=0.9, closed_frac=0.05)
+    sc.fundamental_valid[1, 2] = 0
+    assert max(sc.n_segments(v) for v in range(4)) > 4096
+    seeds = syn.sample_seeds(E.sample_seeds, sc, per_view=70)
+    with E.DeviceScene(sc) as dev:
+        g = dev.epipolar_intersect(seeds)
+    assert_hits_equal(g, O.OracleScene(sc).epipolar_intersect(seeds))
+
+
+def test_k1_empty_batch(small):
+    sc, dev, orc = small
+    seeds = syn.sample_seeds(E.sample_seeds, sc).slice(0, 0)
+    off, h, V, _ = dev.epipolar_intersect(seeds)
+    assert off.tolist() == [0] and len(h) == 0
+
+
+def test_k1_candidates_bit_exact(small):
+    sc, dev, orc = small
+    cands = syn.curve_candidate_sets(sc)
+    seeds = syn.sample_seeds(E.sample_seeds, sc, polylines_per_view=6)
+    seeds.cand_set = (seeds.polyline.astype(np.int32)) % cands.n_sets
+    assert_hits_equal(dev.epipolar_intersect(seeds, cands), orc.epipolar_intersect(seeds, cands))
+
+
+def test_match_seeds_sweep_parity(small):
+    sc, dev, orc = small
+    seeds = syn.sample_seeds(E.sample_seeds, sc)
+    gpu, tm = dev.match_seeds(seeds)
+    ref = orc.match_seeds(seeds)
+    assert ref.n_points > 300
+    assert_points_parity(sc, gpu, ref)
+    assert tm["n_points"] == gpu.n_points and tm["kernel_launches"] >= 5
+
+
+def test_match_polyline_sets_parity(small):
+    sc, dev, orc = small
+    cands = syn.curve_candidate_sets(sc)
+    gpu, _ = dev.match_polyline_sets(cands)
+    ref = orc.match_polyline_sets(cands)
+    assert ref.n_points > 1000
+    assert_points_parity(sc, gpu, ref)
+
+
+def test_match_polyline_sets_view_shards_concatenate(small):
+    # the multi-GPU shard axis (starting views): shards concatenate to the unsharded result
+    sc, dev, orc = small
+    cands = syn.curve_candidate_sets(sc)
+    full, _ = dev.match_polyline_sets(cands)
+    a, _ = dev.match_polyline_sets(cands, 0, 3)
+    b, _ = dev.match_polyline_sets(cands, 3, 6)
+    assert a.n_points + b.n_points == full.n_points
+    keys = sorted((tuple(x.tolist()), k[2]) for x, k in zip(full.xyz, full.identity_keys()))
+    keys2 = sorted((tuple(x.tolist()), k[2]) for p in (a, b) for x, k in zip(p.xyz, p.identity_keys()))
+    assert keys == keys2
+
+
+@pytest.mark.parametrize("seed,views,curves", [(2, 5, 16), (7, 9, 20), (13, 12, 12)])
+def test_match_more_scenes_parity(seed, views, curves):
+    sc = syn.make_scene(n_views=views, n_curves=curves, seed=seed, closed_frac=0.2, drop_view_frac=0.1)
+    cands = syn.curve_candidate_sets(sc, seed=seed)
+    with E.DeviceScene(sc) as dev:
+        gpu, _ = dev.match_polyline_sets(cands)
+        seeds = syn.sample_seeds(E.sample_seeds, sc, per_view=25)
+        gpu2, _ = dev.match_seeds(seeds)
+    orc = O.OracleScene(sc)
+    assert_points_parity(sc, gpu, orc.match_polyline_sets(cands))
+    assert_points_parity(sc, gpu2, orc.match_seeds(seeds))
+
+
+def test_gn64_golden_and_oracle(golden, small):
+    V = golden["cams"].shape[0]
+    sc = FlatScene(640, 480, golden["cams"], np.zeros((V, V, 9)), np.zeros((V, V), np.uint8), np.arange(V + 1), np.arange(V + 1) * 2,
+                   np.tile(np.array([[10, 10], [20, 20]], np.float32), (V, 1)), np.zeros(V, np.uint32), np.ones(V, np.uint32))
+    with E.DeviceScene(sc) as dev:
+        xyz, mse, ok, _ = dev.gn_triangulate(golden["gn64_off"], golden["gn64_view"], golden["gn64_xy"], golden["gn64_init"].astype(np.float32), True)
+    assert np.array_equal(ok, golden["gn64_ok"])
+    sel = ok == 1
+    assert np.abs(xyz[sel] - golden["gn64_X"][sel].astype(np.float32)).max() < 2e-6
+    assert np.abs(mse - golden["gn64_mse"].astype(np.float32)).max() < 1e-4 * max(1.0, np.abs(golden["gn64_mse"]).max())
+
+
+def test_gn32_filter_bit_exact_vs_cv2_golden(golden):
+    V = golden["cams"].shape[0]
+    sc = FlatScene(640, 480, golden["cams"], np.zeros((V, V, 9)), np.zeros((V, V), np.uint8), np.arange(V + 1), np.arange(V + 1) * 2,
+                   np.tile(np.array([[10, 10], [20, 20]], np.float32), (V, 1)), np.zeros(V, np.uint32), np.ones(V, np.uint32))
+    with E.DeviceScene(sc) as dev:
+        xyz, mse, ok, _ = dev.gn_triangulate(golden["gn32_off"], golden["gn32_view"], golden["gn32_xy"], golden["gn32_init"].astype(np.float32), False)
+    assert np.array_equal(ok, golden["gn32_ok"])
+    sel = ok == 1
+    assert np.array_equal(xyz[sel], golden["gn32_X"][sel].astype(np.float32))
+    assert np.array_equal(mse, golden["gn32_mse"].astype(np.float32))
+
+
+def test_dedup_and_filter_parity(small):
+    sc, dev, orc = small
+    cands = syn.curve_candidate_sets(sc)
+    pts, _ = dev.match_polyline_sets(cands)
+    keep = dev.dedup_close_points(pts)
+    assert np.array_equal(keep, orc.dedup_close_points(pts))
+    assert 0 < keep.sum() < len(keep)
+    # filter over SfM tracks + kept edge points (edge_matcher.cpp:132)
+    kept = np.where(keep)[0]
+    xyz = np.concatenate([sc.track_xyz, pts.xyz[kept]])
+    offs = [sc.track_off]
+    views = [sc.track_view]
+    xys = [sc.track_xy]
+    base = int(sc.track_off[-1])
+    lens = (pts.obs_off[kept + 1] - pts.obs_off[kept])
+    offs.append(base + np.cumsum(lens))
+    idx = np.concatenate([np.arange(pts.obs_off[i], pts.obs_off[i + 1]) for i in kept])
+    views.append(pts.obs_view[idx]); xys.append(pts.obs_xy[idx])
+    obs_off = np.concatenate(offs); obs_view = np.concatenate(views); obs_xy = np.concatenate(xys)
+    gx, gi, _ = dev.filter(xyz, obs_off, obs_view, obs_xy, sc.n_tracks)
+    ox, oi = orc.filter(xyz, obs_off, obs_view, obs_xy, sc.n_tracks)
+    assert np.array_equal(gi, oi)
+    assert np.array_equal(gx, ox)      # FP32 filter arithmetic is reproduced operation by operation
+    assert 0 < gi.sum() < len(gi)
