@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py — triangulated 3D edge-points/sec on the BASELINE.json workload (see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|small]
+
+A "step" is one pass of the hot path (K1 epipolar intersection -> K3 triple enumeration / PLG following / view expansion
+-> ordered packing [-> NCCL all-gather of the accepted points when N > 1]) over the whole seed batch of the workload.
+N = 1 runs BASELINE configs[1]: the synthetic 200-view rig, 1920x1080, 8 000 polyline segments per view, 50 000 seeds.
+N > 1 is weak scaling on the same rig: every rank keeps 50 000 seeds (seed spacing 20/N px => 250*N seeds per view) and
+owns a contiguous block of starting views (the reference's outer loop, polyline_matching.cpp:162).
+
+`value` = accepted (pre-dedup) 3D edge-points of all ranks / max-over-ranks device time of a step (CUDA events on the
+library's stream; inputs already resident).  `e2e` = the same count / wall time of the C-ABI call sequence a user makes
+with HOST buffers: eg3d_match_seeds (pinned seeds H2D + kernels) + eg3d_points_get (D2H of the result into pinned memory).
+--impl reference times the CPU oracle (the reference cannot be compiled in this image: DESIGN.md) on a bounded seed sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from edgegraph3d_b200 import synthetic as syn  # noqa: E402
+
+METRIC = "triangulated 3D edge-points/sec (device-timed)"
+UNIT = "points/s"
+
+
+def build_workload(name, n_gpus):
+    if name == "c2":
+        cfg = dict(n_views=200, width=1920, height=1080, focal=1600.0, n_curves=400, segs_per_curve=20, curve_len=0.2,
+                   seed=1234, extent=0.9, closed_frac=0.05)
+        per_view = 250
+    elif name == "small":
+        cfg = dict(n_views=24, width=1280, height=720, focal=1000.0, n_curves=120, segs_per_curve=20, curve_len=0.3,
+                   seed=1234, extent=0.8, closed_frac=0.05)
+        per_view = 120
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    scene = syn.make_scene(**cfg)
+    return scene, cfg, per_view
+
+
+def make_seeds(scene, sampler, per_view, n_gpus, rank):
+    """250*N seeds per view at spacing 20/N px, first polylines first; rank r owns starting views [r*V/N, (r+1)*V/N)."""
+    V = scene.n_views
+    lo, hi = (rank * V) // n_gpus, ((rank + 1) * V) // n_gpus
+    return syn.sample_seeds(sampler, scene, per_view=per_view * n_gpus, spacing=20.0 / n_gpus, views=range(lo, hi))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def pinned_seeds(seeds):
+    """Move the seed arrays into page-locked host memory (the e2e contract copies inputs from pinned memory)."""
+    import torch
+    from edgegraph3d_b200.scene import SeedBatch
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+    keep = []
+    out = []
+    for a in (seeds.view, seeds.polyline.view(np.int32), seeds.segment.view(np.int32), seeds.xy):
+        n, t = pin(a)
+        keep.append(t)
+        out.append(n)
+    sb = SeedBatch(out[0], out[1].view(np.uint32), out[2].view(np.uint32), out[3], None)
+    sb._pinned = keep
+    return sb
+
+
+def cpu_baseline(scene, seeds, target_seconds=15.0, threads=None):
+    """The CPU oracle (the port of the reference path) on a bounded stratified sample of the same seed batch."""
+    from tests import oracle_lib as O
+    threads = threads or os.cpu_count()
+    osc = O.OracleScene(scene)
+    n = len(seeds)
+    probe = seeds.take(np.linspace(0, n - 1, min(n, 64)).astype(np.int64))
+    t = time.perf_counter()
+    osc.match_seeds(probe, n_threads=threads)
+    per_seed = max((time.perf_counter() - t) / len(probe), 1e-6)
+    m = int(min(n, max(64, target_seconds / per_seed)))
+    sample = seeds.take(np.linspace(0, n - 1, m).astype(np.int64))
+    t = time.perf_counter()
+    pts = osc.match_seeds(sample, n_threads=threads)
+    dt = time.perf_counter() - t
+    return {"value": pts.n_points / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{m} of {n} seeds (stratified: every {n / m:.1f}th seed of the batch), full per-seed path (K1 sweep + "
+                      f"triples + PLG following + view expansion), {pts.n_points} points in {dt:.2f} s",
+            "seconds": dt, "seeds": m, "points": pts.n_points}, osc, sample
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (reference unbuildable here)."""
+    if rank != 0:
+        return
+    from tests import oracle_lib as O
+    scene, cfg, per_view = build_workload(args.workload, 1)
+    seeds = make_seeds(scene, O.sample_seeds, per_view, 1, 0)
+    threads = os.cpu_count()
+    osc = O.OracleScene(scene)
+    n = len(seeds)
+    probe = seeds.take(np.linspace(0, n - 1, 64).astype(np.int64))
+    t = time.perf_counter(); osc.match_seeds(probe, n_threads=threads); per_seed = (time.perf_counter() - t) / 64
+    budget = 150.0 / max(1, args.steps + args.warmup)             # whole run within a few minutes
+    m = int(min(n, max(64, budget / max(per_seed, 1e-6))))
+    sample = seeds.take(np.linspace(0, n - 1, m).astype(np.int64))
+    for _ in range(args.warmup):
+        osc.match_seeds(sample, n_threads=threads)
+    t0 = time.perf_counter()
+    npts = 0
+    for _ in range(args.steps):
+        npts += osc.match_seeds(sample, n_threads=threads).n_points
+    dt = time.perf_counter() - t0
+    value = npts / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, cfg, per_view, 1), "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"each step = {m} of {n} seeds (stratified), OpenMP over seeds on {threads} threads; "
+                                       "the reference itself is effectively single-threaded (orphaned omp for, SURVEY finding 4)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(name, cfg, per_view, n):
+    if name == "c2":
+        return (f"BASELINE configs[1]: synthetic {cfg['n_views']}-view rig, {cfg['width']}x{cfg['height']}, "
+                f"{cfg['n_curves'] * cfg['segs_per_curve']} polyline segments/view, {per_view * cfg['n_views']} seeds per GPU "
+                f"({per_view * n}/view at {20.0 / n:g} px), all-segment sweep, seed {cfg['seed']}")
+    return f"{name}: {cfg}"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from edgegraph3d_b200 import lib as E
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+
+    scene, cfg, per_view = build_workload(args.workload, n_gpus)
+    seeds = pinned_seeds(make_seeds(scene, E.sample_seeds, per_view, n_gpus, rank))
+    t = time.perf_counter()
+    dev = E.DeviceScene(scene)
+    torch.cuda.synchronize()
+    scene_ms = 1e3 * (time.perf_counter() - t)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allgather_points(dp):
+        """The path's one exchange step: accepted records of every rank to every rank over NCCL (NVLink)."""
+        v = dp.device_view()
+        n, m = int(v.n_points), int(v.n_obs)
+        cnt = torch.tensor([n, m], dtype=torch.int64, device="cuda")
+        cnts = torch.empty(world * 2, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(cnts, cnt)
+        cnts = cnts.view(world, 2).cpu()
+        maxn, maxm = int(cnts[:, 0].max()), int(cnts[:, 1].max())
+
+        def wrap(ptr, nbytes):
+            import ctypes
+            if nbytes == 0:
+                return torch.empty(0, dtype=torch.uint8, device="cuda")
+            addr = ctypes.cast(ptr, ctypes.c_void_p).value
+
+            class _W:
+                __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (addr, False), "version": 2}
+            return torch.as_tensor(_W(), device="cuda")
+        total = 0
+        for ptr, per, mx, k in ((v.xyz, 12, maxn, n), (v.seed, 4, maxn, n), (v.chain_pos, 4, maxn, n), (v.obs_off, 8, maxn + 1, n + 1),
+                                (v.obs_view, 4, maxm, m), (v.obs_poly, 4, maxm, m), (v.obs_seg, 4, maxm, m), (v.obs_xy, 8, maxm, m)):
+            send = torch.zeros(mx * per, dtype=torch.uint8, device="cuda")
+            send[:k * per] = wrap(ptr, k * per)
+            recv = torch.empty(world * mx * per, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(recv, send)
+            total += recv.numel()
+        return int(cnts[:, 0].sum()), total
+
+    def step(timed):
+        flush.fill_(1)                                   # evict L2 between iterations
+        barrier()
+        t0 = time.perf_counter()
+        dp, tm = dev.match_seeds(seeds, fetch=False)     # pinned seeds H2D + K1 + K3 + pack (device-resident result)
+        ag_ms, total_pts = 0.0, tm["n_points"]
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            total_pts, _ = allgather_points(dp)
+            e1.record(); torch.cuda.synchronize()
+            ag_ms = e0.elapsed_time(e1)
+        d2h = dp.fetch_raw()                             # D2H of this rank's result into pinned host memory
+        t1 = time.perf_counter()
+        dp.free()
+        return tm, ag_ms, d2h, t1 - t0, total_pts
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_ms, e2e_s, launches = [], [], 0
+    k1_ms, k3_ms, pack_ms, ag_all = [], [], [], []
+    last_tm = None
+    pts_total = 0
+    for _ in range(args.steps):
+        tm, ag_ms, d2h, wall, total_pts = step(True)
+        dev_ms.append(tm["total_ms"] + ag_ms); e2e_s.append(wall); launches += tm["kernel_launches"] + (9 if world > 1 else 0)
+        k1_ms.append((tm["k1_count_ms"], tm["k1_fill_ms"])); k3_ms.append(tm["k3_ms"]); pack_ms.append(tm["pack_ms"]); ag_all.append(ag_ms)
+        last_tm = tm; pts_total = total_pts; d2h_bytes = d2h
+    clocks = sampler.stop() if rank == 0 else None
+    # max over ranks of the summed device time / wall time
+    tdev = torch.tensor([sum(dev_ms), sum(e2e_s)], dtype=torch.float64, device="cuda")
+    npts_local = torch.tensor([last_tm["n_points"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tdev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(npts_local, op=dist.ReduceOp.SUM)
+    dev_total_ms, e2e_total_s = float(tdev[0]), float(tdev[1])
+    job_points = float(npts_local[0])                   # accepted points of all ranks per step
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = job_points * args.steps / (dev_total_ms / 1e3)
+    e2e_value = job_points * args.steps / e2e_total_s
+    peak, peak_src = measured_peaks()
+    k1c = float(np.mean([a for a, _ in k1_ms])); k1f = float(np.mean([b for _, b in k1_ms])); k3 = float(np.mean(k3_ms))
+    step_ms = dev_total_ms / args.steps
+    k1_bytes = last_tm["k1_algorithmic_bytes"]
+    k1_avg_launch_ms = (k1c + k1f) / 2
+    # K3 algorithmic bytes: the hit lists it reads (16 B/hit) + the observations it writes (20 B/obs) + point headers
+    k3_bytes = 16 * last_tm["n_hits"] + 20 * last_tm["n_obs"] + 24 * last_tm["n_points"]
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, cfg, per_view, n_gpus),
+                   "l2": "flushed between iterations (256 MiB write); per-step hit lists (GBs) exceed L2 anyway",
+                   "seeds_per_gpu": len(seeds), "points_per_step": job_points, "scene_upload_ms": scene_ms,
+                   "parallelism": f"starting views block-sharded over {n_gpus} GPU(s); one NCCL all-gather of accepted records" if n_gpus > 1 else "1 GPU"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": seeds.nbytes(), "d2h_bytes_per_step": int(d2h_bytes),
+                "ms_per_step": 1e3 * e2e_total_s / args.steps,
+                "note": "eg3d_match_seeds (pinned seeds H2D + kernels) + eg3d_points_get (D2H into pinned memory); the scene handle "
+                        "is resident, as the reference's PLGs / plmaps are across its per-match calls"},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "k3_chain_kernel (triples + PLG following + view expansion)", "bound": "hbm",
+                     "achieved": k3_bytes / (k3 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": k3_bytes / (k3 * 1e-3) / 1e9 / peak,
+                     "traffic": None, "peak_source": peak_src, "share_of_step": k3 / step_ms,
+                     "note": "dominant kernel of the step; FP64-latency/ALU bound (sequential per-seed walk with Gauss-Newton solves), "
+                             "not bandwidth bound: the HBM fraction is reported because the contract asks for it"},
+        "roofline_k1": {"kernel": "k1_sweep_kernel (epipolar intersection, north_star's roofline kernel)", "bound": "hbm",
+                        "achieved": k1_bytes / (k1_avg_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": k1_bytes / (k1_avg_launch_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                        "share_of_step": (k1c + k1f) / step_ms, "launches_per_step": 2, "avg_launch_ms": k1_avg_launch_ms,
+                        "algorithmic_bytes_per_launch": k1_bytes, "segment_tests_per_launch": last_tm["n_segment_tests"],
+                        "note": "algorithmic (streaming) bytes per SURVEY 8(d); a view's segments are staged once per CTA in shared "
+                                "memory, so real DRAM traffic is far lower and the fraction may exceed 1"},
+        "kernel_ms": {"k1_count": k1c, "k1_fill": k1f, "k3": k3, "pack": float(np.mean(pack_ms)), "allgather": float(np.mean(ag_all))},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and n_gpus == 1:
+        cb, _, _ = cpu_baseline(scene, seeds)
+        line["cpu_baseline"] = cb
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

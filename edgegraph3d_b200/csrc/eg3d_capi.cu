@@ -28,19 +28,27 @@ static eg3d_status fail(eg3d_status s, const std::string& m) { g_err = m; return
     }                                                                                                         \
   } while (0)
 
+// Device buffers come from the stream-ordered memory pool (cudaMallocAsync) of the current device; the pool's release
+// threshold is raised at scene creation so that the GB-sized per-call temporaries are recycled instead of being
+// returned to the driver after every call.
+static thread_local cudaStream_t g_alloc_stream = nullptr;
 template <typename T>
 struct DBuf {  // owning device buffer
-  T* p = nullptr; size_t n = 0;
+  T* p = nullptr; size_t n = 0; cudaStream_t s = nullptr;
   DBuf() {}
   DBuf(const DBuf&) = delete; DBuf& operator=(const DBuf&) = delete;
-  ~DBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t count) { if (p) cudaFree(p); p = nullptr; n = count; return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T)); }
-  cudaError_t upload(const T* h, size_t count, cudaStream_t s) {
+  ~DBuf() { release(); }
+  void release() { if (p) { cudaFreeAsync(p, s); p = nullptr; } }
+  cudaError_t alloc(size_t count) {
+    release(); n = count; s = g_alloc_stream;
+    return cudaMallocAsync((void**)&p, std::max<size_t>(count, 1) * sizeof(T), s);
+  }
+  cudaError_t upload(const T* h, size_t count, cudaStream_t st) {
     cudaError_t e = alloc(count); if (e != cudaSuccess) return e;
-    if (count) e = cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    if (count) e = cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st);
     return e;
   }
-  cudaError_t upload(const std::vector<T>& h, cudaStream_t s) { return upload(h.data(), h.size(), s); }
+  cudaError_t upload(const std::vector<T>& h, cudaStream_t st) { return upload(h.data(), h.size(), st); }
 };
 
 struct HostGrid { float cell; int w, h; std::vector<int> off; std::vector<uint32_t> ids; };
@@ -64,9 +72,23 @@ struct eg3d_scene {
   int max_view_segs = 0;
 };
 
+template <typename T>
+struct PBuf {  // pinned host buffer (page-locked so D2H runs at full PCIe/C2C rate)
+  T* p = nullptr; size_t n = 0;
+  PBuf() {}
+  PBuf(const PBuf&) = delete; PBuf& operator=(const PBuf&) = delete;
+  ~PBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t alloc(size_t count) { if (p) cudaFreeHost(p); p = nullptr; n = count; return cudaMallocHost((void**)&p, std::max<size_t>(count, 1) * sizeof(T)); }
+};
+
 struct eg3d_points {
-  std::vector<float> xyz; std::vector<int32_t> seed, chain_pos; std::vector<int64_t> obs_off;
-  std::vector<int32_t> obs_view; std::vector<uint32_t> obs_poly, obs_seg; std::vector<float> obs_xy;
+  int device = 0; cudaStream_t stream = nullptr;
+  int64_t n_points = 0, n_obs = 0;
+  // device-resident, ordered by (seed, chain position)
+  DBuf<float> d_xyz; DBuf<int> d_seed, d_pos; DBuf<int64_t> d_obs_off; DBuf<int> d_ov; DBuf<uint32_t> d_opl, d_oseg; DBuf<float> d_oxy;
+  // host copies (filled on first eg3d_points_get)
+  bool on_host = false;
+  PBuf<float> xyz; PBuf<int32_t> seed, chain_pos; PBuf<int64_t> obs_off; PBuf<int32_t> obs_view; PBuf<uint32_t> obs_poly, obs_seg; PBuf<float> obs_xy;
 };
 struct eg3d_hits { int64_t n_seeds; int V; std::vector<int64_t> off; std::vector<eg3d_hit> hits; };
 
@@ -213,8 +235,8 @@ static eg3d_status run_k1(eg3d_scene* sc, const DevSeeds& ds, const DevCand* dc,
 // K3 + ordered packing + D2H into an eg3d_points
 static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_off, const eg3d_hit* d_hits, eg3d_points* out, eg3d_timing* tm) {
   const int V = sc->V; const int n = ds.n;
-  out->obs_off.assign(1, 0);
-  if (n == 0) return EG3D_OK;
+  out->device = sc->device; out->stream = sc->stream;
+  if (n == 0) { CK(out->d_obs_off.alloc(1)); CK(cudaMemsetAsync(out->d_obs_off.p, 0, sizeof(int64_t), sc->stream)); CK(cudaStreamSynchronize(sc->stream)); return EG3D_OK; }
   const int capf = sc->prm.max_follow_points, capc = sc->prm.max_chain_points, oc = V + 16;
   const size_t spw = k3_scratch_bytes(V, capf, capc, oc);
   int blocks_per_sm = 8;  // 32 warps per SM
@@ -265,42 +287,53 @@ static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_o
     CK(cudaStreamSynchronize(sc->stream));
   }
   const int64_t npts = (int64_t)cnt[0], nobs = (int64_t)cnt[1];
-  DBuf<float> xyz; DBuf<int> pseed, ppos; DBuf<int64_t> obs_off, src;
-  CK(xyz.alloc(3 * npts)); CK(pseed.alloc(npts)); CK(ppos.alloc(npts)); CK(obs_off.alloc(npts + 1)); CK(src.alloc(npts));
-  CK(cudaMemsetAsync(obs_off.p + npts, 0, sizeof(int64_t), sc->stream));
-  pack_points_kernel<<<(n + 127) / 128, 128, 0, sc->stream>>>(n, snp.p, spb.p, pt_off.p, uX.p, unobs.p, xyz.p, pseed.p, ppos.p, obs_off.p, src.p);
+  out->device = sc->device; out->stream = sc->stream; out->n_points = npts; out->n_obs = nobs;
+  DBuf<int64_t> src;
+  CK(out->d_xyz.alloc(3 * npts)); CK(out->d_seed.alloc(npts)); CK(out->d_pos.alloc(npts)); CK(out->d_obs_off.alloc(npts + 1)); CK(src.alloc(npts));
+  CK(cudaMemsetAsync(out->d_obs_off.p + npts, 0, sizeof(int64_t), sc->stream));
+  pack_points_kernel<<<(n + 127) / 128, 128, 0, sc->stream>>>(n, snp.p, spb.p, pt_off.p, uX.p, unobs.p, out->d_xyz.p, out->d_seed.p, out->d_pos.p,
+                                                             out->d_obs_off.p, src.p);
   {
     size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, obs_off.p, obs_off.p, npts + 1, sc->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, out->d_obs_off.p, out->d_obs_off.p, npts + 1, sc->stream);
     DBuf<unsigned char> tmp; CK(tmp.alloc(tb));
-    cub::DeviceScan::ExclusiveSum(tmp.p, tb, obs_off.p, obs_off.p, npts + 1, sc->stream);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, out->d_obs_off.p, out->d_obs_off.p, npts + 1, sc->stream);
     CK(cudaStreamSynchronize(sc->stream));
   }
-  DBuf<int> ov; DBuf<uint32_t> opl, oseg; DBuf<float> oxy;
-  CK(ov.alloc(nobs)); CK(opl.alloc(nobs)); CK(oseg.alloc(nobs)); CK(oxy.alloc(2 * nobs));
+  CK(out->d_ov.alloc(nobs)); CK(out->d_opl.alloc(nobs)); CK(out->d_oseg.alloc(nobs)); CK(out->d_oxy.alloc(2 * nobs));
   if (npts > 0) {
     int64_t threads = npts * 32;
-    pack_obs_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, sc->stream>>>(npts, obs_off.p, src.p, uobase.p, uv.p, upl.p, useg.p, ux.p, uy.p,
-                                                                            ov.p, opl.p, oseg.p, oxy.p);
+    pack_obs_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, sc->stream>>>(npts, out->d_obs_off.p, src.p, uobase.p, uv.p, upl.p, useg.p, ux.p, uy.p,
+                                                                            out->d_ov.p, out->d_opl.p, out->d_oseg.p, out->d_oxy.p);
   }
   tp.stop();
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(sc->stream));
   if (tm) { tm->pack_ms += tp.ms(); tm->kernel_launches += 4; tm->n_points += npts; tm->n_obs += nobs; }
-  // D2H
-  out->xyz.resize(3 * npts); out->seed.resize(npts); out->chain_pos.resize(npts); out->obs_off.resize(npts + 1);
-  out->obs_view.resize(nobs); out->obs_poly.resize(nobs); out->obs_seg.resize(nobs); out->obs_xy.resize(2 * nobs);
+  return EG3D_OK;
+}
+
+// lazily bring a result to (pinned) host memory
+static eg3d_status points_to_host(eg3d_points* p) {
+  if (p->on_host) return EG3D_OK;
+  CK(cudaSetDevice(p->device));
+  const int64_t npts = p->n_points, nobs = p->n_obs;
+  CK(p->xyz.alloc(3 * npts)); CK(p->seed.alloc(npts)); CK(p->chain_pos.alloc(npts)); CK(p->obs_off.alloc(npts + 1));
+  CK(p->obs_view.alloc(nobs)); CK(p->obs_poly.alloc(nobs)); CK(p->obs_seg.alloc(nobs)); CK(p->obs_xy.alloc(2 * nobs));
+  p->obs_off.p[0] = 0;
   if (npts > 0) {
-    CK(cudaMemcpyAsync(out->xyz.data(), xyz.p, 3 * npts * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
-    CK(cudaMemcpyAsync(out->seed.data(), pseed.p, npts * sizeof(int), cudaMemcpyDeviceToHost, sc->stream));
-    CK(cudaMemcpyAsync(out->chain_pos.data(), ppos.p, npts * sizeof(int), cudaMemcpyDeviceToHost, sc->stream));
-    CK(cudaMemcpyAsync(out->obs_view.data(), ov.p, nobs * sizeof(int), cudaMemcpyDeviceToHost, sc->stream));
-    CK(cudaMemcpyAsync(out->obs_poly.data(), opl.p, nobs * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc->stream));
-    CK(cudaMemcpyAsync(out->obs_seg.data(), oseg.p, nobs * sizeof(uint32_t), cudaMemcpyDeviceToHost, sc->stream));
-    CK(cudaMemcpyAsync(out->obs_xy.data(), oxy.p, 2 * nobs * sizeof(float), cudaMemcpyDeviceToHost, sc->stream));
+    cudaStream_t s = p->stream;
+    CK(cudaMemcpyAsync(p->xyz.p, p->d_xyz.p, 3 * npts * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->seed.p, p->d_seed.p, npts * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->chain_pos.p, p->d_pos.p, npts * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->obs_off.p, p->d_obs_off.p, (npts + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->obs_view.p, p->d_ov.p, nobs * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->obs_poly.p, p->d_opl.p, nobs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->obs_seg.p, p->d_oseg.p, nobs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->obs_xy.p, p->d_oxy.p, 2 * nobs * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
   }
-  CK(cudaMemcpyAsync(out->obs_off.data(), obs_off.p, (npts + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, sc->stream));
-  CK(cudaStreamSynchronize(sc->stream));
+  p->on_host = true;
   return EG3D_OK;
 }
 
@@ -358,6 +391,11 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, sc->device));
   sc->num_sms = prop.multiProcessorCount;
   CK(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+  g_alloc_stream = sc->stream;
+  {
+    cudaMemPool_t pool; CK(cudaDeviceGetDefaultMemPool(&pool, sc->device));
+    uint64_t thr = ~0ull; CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  }
   if (params) sc->prm = *params; else eg3d_params_default(&sc->prm);
   const int V = sc->V = d->n_views; sc->width = d->width; sc->height = d->height;
   const int64_t NP = d->view_poly_off[V], NV = d->poly_vert_off[NP];
@@ -424,8 +462,10 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
 void eg3d_scene_destroy(eg3d_scene* sc) {
   if (!sc) return;
   cudaSetDevice(sc->device);
-  if (sc->stream) cudaStreamDestroy(sc->stream);
-  delete sc;
+  cudaStream_t st = sc->stream;
+  if (st) cudaStreamSynchronize(st);
+  delete sc;   // buffers are returned to the pool on the (still live) stream
+  if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
 }
 
 eg3d_status eg3d_sample_seeds(const eg3d_scene_desc* d, const int32_t* views, const uint32_t* polylines, int64_t n_pl, float spacing,
@@ -471,6 +511,7 @@ eg3d_status eg3d_epipolar_intersect(eg3d_scene* sc, const eg3d_seeds* seeds, con
   eg3d_status st = require_device(); if (st != EG3D_OK) return st;
   st = check_seeds(sc, seeds, cands); if (st != EG3D_OK) return st;
   CK(cudaSetDevice(sc->device));
+  g_alloc_stream = sc->stream;
   eg3d_timing local; memset(&local, 0, sizeof local);
   DevSeeds ds; st = upload_seeds(sc, seeds, cands != nullptr, ds); if (st != EG3D_OK) return st;
   DevCand dc; if (cands) { st = upload_cands(sc, cands, dc); if (st != EG3D_OK) return st; }
@@ -497,6 +538,7 @@ eg3d_status eg3d_match_seeds(eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d
   eg3d_status st = require_device(); if (st != EG3D_OK) return st;
   st = check_seeds(sc, seeds, cands); if (st != EG3D_OK) return st;
   CK(cudaSetDevice(sc->device));
+  g_alloc_stream = sc->stream;
   eg3d_timing local; memset(&local, 0, sizeof local);
   DevSeeds ds; st = upload_seeds(sc, seeds, cands != nullptr, ds); if (st != EG3D_OK) return st;
   DevCand dc; if (cands) { st = upload_cands(sc, cands, dc); if (st != EG3D_OK) return st; }
@@ -539,14 +581,23 @@ eg3d_status eg3d_match_polyline_sets(eg3d_scene* sc, const eg3d_candidates* c, i
   return eg3d_match_seeds(sc, &s, c, out, tm);
 }
 
-eg3d_status eg3d_points_get(const eg3d_points* p, eg3d_points_view* v) {
-  if (!p || !v) return fail(EG3D_ERR_INVALID_ARG, "null argument");
-  v->n_points = (int64_t)p->seed.size(); v->n_obs = (int64_t)p->obs_view.size();
-  v->xyz = p->xyz.data(); v->seed = p->seed.data(); v->chain_pos = p->chain_pos.data(); v->obs_off = p->obs_off.data();
-  v->obs_view = p->obs_view.data(); v->obs_poly = p->obs_poly.data(); v->obs_seg = p->obs_seg.data(); v->obs_xy = p->obs_xy.data();
+eg3d_status eg3d_points_get(const eg3d_points* pc, eg3d_points_view* v) {
+  if (!pc || !v) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  eg3d_points* p = const_cast<eg3d_points*>(pc);
+  eg3d_status st = points_to_host(p); if (st != EG3D_OK) return st;
+  v->n_points = p->n_points; v->n_obs = p->n_obs;
+  v->xyz = p->xyz.p; v->seed = p->seed.p; v->chain_pos = p->chain_pos.p; v->obs_off = p->obs_off.p;
+  v->obs_view = p->obs_view.p; v->obs_poly = p->obs_poly.p; v->obs_seg = p->obs_seg.p; v->obs_xy = p->obs_xy.p;
   return EG3D_OK;
 }
-void eg3d_points_free(eg3d_points* p) { delete p; }
+eg3d_status eg3d_points_device_get(const eg3d_points* p, eg3d_points_view* v) {
+  if (!p || !v) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  v->n_points = p->n_points; v->n_obs = p->n_obs;
+  v->xyz = p->d_xyz.p; v->seed = p->d_seed.p; v->chain_pos = p->d_pos.p; v->obs_off = p->d_obs_off.p;
+  v->obs_view = p->d_ov.p; v->obs_poly = p->d_opl.p; v->obs_seg = p->d_oseg.p; v->obs_xy = p->d_oxy.p;
+  return EG3D_OK;
+}
+void eg3d_points_free(eg3d_points* p) { if (p) { cudaSetDevice(p->device); delete p; } }
 
 static eg3d_status launch_gn(eg3d_scene* sc, const GnProblem& pr, int fp64, eg3d_timing* tm) {
   const size_t smem = (size_t)sc->V * 12 * sizeof(float);
@@ -573,6 +624,7 @@ eg3d_status eg3d_gn_triangulate(eg3d_scene* sc, int64_t n, const int64_t* obs_of
   eg3d_status st = require_device(); if (st != EG3D_OK) return st;
   if (!sc || !obs_off) return fail(EG3D_ERR_INVALID_ARG, "null argument");
   CK(cudaSetDevice(sc->device));
+  g_alloc_stream = sc->stream;
   if (tm) memset(tm, 0, sizeof *tm);
   const int64_t no = obs_off[n];
   DBuf<int64_t> d_off; DBuf<int> d_v; DBuf<float2> d_xy; DBuf<float> d_init, d_x, d_m; DBuf<uint8_t> d_ok;
@@ -594,6 +646,7 @@ eg3d_status eg3d_gn_triangulate_device(eg3d_scene* sc, int64_t n, int32_t k, con
   eg3d_status st = require_device(); if (st != EG3D_OK) return st;
   if (!sc) return fail(EG3D_ERR_INVALID_ARG, "null scene");
   CK(cudaSetDevice(sc->device));
+  g_alloc_stream = sc->stream;
   if (tm) memset(tm, 0, sizeof *tm);
   GnProblem pr; memset(&pr, 0, sizeof pr);
   pr.n = n; pr.obs_off = nullptr; pr.k = k; pr.obs_view = d_obs_view; pr.obs_xy = (const float2*)d_obs_xy; pr.init = d_init;
@@ -617,7 +670,12 @@ eg3d_status eg3d_dedup_close_points(eg3d_scene* sc, const eg3d_points_view* pts,
       if (!b[cell(o)]) { is_new = true; break; }
     }
     keep[i] = is_new;
-    if (is_new) for (int64_t o = pts->obs_off[i]; o < pts->obs_off[i + 1]; o++) bm[pts->obs_view[o]][cell(o)] = 1;
+    if (is_new)
+      for (int64_t o = pts->obs_off[i]; o < pts->obs_off[i + 1]; o++) {
+        auto& b = bm[pts->obs_view[o]];
+        if (b.empty()) b.assign((size_t)w * h, 0);
+        b[cell(o)] = 1;
+      }
   }
   return EG3D_OK;
 }
@@ -627,6 +685,7 @@ eg3d_status eg3d_filter(eg3d_scene* sc, int64_t n, float* xyz, const int64_t* ob
   eg3d_status st = require_device(); if (st != EG3D_OK) return st;
   if (!sc || !obs_off) return fail(EG3D_ERR_INVALID_ARG, "null argument");
   CK(cudaSetDevice(sc->device));
+  g_alloc_stream = sc->stream;
   if (tm) memset(tm, 0, sizeof *tm);
   const int64_t no = obs_off[n];
   DBuf<int64_t> d_off; DBuf<int> d_v; DBuf<float2> d_xy; DBuf<float> d_x; DBuf<uint8_t> d_ok;

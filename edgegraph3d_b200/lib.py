@@ -16,7 +16,7 @@ _lib = None
 EXPORTS = [
     "eg3d_last_error", "eg3d_device_count", "eg3d_params_default", "eg3d_scene_create", "eg3d_scene_destroy",
     "eg3d_sample_seeds", "eg3d_epipolar_intersect", "eg3d_hits_get", "eg3d_hits_free", "eg3d_match_seeds",
-    "eg3d_match_polyline_sets", "eg3d_match_refpoints", "eg3d_points_get", "eg3d_points_free", "eg3d_gn_triangulate",
+    "eg3d_match_polyline_sets", "eg3d_match_refpoints", "eg3d_points_get", "eg3d_points_device_get", "eg3d_points_free", "eg3d_gn_triangulate",
     "eg3d_gn_triangulate_device", "eg3d_dedup_close_points", "eg3d_filter",
 ]
 
@@ -49,6 +49,7 @@ def load():
     L.eg3d_match_polyline_sets.argtypes = [C.c_void_p, C.POINTER(A.Candidates), C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(A.Timing)]
     L.eg3d_match_refpoints.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p), C.POINTER(A.Timing)]
     L.eg3d_points_get.argtypes = [C.c_void_p, C.POINTER(A.PointsView)]
+    L.eg3d_points_device_get.argtypes = [C.c_void_p, C.POINTER(A.PointsView)]
     L.eg3d_points_free.argtypes = [C.c_void_p]
     L.eg3d_gn_triangulate.argtypes = [C.c_void_p, C.c_int64, A.c_i64p, A.c_i32p, A.c_f32p, A.c_f32p, C.c_int, A.c_f32p, A.c_f32p,
                                       A.c_u8p, C.POINTER(A.Timing)]
@@ -94,6 +95,48 @@ def sample_seeds(scene, views, polylines, spacing):
         cap = int(n.value)
 
 
+class DevicePoints:
+    """Handle to a device-resident result (eg3d_points)."""
+
+    def __init__(self, handle):
+        self.h = handle
+
+    def info(self):
+        v = A.PointsView()
+        _check(load().eg3d_points_device_get(self.h, C.byref(v)))
+        return int(v.n_points), int(v.n_obs)
+
+    def device_view(self):
+        """eg3d_points_view whose pointers are DEVICE pointers (for device-side consumers, e.g. the all-gather)."""
+        v = A.PointsView()
+        _check(load().eg3d_points_device_get(self.h, C.byref(v)))
+        return v
+
+    def fetch(self):
+        """Device -> page-locked host -> numpy copies."""
+        v = A.PointsView()
+        _check(load().eg3d_points_get(self.h, C.byref(v)))
+        return PointSet.from_view(v)
+
+    def fetch_raw(self):
+        """D2H into the handle's pinned buffers only (what a C caller of eg3d_points_get pays); returns bytes moved."""
+        v = A.PointsView()
+        _check(load().eg3d_points_get(self.h, C.byref(v)))
+        n, m = int(v.n_points), int(v.n_obs)
+        return n * (12 + 4 + 4) + (n + 1) * 8 + m * (4 + 4 + 4 + 8)
+
+    def free(self):
+        if self.h:
+            load().eg3d_points_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class DeviceScene:
     """Device-resident scene handle (eg3d_scene)."""
 
@@ -123,12 +166,12 @@ class DeviceScene:
     def __exit__(self, *a):
         self.close()
 
-    def _points(self, handle):
-        L = load()
-        v = A.PointsView()
-        _check(L.eg3d_points_get(handle, C.byref(v)))
-        ps = PointSet.from_view(v)
-        L.eg3d_points_free(handle)
+    def _points(self, handle, fetch=True):
+        dp = DevicePoints(handle)
+        if not fetch:
+            return dp
+        ps = dp.fetch()
+        dp.free()
         return ps
 
     def epipolar_intersect(self, seeds, cands=None):
@@ -152,7 +195,7 @@ class DeviceScene:
         L.eg3d_hits_free(h)
         return off_np, hn, int(V.value), tm.as_dict()
 
-    def match_seeds(self, seeds, cands=None):
+    def match_seeds(self, seeds, cands=None, fetch=True):
         L = load()
         sd = seeds.desc()
         cd = cands.desc() if cands is not None else None
@@ -161,7 +204,7 @@ class DeviceScene:
         st = L.eg3d_match_seeds(self.h, C.byref(sd), C.byref(cd) if cd is not None else None, C.byref(h), C.byref(tm))
         self.last_timing = tm.as_dict()
         _check(st)
-        return self._points(h), tm.as_dict()
+        return self._points(h, fetch), tm.as_dict()
 
     def match_polyline_sets(self, cands, view_begin=0, view_end=None):
         L = load()

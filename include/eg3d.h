@@ -202,7 +202,11 @@ eg3d_status eg3d_match_polyline_sets(eg3d_scene*, const eg3d_candidates*, int32_
 eg3d_status eg3d_match_refpoints(eg3d_scene*, int64_t track_begin, int64_t track_end,
                                  eg3d_points** out, eg3d_timing* timing);
 
+/* Results stay on the device until asked for: eg3d_points_get copies them (once) into page-locked host memory owned by
+ * the handle; eg3d_points_device_get exposes the device-resident arrays (same layout, device pointers on the scene's
+ * device) for device-side consumers such as the multi-GPU all-gather. */
 eg3d_status eg3d_points_get(const eg3d_points*, eg3d_points_view* view);
+eg3d_status eg3d_points_device_get(const eg3d_points*, eg3d_points_view* device_view);
 void        eg3d_points_free(eg3d_points*);
 
 /* K2 alone (B5/B6 primitives).  Hypotheses: CSR of (view, xy) observations + initial X.
