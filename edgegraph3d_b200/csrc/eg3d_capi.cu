@@ -57,7 +57,7 @@ struct eg3d_scene {
   int device = 0; cudaStream_t stream = nullptr;
   int V = 0, width = 0, height = 0, num_sms = 0;
   eg3d_params prm;
-  DBuf<float> P; DBuf<double> F; DBuf<uint8_t> Fvalid;
+  DBuf<float> P; DBuf<double> P64; DBuf<double> F; DBuf<uint8_t> Fvalid;
   DBuf<int> view_poly_off, poly_vert_off, view_seg_off, poly_seg_off;
   DBuf<float2> verts; DBuf<uint32_t> poly_start, poly_end;
   DBuf<float4> seg; DBuf<uint2> seg_id;
@@ -426,6 +426,7 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   if (tracks) build_grid(*sc, sc->prm.detection_starting_radius * sc->prm.detection_mult, sc->hg30);
   cudaStream_t s = sc->stream;
   CK(sc->P.upload(d->cameras, (size_t)V * 12, s));
+  { std::vector<double> p64((size_t)V * 12); for (size_t i = 0; i < p64.size(); i++) p64[i] = (double)d->cameras[i]; CK(sc->P64.upload(p64, s)); CK(cudaStreamSynchronize(s)); }
   CK(sc->F.upload(d->fundamental, (size_t)V * V * 9, s));
   CK(sc->Fvalid.upload(d->fundamental_valid, (size_t)V * V, s));
   CK(sc->view_poly_off.upload(sc->h_view_poly_off, s)); CK(sc->poly_vert_off.upload(sc->h_poly_vert_off, s));
@@ -445,7 +446,7 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   CK(cudaStreamSynchronize(s));
   DevScene& D = sc->dev; memset(&D, 0, sizeof D);
   D.V = V; D.width = sc->width; D.height = sc->height;
-  D.P = sc->P.p; D.F = sc->F.p; D.Fvalid = sc->Fvalid.p;
+  D.P = sc->P.p; D.P64 = sc->P64.p; D.F = sc->F.p; D.Fvalid = sc->Fvalid.p;
   D.view_poly_off = sc->view_poly_off.p; D.poly_vert_off = sc->poly_vert_off.p; D.verts = sc->verts.p;
   D.poly_start = sc->poly_start.p; D.poly_end = sc->poly_end.p;
   D.view_seg_off = sc->view_seg_off.p; D.seg = sc->seg.p; D.seg_id = sc->seg_id.p; D.poly_seg_off = sc->poly_seg_off.p;

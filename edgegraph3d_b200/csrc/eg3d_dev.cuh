@@ -24,6 +24,7 @@ struct DevGrid {            // uniform polyline grid, PolyLine2DMap (polyLine_2d
 struct DevScene {
   int V, width, height;
   const float* P;               // [V][12]
+  const double* P64;            // [V][12] the same matrices widened once (triangulation.cpp:301-306 converts per call)
   const double* F;              // [V*V][9]
   const uint8_t* Fvalid;        // [V*V]
   const int* view_poly_off;     // [V+1]
@@ -283,23 +284,21 @@ EG3D_HD bool grid_unique(const DevGrid& g, int view, int img_w, int img_h, float
 // 2-view DLT initialiser = cv::triangulatePoints (triangulation.cpp:216,290): null vector of the 4x4 DLT matrix by
 // one-sided Jacobi SVD in double, cast to float.  Same operation sequence as the oracle's restatement.
 EG3D_HD_NI void dlt_null(const float* P1, const float* P2, float2 x1, float2 x2, float out4[4]) {
-  double A[4][4], Vm[4][4];
-#pragma unroll
+  double A[4][4], Vm[4][4];   // runtime-indexed on purpose (compact code); same operation order as the oracle
   for (int k = 0; k < 4; k++) {
     A[0][k] = (double)x1.x * (double)P1[8 + k] - (double)P1[k];
     A[1][k] = (double)x1.y * (double)P1[8 + k] - (double)P1[4 + k];
     A[2][k] = (double)x2.x * (double)P2[8 + k] - (double)P2[k];
     A[3][k] = (double)x2.y * (double)P2[8 + k] - (double)P2[4 + k];
   }
-#pragma unroll
   for (int i = 0; i < 4; i++)
-#pragma unroll
     for (int j = 0; j < 4; j++) Vm[i][j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll 1
   for (int sweep = 0; sweep < 60; sweep++) {
     double off = 0;
-#pragma unroll
+#pragma unroll 1
     for (int p = 0; p < 3; p++)
-#pragma unroll
+#pragma unroll 1
       for (int q = p + 1; q < 4; q++) {
         double alpha = 0, beta = 0, gamma = 0;
 #pragma unroll
@@ -321,23 +320,13 @@ EG3D_HD_NI void dlt_null(const float* P1, const float* P2, float2 x1, float2 x2,
       }
     if (off < 1e-15) break;
   }
-  double nn[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    double s = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) s += A[i][j] * A[i][j];
-    nn[j] = s;
-  }
   int best = 0; double bestn = 1e300;
-#pragma unroll
-  for (int j = 0; j < 4; j++) if (nn[j] < bestn) { bestn = nn[j]; best = j; }
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    double v = Vm[i][0];
-    if (best == 1) v = Vm[i][1]; else if (best == 2) v = Vm[i][2]; else if (best == 3) v = Vm[i][3];
-    out4[i] = (float)v;
+  for (int j = 0; j < 4; j++) {
+    double nn = 0;
+    for (int i = 0; i < 4; i++) nn += A[i][j] * A[i][j];
+    if (nn < bestn) { bestn = nn; best = j; }
   }
+  for (int i = 0; i < 4; i++) out4[i] = (float)Vm[i][best];
 }
 
 EG3D_HD double det3d(const double* m) {
@@ -476,49 +465,86 @@ EG3D_D int gn_update(const GnAcc& a, int n, const eg3d_params& prm, double& last
   return 0;
 }
 
-template <typename ObsFn>
-EG3D_D bool gn_thread(const DevScene& S, int n, ObsFn obs, double X[3], double* last_mse_out = nullptr) {
-  double last_mse = 0;
-  for (int it = 0; it < S.prm.gn_max_iters; it++) {
-    GnAcc a = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < n; i++) {
-      int v; float x, y;
-      obs(i, v, x, y);
-      gn_accumulate(S.P + 12 * v, x, y, X, a);
-    }
-    int r = gn_update(a, n, S.prm, last_mse, X);
-    if (r == 1) break;
-    if (r == -1) { if (last_mse_out) *last_mse_out = last_mse; return false; }
+// Observation source shared by every multi-observation GN call of K3: observation q is entry idx[q] (or q when idx is
+// null) of the arrays (v, x, y) for q < n, followed by one optional extra observation (q == n).
+struct ObsSrc {
+  const int* v; const float* x; const float* y; const int* idx; int n;
+  int has_extra; int ev; float ex, ey;
+  EG3D_D int count() const { return n + has_extra; }
+  EG3D_D void get(int q, int& view, float& px, float& py) const {
+    if (q < n) { int s = idx ? idx[q] : q; view = v[s]; px = x[s]; py = y[s]; }
+    else { view = ev; px = ex; py = ey; }
   }
-  if (last_mse_out) *last_mse_out = last_mse;
-  return last_mse < S.prm.gn_accept_mse;
+};
+
+// Residual / Jacobian / normal-equation accumulation of one observation for the multi-observation solves of K3.
+// Algebraically identical to em_point2D3DJacobian + the residual loop (triangulation.cpp:53-103,127-148) but arranged
+// for FP64 throughput: one reciprocal of the projective depth instead of eight divisions ((p0*z - p8*x)/z^2 ==
+// (p0 - p8*(x/z))/z), explicit fused multiply-adds, cameras pre-widened to double.  Differs from the division form by
+// rounding only (~1e-16 relative); the thresholded 3-view solves use gn3_exact instead.
+EG3D_D void gn_accumulate_fast(const double* __restrict__ P, float px, float py, const double X[3], GnAcc& a) {
+  const double2* P2 = reinterpret_cast<const double2*>(P);
+  double2 q0 = P2[0], q1 = P2[1], q2 = P2[2], q3 = P2[3], q4 = P2[4], q5 = P2[5];
+  double h0 = fma(q0.x, X[0], fma(q0.y, X[1], fma(q1.x, X[2], q1.y)));
+  double h1 = fma(q2.x, X[0], fma(q2.y, X[1], fma(q3.x, X[2], q3.y)));
+  double h2 = fma(q4.x, X[0], fma(q4.y, X[1], fma(q5.x, X[2], q5.y)));
+  double inv = 1.0 / h2;
+  double u = h0 * inv, v = h1 * inv;
+  double rx = (double)px - u, ry = (double)py - v;
+  a.mse = fma(rx, rx, a.mse); a.mse = fma(ry, ry, a.mse);
+  double jx0 = fma(-q4.x, u, q0.x) * inv, jx1 = fma(-q4.y, u, q0.y) * inv, jx2 = fma(-q5.x, u, q1.x) * inv;
+  double jy0 = fma(-q4.x, v, q2.x) * inv, jy1 = fma(-q4.y, v, q2.y) * inv, jy2 = fma(-q5.x, v, q3.x) * inv;
+  a.h00 = fma(jx0, jx0, a.h00); a.h00 = fma(jy0, jy0, a.h00);
+  a.h01 = fma(jx0, jx1, a.h01); a.h01 = fma(jy0, jy1, a.h01);
+  a.h02 = fma(jx0, jx2, a.h02); a.h02 = fma(jy0, jy2, a.h02);
+  a.h11 = fma(jx1, jx1, a.h11); a.h11 = fma(jy1, jy1, a.h11);
+  a.h12 = fma(jx1, jx2, a.h12); a.h12 = fma(jy1, jy2, a.h12);
+  a.h22 = fma(jx2, jx2, a.h22); a.h22 = fma(jy2, jy2, a.h22);
+  a.g0 = fma(jx0, rx, a.g0); a.g0 = fma(jy0, ry, a.g0);
+  a.g1 = fma(jx1, rx, a.g1); a.g1 = fma(jy1, ry, a.g1);
+  a.g2 = fma(jx2, rx, a.g2); a.g2 = fma(jy2, ry, a.g2);
 }
 
-// Same problem solved by a whole warp: lanes stride over the observations, the ten sums are butterfly-reduced so every
-// lane holds identical values and control flow stays warp-uniform.  Must be called by all 32 lanes.
-EG3D_D double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-template <typename ObsFn>
-EG3D_D bool gn_warp(const DevScene& S, int n, ObsFn obs, double X[3], int lane) {
+// Gauss-Newton (em_GaussNewton, triangulation.cpp:105-176) for up to 32/G independent problems per warp: the warp is
+// split into groups of G lanes (G a power of two, 1..32); group g = lane / G solves the problem described by `o`
+// (identical in all lanes of a group), its lanes stride over the observations and the ten sums are butterfly-reduced
+// inside the group, so every lane of a group holds the same iterate.  Must be called by all 32 lanes; groups without
+// a problem pass active = false.  Returns the accept decision (last_mse < 9) of the caller's group.
+static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o, bool active, int G, int lane, double X[3]) {
+  const int sub = lane & (G - 1);
+  const int n = o.count();
   double last_mse = 0;
+  bool running = active, failed = false;
   for (int it = 0; it < S.prm.gn_max_iters; it++) {
+    if (!__any_sync(0xffffffffu, running)) break;
     GnAcc a = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int i = lane; i < n; i += 32) {
-      int v; float x, y;
-      obs(i, v, x, y);
-      gn_accumulate(S.P + 12 * v, x, y, X, a);
+    if (running) {
+#pragma unroll 1
+      for (int i = sub; i < n; i += G) {
+        int v; float x, y;
+        o.get(i, v, x, y);
+        gn_accumulate_fast(S.P64 + 12 * v, x, y, X, a);
+      }
     }
-    a.mse = warp_sum(a.mse); a.h00 = warp_sum(a.h00); a.h01 = warp_sum(a.h01); a.h02 = warp_sum(a.h02);
-    a.h11 = warp_sum(a.h11); a.h12 = warp_sum(a.h12); a.h22 = warp_sum(a.h22);
-    a.g0 = warp_sum(a.g0); a.g1 = warp_sum(a.g1); a.g2 = warp_sum(a.g2);
-    int r = gn_update(a, n, S.prm, last_mse, X);
-    if (r == 1) break;
-    if (r == -1) return false;
+#pragma unroll 1
+    for (int off = G >> 1; off > 0; off >>= 1) {
+      a.mse += __shfl_xor_sync(0xffffffffu, a.mse, off);
+      a.h00 += __shfl_xor_sync(0xffffffffu, a.h00, off); a.h01 += __shfl_xor_sync(0xffffffffu, a.h01, off);
+      a.h02 += __shfl_xor_sync(0xffffffffu, a.h02, off); a.h11 += __shfl_xor_sync(0xffffffffu, a.h11, off);
+      a.h12 += __shfl_xor_sync(0xffffffffu, a.h12, off); a.h22 += __shfl_xor_sync(0xffffffffu, a.h22, off);
+      a.g0 += __shfl_xor_sync(0xffffffffu, a.g0, off); a.g1 += __shfl_xor_sync(0xffffffffu, a.g1, off);
+      a.g2 += __shfl_xor_sync(0xffffffffu, a.g2, off);
+    }
+    if (running) {
+      int r = gn_update(a, n, S.prm, last_mse, X);
+      if (r == 1) running = false;
+      else if (r == -1) { running = false; failed = true; }
+    }
   }
-  return last_mse < S.prm.gn_accept_mse;
+  return active && !failed && last_mse < S.prm.gn_accept_mse;
 }
+
+// lanes per problem for `p` (1..32) simultaneous problems
+EG3D_D int gn_group_width(int p) { return p > 16 ? 1 : p > 8 ? 2 : p > 4 ? 4 : p > 2 ? 8 : p > 1 ? 16 : 32; }
 
 }  // namespace eg3d

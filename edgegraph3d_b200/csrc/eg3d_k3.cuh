@@ -100,7 +100,7 @@ struct Ctx {
 
 // 3-view compatible, plg_matching.cpp:51-132.  cur / next: (pl, seg, c) per view a,b,c in sel order.
 struct Cur3 { uint32_t pl[3], seg[3]; float2 c[3]; };
-EG3D_D bool step3(const DevScene& S, const int ids[3], const Cur3& cur, const uint32_t dir[3], Cur3& next, float X[3]) {
+static __device__ __noinline__ bool step3(const DevScene& S, const int ids[3], const Cur3& cur, const uint32_t dir[3], Cur3& next, float X[3]) {
   Pl pla = get_pl(S, ids[0], cur.pl[0]), plb = get_pl(S, ids[1], cur.pl[1]), plc = get_pl(S, ids[2], cur.pl[2]);
   bool reached;
   PlP ia; ia.seg = cur.seg[0]; ia.c = cur.c[0];
@@ -134,7 +134,7 @@ EG3D_D void store_pt3(Pt3* dst, const Cur3& c, const float X[3]) {
 
 // find_direction_given_first_extreme, plg_matching.cpp:142-203: the four (end_b, end_c) combos advance in lock-step,
 // one combo per lane; the last survivor wins.  Returns the number of points (0 = fail) copied into `dst`.
-EG3D_D int first_extreme(Ctx& c, const Cur3& start, uint32_t first_dir, uint32_t dir_out[3], Pt3* dst) {
+static __device__ __noinline__ int first_extreme(Ctx& c, const Cur3& start, uint32_t first_dir, uint32_t dir_out[3], Pt3* dst) {
   const DevScene& S = *c.S;
   const int lane = c.lane;
   Pl plb = get_pl(S, c.sel[1], start.pl[1]), plc = get_pl(S, c.sel[2], start.pl[2]);
@@ -171,7 +171,7 @@ EG3D_D int first_extreme(Ctx& c, const Cur3& start, uint32_t first_dir, uint32_t
 
 // all-view compatible (plg_matching.cpp:633-759) specialised to a 3-view point: exactly three observations survive or
 // the attempt is skipped; the combination fallback (:708-733) degenerates to the same 3-subset, so it cannot succeed.
-EG3D_D bool step_all3(const DevScene& S, const int sel[3], const uint32_t dirs[3], const Pt3& cur, Pt3& out) {
+static __device__ __noinline__ bool step_all3(const DevScene& S, const int sel[3], const uint32_t dirs[3], const Pt3& cur, Pt3& out) {
   for (int si = 0; si < 3; si++) {
     const int k = cur.perm[si];
     const int sv = sel[k];
@@ -209,7 +209,7 @@ EG3D_D bool step_all3(const DevScene& S, const int sel[3], const uint32_t dirs[3
 }
 
 // follow_direction on a 3-view list, plg_matching.cpp:765-769
-EG3D_D void follow3(Ctx& c, const uint32_t dirs[3], Pt3* list, int& n) {
+static __device__ __noinline__ void follow3(Ctx& c, const uint32_t dirs[3], Pt3* list, int& n) {
   while (true) {
     Pt3 cur = list[n - 1];
     Pt3 np;
@@ -225,7 +225,7 @@ EG3D_D void follow3(Ctx& c, const uint32_t dirs[3], Pt3* list, int& n) {
 // compatible_new_plg_point, plg_matching.cpp:1276-1287 (-> :1249-1270 -> :1060-1076 -> :325-370 -> :205-265).
 // D1/D2 (and their counts) persist across the triples of a seed and are only overwritten when the corresponding
 // direction is valid for THIS hypothesis.
-EG3D_D bool plg_compatible(Ctx& c, const Cur3& cand, int& n1, int& n2, uint32_t d1[3], uint32_t d2[3]) {
+static __device__ __noinline__ bool plg_compatible(Ctx& c, const Cur3& cand, int& n1, int& n2, uint32_t d1[3], uint32_t d2[3]) {
   const DevScene& S = *c.S;
   Pl pla = get_pl(S, c.sel[0], cand.pl[0]), plb = get_pl(S, c.sel[1], cand.pl[1]), plc = get_pl(S, c.sel[2], cand.pl[2]);
   bool d1ok = false, d2ok = false;
@@ -270,20 +270,15 @@ EG3D_D bool plg_compatible(Ctx& c, const Cur3& cand, int& n1, int& n2, uint32_t 
 // expansion phase: chain of "big" points held in slots
 EG3D_D int slot_of(const Ctx& c, int pos) { return c.w.order[pos]; }
 
-struct SlotObs {  // observation accessor of a slot, optionally followed by one extra observation
-  const int* v; const float* x; const float* y; int n; int ev; float ex, ey;
-  EG3D_D void operator()(int i, int& view, float& px, float& py) const {
-    if (i < n) { view = v[i]; px = x[i]; py = y[i]; } else { view = ev; px = ex; py = ey; }
-  }
-};
-EG3D_D SlotObs slot_obs(const Ctx& c, int slot, int n, int ev, float ex, float ey) {
-  SlotObs o; size_t b = (size_t)slot * c.w.oc;
-  o.v = c.w.ov + b; o.x = c.w.ox + b; o.y = c.w.oy + b; o.n = n; o.ev = ev; o.ex = ex; o.ey = ey;
+EG3D_D ObsSrc slot_obs(const Ctx& c, int slot, int n, bool extra, int ev, float ex, float ey) {
+  ObsSrc o; size_t b = (size_t)slot * c.w.oc;
+  o.v = c.w.ov + b; o.x = c.w.ox + b; o.y = c.w.oy + b; o.idx = nullptr; o.n = n;
+  o.has_extra = extra ? 1 : 0; o.ev = ev; o.ex = ex; o.ey = ey;
   return o;
 }
 
 // append one observation to a slot (lane 0 writes; callers sync)
-EG3D_D void slot_append(Ctx& c, int slot, int view, uint32_t pl, uint32_t seg, float x, float y, const float X[3]) {
+static __device__ __noinline__ void slot_append(Ctx& c, int slot, int view, uint32_t pl, uint32_t seg, float x, float y, const float X[3]) {
   int n = c.w.snobs[slot];
   if (n >= c.w.oc) { c.overflow = true; return; }
   if (c.lane == 0) {
@@ -296,7 +291,7 @@ EG3D_D void slot_append(Ctx& c, int slot, int view, uint32_t pl, uint32_t seg, f
 
 // em_estimate3Dpositions over the n observations of a slot (triangulation.cpp:178-250): DLT from (first arg-min view,
 // last entry) + warp-cooperative GN.
-EG3D_D bool est_slot(Ctx& c, int slot, int n, float Xo[3]) {
+static __device__ __noinline__ bool est_slot(Ctx& c, int slot, int n, float Xo[3]) {
   const DevScene& S = *c.S;
   const size_t b = (size_t)slot * c.w.oc;
   const int* ov = c.w.ov + b;
@@ -314,7 +309,7 @@ EG3D_D bool est_slot(Ctx& c, int slot, int n, float Xo[3]) {
   float t4[4];
   dlt_null(S.P + 12 * ov[mi], S.P + 12 * ov[ma], make_float2(c.w.ox[b + mi], c.w.oy[b + mi]), make_float2(c.w.ox[b + ma], c.w.oy[b + ma]), t4);
   double X[3] = {(double)(t4[0] / t4[3]), (double)(t4[1] / t4[3]), (double)(t4[2] / t4[3])};
-  if (!gn_warp(S, n, slot_obs(c, slot, n, 0, 0.f, 0.f), X, c.lane)) return false;
+  if (!gn_group(S, slot_obs(c, slot, n, false, 0, 0.f, 0.f), true, 32, c.lane, X)) return false;
   Xo[0] = (float)X[0]; Xo[1] = (float)X[1]; Xo[2] = (float)X[2];
   return true;
 }
@@ -330,7 +325,7 @@ EG3D_D bool next_comb3(int& i, int& j, int& k, int n) {
 // compute_3d_point_coords_combinations(min_combinations = 3), triangulation.cpp:1105-1158, on the observations of a
 // slot.  On success the slot is compacted to the selected observations in their ORIGINAL order
 // (plg_matching.cpp:720-732) and n / Xo are updated.
-EG3D_D bool combos_slot(Ctx& c, int slot, int& n, float Xo[3]) {
+static __device__ __noinline__ bool combos_slot(Ctx& c, int slot, int& n, float Xo[3]) {
   const DevScene& S = *c.S;
   const size_t b = (size_t)slot * c.w.oc;
   int* ov = c.w.ov + b; float* ox = c.w.ox + b; float* oy = c.w.oy + b; uint32_t* opl = c.w.opl + b; uint32_t* oseg = c.w.oseg + b;
@@ -368,13 +363,9 @@ EG3D_D bool combos_slot(Ctx& c, int slot, int& n, float Xo[3]) {
   int m = 3;
   for (int i = 0; i < n; i++) {
     if (c.w.selmask[i]) continue;
-    const int* idx = c.w.idx;
-    auto obs = [&](int q, int& view, float& px, float& py) {
-      int s = (q < m) ? idx[q] : i;
-      view = ov[s]; px = ox[s]; py = oy[s];
-    };
+    ObsSrc obs; obs.v = ov; obs.x = ox; obs.y = oy; obs.idx = c.w.idx; obs.n = m; obs.has_extra = 1; obs.ev = ov[i]; obs.ex = ox[i]; obs.ey = oy[i];
     double Xd[3] = {X[0], X[1], X[2]};
-    if (gn_warp(S, m + 1, obs, Xd, c.lane)) {
+    if (gn_group(S, obs, true, 32, c.lane, Xd)) {
       X[0] = (float)Xd[0]; X[1] = (float)Xd[1]; X[2] = (float)Xd[2];
       __syncwarp();
       if (c.lane == 0) { c.w.selmask[i] = 1; c.w.idx[m] = i; }
@@ -399,7 +390,7 @@ EG3D_D bool combos_slot(Ctx& c, int slot, int& n, float Xo[3]) {
 
 // all-view compatible (plg_matching.cpp:633-759) on a chain point with many views.  Builds the candidate in slot
 // c.nslots (not yet claimed); returns true and leaves the new point there when a step is found.
-EG3D_D bool step_all_big(Ctx& c, const uint32_t* dirs, int cur_slot) {
+static __device__ __noinline__ bool step_all_big(Ctx& c, const uint32_t* dirs, int cur_slot) {
   const DevScene& S = *c.S;
   if (c.nslots >= c.w.capc) { c.overflow = true; return false; }
   const int t = c.nslots;
@@ -451,7 +442,7 @@ EG3D_D bool step_all_big(Ctx& c, const uint32_t* dirs, int cur_slot) {
 }
 
 // follow_direction_vector_start / _end, plg_matching.cpp:771-795.  Returns the number of points added.
-EG3D_D int follow_big(Ctx& c, const uint32_t* dirs, bool at_start) {
+static __device__ __noinline__ int follow_big(Ctx& c, const uint32_t* dirs, bool at_start) {
   int added = 0;
   while (true) {
     int cur_slot = slot_of(c, at_start ? 0 : c.len - 1);
@@ -473,7 +464,7 @@ EG3D_D int follow_big(Ctx& c, const uint32_t* dirs, bool at_start) {
 // compatible_direction_noupdate_vector, plg_matching.cpp:866-914.  The polyline walk is sequential and cheap; the
 // warm-started GNs of the visited chain points are independent, so they run one per lane and the list is truncated at
 // the first failure.  Returns the number of accepted neighbours (entries of tmp[]).
-EG3D_D int walk_dir(Ctx& c, int v, const Plg& p, uint32_t dir, bool towards_start, int lo, int cur, int hi, NTmp* tmp) {
+static __device__ __noinline__ int walk_dir(Ctx& c, int v, const Plg& p, uint32_t dir, bool towards_start, int lo, int cur, int hi, NTmp* tmp) {
   const DevScene& S = *c.S;
   Pl pl = get_pl(S, v, p.pl);
   PlP q; q.seg = p.seg; q.c = p.c;
@@ -494,20 +485,29 @@ EG3D_D int walk_dir(Ctx& c, int v, const Plg& p, uint32_t dir, bool towards_star
   }
   __syncwarp();
   int keep = cnt;
-  for (int base = 0; base < cnt; base += 32) {
-    const int k = base + c.lane;
+  for (int base = 0; base < cnt;) {
+    const int P = min(32, cnt - base);
+    const int G = gn_group_width(P);
+    const int k = base + c.lane / G;
+    const bool active = (c.lane / G) < P;
     bool fail = false;
-    if (k < cnt) {
+    int slot = 0, n = 0; float ex = 0.f, ey = 0.f;
+    double X[3] = {0, 0, 0};
+    if (active) {
       const int jj = towards_start ? cur - 1 - k : cur + 1 + k;
-      const int slot = slot_of(c, jj);
-      const int n = c.w.snobs[slot];
-      double X[3] = {c.w.sX[3 * slot], c.w.sX[3 * slot + 1], c.w.sX[3 * slot + 2]};
-      if (gn_thread(S, n + 1, slot_obs(c, slot, n, v, tmp[k].cx, tmp[k].cy), X)) {
-        tmp[k].X[0] = (float)X[0]; tmp[k].X[1] = (float)X[1]; tmp[k].X[2] = (float)X[2];
-      } else fail = true;
+      slot = slot_of(c, jj);
+      n = c.w.snobs[slot];
+      X[0] = c.w.sX[3 * slot]; X[1] = c.w.sX[3 * slot + 1]; X[2] = c.w.sX[3 * slot + 2];
+      ex = tmp[k].cx; ey = tmp[k].cy;
+    }
+    bool ok = gn_group(S, slot_obs(c, slot, n, true, v, ex, ey), active, G, c.lane, X);
+    if (active) {
+      if (ok) { if ((c.lane & (G - 1)) == 0) { tmp[k].X[0] = (float)X[0]; tmp[k].X[1] = (float)X[1]; tmp[k].X[2] = (float)X[2]; } }
+      else fail = true;
     }
     unsigned fm = __ballot_sync(0xffffffffu, fail);
-    if (fm) { keep = base + __ffs(fm) - 1; break; }
+    if (fm) { keep = base + (__ffs(fm) - 1) / G; break; }
+    base += P;
   }
   __syncwarp();
   return keep;
@@ -515,7 +515,7 @@ EG3D_D int walk_dir(Ctx& c, int v, const Plg& p, uint32_t dir, bool towards_star
 
 // add_view_to_3dpoint_and_sides_plgp_matches_vector after its first GN succeeded (plg_matching.cpp:1345-1412;
 // neighbour search = find_directions_on_plg_known_3D_point_no_update_vector :1011-1058)
-EG3D_D bool add_view_finish(Ctx& c, int v, const Plg& p, const float Xc[3], int lo, int cur, int hi, int& ns, int& ne) {
+static __device__ __noinline__ bool add_view_finish(Ctx& c, int v, const Plg& p, const float Xc[3], int lo, int cur, int hi, int& ns, int& ne) {
   const DevScene& S = *c.S;
   Pl pl = get_pl(S, v, p.pl);
   int n1 = 0, n2 = 0; uint32_t nd1 = 0, nd2 = 0;
@@ -564,29 +564,30 @@ EG3D_D bool add_view_finish(Ctx& c, int v, const Plg& p, const float Xc[3], int 
 }
 
 // expand_allpoints_to_other_view_using_plmap, triangulation.cpp:742-830
-EG3D_D void expand_view(Ctx& c, int v) {
+static __device__ __noinline__ void expand_view(Ctx& c, int v) {
   const DevScene& S = *c.S;
   const int64_t h0 = c.A->hit_off[(size_t)c.seed * S.V + v];
   const int nh = (int)(c.A->hit_off[(size_t)c.seed * S.V + v + 1] - h0);
   const eg3d_hit* epcs = c.A->hits + h0;
   bool matched = false; int iv0 = 0, iv1 = 0;
   // the epipolar hits on the central point: one warm-started GN per lane, first complete success in order wins
-  for (int base = 0; base < nh && !matched; base += 32) {
-    const int e = base + c.lane;
+  for (int base = 0; base < nh && !matched;) {
+    const int P = min(32, nh - base);
+    const int G = gn_group_width(P);
+    const int e = base + c.lane / G;
+    const bool active = (c.lane / G) < P;
     const int cslot = slot_of(c, c.central);
     const int n = c.w.snobs[cslot];
-    bool ok = false; float Xe[3] = {0, 0, 0};
-    if (e < nh) {
-      eg3d_hit h = epcs[e];
-      double X[3] = {c.w.sX[3 * cslot], c.w.sX[3 * cslot + 1], c.w.sX[3 * cslot + 2]};
-      ok = gn_thread(S, n + 1, slot_obs(c, cslot, n, v, h.x, h.y), X);
-      Xe[0] = (float)X[0]; Xe[1] = (float)X[1]; Xe[2] = (float)X[2];
-    }
-    unsigned m = __ballot_sync(0xffffffffu, ok);
+    float hx = 0.f, hy = 0.f;
+    if (active) { eg3d_hit h = epcs[e]; hx = h.x; hy = h.y; }
+    double X[3] = {c.w.sX[3 * cslot], c.w.sX[3 * cslot + 1], c.w.sX[3 * cslot + 2]};
+    bool ok = gn_group(S, slot_obs(c, cslot, n, true, v, hx, hy), active, G, c.lane, X);
+    float Xe[3] = {(float)X[0], (float)X[1], (float)X[2]};
+    unsigned m = __ballot_sync(0xffffffffu, ok && ((c.lane & (G - 1)) == 0));
     while (m && !matched) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
-      eg3d_hit h = epcs[base + b];
+      eg3d_hit h = epcs[base + b / G];
       float Xc[3] = {__shfl_sync(0xffffffffu, Xe[0], b), __shfl_sync(0xffffffffu, Xe[1], b), __shfl_sync(0xffffffffu, Xe[2], b)};
       Plg p; p.pl = h.polyline; p.seg = h.segment; p.c = make_float2(h.x, h.y);
       int ns = 0, ne = 0;
@@ -598,6 +599,7 @@ EG3D_D void expand_view(Ctx& c, int v) {
       }
       if (c.overflow) return;
     }
+    base += P;
   }
   int last = -1;
   for (int cur = 0; cur < c.len; cur++) {
@@ -612,7 +614,7 @@ EG3D_D void expand_view(Ctx& c, int v) {
     const int hi = matched ? (cur <= iv0 ? iv0 : c.len) : c.len;
     const int n = c.w.snobs[slot];
     double X[3] = {c.w.sX[3 * slot], c.w.sX[3 * slot + 1], c.w.sX[3 * slot + 2]};
-    if (!gn_warp(S, n + 1, slot_obs(c, slot, n, v, init.c.x, init.c.y), X, c.lane)) continue;
+    if (!gn_group(S, slot_obs(c, slot, n, true, v, init.c.x, init.c.y), true, 32, c.lane, X)) continue;
     float Xc[3] = {(float)X[0], (float)X[1], (float)X[2]};
     int ns = 0, ne = 0;
     if (add_view_finish(c, v, init, Xc, last + 1, cur, hi, ns, ne)) {
@@ -625,7 +627,7 @@ EG3D_D void expand_view(Ctx& c, int v) {
 }
 
 // materialise a 3-view point as a chain slot
-EG3D_D void slot_from_pt3(Ctx& c, int slot, const Pt3& p) {
+static __device__ __noinline__ void slot_from_pt3(Ctx& c, int slot, const Pt3& p) {
   if (c.lane == 0) {
     size_t b = (size_t)slot * c.w.oc;
     for (int i = 0; i < 3; i++) {
@@ -636,7 +638,7 @@ EG3D_D void slot_from_pt3(Ctx& c, int slot, const Pt3& p) {
   }
 }
 
-EG3D_D void process_seed(Ctx& c) {
+static __device__ __noinline__ void process_seed(Ctx& c) {
   const DevScene& S = *c.S; const K3Args& A = *c.A;
   const int V = S.V, lane = c.lane;
   const int64_t* off = A.hit_off + (size_t)c.seed * V;
@@ -736,7 +738,7 @@ EG3D_D void process_seed(Ctx& c) {
   }
 }
 
-__global__ void __launch_bounds__(K3_THREADS) k3_chain_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
+__global__ void __launch_bounds__(K3_THREADS, 4) k3_chain_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   Ctx c;
