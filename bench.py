@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seeds-limit", type=int, default=0, help="profiling aid: keep only a stratified subset of the seed batch (NOT a bench configuration)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,7 +220,10 @@ def main():
     n_gpus = world
 
     scene, cfg, per_view = build_workload(args.workload, n_gpus)
-    seeds = pinned_seeds(make_seeds(scene, E.sample_seeds, per_view, n_gpus, rank))
+    seeds = make_seeds(scene, E.sample_seeds, per_view, n_gpus, rank)
+    if args.seeds_limit and args.seeds_limit < len(seeds):
+        seeds = seeds.take(np.linspace(0, len(seeds) - 1, args.seeds_limit).astype(np.int64))
+    seeds = pinned_seeds(seeds)
     t = time.perf_counter()
     dev = E.DeviceScene(scene)
     torch.cuda.synchronize()

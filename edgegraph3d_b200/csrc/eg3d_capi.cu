@@ -239,7 +239,7 @@ static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_o
   if (n == 0) { CK(out->d_obs_off.alloc(1)); CK(cudaMemsetAsync(out->d_obs_off.p, 0, sizeof(int64_t), sc->stream)); CK(cudaStreamSynchronize(sc->stream)); return EG3D_OK; }
   const int capf = sc->prm.max_follow_points, capc = sc->prm.max_chain_points, oc = V + 16;
   const size_t spw = k3_scratch_bytes(V, capf, capc, oc);
-  int blocks_per_sm = 8;  // 32 warps per SM
+  int blocks_per_sm = 16;  // upper bound; residency is set by the kernel's register budget
   int nblocks = sc->num_sms * blocks_per_sm;
   const int warps_per_block = K3_THREADS / 32;
   int max_useful = (n + warps_per_block - 1) / warps_per_block;

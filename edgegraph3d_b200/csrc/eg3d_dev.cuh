@@ -12,8 +12,12 @@
 #define EG3D_HD __host__ __device__ __forceinline__
 #define EG3D_D __device__ __forceinline__
 #define EG3D_HD_NI static __host__ __device__ __noinline__
+#ifndef EG3D_GN_UNROLL
+#define EG3D_GN_UNROLL 1
+#endif
 
 namespace eg3d {
+constexpr int kGnUnroll = EG3D_GN_UNROLL;
 
 struct DevGrid {            // uniform polyline grid, PolyLine2DMap (polyLine_2d_map.cpp:40-58), CSR per (view, cell)
   float cell; int w, h;
@@ -63,10 +67,10 @@ EG3D_HD float sqdist2(float2 a, float2 b) {
   float dx = a.x - b.x, dy = a.y - b.y;
   return (float)((double)dx * (double)dx + (double)dy * (double)dy);
 }
-EG3D_HD float dist2(float2 a, float2 b) { return sqrtf(sqdist2(a, b)); }  // :571-573
+EG3D_HD_NI float dist2(float2 a, float2 b) { return sqrtf(sqdist2(a, b)); }  // :571-573
 
 // geometric_utilities.cpp:824-843 -> cv::computeCorrespondEpilines(whichImage = 1)
-EG3D_HD bool epiline(const DevScene& S, int a, int b, float2 p, float3& l) {
+EG3D_HD_NI bool epiline(const DevScene& S, int a, int b, float2 p, float3& l) {
   size_t idx = (size_t)a * S.V + b;
   if (!S.Fvalid[idx]) return false;
   const double* F = S.F + idx * 9;
@@ -98,7 +102,7 @@ EG3D_HD float dist_point_line(float px, float py, float3 l) {  // geometric_util
 }
 
 // geometric_utilities.cpp:365-430.  Returns bit0 = intersection_found, bit1 = quasiparallel_within_distance.
-EG3D_HD int isect_seg_line_nqp(float x1, float y1, float x2, float y2, float3 l, float max_cos, float max_dist, float2& inter) {
+EG3D_HD_NI int isect_seg_line_nqp(float x1, float y1, float x2, float y2, float3 l, float max_cos, float max_dist, float2& inter) {
   float dx = x2 - x1, dy = y2 - y1;
   int res = 0;
   float num = l.x * x1 + l.y * y1 + l.z;
@@ -208,7 +212,7 @@ EG3D_HD_NI bool walk_line(const Pl& pl, PlP init, uint32_t dir, float3 line, con
 }
 
 // minimum_distancesq, geometric_utilities.cpp:940-954
-EG3D_HD float min_distsq_seg(float2 p, float2 v, float2 w, float2& proj) {
+EG3D_HD_NI float min_distsq_seg(float2 p, float2 v, float2 w, float2& proj) {
   const float l2 = sqdist2(v, w);
   if (l2 == 0.0) { proj = v; return sqdist2(p, v); }
   float pvx = p.x - v.x, pvy = p.y - v.y, wvx = w.x - v.x, wvy = w.y - v.y;
@@ -244,7 +248,7 @@ EG3D_HD bool is_multiple_of(float m, float n) {
 }
 
 // compute_projection, geometric_utilities.cpp:973-983 (glm row-vector product)
-EG3D_HD float2 project(const float* P, float X, float Y, float Z) {
+EG3D_HD_NI float2 project(const float* P, float X, float Y, float Z) {
   float h0 = P[0] * X + P[1] * Y + P[2] * Z + P[3] * 1.0f;
   float h1 = P[4] * X + P[5] * Y + P[6] * Z + P[7] * 1.0f;
   float h2 = P[8] * X + P[9] * Y + P[10] * Z + P[11] * 1.0f;
@@ -271,7 +275,7 @@ EG3D_HD void grid_visit(const DevGrid& g, int view, int img_w, int img_h, float2
       for (int k = off[cidx]; k < off[cidx + 1]; k++) visit(g.ids[k]);
     }
 }
-EG3D_HD bool grid_unique(const DevGrid& g, int view, int img_w, int img_h, float2 c, uint32_t& pl_id) {
+EG3D_HD_NI bool grid_unique(const DevGrid& g, int view, int img_w, int img_h, float2 c, uint32_t& pl_id) {
   int cnt = 0; uint32_t first = 0; bool multi = false;
   grid_visit(g, view, img_w, img_h, c, [&](uint32_t id) {
     if (cnt == 0) { first = id; cnt = 1; } else if (id != first) multi = true;
@@ -344,27 +348,27 @@ EG3D_HD void inv3d(const double* m, double d, double* t) {  // cv::invert closed
 // oracle (J and r kept in registers, H = J^T J accumulated row by row, update = (H^-1 J^T) r) => bit-identical results.
 // Returns true when accepted (last_mse < accept); X holds the result.
 EG3D_HD bool gn3_exact(const DevScene& S, const int v[3], const float2 pt[3], double X[3]) {
-  double Pd[3][12];
-#pragma unroll
-  for (int m = 0; m < 3; m++) {
-    const float* P = S.P + 12 * v[m];
-#pragma unroll
-    for (int i = 0; i < 12; i++) Pd[m][i] = (double)P[i];
-  }
+  // Deliberately rolled loops with J / r in (L1-resident) local arrays: the routine is called from many divergent
+  // sites and an unrolled body (24 double divisions) would not fit the instruction caches.
   double last_mse = 0;
   const eg3d_params& prm = S.prm;
+  double r[6], J[18];
   for (int it = 0; it < prm.gn_max_iters; it++) {
-    double r[6], J[18], mse = 0;
-#pragma unroll
+    double mse = 0;
+#pragma unroll 1
     for (int m = 0; m < 3; m++) {
-      const double* P = Pd[m];
+      const float* Pf = S.P + 12 * v[m];
+      double P[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) P[i] = (double)Pf[i];
       double h0 = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3] * 1.0;
       double h1 = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7] * 1.0;
       double h2 = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11] * 1.0;
-      r[2 * m] = (double)pt[m].x - h0 / h2;
-      mse += r[2 * m] * r[2 * m];
-      r[2 * m + 1] = (double)pt[m].y - h1 / h2;
-      mse += r[2 * m + 1] * r[2 * m + 1];
+      double rx = (double)pt[m].x - h0 / h2;
+      mse += rx * rx;
+      double ry = (double)pt[m].y - h1 / h2;
+      mse += ry * ry;
+      r[2 * m] = rx; r[2 * m + 1] = ry;
       double zz = h2 * h2;
       J[6 * m + 0] = (P[0] * h2 - P[8] * h0) / zz;  J[6 * m + 3] = (P[4] * h2 - P[8] * h1) / zz;
       J[6 * m + 1] = (P[1] * h2 - P[9] * h0) / zz;  J[6 * m + 4] = (P[5] * h2 - P[9] * h1) / zz;
@@ -374,27 +378,26 @@ EG3D_HD bool gn3_exact(const DevScene& S, const int v[3], const float2 pt[3], do
     last_mse = mse / 6;
     double H[9];
 #pragma unroll
-    for (int a = 0; a < 3; a++)
-#pragma unroll
-      for (int b = 0; b < 3; b++) {
-        double acc = 0;
-#pragma unroll
-        for (int k = 0; k < 6; k++) acc += J[3 * k + a] * J[3 * k + b];
-        H[3 * a + b] = acc;
-      }
+    for (int a = 0; a < 9; a++) H[a] = 0;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+      double j0 = J[3 * k], j1 = J[3 * k + 1], j2 = J[3 * k + 2];
+      H[0] += j0 * j0; H[1] += j0 * j1; H[2] += j0 * j2;
+      H[3] += j1 * j0; H[4] += j1 * j1; H[5] += j1 * j2;
+      H[6] += j2 * j0; H[7] += j2 * j1; H[8] += j2 * j2;
+    }
     double d = det3d(H);
     if (d < prm.gn_det_min) return false;
     double Hi[9]; inv3d(H, d, Hi);
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      double acc = 0;
-#pragma unroll
-      for (int k = 0; k < 6; k++) {
-        double mk = Hi[3 * a + 0] * J[3 * k + 0] + Hi[3 * a + 1] * J[3 * k + 1] + Hi[3 * a + 2] * J[3 * k + 2];
-        acc += mk * r[k];
-      }
-      X[a] += acc;
+    double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 1
+    for (int k = 0; k < 6; k++) {
+      double j0 = J[3 * k], j1 = J[3 * k + 1], j2 = J[3 * k + 2], rk = r[k];
+      a0 += (Hi[0] * j0 + Hi[1] * j1 + Hi[2] * j2) * rk;
+      a1 += (Hi[3] * j0 + Hi[4] * j1 + Hi[5] * j2) * rk;
+      a2 += (Hi[6] * j0 + Hi[7] * j1 + Hi[8] * j2) * rk;
     }
+    X[0] += a0; X[1] += a1; X[2] += a2;
   }
   return last_mse < prm.gn_accept_mse;
 }
@@ -519,7 +522,7 @@ static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o,
     if (!__any_sync(0xffffffffu, running)) break;
     GnAcc a = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (running) {
-#pragma unroll 1
+#pragma unroll kGnUnroll
       for (int i = sub; i < n; i += G) {
         int v; float x, y;
         o.get(i, v, x, y);

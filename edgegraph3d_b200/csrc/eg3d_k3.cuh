@@ -15,6 +15,9 @@
 
 namespace eg3d {
 
+#ifndef EG3D_K3_MIN_BLOCKS
+#define EG3D_K3_MIN_BLOCKS 8
+#endif
 constexpr int K3_THREADS = 128;  // 4 warps per CTA
 
 struct Pt3 {  // a 3-view point of the following phase (64 B)
@@ -396,46 +399,66 @@ static __device__ __noinline__ bool step_all_big(Ctx& c, const uint32_t* dirs, i
   const int t = c.nslots;
   const int n = c.w.snobs[cur_slot];
   const size_t cb = (size_t)cur_slot * c.w.oc, tb = (size_t)t * c.w.oc;
-  for (int si = 0; si < n; si++) {
-    const int sv = c.w.ov[cb + si];
-    const uint32_t spl = c.w.opl[cb + si];
-    Pl pls = get_pl(S, sv, spl);
-    PlP ip; ip.seg = c.w.oseg[cb + si]; ip.c = make_float2(c.w.ox[cb + si], c.w.oy[cb + si]);
-    bool reached;
-    PlP ns = step_by_distance(pls, ip, dirs[sv], S.prm.follow_first_image_distance, reached);
-    if (reached) continue;
-    __syncwarp();
-    if (c.lane == 0) { c.w.ov[tb] = sv; c.w.opl[tb] = spl; c.w.oseg[tb] = ns.seg; c.w.ox[tb] = ns.c.x; c.w.oy[tb] = ns.c.y; }
-    int count = 1;
-    for (int base = 0; base < n; base += 32) {
-      const int i = base + c.lane;
-      bool found = false; PlP np; int vv = 0; uint32_t ipl = 0;
-      if (i < n && i != si) {
-        vv = c.w.ov[cb + i]; ipl = c.w.opl[cb + i];
-        float3 l;
-        if (epiline(S, sv, vv, ns.c, l)) {
-          Pl pl = get_pl(S, vv, ipl);
-          PlP iq; iq.seg = c.w.oseg[cb + i]; iq.c = make_float2(c.w.ox[cb + i], c.w.oy[cb + i]);
-          found = walk_line(pl, iq, dirs[vv], l, S.prm, true, np);
-        }
+  // The driving-view loop (`for starting_plg_index`, plg_matching.cpp:635) mostly meets views whose polyline is already
+  // at its extreme: the 10 px step of 32 candidate driving views is evaluated at once, and only the views that can
+  // still advance are processed, in order.
+  for (int sbase = 0; sbase < n; sbase += 32) {
+    bool can = false;
+    {
+      const int si = sbase + c.lane;
+      if (si < n) {
+        const int sv = c.w.ov[cb + si];
+        Pl pls = get_pl(S, sv, c.w.opl[cb + si]);
+        PlP ip; ip.seg = c.w.oseg[cb + si]; ip.c = make_float2(c.w.ox[cb + si], c.w.oy[cb + si]);
+        bool reached;
+        (void)step_by_distance(pls, ip, dirs[sv], S.prm.follow_first_image_distance, reached);
+        can = !reached;
       }
-      unsigned m = __ballot_sync(0xffffffffu, found);
-      if (found) {
-        int pos = count + __popc(m & ((1u << c.lane) - 1u));
-        c.w.ov[tb + pos] = vv; c.w.opl[tb + pos] = ipl; c.w.oseg[tb + pos] = np.seg; c.w.ox[tb + pos] = np.c.x; c.w.oy[tb + pos] = np.c.y;
-      }
-      count += __popc(m);
     }
-    __syncwarp();
-    if (count < 3) continue;
-    float X[3];
-    bool valid = est_slot(c, t, count, X);
-    if (!valid) valid = combos_slot(c, t, count, X);
-    if (valid) {
+    unsigned cm = __ballot_sync(0xffffffffu, can);
+    while (cm) {
+      const int si = sbase + __ffs(cm) - 1;
+      cm &= cm - 1;
+      const int sv = c.w.ov[cb + si];
+      const uint32_t spl = c.w.opl[cb + si];
+      Pl pls = get_pl(S, sv, spl);
+      PlP ip; ip.seg = c.w.oseg[cb + si]; ip.c = make_float2(c.w.ox[cb + si], c.w.oy[cb + si]);
+      bool reached;
+      PlP ns = step_by_distance(pls, ip, dirs[sv], S.prm.follow_first_image_distance, reached);
+      if (reached) continue;
       __syncwarp();
-      if (c.lane == 0) { c.w.snobs[t] = count; c.w.sX[3 * t] = X[0]; c.w.sX[3 * t + 1] = X[1]; c.w.sX[3 * t + 2] = X[2]; }
+      if (c.lane == 0) { c.w.ov[tb] = sv; c.w.opl[tb] = spl; c.w.oseg[tb] = ns.seg; c.w.ox[tb] = ns.c.x; c.w.oy[tb] = ns.c.y; }
+      int count = 1;
+      for (int base = 0; base < n; base += 32) {
+        const int i = base + c.lane;
+        bool found = false; PlP np; int vv = 0; uint32_t ipl = 0;
+        if (i < n && i != si) {
+          vv = c.w.ov[cb + i]; ipl = c.w.opl[cb + i];
+          float3 l;
+          if (epiline(S, sv, vv, ns.c, l)) {
+            Pl pl = get_pl(S, vv, ipl);
+            PlP iq; iq.seg = c.w.oseg[cb + i]; iq.c = make_float2(c.w.ox[cb + i], c.w.oy[cb + i]);
+            found = walk_line(pl, iq, dirs[vv], l, S.prm, true, np);
+          }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, found);
+        if (found) {
+          int pos = count + __popc(m & ((1u << c.lane) - 1u));
+          c.w.ov[tb + pos] = vv; c.w.opl[tb + pos] = ipl; c.w.oseg[tb + pos] = np.seg; c.w.ox[tb + pos] = np.c.x; c.w.oy[tb + pos] = np.c.y;
+        }
+        count += __popc(m);
+      }
       __syncwarp();
-      return true;
+      if (count < 3) continue;
+      float X[3];
+      bool valid = est_slot(c, t, count, X);
+      if (!valid) valid = combos_slot(c, t, count, X);
+      if (valid) {
+        __syncwarp();
+        if (c.lane == 0) { c.w.snobs[t] = count; c.w.sX[3 * t] = X[0]; c.w.sX[3 * t + 1] = X[1]; c.w.sX[3 * t + 2] = X[2]; }
+        __syncwarp();
+        return true;
+      }
     }
   }
   return false;
@@ -683,9 +706,16 @@ static __device__ __noinline__ void process_seed(Ctx& c) {
     bool ok = false; float X[3] = {0, 0, 0};
     int i0 = 0, i1 = 0, i2 = 0;
     if (t < total) {
-      i0 = (int)(t / ((long long)n1h * n2h));
-      long long rem = t - (long long)i0 * n1h * n2h;
-      i1 = (int)(rem / n2h); i2 = (int)(rem - (long long)i1 * n2h);
+      if (total <= 0x7fffffffLL) {
+        const unsigned tu = (unsigned)t, n12 = (unsigned)(n1h * n2h);
+        i0 = (int)(tu / n12);
+        unsigned rem = tu - (unsigned)i0 * n12;
+        i1 = (int)(rem / (unsigned)n2h); i2 = (int)(rem - (unsigned)i1 * (unsigned)n2h);
+      } else {
+        i0 = (int)(t / ((long long)n1h * n2h));
+        long long rem = t - (long long)i0 * n1h * n2h;
+        i1 = (int)(rem / n2h); i2 = (int)(rem - (long long)i1 * n2h);
+      }
       float2 pts[3] = {make_float2(h0[i0].x, h0[i0].y), make_float2(h1[i1].x, h1[i1].y), make_float2(h2[i2].x, h2[i2].y)};
       ok = est3(S, c.sel, pts, X);
     }
@@ -738,7 +768,7 @@ static __device__ __noinline__ void process_seed(Ctx& c) {
   }
 }
 
-__global__ void __launch_bounds__(K3_THREADS, 4) k3_chain_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
+__global__ void __launch_bounds__(K3_THREADS, EG3D_K3_MIN_BLOCKS) k3_chain_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   Ctx c;

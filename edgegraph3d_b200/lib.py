@@ -10,7 +10,7 @@ from . import _abi as A
 from .scene import PointSet
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeg3d.so")
+LIB_PATH = os.environ.get("EG3D_LIB", os.path.join(_HERE, "libeg3d.so"))  # EG3D_LIB: A/B builds of the same library
 _lib = None
 
 EXPORTS = [

@@ -1,0 +1,221 @@
+// eg3d_ref_api.hpp — header-only C++ shim that keeps EdgeGraph3D's own names and signatures for the hot path on top of
+// the C-ABI of libeg3d.so (include/eg3d.h).  A maintainer of the reference includes this file instead of
+// polyline_matching.hpp / outliers_filtering.hpp / filtering_close_plgps.hpp in pipelines.cpp and edge_matcher.cpp
+// (INTEGRATION.md shows the patch).  Inside the reference tree define EG3D_REF_USE_REFERENCE_TYPES before including it
+// and the shim binds to the real SfMData / PolyLineGraph2DHMapImpl / cv::Mat types; stand-alone (this repository's
+// tests) it declares layout-compatible minimal versions of those types.
+#pragma once
+#include <cstdint>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <utility>
+#include <vector>
+#include "eg3d.h"
+
+#ifndef EG3D_REF_USE_REFERENCE_TYPES
+namespace eg3d_ref {
+typedef unsigned long ulong;
+struct vec2 { float x, y; vec2() : x(0), y(0) {} vec2(float a, float b) : x(a), y(b) {} float& operator[](int i) { return i ? y : x; } float operator[](int i) const { return i ? y : x; } };
+struct vec3 { float x, y, z; vec3() : x(0), y(0), z(0) {} vec3(float a, float b, float c) : x(a), y(b), z(c) {} float& operator[](int i) { return i == 0 ? x : (i == 1 ? y : z); } float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); } };
+struct mat4 { float m[4][4]; const float* operator[](int i) const { return m[i]; } float* operator[](int i) { return m[i]; } };
+// external/manifoldReconstructor/include/types_reconstructor.hpp:68-82 (fields the path reads)
+struct CameraType { mat4 cameraMatrix; int imageWidth = 0, imageHeight = 0; };
+// external/manifoldReconstructor/include/SfMData.h:16-30
+struct SfMData {
+  int numPoints_ = 0, numCameras_ = 0;
+  std::vector<vec3> points_;
+  std::vector<CameraType> camerasList_;
+  std::vector<std::vector<int>> camViewingPointN_;
+  std::vector<std::vector<int>> pointsVisibleFromCamN_;
+  std::vector<std::vector<vec2>> point2DoncamViewingPoint_;
+  int imageWidth_ = 0, imageHeight_ = 0;
+};
+// include/edgegraph3d/plgs/polyline_graph_2d.hpp:85-119, 278-294
+struct PolyLineGraph2D {
+  struct polyline {
+    struct pl_point { ulong segment_index; vec2 coords; pl_point() : segment_index(0) {} pl_point(ulong s, const vec2& c) : segment_index(s), coords(c) {} };
+    ulong start = 0, end = 0;
+    std::vector<vec2> polyline_coords;
+  };
+  struct plg_point {
+    ulong polyline_id; polyline::pl_point plp;
+    plg_point() : polyline_id(0) {}
+    plg_point(ulong id, ulong seg, const vec2& c) : polyline_id(id), plp(seg, c) {}
+  };
+  std::vector<polyline> polylines;
+};
+typedef PolyLineGraph2D PolyLineGraph2DHMapImpl;
+}  // namespace eg3d_ref
+#define EG3D_REF_NS eg3d_ref
+#else
+#define EG3D_REF_NS
+#endif
+
+namespace eg3d_shim {
+using namespace EG3D_REF_NS;
+typedef unsigned long ulong_t;
+
+// polyline_graph_2d.hpp:451
+typedef std::tuple<vec3, std::vector<PolyLineGraph2D::plg_point>, std::vector<int>> new_3dpoint_plgp_matches;
+
+inline void check(eg3d_status st) {
+  if (st != EG3D_OK) throw std::runtime_error(std::string("libeg3d: ") + eg3d_last_error());
+}
+
+// `const Mat** all_fundamental_matrices` (edge_graph_3d_utilities.cpp:581-589) flattened: F[a][b] row-major 3x3 doubles,
+// valid[a][b] = 0 for the 1x1 dummy Mat of pairs with < 10 common tracks (geometric_utilities.cpp:780).
+struct FundamentalSet {
+  std::vector<double> F; std::vector<uint8_t> valid; int V = 0;
+  explicit FundamentalSet(int n = 0) : F((size_t)n * n * 9, 0.0), valid((size_t)n * n, 0), V(n) {}
+  void set(int a, int b, const double f9[9]) { for (int i = 0; i < 9; i++) F[((size_t)a * V + b) * 9 + i] = f9[i]; valid[(size_t)a * V + b] = 1; }
+#ifdef EG3D_REF_USE_REFERENCE_TYPES
+  FundamentalSet(const cv::Mat** all_fundamental_matrices, int n) : FundamentalSet(n) {
+    for (int a = 0; a < n; a++) for (int b = 0; b < n; b++) {
+      const cv::Mat& m = all_fundamental_matrices[a][b];
+      if (a != b && m.rows == 3 && m.cols == 3) { double f[9]; for (int i = 0; i < 9; i++) f[i] = m.at<double>(i / 3, i % 3); set(a, b, f); }
+    }
+  }
+#endif
+};
+
+// Owns the device-resident scene: the role `plgs`, `plmaps`, `all_fundamental_matrices`, `em` play as long-lived
+// arguments of the reference's entry points (edge_matcher.cpp:83-115 builds them once).
+class Eg3dScene {
+ public:
+  Eg3dScene(const SfMData& sfmd, const std::vector<PolyLineGraph2DHMapImpl>& plgs, const FundamentalSet& F, const eg3d_params* params = nullptr) {
+    const int V = (int)plgs.size();
+    cams_.resize((size_t)V * 12);
+    for (int v = 0; v < V; v++)   // convert_glm_mat4_to_cv_Mat34: glm_mat[row][col] (edge_graph_3d_utilities.cpp:190-206)
+      for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) cams_[(size_t)v * 12 + r * 4 + c] = sfmd.camerasList_[v].cameraMatrix[r][c];
+    view_poly_off_.assign(1, 0); poly_vert_off_.assign(1, 0);
+    for (int v = 0; v < V; v++) {
+      for (const auto& pl : plgs[v].polylines) {
+        for (const auto& c : pl.polyline_coords) { verts_.push_back(c[0]); verts_.push_back(c[1]); }
+        poly_vert_off_.push_back((int64_t)verts_.size() / 2);
+        start_.push_back((uint32_t)pl.start); end_.push_back((uint32_t)pl.end);
+      }
+      view_poly_off_.push_back((int64_t)start_.size());
+    }
+    track_off_.assign(1, 0);
+    for (size_t t = 0; t < sfmd.points_.size(); t++) {
+      track_xyz_.push_back(sfmd.points_[t][0]); track_xyz_.push_back(sfmd.points_[t][1]); track_xyz_.push_back(sfmd.points_[t][2]);
+      for (size_t k = 0; k < sfmd.camViewingPointN_[t].size(); k++) {
+        track_view_.push_back(sfmd.camViewingPointN_[t][k]);
+        track_xy_.push_back(sfmd.point2DoncamViewingPoint_[t][k][0]); track_xy_.push_back(sfmd.point2DoncamViewingPoint_[t][k][1]);
+      }
+      track_off_.push_back((int64_t)track_view_.size());
+    }
+    desc_ = eg3d_scene_desc();
+    desc_.n_views = V; desc_.width = sfmd.imageWidth_; desc_.height = sfmd.imageHeight_;
+    desc_.cameras = cams_.data(); desc_.fundamental = F.F.data(); desc_.fundamental_valid = F.valid.data();
+    desc_.view_poly_off = view_poly_off_.data(); desc_.poly_vert_off = poly_vert_off_.data(); desc_.verts = verts_.data();
+    desc_.poly_start = start_.data(); desc_.poly_end = end_.data();
+    desc_.n_tracks = (int64_t)sfmd.points_.size(); desc_.track_xyz = track_xyz_.data(); desc_.track_off = track_off_.data();
+    desc_.track_view = track_view_.data(); desc_.track_xy = track_xy_.data();
+    check(eg3d_scene_create(&desc_, params, &scene_));
+  }
+  ~Eg3dScene() { if (scene_) eg3d_scene_destroy(scene_); }
+  Eg3dScene(const Eg3dScene&) = delete;
+  Eg3dScene& operator=(const Eg3dScene&) = delete;
+  eg3d_scene* handle() const { return scene_; }
+  const eg3d_scene_desc& desc() const { return desc_; }
+  int n_views() const { return desc_.n_views; }
+
+ private:
+  std::vector<float> cams_, verts_, track_xyz_, track_xy_;
+  std::vector<int64_t> view_poly_off_, poly_vert_off_, track_off_;
+  std::vector<uint32_t> start_, end_;
+  std::vector<int32_t> track_view_;
+  eg3d_scene_desc desc_;
+  eg3d_scene* scene_ = nullptr;
+};
+
+inline std::vector<new_3dpoint_plgp_matches> points_to_reference(eg3d_points* pts) {
+  eg3d_points_view v; check(eg3d_points_get(pts, &v));
+  std::vector<new_3dpoint_plgp_matches> res((size_t)v.n_points);
+  for (int64_t i = 0; i < v.n_points; i++) {
+    std::get<0>(res[i]) = vec3(v.xyz[3 * i], v.xyz[3 * i + 1], v.xyz[3 * i + 2]);
+    for (int64_t o = v.obs_off[i]; o < v.obs_off[i + 1]; o++) {
+      std::get<1>(res[i]).push_back(PolyLineGraph2D::plg_point(v.obs_poly[o], v.obs_seg[o], vec2(v.obs_xy[2 * o], v.obs_xy[2 * o + 1])));
+      std::get<2>(res[i]).push_back(v.obs_view[o]);
+    }
+  }
+  eg3d_points_free(pts);
+  return res;
+}
+
+// B1 (polyline_matching.hpp:55-56), batched over polyline matches exactly as the loop at pipelines.cpp:92-100 /
+// :138-147 calls it: one `vector<set<ulong>>` per match.  The PLGMatchesManager argument of the reference is not needed:
+// with SWITCH_RUNPARALLEL it is never written on this path (SURVEY finding 5).
+inline std::vector<new_3dpoint_plgp_matches> find_new_3d_points_from_compatible_polylines_expandallviews_parallel(
+    Eg3dScene& scene, const std::vector<std::vector<std::set<ulong_t>>>& potentially_compatible_polylines_per_match,
+    int starting_view_begin = 0, int starting_view_end = -1) {
+  const int V = scene.n_views();
+  std::vector<int64_t> off(1, 0); std::vector<uint32_t> ids;
+  for (const auto& match : potentially_compatible_polylines_per_match)
+    for (int v = 0; v < V; v++) { for (ulong_t id : match[v]) ids.push_back((uint32_t)id); off.push_back((int64_t)ids.size()); }
+  eg3d_candidates c; c.n_sets = (int32_t)potentially_compatible_polylines_per_match.size(); c.off = off.data(); c.polyline = ids.data();
+  eg3d_points* pts = nullptr;
+  check(eg3d_match_polyline_sets(scene.handle(), &c, starting_view_begin, starting_view_end < 0 ? V : starting_view_end, &pts, nullptr));
+  return points_to_reference(pts);
+}
+
+// B2 (plg_matching_from_refpoints.hpp:53-55)
+inline std::vector<new_3dpoint_plgp_matches> plg_matching_from_refpoints_parallel(Eg3dScene& scene, int64_t refpoint_begin = 0, int64_t refpoint_end = -1) {
+  eg3d_points* pts = nullptr;
+  check(eg3d_match_refpoints(scene.handle(), refpoint_begin, refpoint_end < 0 ? scene.desc().n_tracks : refpoint_end, &pts, nullptr));
+  return points_to_reference(pts);
+}
+
+// a13 (filtering_close_plgps.hpp): first-come-first-kept density limiter over the gathered points
+inline std::vector<new_3dpoint_plgp_matches> filter_3d_points_close_2d_array(Eg3dScene& scene, const std::vector<new_3dpoint_plgp_matches>& p3ds) {
+  std::vector<float> xyz, xy; std::vector<int32_t> seed(p3ds.size(), 0), pos(p3ds.size(), 0), view; std::vector<uint32_t> pl, seg; std::vector<int64_t> off(1, 0);
+  for (const auto& p : p3ds) {
+    xyz.push_back(std::get<0>(p)[0]); xyz.push_back(std::get<0>(p)[1]); xyz.push_back(std::get<0>(p)[2]);
+    for (size_t k = 0; k < std::get<1>(p).size(); k++) {
+      const auto& q = std::get<1>(p)[k];
+      view.push_back(std::get<2>(p)[k]); pl.push_back((uint32_t)q.polyline_id); seg.push_back((uint32_t)q.plp.segment_index);
+      xy.push_back(q.plp.coords[0]); xy.push_back(q.plp.coords[1]);
+    }
+    off.push_back((int64_t)view.size());
+  }
+  eg3d_points_view v; v.n_points = (int64_t)p3ds.size(); v.n_obs = (int64_t)view.size(); v.xyz = xyz.data(); v.seed = seed.data(); v.chain_pos = pos.data();
+  v.obs_off = off.data(); v.obs_view = view.data(); v.obs_poly = pl.data(); v.obs_seg = seg.data(); v.obs_xy = xy.data();
+  std::vector<uint8_t> keep(p3ds.size());
+  check(eg3d_dedup_close_points(scene.handle(), &v, keep.data()));
+  std::vector<new_3dpoint_plgp_matches> res;
+  for (size_t i = 0; i < p3ds.size(); i++) if (keep[i]) res.push_back(p3ds[i]);
+  return res;
+}
+
+// B6 (outliers_filtering.hpp:18-21): GN refinement + inlier test + view-count rule + removeOutliers compaction
+inline void filter(Eg3dScene& scene, SfMData& sfmd, int first_edgepoint, float gn_max_mse = 2.25f, int forced_min_filter = -1) {
+  const int64_t n = (int64_t)sfmd.points_.size();
+  std::vector<float> xyz, xy; std::vector<int32_t> view; std::vector<int64_t> off(1, 0);
+  for (int64_t i = 0; i < n; i++) {
+    xyz.push_back(sfmd.points_[i][0]); xyz.push_back(sfmd.points_[i][1]); xyz.push_back(sfmd.points_[i][2]);
+    for (size_t k = 0; k < sfmd.camViewingPointN_[i].size(); k++) {
+      view.push_back(sfmd.camViewingPointN_[i][k]);
+      xy.push_back(sfmd.point2DoncamViewingPoint_[i][k][0]); xy.push_back(sfmd.point2DoncamViewingPoint_[i][k][1]);
+    }
+    off.push_back((int64_t)view.size());
+  }
+  std::vector<uint8_t> inl((size_t)n);
+  check(eg3d_filter(scene.handle(), n, xyz.data(), off.data(), view.data(), xy.data(), first_edgepoint, gn_max_mse, forced_min_filter, inl.data(), nullptr));
+  SfMData res;   // removeOutliers, outliers_filtering.cpp:66-92
+  res.camerasList_ = sfmd.camerasList_; res.numCameras_ = sfmd.numCameras_; res.imageWidth_ = sfmd.imageWidth_; res.imageHeight_ = sfmd.imageHeight_;
+  res.pointsVisibleFromCamN_.resize(res.numCameras_);
+  int cur = 0;
+  for (int64_t i = 0; i < n; i++) if (inl[i]) {
+    res.points_.push_back(vec3(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]));   // GN inliers carry the refined position (gauss_newton.cpp:168-173)
+    res.camViewingPointN_.push_back(sfmd.camViewingPointN_[i]); res.point2DoncamViewingPoint_.push_back(sfmd.point2DoncamViewingPoint_[i]);
+    for (int cam : sfmd.camViewingPointN_[i]) res.pointsVisibleFromCamN_[cam].push_back(cur);
+    cur++;
+  }
+  res.numPoints_ = (int)res.points_.size();
+  sfmd = res;
+}
+
+}  // namespace eg3d_shim
