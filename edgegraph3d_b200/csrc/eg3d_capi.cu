@@ -57,7 +57,7 @@ struct eg3d_scene {
   int device = 0; cudaStream_t stream = nullptr;
   int V = 0, width = 0, height = 0, num_sms = 0;
   eg3d_params prm;
-  DBuf<float> P; DBuf<double> P64; DBuf<double> F; DBuf<uint8_t> Fvalid;
+  DBuf<float> P; DBuf<double> P64; DBuf<double> F; DBuf<double> Fp; DBuf<uint8_t> Fvalid;
   DBuf<int> view_poly_off, poly_vert_off, view_seg_off, poly_seg_off;
   DBuf<float2> verts; DBuf<uint32_t> poly_start, poly_end;
   DBuf<float4> seg; DBuf<uint2> seg_id;
@@ -127,6 +127,39 @@ static void build_grid(const eg3d_scene& sc, float cell, HostGrid& g) {
       g.off[(size_t)v * ncell + c + 1] = (int)g.ids.size();
     }
   }
+}
+
+// Fundamental matrices of the cameras themselves: F_ji = (-1)^(i+j) det[ rows of P_a without i ; rows of P_b without j ]
+// (Hartley & Zisserman, Multiple View Geometry, eq. 17.3), so that x_b^T F x_a = 0 for the projections of any X.
+static double det4(const double m[4][4]) {
+  double d = 0;
+  for (int c = 0; c < 4; c++) {
+    double sub[3][3];
+    for (int i = 1; i < 4; i++) { int cc = 0; for (int j = 0; j < 4; j++) { if (j == c) continue; sub[i - 1][cc++] = m[i][j]; } }
+    double d3 = sub[0][0] * (sub[1][1] * sub[2][2] - sub[1][2] * sub[2][1]) - sub[0][1] * (sub[1][0] * sub[2][2] - sub[1][2] * sub[2][0]) +
+                sub[0][2] * (sub[1][0] * sub[2][1] - sub[1][1] * sub[2][0]);
+    d += ((c & 1) ? -1.0 : 1.0) * m[0][c] * d3;
+  }
+  return d;
+}
+static void camera_fundamentals(const float* cams, int V, std::vector<double>& Fp) {
+  Fp.assign((size_t)V * V * 9, 0.0);
+  for (int a = 0; a < V; a++)
+    for (int b = 0; b < V; b++) {
+      if (a == b) continue;
+      double* F = &Fp[((size_t)a * V + b) * 9];
+      double nrm = 0;
+      for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++) {
+          double m[4][4]; int r = 0;
+          for (int k = 0; k < 3; k++) if (k != i) { for (int c = 0; c < 4; c++) m[r][c] = (double)cams[(size_t)a * 12 + k * 4 + c]; r++; }
+          for (int k = 0; k < 3; k++) if (k != j) { for (int c = 0; c < 4; c++) m[r][c] = (double)cams[(size_t)b * 12 + k * 4 + c]; r++; }
+          double v = (((i + j) & 1) ? -1.0 : 1.0) * det4(m);
+          F[j * 3 + i] = v; nrm += v * v;
+        }
+      nrm = nrm > 0 ? 1.0 / sqrt(nrm) : 1.0;
+      for (int k = 0; k < 9; k++) F[k] *= nrm;
+    }
 }
 
 static eg3d_status require_device() {
@@ -264,6 +297,9 @@ static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_o
   a.o_X = uX.p; a.o_nobs = unobs.p; a.o_obase = uobase.p;
   a.ob_view = uv.p; a.ob_pl = upl.p; a.ob_seg = useg.p; a.ob_x = ux.p; a.ob_y = uy.p;
   a.seed_npts = snp.p; a.seed_pbase = spb.p; a.seed_nobs = sno.p;
+  DBuf<unsigned long long> prof;
+  const bool do_prof = getenv("EG3D_K3_PROF") != nullptr;
+  if (do_prof) { CK(prof.alloc(16)); CK(cudaMemsetAsync(prof.p, 0, 16 * sizeof(unsigned long long), sc->stream)); a.prof = prof.p; }
   Timer t3(sc->stream), tp(sc->stream);
   t3.start();
   k3_chain_kernel<<<nblocks, K3_THREADS, 0, sc->stream>>>(sc->dev, a);
@@ -273,6 +309,12 @@ static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_o
   CK(cudaMemcpyAsync(cnt, oc4.p, sizeof cnt, cudaMemcpyDeviceToHost, sc->stream));
   CK(cudaStreamSynchronize(sc->stream));
   if (tm) { tm->k3_ms += t3.ms(); tm->kernel_launches += 1; tm->n_capacity_overflows += (int)(cnt[2] + cnt[3]); }
+  if (do_prof) {
+    unsigned long long pr[16]; CK(cudaMemcpy(pr, prof.p, sizeof pr, cudaMemcpyDeviceToHost));
+    const char* nm[12] = {"A.scan+prune", "A.est3", "A.plg_compatible", "B.epc_prune", "B.epc_gn", "B.add_view_finish(epc)", "B.main_loop", "seed_total", "#est3_lanes", "#est3_rounds", "#plg_compat", "#epc_solved"};
+    for (int k = 0; k < 12; k++) fprintf(stderr, "[k3prof] %-26s %14llu%s\n", nm[k], pr[k], k < 8 ? " warp-cycles" : "");
+    fprintf(stderr, "[k3prof] max seed cycles %llu (%.1f ms at 1.9 GHz); seeds > 50M cycles: %llu; > 200M cycles: %llu\n", pr[12], pr[12] / 1.9e6, pr[13], pr[14]);
+  }
   if (cnt[3]) return fail(EG3D_ERR_CAPACITY, "accepted-point output buffer exceeded (internal bound); split the seed batch");
   if (cnt[2]) return fail(EG3D_ERR_CAPACITY, "a per-seed capacity (max_chain_points / max_follow_points / observations per point) was exceeded; raise eg3d_params capacities");
   // ordered packing
@@ -367,6 +409,10 @@ static void k1_accounting(const eg3d_scene* sc, const eg3d_seeds* seeds, const e
 extern "C" {
 
 const char* eg3d_last_error(void) { return g_err.c_str(); }
+void eg3d_camera_fundamentals(const float* cameras, int32_t n_views, double* out) {
+  std::vector<double> fp; camera_fundamentals(cameras, n_views, fp);
+  memcpy(out, fp.data(), fp.size() * sizeof(double));
+}
 int eg3d_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
 void eg3d_params_default(eg3d_params* p) {
@@ -428,6 +474,7 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   CK(sc->P.upload(d->cameras, (size_t)V * 12, s));
   { std::vector<double> p64((size_t)V * 12); for (size_t i = 0; i < p64.size(); i++) p64[i] = (double)d->cameras[i]; CK(sc->P64.upload(p64, s)); CK(cudaStreamSynchronize(s)); }
   CK(sc->F.upload(d->fundamental, (size_t)V * V * 9, s));
+  { std::vector<double> fp; camera_fundamentals(d->cameras, V, fp); CK(sc->Fp.upload(fp, s)); CK(cudaStreamSynchronize(s)); }
   CK(sc->Fvalid.upload(d->fundamental_valid, (size_t)V * V, s));
   CK(sc->view_poly_off.upload(sc->h_view_poly_off, s)); CK(sc->poly_vert_off.upload(sc->h_poly_vert_off, s));
   CK(sc->verts.upload(sc->h_verts, s)); CK(sc->poly_start.upload(sc->h_start, s)); CK(sc->poly_end.upload(sc->h_end, s));
@@ -446,7 +493,7 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   CK(cudaStreamSynchronize(s));
   DevScene& D = sc->dev; memset(&D, 0, sizeof D);
   D.V = V; D.width = sc->width; D.height = sc->height;
-  D.P = sc->P.p; D.P64 = sc->P64.p; D.F = sc->F.p; D.Fvalid = sc->Fvalid.p;
+  D.P = sc->P.p; D.P64 = sc->P64.p; D.F = sc->F.p; D.Fp = sc->Fp.p; D.Fvalid = sc->Fvalid.p;
   D.view_poly_off = sc->view_poly_off.p; D.poly_vert_off = sc->poly_vert_off.p; D.verts = sc->verts.p;
   D.poly_start = sc->poly_start.p; D.poly_end = sc->poly_end.p;
   D.view_seg_off = sc->view_seg_off.p; D.seg = sc->seg.p; D.seg_id = sc->seg_id.p; D.poly_seg_off = sc->poly_seg_off.p;

@@ -30,6 +30,8 @@ struct DevScene {
   const float* P;               // [V][12]
   const double* P64;            // [V][12] the same matrices widened once (triangulation.cpp:301-306 converts per call)
   const double* F;              // [V*V][9]
+  const double* Fp;             // [V*V][9] fundamental matrices derived from the cameras P themselves (exact two-view geometry of
+                                //          the GN problems; the input F may come from LMedS and is NOT used for pruning)
   const uint8_t* Fvalid;        // [V*V]
   const int* view_poly_off;     // [V+1]
   const int* poly_vert_off;     // [NP+1]
@@ -468,16 +470,38 @@ EG3D_D int gn_update(const GnAcc& a, int n, const eg3d_params& prm, double& last
   return 0;
 }
 
-// Observation source shared by every multi-observation GN call of K3: observation q is entry idx[q] (or q when idx is
-// null) of the arrays (v, x, y) for q < n, followed by one optional extra observation (q == n).
+// ---------------------------------------------------------------------------------------------------------------
+// Exact-safe pruning of hopeless Gauss-Newton problems.
+// em_GaussNewton accepts iff last_mse < 9 (triangulation.cpp:168) where last_mse is the mean squared residual at one of
+// its iterates, hence >= the global minimum over X, hence >= (minimal cost of ANY two of the observations) / (2n).
+// For two observations pa (view a), pb (view b) every X reprojects to (qa, qb) with qb on the epipolar line F qa of the
+// cameras' own geometry (Fp), so the 2-view cost is >= min_t [ t^2 + dist(pb, line(F(pa + d)))^2 ], |d| = t.  With
+// s0 = pb~^T F pa~, g = |(F^T pb~)_xy|, n0 = |(F pa~)_xy|, h = |F[0:2,0:2]|_F:
+//   dist >= (|s0| - g t) / (n0 + h t)   (numerator falls, denominator grows with t)
+// so cost >= min(T^2, ((|s0| - g T)/(n0 + h T))^2) for any T.  If that is >= budget = accept_mse * 2n (with a safety
+// margin for rounding) the solve cannot be accepted and is skipped; a rejected solve has no side effects in the
+// reference, so results are unchanged.  (A first-iteration break needs mse < 3e-6 and cannot occur here.)
+EG3D_D bool pair_cannot_fit(const double* __restrict__ F, float2 pa, float2 pb, double T) {
+  const double ax = pa.x, ay = pa.y, bx = pb.x, by = pb.y;
+  const double l0 = F[0] * ax + F[1] * ay + F[2], l1 = F[3] * ax + F[4] * ay + F[5], l2 = F[6] * ax + F[7] * ay + F[8];
+  const double s0 = fabs(bx * l0 + by * l1 + l2);
+  const double n0 = sqrt(l0 * l0 + l1 * l1);
+  const double m0 = F[0] * bx + F[3] * by + F[6], m1 = F[1] * bx + F[4] * by + F[7];
+  const double g = sqrt(m0 * m0 + m1 * m1);
+  const double h = sqrt(F[0] * F[0] + F[1] * F[1] + F[3] * F[3] + F[4] * F[4]);
+  const double num = s0 - g * T;
+  return num > 0 && num >= T * (n0 + h * T);
+}
+EG3D_D double prune_radius(const eg3d_params& prm, int n_obs) {  // T with T^2 = accept_mse * 2n * 1.02
+  return sqrt(prm.gn_accept_mse * (double)(2 * n_obs) * 1.02);
+}
+
+// Observation source shared by every multi-observation GN call of K3: the n observations of the arrays (v, x, y)
+// followed by one optional extra observation.
 struct ObsSrc {
-  const int* v; const float* x; const float* y; const int* idx; int n;
+  const int* v; const float* x; const float* y; int n;
   int has_extra; int ev; float ex, ey;
   EG3D_D int count() const { return n + has_extra; }
-  EG3D_D void get(int q, int& view, float& px, float& py) const {
-    if (q < n) { int s = idx ? idx[q] : q; view = v[s]; px = x[s]; py = y[s]; }
-    else { view = ev; px = ex; py = ey; }
-  }
 };
 
 // Residual / Jacobian / normal-equation accumulation of one observation for the multi-observation solves of K3.
@@ -514,20 +538,28 @@ EG3D_D void gn_accumulate_fast(const double* __restrict__ P, float px, float py,
 // inside the group, so every lane of a group holds the same iterate.  Must be called by all 32 lanes; groups without
 // a problem pass active = false.  Returns the accept decision (last_mse < 9) of the caller's group.
 static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o, bool active, int G, int lane, double X[3]) {
+  // everything the loop needs is pulled into registers first: the structs live in the callers' stack frames
+  const int* __restrict__ ov = o.v;
+  const float* __restrict__ ox = o.x;
+  const float* __restrict__ oy = o.y;
+  const double* __restrict__ P64 = S.P64;
+  const int n = o.n, ntot = o.n + o.has_extra;
   const int sub = lane & (G - 1);
-  const int n = o.count();
+  const bool mine_extra = o.has_extra && (sub == (n & (G - 1)));
+  const int ev = o.ev; const float ex = o.ex, ey = o.ey;
+  const int max_iters = S.prm.gn_max_iters;
+  const double stop = S.prm.gn_stop, det_min = S.prm.gn_det_min, accept = S.prm.gn_accept_mse;
+  double X0 = X[0], X1 = X[1], X2 = X[2];
   double last_mse = 0;
   bool running = active, failed = false;
-  for (int it = 0; it < S.prm.gn_max_iters; it++) {
+  for (int it = 0; it < max_iters; it++) {
     if (!__any_sync(0xffffffffu, running)) break;
     GnAcc a = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (running) {
-#pragma unroll kGnUnroll
-      for (int i = sub; i < n; i += G) {
-        int v; float x, y;
-        o.get(i, v, x, y);
-        gn_accumulate_fast(S.P64 + 12 * v, x, y, X, a);
-      }
+      const double Xl[3] = {X0, X1, X2};
+#pragma unroll 1
+      for (int i = sub; i < n; i += G) gn_accumulate_fast(P64 + 12 * ov[i], ox[i], oy[i], Xl, a);
+      if (mine_extra) gn_accumulate_fast(P64 + 12 * ev, ex, ey, Xl, a);
     }
 #pragma unroll 1
     for (int off = G >> 1; off > 0; off >>= 1) {
@@ -539,12 +571,24 @@ static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o,
       a.g2 += __shfl_xor_sync(0xffffffffu, a.g2, off);
     }
     if (running) {
-      int r = gn_update(a, n, S.prm, last_mse, X);
-      if (r == 1) running = false;
-      else if (r == -1) { running = false; failed = true; }
+      const double cur = a.mse / (ntot * 2);
+      if (fabs(cur - last_mse) < stop) running = false;
+      else {
+        last_mse = cur;
+        const double H[9] = {a.h00, a.h01, a.h02, a.h01, a.h11, a.h12, a.h02, a.h12, a.h22};
+        const double d = det3d(H);
+        if (d < det_min) { running = false; failed = true; }
+        else {
+          double Hi[9]; inv3d(H, d, Hi);
+          X0 += Hi[0] * a.g0 + Hi[1] * a.g1 + Hi[2] * a.g2;
+          X1 += Hi[3] * a.g0 + Hi[4] * a.g1 + Hi[5] * a.g2;
+          X2 += Hi[6] * a.g0 + Hi[7] * a.g1 + Hi[8] * a.g2;
+        }
+      }
     }
   }
-  return active && !failed && last_mse < S.prm.gn_accept_mse;
+  X[0] = X0; X[1] = X1; X[2] = X2;
+  return active && !failed && last_mse < accept;
 }
 
 // lanes per problem for `p` (1..32) simultaneous problems

@@ -42,6 +42,7 @@ struct K3Args {
   float* o_X; int* o_nobs; int64_t* o_obase;
   int* ob_view; uint32_t* ob_pl; uint32_t* ob_seg; float* ob_x; float* ob_y;
   int* seed_npts; int64_t* seed_pbase; int64_t* seed_nobs;
+  unsigned long long* prof;   // optional [16] per-phase warp-cycle / event counters (null = off)
 };
 
 struct WS {  // per-warp scratch view
@@ -52,6 +53,7 @@ struct WS {  // per-warp scratch view
   NTmp *tmp1, *tmp2;                               // [capc]
   int* idx;                                        // [oc] scratch index list (combination fallback)
   unsigned char* selmask;                          // [oc]
+  int* tq;                                         // [3*64] queue of triples that survived pruning
   int capf, capc, oc;
 };
 
@@ -59,11 +61,12 @@ inline __host__ __device__ size_t k3_align(size_t x) { return (x + 15) & ~(size_
 inline __host__ __device__ size_t k3_scratch_bytes(int V, int capf, int capc, int oc) {
   size_t b = 0;
   b += k3_align(sizeof(Pt3) * (size_t)capf * 8);
-  b += k3_align(sizeof(int) * (size_t)capc * oc) * 5;
+  b += k3_align(sizeof(int) * (size_t)(capc + 1) * oc) * 5;
   b += k3_align(sizeof(float) * 3 * capc) + k3_align(sizeof(int) * capc) * 2;
   b += k3_align(sizeof(uint32_t) * V) * 2;
   b += k3_align(sizeof(NTmp) * capc) * 2;
   b += k3_align(sizeof(int) * oc) + k3_align(oc);
+  b += k3_align(sizeof(int) * 3 * 64);
   return b;
 }
 EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
@@ -71,11 +74,11 @@ EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
   auto take = [&](size_t bytes) { unsigned char* p = base + o; o += k3_align(bytes); return p; };
   Pt3* p3 = (Pt3*)take(sizeof(Pt3) * (size_t)capf * 8);
   w.tri = p3; w.D1 = p3 + 4 * capf; w.D2 = p3 + 5 * capf; w.fD1 = p3 + 6 * capf; w.fD2 = p3 + 7 * capf;
-  w.ov = (int*)take(sizeof(int) * (size_t)capc * oc);
-  w.opl = (uint32_t*)take(sizeof(int) * (size_t)capc * oc);
-  w.oseg = (uint32_t*)take(sizeof(int) * (size_t)capc * oc);
-  w.ox = (float*)take(sizeof(int) * (size_t)capc * oc);
-  w.oy = (float*)take(sizeof(int) * (size_t)capc * oc);
+  w.ov = (int*)take(sizeof(int) * (size_t)(capc + 1) * oc);
+  w.opl = (uint32_t*)take(sizeof(int) * (size_t)(capc + 1) * oc);
+  w.oseg = (uint32_t*)take(sizeof(int) * (size_t)(capc + 1) * oc);
+  w.ox = (float*)take(sizeof(int) * (size_t)(capc + 1) * oc);
+  w.oy = (float*)take(sizeof(int) * (size_t)(capc + 1) * oc);
   w.sX = (float*)take(sizeof(float) * 3 * capc);
   w.snobs = (int*)take(sizeof(int) * capc);
   w.order = (int*)take(sizeof(int) * capc);
@@ -85,6 +88,7 @@ EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
   w.tmp2 = (NTmp*)take(sizeof(NTmp) * capc);
   w.idx = (int*)take(sizeof(int) * oc);
   w.selmask = (unsigned char*)take(oc);
+  w.tq = (int*)take(sizeof(int) * 3 * 64);
   w.capf = capf; w.capc = capc; w.oc = oc;
   return w;
 }
@@ -93,6 +97,7 @@ EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
 // per-seed context (registers; identical in every lane)
 struct Ctx {
   const DevScene* S; const K3Args* A; WS w;
+  long long pc[12];   // profiling accumulators
   int lane, seed, sv;
   int sel[3];
   int len;         // chain length
@@ -101,9 +106,13 @@ struct Ctx {
   bool overflow;
 };
 
+#define K3P_BEGIN(t) long long t = clock64()
+#define K3P_END(c, slot, t) (c).pc[slot] += clock64() - (t)
+
 // 3-view compatible, plg_matching.cpp:51-132.  cur / next: (pl, seg, c) per view a,b,c in sel order.
 struct Cur3 { uint32_t pl[3], seg[3]; float2 c[3]; };
-static __device__ __noinline__ bool step3(const DevScene& S, const int ids[3], const Cur3& cur, const uint32_t dir[3], Cur3& next, float X[3]) {
+// geometry of the 3-view step (plg_matching.cpp:66-108): 10 px along polyline a, epipolar walks on b and c
+static __device__ __noinline__ bool geo3(const DevScene& S, const int ids[3], const Cur3& cur, const uint32_t dir[3], Cur3& next) {
   Pl pla = get_pl(S, ids[0], cur.pl[0]), plb = get_pl(S, ids[1], cur.pl[1]), plc = get_pl(S, ids[2], cur.pl[2]);
   bool reached;
   PlP ia; ia.seg = cur.seg[0]; ia.c = cur.c[0];
@@ -118,12 +127,16 @@ static __device__ __noinline__ bool step3(const DevScene& S, const int ids[3], c
   PlP ic; ic.seg = cur.seg[2]; ic.c = cur.c[2];
   PlP nc;
   if (!walk_line(plc, ic, dir[2], l, S.prm, false, nc)) return false;
-  float2 pts[3] = {na.c, nb.c, nc.c};
-  if (!est3(S, ids, pts, X)) return false;
   next.pl[0] = cur.pl[0]; next.pl[1] = cur.pl[1]; next.pl[2] = cur.pl[2];
   next.seg[0] = na.seg; next.seg[1] = nb.seg; next.seg[2] = nc.seg;
   next.c[0] = na.c; next.c[1] = nb.c; next.c[2] = nc.c;
   return true;
+}
+// 3-view compatible, plg_matching.cpp:51-132
+static __device__ __noinline__ bool step3(const DevScene& S, const int ids[3], const Cur3& cur, const uint32_t dir[3], Cur3& next, float X[3]) {
+  if (!geo3(S, ids, cur, dir, next)) return false;
+  float2 pts[3] = {next.c[0], next.c[1], next.c[2]};
+  return est3(S, ids, pts, X);
 }
 
 EG3D_D void store_pt3(Pt3* dst, const Cur3& c, const float X[3]) {
@@ -135,33 +148,75 @@ EG3D_D void store_pt3(Pt3* dst, const Cur3& c, const float X[3]) {
   *dst = p;
 }
 
-// find_direction_given_first_extreme, plg_matching.cpp:142-203: the four (end_b, end_c) combos advance in lock-step,
-// one combo per lane; the last survivor wins.  Returns the number of points (0 = fail) copied into `dst`.
+// est3 of a stored 3-view candidate (views = sel[perm[i]]); writes X on success
+EG3D_D bool est_pt3(const DevScene& S, const int sel[3], Pt3* p) {
+  int v[3] = {sel[p->perm[0]], sel[p->perm[1]], sel[p->perm[2]]};
+  float2 pt[3] = {make_float2(p->cx[0], p->cy[0]), make_float2(p->cx[1], p->cy[1]), make_float2(p->cx[2], p->cy[2])};
+  float X[3];
+  if (!est3(S, v, pt, X)) return false;
+  p->X[0] = X[0]; p->X[1] = X[1]; p->X[2] = X[2];
+  return true;
+}
+
+// find_direction_given_first_extreme, plg_matching.cpp:142-203: the four (end_b, end_c) combos advance in lock-step and
+// the last survivor wins.  A combo's fate depends only on its own chain, and the triangulated X of a step only gates
+// validity (the next 2D step starts from the 2D points), so: lanes 0..3 walk their combo's geometry up to 8 steps
+// ahead, the up-to-32 DLT+GN solves of a batch run one per lane, and each combo's lifetime L_k is the number of
+// leading successes.  The lock-step loop `while (amount_of_valid > 1)` ends after round r* = L_(2) + 1 (second-largest
+// lifetime + 1); the survivor (if its lifetime is larger) keeps exactly its first r* points.  Returns the number of
+// points copied into `dst` (0 = fail).
 static __device__ __noinline__ int first_extreme(Ctx& c, const Cur3& start, uint32_t first_dir, uint32_t dir_out[3], Pt3* dst) {
   const DevScene& S = *c.S;
   const int lane = c.lane;
+  constexpr int R = 8;
   Pl plb = get_pl(S, c.sel[1], start.pl[1]), plc = get_pl(S, c.sel[2], start.pl[2]);
   uint32_t dir[3] = {first_dir, (lane & 2) ? plb.end : plb.start, (lane & 1) ? plc.end : plc.start};
-  bool valid = lane < 4;
+  bool alive = lane < 4;
   Cur3 cur = start;
-  int cnt = 0;
+  int L = 0;                                  // successful steps so far (lanes 0..3)
   Pt3* mine = c.w.tri + (size_t)(lane & 3) * c.w.capf;
-  unsigned vm = __ballot_sync(0xffffffffu, valid);
-  while (__popc(vm) > 1) {
-    if (valid) {
-      Cur3 nx; float X[3];
-      if (step3(S, c.sel, cur, dir, nx, X)) {
-        cur = nx;
-        if (cnt < c.w.capf) store_pt3(mine + cnt, nx, X);
-        cnt++;
-      } else valid = false;
+  while (true) {
+    int g = 0;                                // geometric steps of this batch
+    if (alive) {
+      if (L + R > c.w.capf) c.overflow = true;
+      else {
+        for (; g < R; g++) {
+          Cur3 nx;
+          if (!geo3(S, c.sel, cur, dir, nx)) break;
+          float X0[3] = {0.f, 0.f, 0.f};
+          store_pt3(mine + L + g, nx, X0);
+          cur = nx;
+        }
+      }
     }
-    vm = __ballot_sync(0xffffffffu, valid);
-    if (__any_sync(0xffffffffu, cnt > c.w.capf)) { c.overflow = true; return 0; }
+    if (__any_sync(0xffffffffu, c.overflow)) { c.overflow = true; return 0; }
+    __syncwarp();
+    // verification: lane (k*8 + r) solves candidate r of combo k
+    const int kk = lane >> 3, rr = lane & 7;
+    const int gk = __shfl_sync(0xffffffffu, g, kk), Lk = __shfl_sync(0xffffffffu, L, kk);
+    bool ok = false;
+    if (rr < gk) ok = est_pt3(S, c.sel, c.w.tri + (size_t)kk * c.w.capf + Lk + rr);
+    unsigned okm = __ballot_sync(0xffffffffu, ok);
+    __syncwarp();
+    if (alive) {
+      unsigned mine_ok = (okm >> (lane * 8)) & 0xffu;
+      int lead = __ffs(~mine_ok) - 1;         // leading successes (8 when all ok)
+      if (lead > g) lead = g;
+      L += lead;
+      if (lead < R) alive = false;            // geometry ended or a solve failed: lifetime is final
+    }
+    unsigned am = __ballot_sync(0xffffffffu, alive);
+    if (__popc(am) <= 1) break;
   }
-  if (vm == 0) return 0;
-  int win = 31 - __clz(vm);
-  int n = __shfl_sync(0xffffffffu, cnt, win);
+  // lifetimes of the four combos
+  int L0 = __shfl_sync(0xffffffffu, L, 0), L1 = __shfl_sync(0xffffffffu, L, 1), L2 = __shfl_sync(0xffffffffu, L, 2), L3 = __shfl_sync(0xffffffffu, L, 3);
+  int Ls[4] = {L0, L1, L2, L3};
+  int win = 0;
+  for (int k = 1; k < 4; k++) if (Ls[k] > Ls[win]) win = k;
+  int second = -1;
+  for (int k = 0; k < 4; k++) if (k != win && Ls[k] > second) second = Ls[k];
+  if (Ls[win] <= second) return 0;            // the best two die in the same round: no survivor
+  const int n = second + 1;                   // rounds executed by the reference's loop
   dir_out[0] = first_dir;
   dir_out[1] = __shfl_sync(0xffffffffu, dir[1], win);
   dir_out[2] = __shfl_sync(0xffffffffu, dir[2], win);
@@ -172,56 +227,87 @@ static __device__ __noinline__ int first_extreme(Ctx& c, const Cur3& start, uint
   return n;
 }
 
-// all-view compatible (plg_matching.cpp:633-759) specialised to a 3-view point: exactly three observations survive or
-// the attempt is skipped; the combination fallback (:708-733) degenerates to the same 3-subset, so it cannot succeed.
-static __device__ __noinline__ bool step_all3(const DevScene& S, const int sel[3], const uint32_t dirs[3], const Pt3& cur, Pt3& out) {
-  for (int si = 0; si < 3; si++) {
-    const int k = cur.perm[si];
-    const int sv = sel[k];
-    Pl pls = get_pl(S, sv, cur.pl[si]);
-    bool reached;
-    PlP ip; ip.seg = cur.seg[si]; ip.c = make_float2(cur.cx[si], cur.cy[si]);
-    PlP ns = step_by_distance(pls, ip, dirs[k], S.prm.follow_first_image_distance, reached);
-    if (reached) continue;
-    int nv = 1;
-    int v[3]; float2 pt[3]; uint32_t opl[3], oseg[3]; uint8_t perm[3];
-    v[0] = sv; pt[0] = ns.c; opl[0] = cur.pl[si]; oseg[0] = ns.seg; perm[0] = (uint8_t)k;
-    for (int i = 0; i < 3; i++) {
-      if (i == si) continue;
-      const int ki = cur.perm[i];
-      const int vv = sel[ki];
-      float3 l;
-      if (!epiline(S, sv, vv, ns.c, l)) continue;
-      Pl pl = get_pl(S, vv, cur.pl[i]);
-      PlP iq; iq.seg = cur.seg[i]; iq.c = make_float2(cur.cx[i], cur.cy[i]);
-      PlP np;
-      if (walk_line(pl, iq, dirs[ki], l, S.prm, true, np)) {
-        v[nv] = vv; pt[nv] = np.c; opl[nv] = cur.pl[i]; oseg[nv] = np.seg; perm[nv] = (uint8_t)ki; nv++;
-      }
+// Geometry of the all-view compatible (plg_matching.cpp:633-706) for a 3-view point and ONE driving view `si`:
+// 10 px on the driving view, bounded epipolar walks on the other two.  Exactly three observations must survive
+// (fewer => the attempt is skipped, :708-709); the combination fallback (:715-733) degenerates to the same 3-subset
+// and cannot succeed, so a failed solve simply moves on to the next driving view.
+static __device__ __noinline__ bool geo_all3(const DevScene& S, const int sel[3], const uint32_t dirs[3], const Pt3& cur, int si, Pt3& out) {
+  const int k = cur.perm[si];
+  const int sv = sel[k];
+  Pl pls = get_pl(S, sv, cur.pl[si]);
+  bool reached;
+  PlP ip; ip.seg = cur.seg[si]; ip.c = make_float2(cur.cx[si], cur.cy[si]);
+  PlP ns = step_by_distance(pls, ip, dirs[k], S.prm.follow_first_image_distance, reached);
+  if (reached) return false;
+  int nv = 1;
+  out.perm[0] = (uint8_t)k; out.pl[0] = cur.pl[si]; out.seg[0] = ns.seg; out.cx[0] = ns.c.x; out.cy[0] = ns.c.y; out.perm[3] = 0;
+  for (int i = 0; i < 3; i++) {
+    if (i == si) continue;
+    const int ki = cur.perm[i];
+    const int vv = sel[ki];
+    float3 l;
+    if (!epiline(S, sv, vv, ns.c, l)) continue;
+    Pl pl = get_pl(S, vv, cur.pl[i]);
+    PlP iq; iq.seg = cur.seg[i]; iq.c = make_float2(cur.cx[i], cur.cy[i]);
+    PlP np;
+    if (walk_line(pl, iq, dirs[ki], l, S.prm, true, np)) {
+      if (nv < 3) { out.perm[nv] = (uint8_t)ki; out.pl[nv] = cur.pl[i]; out.seg[nv] = np.seg; out.cx[nv] = np.c.x; out.cy[nv] = np.c.y; }
+      nv++;
     }
-    if (nv < 3) continue;
-    float X[3];
-    if (!est3(S, v, pt, X)) continue;
-    out.X[0] = X[0]; out.X[1] = X[1]; out.X[2] = X[2];
-#pragma unroll
-    for (int i = 0; i < 3; i++) { out.perm[i] = perm[i]; out.pl[i] = opl[i]; out.seg[i] = oseg[i]; out.cx[i] = pt[i].x; out.cy[i] = pt[i].y; }
-    out.perm[3] = 0;
-    return true;
   }
-  return false;
+  return nv >= 3;
 }
 
-// follow_direction on a 3-view list, plg_matching.cpp:765-769
+// follow_direction on a 3-view list (plg_matching.cpp:765-769).  Speculative form: the 2D chain is walked ahead with
+// the first driving view whose geometry works at every step, the solves of up to 32 steps run one per lane, and the
+// chain is cut at the first failed solve — where the reference's remaining driving views are then tried in order.
 static __device__ __noinline__ void follow3(Ctx& c, const uint32_t dirs[3], Pt3* list, int& n) {
+  const DevScene& S = *c.S;
+  Pt3* cand = c.w.tri;                        // scratch (first_extreme is done with it)
+  int* si_used = c.w.idx;
   while (true) {
+    int K = 0;
     Pt3 cur = list[n - 1];
-    Pt3 np;
-    if (!step_all3(*c.S, c.sel, dirs, cur, np)) break;
-    if (n >= c.w.capf) { c.overflow = true; break; }
+    for (; K < 32; K++) {
+      Pt3 nx; int si = 0; bool got = false;
+      for (; si < 3; si++) if (geo_all3(S, c.sel, dirs, cur, si, nx)) { got = true; break; }
+      if (!got) break;
+      nx.X[0] = nx.X[1] = nx.X[2] = 0.f;
+      __syncwarp();
+      if (c.lane == 0) { cand[K] = nx; si_used[K] = si; }
+      cur = nx;
+    }
+    if (K == 0) break;
     __syncwarp();
-    if (c.lane == 0) list[n] = np;
+    bool bad = false;
+    if (c.lane < K) bad = !est_pt3(S, c.sel, cand + c.lane);
+    unsigned fm = __ballot_sync(0xffffffffu, bad);
+    const int f = fm ? (__ffs(fm) - 1) : K;
     __syncwarp();
-    n++;
+    if (n + f > c.w.capf) { c.overflow = true; return; }
+    for (int i = c.lane; i < f; i += 32) list[n + i] = cand[i];
+    __syncwarp();
+    n += f;
+    if (f == K) { if (K < 32) break; else continue; }
+    // the solve of step f failed for driving view si_used[f]: the reference goes on with the remaining driving views
+    Pt3 base = list[n - 1];
+    bool found = false;
+    for (int si = si_used[f] + 1; si < 3 && !found; si++) {
+      Pt3 nx;
+      if (!geo_all3(S, c.sel, dirs, base, si, nx)) continue;
+      __syncwarp();
+      if (c.lane == 0) cand[0] = nx;
+      __syncwarp();
+      bool ok = est_pt3(S, c.sel, cand);      // uniform: every lane computes the same solve; identical stores
+      __syncwarp();
+      if (ok) {
+        if (n >= c.w.capf) { c.overflow = true; return; }
+        if (c.lane == 0) list[n] = cand[0];
+        __syncwarp();
+        n++; found = true;
+      }
+    }
+    if (!found) break;
   }
 }
 
@@ -275,7 +361,7 @@ EG3D_D int slot_of(const Ctx& c, int pos) { return c.w.order[pos]; }
 
 EG3D_D ObsSrc slot_obs(const Ctx& c, int slot, int n, bool extra, int ev, float ex, float ey) {
   ObsSrc o; size_t b = (size_t)slot * c.w.oc;
-  o.v = c.w.ov + b; o.x = c.w.ox + b; o.y = c.w.oy + b; o.idx = nullptr; o.n = n;
+  o.v = c.w.ov + b; o.x = c.w.ox + b; o.y = c.w.oy + b; o.n = n;
   o.has_extra = extra ? 1 : 0; o.ev = ev; o.ex = ex; o.ey = ey;
   return o;
 }
@@ -358,20 +444,27 @@ static __device__ __noinline__ bool combos_slot(Ctx& c, int slot, int& n, float 
     }
   }
   if (!got) return false;
-  // 2) greedily add the remaining observations in index order (warm-started GN each)
+  // 2) greedily add the remaining observations in index order (warm-started GN each); the selected observations are
+  //    kept as a compact copy in the spare slot (index capc) in the order they were selected
   __syncwarp();
+  const size_t tb = (size_t)c.w.capc * c.w.oc;
+  int* tv = c.w.ov + tb; float* tx = c.w.ox + tb; float* ty = c.w.oy + tb;
   for (int i = c.lane; i < n; i += 32) c.w.selmask[i] = (i == si || i == sj || i == sk) ? 1 : 0;
-  if (c.lane == 0) { c.w.idx[0] = si; c.w.idx[1] = sj; c.w.idx[2] = sk; }
+  if (c.lane == 0) {
+    tv[0] = ov[si]; tx[0] = ox[si]; ty[0] = oy[si];
+    tv[1] = ov[sj]; tx[1] = ox[sj]; ty[1] = oy[sj];
+    tv[2] = ov[sk]; tx[2] = ox[sk]; ty[2] = oy[sk];
+  }
   __syncwarp();
   int m = 3;
   for (int i = 0; i < n; i++) {
     if (c.w.selmask[i]) continue;
-    ObsSrc obs; obs.v = ov; obs.x = ox; obs.y = oy; obs.idx = c.w.idx; obs.n = m; obs.has_extra = 1; obs.ev = ov[i]; obs.ex = ox[i]; obs.ey = oy[i];
+    ObsSrc obs; obs.v = tv; obs.x = tx; obs.y = ty; obs.n = m; obs.has_extra = 1; obs.ev = ov[i]; obs.ex = ox[i]; obs.ey = oy[i];
     double Xd[3] = {X[0], X[1], X[2]};
     if (gn_group(S, obs, true, 32, c.lane, Xd)) {
       X[0] = (float)Xd[0]; X[1] = (float)Xd[1]; X[2] = (float)Xd[2];
       __syncwarp();
-      if (c.lane == 0) { c.w.selmask[i] = 1; c.w.idx[m] = i; }
+      if (c.lane == 0) { c.w.selmask[i] = 1; tv[m] = ov[i]; tx[m] = ox[i]; ty[m] = oy[i]; }
       __syncwarp();
       m++;
     }
@@ -594,37 +687,86 @@ static __device__ __noinline__ void expand_view(Ctx& c, int v) {
   const eg3d_hit* epcs = c.A->hits + h0;
   bool matched = false; int iv0 = 0, iv1 = 0;
   // the epipolar hits on the central point: one warm-started GN per lane, first complete success in order wins
-  for (int base = 0; base < nh && !matched;) {
-    const int P = min(32, nh - base);
+  // Exact-safe pruning (pair_cannot_fit): a hit whose 2-view cost against one of the central point's observations
+  // already exceeds the acceptance budget of the (n+1)-observation solve cannot be accepted; the survivors keep their
+  // order (the first complete success wins, triangulation.cpp:753-768) and are solved in groups of lanes.
+  int* hq = c.w.tq;                           // bounded queue (<= 63) of surviving hit indices, ascending
+  int nq = 0, enext = 0;
+  while (!matched) {
+    K3P_BEGIN(te0);
+    {
+      const int cslot = slot_of(c, c.central);
+      const int n = c.w.snobs[cslot];
+      const size_t cb = (size_t)cslot * c.w.oc;
+      const double Tp = prune_radius(S.prm, n + 1);
+      const int probe[4] = {0, n / 3, (2 * n) / 3, n - 1};
+      while (nq < 32 && enext < nh) {
+        const int e = enext + c.lane;
+        bool pass = false;
+        if (e < nh) {
+          const float2 hp = make_float2(epcs[e].x, epcs[e].y);
+          pass = true;
+          for (int k = 0; k < 4 && pass; k++) {
+            const int i = probe[k];
+            const int vi = c.w.ov[cb + i];
+            if (vi == v) continue;
+            const double* F = S.Fp + ((size_t)vi * S.V + v) * 9;
+            if (pair_cannot_fit(F, make_float2(c.w.ox[cb + i], c.w.oy[cb + i]), hp, Tp)) pass = false;
+          }
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, pass);
+        if (pass) hq[nq + __popc(pm & ((1u << c.lane) - 1u))] = e;
+        nq += __popc(pm);
+        enext += 32;
+      }
+      __syncwarp();
+    }
+    K3P_END(c, 3, te0);
+    if (nq == 0) break;
+    const int P = nq < 32 ? nq : 32;
+    c.pc[11] += P;
     const int G = gn_group_width(P);
-    const int e = base + c.lane / G;
     const bool active = (c.lane / G) < P;
+    const int e = active ? hq[c.lane / G] : 0;
+    // keep the unsolved tail of the queue
+    const int rest = nq - P;
+    int tail = 0;
+    if (c.lane < rest) tail = hq[P + c.lane];
+    __syncwarp();
+    if (c.lane < rest) hq[c.lane] = tail;
+    nq = rest;
+    __syncwarp();
     const int cslot = slot_of(c, c.central);
     const int n = c.w.snobs[cslot];
     float hx = 0.f, hy = 0.f;
     if (active) { eg3d_hit h = epcs[e]; hx = h.x; hy = h.y; }
     double X[3] = {c.w.sX[3 * cslot], c.w.sX[3 * cslot + 1], c.w.sX[3 * cslot + 2]};
+    K3P_BEGIN(te1);
     bool ok = gn_group(S, slot_obs(c, cslot, n, true, v, hx, hy), active, G, c.lane, X);
+    K3P_END(c, 4, te1);
     float Xe[3] = {(float)X[0], (float)X[1], (float)X[2]};
     unsigned m = __ballot_sync(0xffffffffu, ok && ((c.lane & (G - 1)) == 0));
     while (m && !matched) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
-      eg3d_hit h = epcs[base + b / G];
+      eg3d_hit h = epcs[__shfl_sync(0xffffffffu, e, b)];
       float Xc[3] = {__shfl_sync(0xffffffffu, Xe[0], b), __shfl_sync(0xffffffffu, Xe[1], b), __shfl_sync(0xffffffffu, Xe[2], b)};
       Plg p; p.pl = h.polyline; p.seg = h.segment; p.c = make_float2(h.x, h.y);
       int ns = 0, ne = 0;
       const int cc = c.central;
-      if (add_view_finish(c, v, p, Xc, 0, cc, c.len, ns, ne)) {
+      K3P_BEGIN(te2);
+      const bool avf = add_view_finish(c, v, p, Xc, 0, cc, c.len, ns, ne);
+      K3P_END(c, 5, te2);
+      if (avf) {
         matched = true;
         if (ns > cc) { c.central = ns; iv0 = 0; iv1 = ns + ne; }
         else { iv0 = cc - ns; iv1 = cc + ne; }
       }
       if (c.overflow) return;
     }
-    base += P;
   }
   int last = -1;
+  K3P_BEGIN(te3);
   for (int cur = 0; cur < c.len; cur++) {
     if (matched && cur == iv0) { cur = iv1; last = iv1; continue; }
     const int slot = slot_of(c, cur);
@@ -647,6 +789,7 @@ static __device__ __noinline__ void expand_view(Ctx& c, int v) {
     }
     if (c.overflow) return;
   }
+  K3P_END(c, 6, te3);
 }
 
 // materialise a 3-view point as a chain slot
@@ -701,24 +844,63 @@ static __device__ __noinline__ void process_seed(Ctx& c) {
   int nD1 = 0, nD2 = 0, fn1 = 0, fn2 = 0;
   uint32_t d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0}, fd1[3] = {0, 0, 0}, fd2[3] = {0, 0, 0};
   Cur3 fcentral; float fX[3] = {0, 0, 0};
-  for (long long base = 0; base < total; base += 32) {
-    const long long t = base + lane;
+  // Triples are visited in the reference's nested order (p0 outer, p2 inner).  Each lane first applies the exact-safe
+  // 2-view bound (pair_cannot_fit) to its triple's three view pairs; survivors are queued IN ORDER and solved 32 at a
+  // time, so the sequence of GN-valid hypotheses handed to plg_compatible is the reference's.
+  const double Tp = prune_radius(S.prm, 3);
+  const double* F01 = S.Fp + ((size_t)c.sel[0] * V + c.sel[1]) * 9;
+  const double* F02 = S.Fp + ((size_t)c.sel[0] * V + c.sel[2]) * 9;
+  const double* F12 = S.Fp + ((size_t)c.sel[1] * V + c.sel[2]) * 9;
+  int* tq = c.w.tq;
+  long long tnext = 0;
+  int qn = 0;
+  while (true) {
+    K3P_BEGIN(tp0);
+    while (qn < 32 && tnext < total) {
+      const long long t = tnext + lane;
+      bool pass = false;
+      int i0 = 0, i1 = 0, i2 = 0;
+      if (t < total) {
+        if (total <= 0x7fffffffLL) {
+          const unsigned tu = (unsigned)t, n12 = (unsigned)(n1h * n2h);
+          i0 = (int)(tu / n12);
+          unsigned rem = tu - (unsigned)i0 * n12;
+          i1 = (int)(rem / (unsigned)n2h); i2 = (int)(rem - (unsigned)i1 * (unsigned)n2h);
+        } else {
+          i0 = (int)(t / ((long long)n1h * n2h));
+          long long rem = t - (long long)i0 * n1h * n2h;
+          i1 = (int)(rem / n2h); i2 = (int)(rem - (long long)i1 * n2h);
+        }
+        const float2 q0 = make_float2(h0[i0].x, h0[i0].y), q1 = make_float2(h1[i1].x, h1[i1].y), q2 = make_float2(h2[i2].x, h2[i2].y);
+        pass = !(pair_cannot_fit(F02, q0, q2, Tp) || pair_cannot_fit(F01, q0, q1, Tp) || pair_cannot_fit(F12, q1, q2, Tp));
+      }
+      const unsigned pm = __ballot_sync(0xffffffffu, pass);
+      if (pass) { const int pos = qn + __popc(pm & ((1u << lane) - 1u)); tq[3 * pos] = i0; tq[3 * pos + 1] = i1; tq[3 * pos + 2] = i2; }
+      qn += __popc(pm);
+      tnext += 32;
+    }
+    K3P_END(c, 0, tp0);
+    if (qn == 0) break;
+    __syncwarp();
+    const int take = qn < 32 ? qn : 32;
+    c.pc[8] += take; c.pc[9] += 1;
+    K3P_BEGIN(tp1);
     bool ok = false; float X[3] = {0, 0, 0};
     int i0 = 0, i1 = 0, i2 = 0;
-    if (t < total) {
-      if (total <= 0x7fffffffLL) {
-        const unsigned tu = (unsigned)t, n12 = (unsigned)(n1h * n2h);
-        i0 = (int)(tu / n12);
-        unsigned rem = tu - (unsigned)i0 * n12;
-        i1 = (int)(rem / (unsigned)n2h); i2 = (int)(rem - (unsigned)i1 * (unsigned)n2h);
-      } else {
-        i0 = (int)(t / ((long long)n1h * n2h));
-        long long rem = t - (long long)i0 * n1h * n2h;
-        i1 = (int)(rem / n2h); i2 = (int)(rem - (long long)i1 * n2h);
-      }
+    if (lane < take) {
+      i0 = tq[3 * lane]; i1 = tq[3 * lane + 1]; i2 = tq[3 * lane + 2];
       float2 pts[3] = {make_float2(h0[i0].x, h0[i0].y), make_float2(h1[i1].x, h1[i1].y), make_float2(h2[i2].x, h2[i2].y)};
       ok = est3(S, c.sel, pts, X);
     }
+    K3P_END(c, 1, tp1);
+    // move the not-yet-solved tail of the queue to the front
+    int r0 = 0, r1 = 0, r2 = 0;
+    const int rest = qn - take;
+    if (lane < rest) { r0 = tq[3 * (take + lane)]; r1 = tq[3 * (take + lane) + 1]; r2 = tq[3 * (take + lane) + 2]; }
+    __syncwarp();
+    if (lane < rest) { tq[3 * lane] = r0; tq[3 * lane + 1] = r1; tq[3 * lane + 2] = r2; }
+    qn = rest;
+    __syncwarp();
     unsigned m = __ballot_sync(0xffffffffu, ok);
     while (m) {
       const int b = __ffs(m) - 1;
@@ -730,7 +912,9 @@ static __device__ __noinline__ void process_seed(Ctx& c) {
       cand.pl[0] = a0.polyline; cand.seg[0] = a0.segment; cand.c[0] = make_float2(a0.x, a0.y);
       cand.pl[1] = a1.polyline; cand.seg[1] = a1.segment; cand.c[1] = make_float2(a1.x, a1.y);
       cand.pl[2] = a2.polyline; cand.seg[2] = a2.segment; cand.c[2] = make_float2(a2.x, a2.y);
+      K3P_BEGIN(tp2);
       bool comp = plg_compatible(c, cand, nD1, nD2, d1, d2);
+      K3P_END(c, 2, tp2); c.pc[10] += 1;
       if (c.overflow) return;
       if (comp) {
         if (found) return;  // a second compatible triple: ambiguous, the seed yields nothing (:587-590)
@@ -781,7 +965,16 @@ __global__ void __launch_bounds__(K3_THREADS, EG3D_K3_MIN_BLOCKS) k3_chain_kerne
     if (seed >= A.n_seeds) break;
     c.seed = seed; c.sv = A.seed_view[seed];
     c.len = 0; c.nslots = 0; c.central = 0; c.overflow = false;
+    for (int k = 0; k < 12; k++) c.pc[k] = 0;
+    K3P_BEGIN(tall);
     process_seed(c);
+    K3P_END(c, 7, tall);
+    if (A.prof && lane == 0) {
+      for (int k = 0; k < 12; k++) if (c.pc[k]) atomicAdd(&A.prof[k], (unsigned long long)c.pc[k]);
+      atomicMax(&A.prof[12], (unsigned long long)c.pc[7]);
+      if (c.pc[7] > 50000000ll) atomicAdd(&A.prof[13], 1ull);
+      if (c.pc[7] > 200000000ll) atomicAdd(&A.prof[14], 1ull);
+    }
     __syncwarp();
     int npts = c.overflow ? 0 : c.len;
     long long nobs = 0;

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("EG3D_LIB", os.path.join(_HERE, "libeg3d.so"))  # EG3D
 _lib = None
 
 EXPORTS = [
-    "eg3d_last_error", "eg3d_device_count", "eg3d_params_default", "eg3d_scene_create", "eg3d_scene_destroy",
+    "eg3d_last_error", "eg3d_camera_fundamentals", "eg3d_device_count", "eg3d_params_default", "eg3d_scene_create", "eg3d_scene_destroy",
     "eg3d_sample_seeds", "eg3d_epipolar_intersect", "eg3d_hits_get", "eg3d_hits_free", "eg3d_match_seeds",
     "eg3d_match_polyline_sets", "eg3d_match_refpoints", "eg3d_points_get", "eg3d_points_device_get", "eg3d_points_free", "eg3d_gn_triangulate",
     "eg3d_gn_triangulate_device", "eg3d_dedup_close_points", "eg3d_filter",
@@ -37,6 +37,7 @@ def load():
     L = C.CDLL(LIB_PATH)
     L.eg3d_last_error.restype = C.c_char_p
     L.eg3d_device_count.restype = C.c_int
+    L.eg3d_camera_fundamentals.argtypes = [A.c_f32p, C.c_int32, A.c_f64p]
     L.eg3d_params_default.argtypes = [C.POINTER(A.Params)]
     L.eg3d_scene_create.argtypes = [C.POINTER(A.SceneDesc), C.POINTER(A.Params), C.POINTER(C.c_void_p)]
     L.eg3d_scene_destroy.argtypes = [C.c_void_p]
@@ -73,6 +74,15 @@ def default_params(**overrides):
     for k, v in overrides.items():
         setattr(p, k, v)
     return p
+
+
+def camera_fundamentals(cameras):
+    """F[a][b] with x_b^T F x_a = 0, from the camera matrices alone (host code; used for exact-safe pruning)."""
+    cams = np.ascontiguousarray(cameras, np.float32).reshape(-1, 12)
+    V = cams.shape[0]
+    out = np.zeros((V, V, 9), np.float64)
+    load().eg3d_camera_fundamentals(A.ptr(cams, A.c_f32p), V, A.ptr(out, A.c_f64p))
+    return out
 
 
 def sample_seeds(scene, views, polylines, spacing):

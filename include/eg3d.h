@@ -158,6 +158,10 @@ typedef struct eg3d_points eg3d_points;  /* opaque, host+device resident result 
 typedef struct eg3d_hits   eg3d_hits;    /* opaque */
 
 const char* eg3d_last_error(void);
+/* Fundamental matrices implied by the camera matrices themselves (x_b^T F[a][b] x_a = 0 for the projections of any X):
+ * the role of findFundamentalMatrixFromRt (geometric_utilities.cpp:683-710) for rigs with known poses.  Host code.
+ * cameras [V][12], out [V][V][9] (row-major, unit Frobenius norm, zero on the diagonal). */
+void        eg3d_camera_fundamentals(const float* cameras, int32_t n_views, double* out);
 int         eg3d_device_count(void);
 
 /* Copies the scene to the current CUDA device and builds the derived structures the path reads:
