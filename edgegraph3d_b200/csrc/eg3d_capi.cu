@@ -211,7 +211,7 @@ struct DevSeeds {
   DBuf<int> view; DBuf<uint32_t> pl, seg; DBuf<float2> xy; DBuf<int> cand_set; int n = 0;
   K1Seeds k1() const { K1Seeds s; s.n = n; s.view = view.p; s.pl = pl.p; s.seg = seg.p; s.xy = xy.p; s.cand_set = cand_set.p; return s; }
 };
-struct DevCand { DBuf<int64_t> off; DBuf<uint32_t> pl; };
+struct DevCand { DBuf<int64_t> off; DBuf<uint32_t> pl; DBuf<float2> center; DBuf<float> seed_r2; bool filtered = false; };
 
 static eg3d_status upload_seeds(eg3d_scene* sc, const eg3d_seeds* s, bool need_cand, DevSeeds& d) {
   d.n = (int)s->n;
@@ -233,6 +233,7 @@ static eg3d_status run_k1(eg3d_scene* sc, const DevSeeds& ds, const DevCand* dc,
   K1Seeds ks = ds.k1();
   dim3 grid((ds.n + K1_THREADS - 1) / K1_THREADS, V);
   K1Cand kc; kc.off = dc ? dc->off.p : nullptr; kc.pl = dc ? dc->pl.p : nullptr;
+  kc.center = (dc && dc->filtered) ? dc->center.p : nullptr; kc.seed_r2 = (dc && dc->filtered) ? dc->seed_r2.p : nullptr;
   const int cblocks = (int)((nsv + 255) / 256);
   t1.start();
   if (ds.n > 0) {
@@ -757,9 +758,81 @@ eg3d_status eg3d_filter(eg3d_scene* sc, int64_t n, float* xyz, const int64_t* ob
   return EG3D_OK;
 }
 
-eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t track_begin, int64_t track_end, eg3d_points** out, eg3d_timing* tm) {
-  (void)sc; (void)track_begin; (void)track_end; (void)out; (void)tm;
-  return fail(EG3D_ERR_INVALID_ARG, "eg3d_match_refpoints: not built yet in this revision");
+// B2 / a6: plg_matching_from_refpoints (plg_matching_from_refpoints.cpp:64-104).  Seeding — the polylines within 30 px of
+// every observation (30 px grid), the seeds within 10 px (projection onto the polyline) and the per-seed radius — is
+// O(#observations x few polylines) and runs on the host (plg_edge_manager.cpp:261-288); the epipolar intersections with
+// the radius filter (:191-259) run in k1_cand_kernel, then K3 exactly as for pipelines 1-2
+// (plgpcm_3views_plg_following.cpp:40-50 scatters the per-observing-view lists into a V-vector = the CSR rows).
+eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_points** out, eg3d_timing* tm) {
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  if (!sc || !out) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  if (sc->dev.n_tracks <= 0) return fail(EG3D_ERR_INVALID_ARG, "the scene was created without SfM tracks");
+  if (tb < 0 || te > sc->dev.n_tracks || tb > te) return fail(EG3D_ERR_INVALID_ARG, "track range out of bounds");
+  CK(cudaSetDevice(sc->device));
+  g_alloc_stream = sc->stream;
+  const int V = sc->V;
+  const eg3d_params& prm = sc->prm;
+  DevScene hs; memset(&hs, 0, sizeof hs);
+  hs.V = V; hs.view_poly_off = sc->h_view_poly_off.data(); hs.poly_vert_off = sc->h_poly_vert_off.data();
+  hs.verts = sc->h_verts.data(); hs.poly_start = sc->h_start.data(); hs.poly_end = sc->h_end.data();
+  DevGrid g; g.cell = sc->hg30.cell; g.w = sc->hg30.w; g.h = sc->hg30.h; g.cell_off = sc->hg30.off.data(); g.ids = sc->hg30.ids.data();
+  const float start_dsq = prm.detection_starting_radius * prm.detection_starting_radius;
+  const float corr_d = prm.detection_starting_radius * prm.detection_mult;
+  const float corr_dsq = corr_d * corr_d;
+  const int64_t nt = te - tb;
+  std::vector<int64_t> coff((size_t)nt * V + 1, 0); std::vector<uint32_t> cpl; std::vector<float2> center((size_t)nt * V, make_float2(0.f, 0.f));
+  std::vector<int32_t> sv, scs; std::vector<uint32_t> spl, sseg; std::vector<float> sxy, sr2;
+  struct SeedTmp { uint32_t pl, seg; float2 c; };
+  for (int64_t rp = tb; rp < te; rp++) {
+    const int64_t o0 = sc->h_track_off[rp], no = sc->h_track_off[rp + 1] - o0;
+    const int32_t* views = sc->h_track_view.data() + o0; const float2* xy = sc->h_track_xy.data() + o0;
+    std::vector<std::vector<uint32_t>> pcp(no); std::vector<std::vector<SeedTmp>> sni(no);
+    auto coords_on = [&](int img) { float2 p = make_float2(0.f, 0.f); for (int64_t i = 0; i < no; i++) if (views[i] == img) p = xy[i]; return p; };  // last match wins
+    for (int64_t i = 0; i < no; i++) {
+      const float2 sp = coords_on(views[i]);
+      std::set<uint32_t> ids;
+      grid_visit(g, views[i], sc->width, sc->height, sp, [&](uint32_t id) { ids.insert(id); });
+      for (uint32_t id : ids) {
+        Pl pl = get_pl(hs, views[i], id);
+        uint32_t cs; float2 proj;
+        const float dsq = pl_distancesq(pl, sp, cs, proj);
+        if (dsq <= start_dsq) { pcp[i].push_back(id); sni[i].push_back(SeedTmp{id, cs, proj}); }
+        else if (dsq <= corr_dsq) pcp[i].push_back(id);
+      }
+    }
+    // candidate CSR rows of this refpoint: (refpoint, view) -> pcp of the observation in that view
+    const size_t row0 = (size_t)(rp - tb) * V;
+    std::vector<const std::vector<uint32_t>*> byview(V, nullptr);
+    for (int64_t j = 0; j < no; j++) { byview[views[j]] = &pcp[j]; center[row0 + views[j]] = xy[j]; }
+    for (int v = 0; v < V; v++) {
+      if (byview[v]) cpl.insert(cpl.end(), byview[v]->begin(), byview[v]->end());
+      coff[row0 + v + 1] = (int64_t)cpl.size();
+    }
+    for (int64_t i = 0; i < no; i++) {
+      const float2 init = coords_on(views[i]);
+      for (const auto& sd : sni[i]) {
+        const float radius = dist2(init, sd.c) * prm.detection_mult;   // plg_edge_manager.cpp:254
+        sv.push_back(views[i]); scs.push_back((int32_t)(rp - tb)); spl.push_back(sd.pl); sseg.push_back(sd.seg);
+        sxy.push_back(sd.c.x); sxy.push_back(sd.c.y); sr2.push_back(radius * radius);
+      }
+    }
+  }
+  eg3d_timing local; memset(&local, 0, sizeof local);
+  eg3d_seeds seeds; seeds.n = (int64_t)sv.size(); seeds.view = sv.data(); seeds.polyline = spl.data(); seeds.segment = sseg.data();
+  seeds.xy = sxy.data(); seeds.cand_set = scs.data();
+  DevSeeds ds; st = upload_seeds(sc, &seeds, true, ds); if (st != EG3D_OK) return st;
+  DevCand dc; dc.filtered = true;
+  CK(dc.off.upload(coff, sc->stream)); CK(dc.pl.upload(cpl, sc->stream)); CK(dc.center.upload(center, sc->stream)); CK(dc.seed_r2.upload(sr2, sc->stream));
+  DBuf<int64_t> off; DBuf<eg3d_hit> hits; int64_t nh = 0;
+  st = run_k1(sc, ds, &dc, off, hits, nh, &local); if (st != EG3D_OK) return st;
+  std::unique_ptr<eg3d_points> pts(new eg3d_points());
+  st = run_k3(sc, ds, off.p, hits.p, pts.get(), &local);
+  local.n_seeds = seeds.n;
+  local.total_ms = local.k1_count_ms + local.scan_ms + local.k1_fill_ms + local.k3_ms + local.pack_ms;
+  if (tm) *tm = local;
+  if (st != EG3D_OK) return st;
+  *out = pts.release();
+  return EG3D_OK;
 }
 
 }  // extern "C"

@@ -136,7 +136,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_const
   }
 }
 
-struct K1Cand { const int64_t* off; const uint32_t* pl; };
+// center/seed_r2 (optional): the refpoint variant keeps a hit only within radius 3*|obs - seed| of that view's own
+// observation of the SfM point (plg_edge_manager.cpp:191-205, :246-259)
+struct K1Cand { const int64_t* off; const uint32_t* pl; const float2* center; const float* seed_r2; };
 
 template <bool FILL>
 __global__ void __launch_bounds__(256) k1_cand_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K1Seeds seeds, const __grid_constant__ K1Cand cand, int64_t* __restrict__ counts,
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(256) k1_cand_kernel(const __grid_constant__ De
           float4 sg = S.seg[s];
           float2 inter;
           if (isect_seg_line(sg.x, sg.y, sg.z, sg.w, l, inter)) {
+            if (cand.center && !(sqdist2(cand.center[ci], inter) <= cand.seed_r2[sidx])) continue;
             if (FILL) { uint2 id = S.seg_id[s]; eg3d_hit h; h.polyline = id.x; h.segment = id.y; h.x = inter.x; h.y = inter.y; hits[obase + cnt] = h; }
             cnt++;
           }

@@ -1,0 +1,71 @@
+"""Multi-GPU plumbing of the hot path: shard planning and the one exchange step.
+
+The path shards by independent units (seeds): ranks own contiguous blocks of STARTING VIEWS (the reference's outer loop,
+polyline_matching.cpp:162) or of SfM point ids (plg_matching_from_refpoints.cpp:90) and hold the full read-only scene.
+The only exchange is one all-gather of the accepted records before the order-dependent density limiter and the filter;
+concatenating the shards in rank order reproduces the reference's loop order, so any GPU count gives identical results.
+torch.distributed is plumbing here (NCCL over NVLink on GPUs; the same code runs on gloo/CPU tensors in the tests).
+"""
+import numpy as np
+from .scene import PointSet
+
+
+def view_block(n_views, world_size, rank):
+    """Contiguous block of starting views owned by `rank`."""
+    return (rank * n_views) // world_size, ((rank + 1) * n_views) // world_size
+
+
+def balanced_view_blocks(seeds_per_view, world_size):
+    """Contiguous view blocks with (nearly) equal seed counts: prefix sums over the per-view seed counts."""
+    c = np.concatenate([[0], np.cumsum(np.asarray(seeds_per_view, np.int64))])
+    total = int(c[-1])
+    cuts = [0]
+    for r in range(1, world_size):
+        cuts.append(int(np.searchsorted(c, total * r / world_size, side="left")))
+    cuts.append(len(seeds_per_view))
+    cuts = np.maximum.accumulate(np.minimum(cuts, len(seeds_per_view)))
+    return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world_size)]
+
+
+_FIELDS = (("xyz", np.float32, 3), ("seed", np.int32, 1), ("chain_pos", np.int32, 1), ("obs_view", np.int32, 1),
+           ("obs_poly", np.uint32, 1), ("obs_seg", np.uint32, 1), ("obs_xy", np.float32, 2))
+
+
+def all_gather_points(local, dist, device=None, seed_offset_by_rank=True):
+    """All-gather a PointSet over the default process group; returns the concatenation in rank order on every rank.
+
+    `local` holds this rank's accepted points (host numpy arrays); tensors are staged on `device` (cuda for NCCL, cpu for
+    gloo).  Seed ordinals are made global by adding the number of seeds... callers that need global ordinals pass seeds
+    already offset; here only the point records travel.  One count all-gather + one padded all-gather per field.
+    """
+    import torch
+    world = dist.get_world_size()
+    dev = device if device is not None else "cpu"
+    lens = np.diff(local.obs_off).astype(np.int64)
+    cnt = torch.tensor([local.n_points, local.n_obs], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    cnts = torch.stack(cnts).cpu().numpy()
+    maxn, maxm = int(cnts[:, 0].max()), int(cnts[:, 1].max())
+
+    def gather(arr, rows, width, dtype):
+        pad = np.zeros((rows, width), dtype)
+        a = np.asarray(arr, dtype).reshape(-1, width)
+        pad[:a.shape[0]] = a
+        t = torch.from_numpy(pad.view(np.uint8).reshape(-1).copy()).to(dev)
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return [o.cpu().numpy().view(dtype).reshape(rows, width) for o in outs]
+
+    got = {}
+    for name, dt, w in _FIELDS:
+        rows = maxm if name.startswith("obs_") else maxn
+        got[name] = gather(getattr(local, name), rows, w, dt)
+    got_len = gather(lens, maxn, 1, np.int64)
+    parts = []
+    for r in range(world):
+        n, m = int(cnts[r, 0]), int(cnts[r, 1])
+        off = np.concatenate([[0], np.cumsum(got_len[r][:n, 0])]).astype(np.int64)
+        parts.append(PointSet(got["xyz"][r][:n], got["seed"][r][:n, 0], got["chain_pos"][r][:n, 0], off,
+                              got["obs_view"][r][:m, 0], got["obs_poly"][r][:m, 0], got["obs_seg"][r][:m, 0], got["obs_xy"][r][:m]))
+    return PointSet.concat(parts), cnts

@@ -1,0 +1,47 @@
+// Compile/link check of the header-only reference-API shim against libeg3d.so (stand-alone types).
+// With a CUDA device it runs pipelines 1-2 on a toy scene; without one it checks the loud EG3D_ERR_NO_DEVICE failure.
+#include <cstdio>
+#include <cmath>
+#include "eg3d_ref_api.hpp"
+using namespace eg3d_shim;
+
+int main() {
+  const int V = 3;
+  SfMData sfmd; sfmd.numCameras_ = V; sfmd.imageWidth_ = 640; sfmd.imageHeight_ = 480; sfmd.camerasList_.resize(V);
+  std::vector<PolyLineGraph2DHMapImpl> plgs(V);
+  for (int v = 0; v < V; v++) {
+    float ang = 0.3f * (v - 1), cs = std::cos(ang), sn = std::sin(ang);
+    float R[3][3] = {{cs, 0, -sn}, {0, 1, 0}, {sn, 0, cs}}, C[3] = {4 * sn, 0, -4 * cs}, K[3][3] = {{500, 0, 320}, {0, 500, 240}, {0, 0, 1}};
+    for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) sfmd.camerasList_[v].cameraMatrix[r][c] = 0;
+    for (int r = 0; r < 3; r++) {
+      float Rt[4] = {R[r][0], R[r][1], R[r][2], -(R[r][0] * C[0] + R[r][1] * C[1] + R[r][2] * C[2])};
+      for (int k = 0; k < 3; k++) for (int c = 0; c < 4; c++) sfmd.camerasList_[v].cameraMatrix[k][c] += K[k][r] * Rt[c];
+    }
+    PolyLineGraph2D::polyline pl; pl.start = 0; pl.end = 1;
+    for (int i = 0; i <= 30; i++) {   // a 3D line segment seen by every view
+      float X[3] = {-0.5f + i / 30.0f, 0.2f * std::sin(i * 0.2f), 0.1f * i / 30.0f};
+      const mat4& P = sfmd.camerasList_[v].cameraMatrix;
+      float h[3]; for (int r = 0; r < 3; r++) h[r] = P[r][0] * X[0] + P[r][1] * X[1] + P[r][2] * X[2] + P[r][3];
+      pl.polyline_coords.push_back(vec2(h[0] / h[2], h[1] / h[2]));
+    }
+    plgs[v].polylines.push_back(pl);
+  }
+  std::vector<double> fp((size_t)V * V * 9);
+  std::vector<float> cams((size_t)V * 12);
+  for (int v = 0; v < V; v++) for (int r = 0; r < 3; r++) for (int c = 0; c < 4; c++) cams[v * 12 + r * 4 + c] = sfmd.camerasList_[v].cameraMatrix[r][c];
+  eg3d_camera_fundamentals(cams.data(), V, fp.data());
+  FundamentalSet F(V);
+  for (int a = 0; a < V; a++) for (int b = 0; b < V; b++) if (a != b) F.set(a, b, &fp[((size_t)a * V + b) * 9]);
+  try {
+    Eg3dScene scene(sfmd, plgs, F);
+    std::vector<std::vector<std::set<ulong_t>>> matches(1, std::vector<std::set<ulong_t>>(V));
+    for (int v = 0; v < V; v++) matches[0][v].insert(0);
+    auto pts = find_new_3d_points_from_compatible_polylines_expandallviews_parallel(scene, matches);
+    auto kept = filter_3d_points_close_2d_array(scene, pts);
+    std::printf("shim ok: %zu points, %zu after the density limiter\n", pts.size(), kept.size());
+    return pts.empty() ? 2 : 0;
+  } catch (const std::exception& e) {
+    std::printf("shim: %s\n", e.what());
+    return eg3d_device_count() == 0 ? 0 : 3;   // without a device the loud failure is the expected behaviour
+  }
+}

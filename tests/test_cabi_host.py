@@ -49,3 +49,15 @@ def test_no_cpu_fallback_without_device():
     with pytest.raises(E.Eg3dError) as ei:
         E.DeviceScene(sc)
     assert ei.value.status == A.EG3D_ERR_NO_DEVICE
+
+
+def test_cpp_reference_api_shim_compiles_and_links(tmp_path):
+    """include/eg3d_ref_api.hpp (the reference-named C++ shim) builds against libeg3d.so; on a CPU box it must fail loudly."""
+    import subprocess
+    exe = str(tmp_path / "shim_smoke")
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([gxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "shim_smoke.cpp"),
+                    E.LIB_PATH, "-Wl,-rpath," + os.path.dirname(E.LIB_PATH), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "shim" in r.stdout

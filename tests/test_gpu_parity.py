@@ -180,3 +180,17 @@ def test_dedup_and_filter_parity(small):
     assert np.array_equal(gi, oi)
     assert np.array_equal(gx, ox)      # FP32 filter arithmetic is reproduced operation by operation
     assert 0 < gi.sum() < len(gi)
+
+
+def test_match_refpoints_parity(small):
+    # pipeline 3 (a6): seeds from SfM tracks via the 30 px grid, hits filtered by the per-seed radius
+    sc, dev, orc = small
+    gpu, tm = dev.match_refpoints()
+    ref = orc.match_refpoints()
+    assert ref.n_points > 200
+    assert_points_parity(sc, gpu, ref)
+    # a shard of the refpoint ids (multi-GPU axis, plg_matching_from_refpoints.cpp:90)
+    a, _ = dev.match_refpoints(0, 70)
+    b, _ = dev.match_refpoints(70, sc.n_tracks)
+    assert a.n_points + b.n_points == gpu.n_points
+    assert np.array_equal(np.concatenate([a.xyz, b.xyz]), gpu.xyz)

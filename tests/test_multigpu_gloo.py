@@ -1,0 +1,63 @@
+"""N>1 path on CPU: two gloo ranks shard the starting views, each computes its shard (with the oracle standing in as the
+per-rank compute — this test is about the shard plan and the gather/merge, not the kernels), all-gather the accepted
+records and check that every rank ends up with exactly the unsharded result in the reference's order."""
+import os
+import socket
+import sys
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from edgegraph3d_b200 import synthetic as syn, multigpu as mg
+    from tests import oracle_lib as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = syn.make_scene(n_views=6, n_curves=12, seed=21)
+    cands = syn.curve_candidate_sets(sc, seed=21)
+    osc = O.OracleScene(sc)
+    lo, hi = mg.view_block(sc.n_views, world, rank)
+    local = osc.match_polyline_sets(cands, lo, hi, n_threads=2)
+    merged, cnts = mg.all_gather_points(local, dist)
+    full = osc.match_polyline_sets(cands, n_threads=2)
+    # the unsharded call iterates (set, view): compare as multisets of (xyz, observation identity), and per-rank order
+    key = lambda p: sorted((tuple(x.tolist()), k[2]) for x, k in zip(p.xyz, p.identity_keys()))
+    ok = merged.n_points == full.n_points and key(merged) == key(full)
+    # rank-order concatenation: rank r's block is contiguous and equal to its local result
+    start = int(cnts[:rank, 0].sum())
+    ok = ok and np.array_equal(merged.xyz[start:start + local.n_points], local.xyz)
+    ok = ok and np.array_equal(merged.obs_off[start:start + local.n_points + 1] - merged.obs_off[start], local.obs_off)
+    q.put((rank, bool(ok), merged.n_points, int(cnts[:, 0].sum())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gather_equals_unsharded():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
+    assert res[0][2] == res[1][2] == res[0][3] > 0
+
+
+def test_balanced_view_blocks():
+    from edgegraph3d_b200 import multigpu as mg
+    blocks = mg.balanced_view_blocks([10, 0, 30, 5, 5, 50, 0, 20], 4)
+    assert blocks[0][0] == 0 and blocks[-1][1] == 8
+    assert all(b[0] <= b[1] for b in blocks) and all(blocks[i][1] == blocks[i + 1][0] for i in range(3))
+    assert mg.view_block(200, 8, 7) == (175, 200) and mg.view_block(6, 2, 0) == (0, 3)
