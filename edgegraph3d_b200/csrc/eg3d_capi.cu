@@ -60,7 +60,7 @@ struct eg3d_scene {
   DBuf<float> P; DBuf<double> P64; DBuf<double> F; DBuf<double> Fp; DBuf<uint8_t> Fvalid;
   DBuf<int> view_poly_off, poly_vert_off, view_seg_off, poly_seg_off;
   DBuf<float2> verts; DBuf<uint32_t> poly_start, poly_end;
-  DBuf<float4> seg; DBuf<uint2> seg_id;
+  DBuf<float4> seg; DBuf<uint2> seg_id; DBuf<float4> grp_box; DBuf<uint32_t> grp_desc; DBuf<int4> chunks; DBuf<int> view_chunk_off;
   DBuf<int> g4_off, g30_off; DBuf<uint32_t> g4_ids, g30_ids;
   DBuf<float> track_xyz; DBuf<int64_t> track_off; DBuf<int32_t> track_view; DBuf<float2> track_xy;
   DevScene dev;
@@ -238,7 +238,7 @@ static eg3d_status run_k1(eg3d_scene* sc, const DevSeeds& ds, const DevCand* dc,
   t1.start();
   if (ds.n > 0) {
     if (dc) k1_cand_kernel<false><<<cblocks, 256, 0, sc->stream>>>(sc->dev, ks, kc, off.p, nullptr, nullptr);
-    else k1_sweep_kernel<false><<<grid, K1_THREADS, K1_SMEM_BYTES, sc->stream>>>(sc->dev, ks, 0, off.p, nullptr, nullptr);
+    else k1_sweep_kernel<false><<<grid, K1_THREADS, K1_SMEM_BYTES2, sc->stream>>>(sc->dev, ks, 0, off.p, nullptr, nullptr);
   }
   t1.stop();
   CK(cudaGetLastError());
@@ -254,7 +254,7 @@ static eg3d_status run_k1(eg3d_scene* sc, const DevSeeds& ds, const DevCand* dc,
   t3.start();
   if (ds.n > 0) {
     if (dc) k1_cand_kernel<true><<<cblocks, 256, 0, sc->stream>>>(sc->dev, ks, kc, nullptr, off.p, hits.p);
-    else k1_sweep_kernel<true><<<grid, K1_THREADS, K1_SMEM_BYTES, sc->stream>>>(sc->dev, ks, 0, nullptr, off.p, hits.p);
+    else k1_sweep_kernel<true><<<grid, K1_THREADS, K1_SMEM_BYTES2, sc->stream>>>(sc->dev, ks, 0, nullptr, off.p, hits.p);
   }
   t3.stop();
   CK(cudaGetLastError());
@@ -468,6 +468,36 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
     sc->max_view_segs = std::max(sc->max_view_segs, sc->h_view_seg_off[v + 1] - sc->h_view_seg_off[v]);
   }
   poly_seg_off[NP] = (int)seg.size();
+  // K1 cull structures: groups (<= 32 segments of one polyline) with inflated boxes; chunks of <= K1_CHUNK segments and
+  // <= K1_GMAX groups aligned to group boundaries (group ranges padded to a multiple of 4 for 16-byte bulk copies)
+  std::vector<float4> gbox; std::vector<uint32_t> gdesc; std::vector<int4> chunks; std::vector<int> view_chunk_off(V + 1, 0);
+  for (int v = 0; v < V; v++) {
+    int cseg0 = sc->h_view_seg_off[v], cnseg = 0, cg0 = (int)gbox.size(), cng = 0;
+    auto flush = [&]() {
+      if (cng == 0) return;
+      while (gbox.size() % 4) { gbox.push_back(make_float4(0.f, 0.f, -1.f, -1.f)); gdesc.push_back(0u); }
+      chunks.push_back(make_int4(cseg0, cnseg, cg0, (int)gbox.size() - cg0));
+      cseg0 += cnseg; cnseg = 0; cg0 = (int)gbox.size(); cng = 0;
+    };
+    for (int g = sc->h_view_poly_off[v]; g < sc->h_view_poly_off[v + 1]; g++) {
+      const int ps0 = poly_seg_off[g], ps1 = (g + 1 <= (int)NP) ? poly_seg_off[g + 1] : (int)seg.size();
+      const int o = sc->h_poly_vert_off[g];
+      for (int k0 = ps0; k0 < ps1; k0 += K1_GROUP) {
+        const int k1 = std::min(ps1, k0 + K1_GROUP), n = k1 - k0;
+        if (cnseg + n > K1_CHUNK || cng + 1 > K1_GMAX - 3) flush();
+        float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
+        for (int k = k0; k <= k1; k++) {   // vertices (k - ps0) .. (k1 - ps0) of the polyline
+          const float2 q = sc->h_verts[o + (k - ps0)];
+          xmin = std::min(xmin, q.x); xmax = std::max(xmax, q.x); ymin = std::min(ymin, q.y); ymax = std::max(ymax, q.y);
+        }
+        gbox.push_back(make_float4(0.5f * (xmin + xmax), 0.5f * (ymin + ymax), 0.5f * (xmax - xmin) + 0.05f, 0.5f * (ymax - ymin) + 0.05f));
+        gdesc.push_back(((uint32_t)cnseg << 6) | (uint32_t)n);
+        cnseg += n; cng++;
+      }
+    }
+    flush();
+    view_chunk_off[v + 1] = (int)chunks.size();
+  }
   HostGrid g4; build_grid(*sc, sc->prm.expand_grid_cell, g4);
   const bool tracks = d->n_tracks > 0;
   if (tracks) build_grid(*sc, sc->prm.detection_starting_radius * sc->prm.detection_mult, sc->hg30);
@@ -481,6 +511,8 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   CK(sc->verts.upload(sc->h_verts, s)); CK(sc->poly_start.upload(sc->h_start, s)); CK(sc->poly_end.upload(sc->h_end, s));
   CK(sc->view_seg_off.upload(sc->h_view_seg_off, s)); CK(sc->poly_seg_off.upload(poly_seg_off, s));
   CK(sc->seg.upload(seg, s)); CK(sc->seg_id.upload(seg_id, s));
+  CK(sc->grp_box.upload(gbox, s)); CK(sc->grp_desc.upload(gdesc, s)); CK(sc->chunks.upload(chunks, s)); CK(sc->view_chunk_off.upload(view_chunk_off, s));
+  CK(cudaStreamSynchronize(s));
   CK(sc->g4_off.upload(g4.off, s)); CK(sc->g4_ids.upload(g4.ids, s));
   if (tracks) {
     CK(sc->g30_off.upload(sc->hg30.off, s)); CK(sc->g30_ids.upload(sc->hg30.ids, s));
@@ -498,12 +530,13 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   D.view_poly_off = sc->view_poly_off.p; D.poly_vert_off = sc->poly_vert_off.p; D.verts = sc->verts.p;
   D.poly_start = sc->poly_start.p; D.poly_end = sc->poly_end.p;
   D.view_seg_off = sc->view_seg_off.p; D.seg = sc->seg.p; D.seg_id = sc->seg_id.p; D.poly_seg_off = sc->poly_seg_off.p;
+  D.grp_box = sc->grp_box.p; D.grp_desc = sc->grp_desc.p; D.chunks = sc->chunks.p; D.view_chunk_off = sc->view_chunk_off.p;
   D.g_expand.cell = g4.cell; D.g_expand.w = g4.w; D.g_expand.h = g4.h; D.g_expand.cell_off = sc->g4_off.p; D.g_expand.ids = sc->g4_ids.p;
   if (tracks) { D.g_corr.cell = sc->hg30.cell; D.g_corr.w = sc->hg30.w; D.g_corr.h = sc->hg30.h; D.g_corr.cell_off = sc->g30_off.p; D.g_corr.ids = sc->g30_ids.p; }
   D.n_tracks = d->n_tracks; D.track_xyz = sc->track_xyz.p; D.track_off = sc->track_off.p; D.track_view = sc->track_view.p; D.track_xy = sc->track_xy.p;
   D.prm = sc->prm;
-  CK(cudaFuncSetAttribute(k1_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k1_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
   *out = guard.release();
   return EG3D_OK;
 }

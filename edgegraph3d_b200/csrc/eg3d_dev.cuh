@@ -44,6 +44,12 @@ struct DevScene {
   const float4* seg;            // [NSEG]
   const uint2* seg_id;          // [NSEG] (polyline id in view, segment_index = i-1)
   const int* poly_seg_off;      // [NP+1] first staged segment of each polyline
+  // K1 cull structures: groups of <= 32 consecutive staged segments of ONE polyline, with an inflated bounding box, and a
+  // per-view table of chunks (<= 2048 segments, <= 128 groups) that the sweep kernel streams through shared memory
+  const int* view_chunk_off;    // [V+1]
+  const int4* chunks;           // (first segment, #segments, first group, #groups padded to a multiple of 4)
+  const float4* grp_box;        // (cx, cy, ex, ey): centre and half extents inflated by 0.05 px; ex < 0 for padding groups
+  const uint32_t* grp_desc;     // (offset of the group's first segment in its chunk << 6) | #segments
   DevGrid g_expand;             // 4 px
   DevGrid g_corr;               // 30 px (only with tracks)
   // tracks

@@ -1,12 +1,13 @@
 // eg3d_k1.cuh — K1: find_epipolar_correspondences (polyline_matching.cpp:45-73 -> polyline::intersect_line,
 // polyline_graph_2d.cpp:312-327 -> intersect_segment_line, geometric_utilities.cpp:272-312).
 //
-// Sweep form (BASELINE configs 2-4): every seed against every segment of every other view.  One CTA owns a tile of
-// seeds (one seed per thread) and one target view; the view's staged segments (x1,y1,dx,dy) stream through a
-// double-buffered shared-memory ring filled by TMA bulk copies (cp.async.bulk + mbarrier complete_tx), and every
-// thread reads the same float4 per step (shared-memory broadcast), so the only per-test traffic is register math.
-// Two passes (count, exclusive scan, fill) give the reference's exact output order without atomics:
-// hits of a (seed, view) pair are in ascending (polyline id, segment index).
+// Sweep form (BASELINE configs 2-4): every seed against every segment of every other view.  One CTA owns one target
+// view and a tile of 256 seeds; the view's staged segments (x1,y1,dx,dy), grouped by polyline into groups of <= 16 with
+// an inflated bounding box each, stream through a double-buffered shared-memory ring filled by TMA bulk copies
+// (cp.async.bulk + mbarrier complete_tx).  Each warp visits its 32 seeds one after the other: the lanes cull 32 group
+// boxes per step against the epipolar line, then test the surviving groups' segments (two groups per step) with the
+// reference predicate and ballot-compact the hits.  Two passes (count, exclusive scan, fill) give the reference's exact
+// output order without atomics: hits of a (seed, view) pair are in ascending (polyline id, segment index).
 //
 // Candidate form (reference semantics, configs 1/4): one thread per (seed, view) walks the few candidate polylines.
 #pragma once
@@ -53,12 +54,21 @@ struct K1Seeds {
   const int* cand_set;  // may be null
 };
 
-// The exact reference predicate is `den != 0 && 0 <= fl(-num/den) <= 1`.  A division per test would dominate the loop,
-// so lanes first apply a conservative filter that can only over-accept (|num| <= |den|(1+eps), opposite signs or a
-// product that underflows), and the rare survivors evaluate the reference expression verbatim.
-EG3D_D bool k1_prefilter(float num, float den) {
-  return (fabsf(num) <= fabsf(den) * 1.000001f) && (num * den <= 1e-30f);
-}
+// Sweep kernel.  One CTA = one target view x a tile of 256 seeds; the view's staged segments and the bounding boxes of
+// their groups of 32 stream through a double-buffered shared-memory ring (TMA bulk copies, mbarrier complete_tx).
+// Each warp owns 32 seeds of the tile and visits them one after the other; for a seed the 32 lanes
+//   1. test 32 group boxes at a time against the epipolar line (|a cx + b cy + c| <= |a| ex + |b| ey + slack) — a
+//      conservative cull: a float hit needs the line within ~1e-3 px of the segment, the boxes are inflated by 0.05 px;
+//   2. for every surviving group test its 32 segments at once with the reference predicate verbatim
+//      (den != 0, t = -num/den, 0 <= t <= 1) and ballot-compact the hits, which keeps the reference's order
+//      (polyline id ascending, segment ascending) because groups and lanes are visited in staging order.
+#ifndef EG3D_K1_GROUP
+#define EG3D_K1_GROUP 16
+#endif
+constexpr int K1_GROUP = EG3D_K1_GROUP;        // max segments per group (one group never spans two polylines)
+constexpr int K1_GPR = 32 / K1_GROUP;          // groups handled per warp step (K1_GROUP lanes each)
+constexpr int K1_GMAX = 4096 / K1_GROUP;       // max groups per chunk
+constexpr int K1_SMEM_BYTES2 = K1_STAGES * (K1_CHUNK * 16 + K1_GMAX * 16 + K1_GMAX * 4) + K1_STAGES * 8;
 
 template <bool FILL>
 __global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K1Seeds seeds, int view_lo,
@@ -66,13 +76,15 @@ __global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_const
                                                               eg3d_hit* __restrict__ hits) {
   extern __shared__ __align__(128) unsigned char k1_smem[];
   float4 (*sbuf)[K1_CHUNK] = reinterpret_cast<float4 (*)[K1_CHUNK]>(k1_smem);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(k1_smem + sizeof(float4) * K1_STAGES * K1_CHUNK);
-  const int tid = threadIdx.x;
+  float4 (*bbuf)[K1_GMAX] = reinterpret_cast<float4 (*)[K1_GMAX]>(k1_smem + sizeof(float4) * K1_STAGES * K1_CHUNK);
+  uint32_t (*dbuf)[K1_GMAX] = reinterpret_cast<uint32_t (*)[K1_GMAX]>(k1_smem + sizeof(float4) * K1_STAGES * (K1_CHUNK + K1_GMAX));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(k1_smem + K1_STAGES * (K1_CHUNK * 16 + K1_GMAX * 16 + K1_GMAX * 4));
+  const int tid = threadIdx.x, lane = tid & 31;
   const int t = view_lo + blockIdx.y;                 // target view
-  const int sidx = blockIdx.x * K1_THREADS + tid;     // my seed
+  const int sidx = blockIdx.x * K1_THREADS + tid;     // the seed whose line / counter this lane keeps
   const int seg0 = S.view_seg_off[t];
-  const int nseg = S.view_seg_off[t + 1] - seg0;
-  const int nchunks = (nseg + K1_CHUNK - 1) / K1_CHUNK;
+  const int ch0 = S.view_chunk_off[t];
+  const int nchunks = S.view_chunk_off[t + 1] - ch0;
 
   if (tid == 0) {
     for (int s = 0; s < K1_STAGES; s++) mbar_init(&bars[s], 1);
@@ -90,43 +102,80 @@ __global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_const
   int cnt = 0;
   int64_t obase = 0;
   if (FILL && sidx < seeds.n) obase = off[(size_t)sidx * S.V + t];
-  const uint2* sid = S.seg_id + seg0;
+  const unsigned amask = __ballot_sync(0xffffffffu, active);
 
   auto issue = [&](int c) {
-    int n = min(K1_CHUNK, nseg - c * K1_CHUNK);
-    uint32_t bytes = (uint32_t)n * 16u;
-    mbar_expect_tx(&bars[c % K1_STAGES], bytes);
-    tma_bulk_g2s(&sbuf[c % K1_STAGES][0], S.seg + seg0 + (size_t)c * K1_CHUNK, bytes, &bars[c % K1_STAGES]);
+    const int4 ch = S.chunks[ch0 + c];               // (first segment, #segments, first group, #groups padded to x4)
+    const uint32_t bytes = (uint32_t)ch.y * 16u, bbytes = (uint32_t)ch.w * 16u, dbytes = (uint32_t)ch.w * 4u;
+    mbar_expect_tx(&bars[c % K1_STAGES], bytes + bbytes + dbytes);
+    tma_bulk_g2s(&sbuf[c % K1_STAGES][0], S.seg + ch.x, bytes, &bars[c % K1_STAGES]);
+    tma_bulk_g2s(&bbuf[c % K1_STAGES][0], S.grp_box + ch.z, bbytes, &bars[c % K1_STAGES]);
+    tma_bulk_g2s(&dbuf[c % K1_STAGES][0], S.grp_desc + ch.z, dbytes, &bars[c % K1_STAGES]);
   };
   if (tid == 0 && nchunks > 0) issue(0);
   for (int c = 0; c < nchunks; c++) {
     if (tid == 0 && c + 1 < nchunks) issue(c + 1);
     mbar_wait(&bars[c % K1_STAGES], (uint32_t)((c / K1_STAGES) & 1));
-    if (active) {
-      const float4* sb = sbuf[c % K1_STAGES];
-      const int n = min(K1_CHUNK, nseg - c * K1_CHUNK);
-#pragma unroll 4
-      for (int j = 0; j < n; j++) {
-        float4 s = sb[j];
-        float num = l.x * s.x + l.y * s.y + l.z;
-        float den = l.x * s.z + l.y * s.w;
-        if (k1_prefilter(num, den)) {
-          if (den != 0) {
-            float tt = -num / den;
-            if (tt >= 0 && tt <= 1) {
-              if (FILL) {
-                uint2 id = sid[c * K1_CHUNK + j];
-                eg3d_hit h; h.polyline = id.x; h.segment = id.y; h.x = s.x + tt * s.z; h.y = s.y + tt * s.w;
-                hits[obase + cnt] = h;
+    const float4* sb = sbuf[c % K1_STAGES];
+    const float4* bb = bbuf[c % K1_STAGES];
+    const uint32_t* db = dbuf[c % K1_STAGES];
+    const int4 ch = S.chunks[ch0 + c];
+    const int ng = ch.w;
+    const uint2* sid = S.seg_id + ch.x;
+    unsigned am = amask;
+    while (am) {                                       // the warp's seeds, one after the other
+      const int j = __ffs(am) - 1;
+      am &= am - 1;
+      const float la = __shfl_sync(0xffffffffu, l.x, j), lb = __shfl_sync(0xffffffffu, l.y, j), lc = __shfl_sync(0xffffffffu, l.z, j);
+      const float aa = fabsf(la), ab = fabsf(lb);
+      int cj = __shfl_sync(0xffffffffu, cnt, j);
+      const int64_t oj = FILL ? __shfl_sync(0xffffffffu, obase, j) : 0;
+      for (int gb = 0; gb < ng; gb += 32) {
+        const int g = gb + lane;
+        bool pass = false;
+        if (g < ng) {
+          const float4 bx = bb[g];                     // (cx, cy, ex, ey), inflated; padding groups have ex < 0
+          pass = fabsf(la * bx.x + lb * bx.y + lc) <= aa * bx.z + ab * bx.w;
+        }
+        unsigned gm = __ballot_sync(0xffffffffu, pass);
+        while (gm) {
+          // K1_GPR surviving groups per step: lanes [k*K1_GROUP, (k+1)*K1_GROUP) take the k-th surviving group, so lane
+          // order == (group ascending, segment ascending) == the reference's hit order
+          const int which = lane / K1_GROUP, sub = lane % K1_GROUP;
+          unsigned m2 = gm;
+#pragma unroll
+          for (int k = 0; k < K1_GPR - 1; k++) if (k < which) m2 &= m2 - 1;
+          const unsigned pos = m2 ? (unsigned)(__ffs(m2) - 1) : 0xffffffffu;   // the (which+1)-th surviving group, if any
+          bool hit = false; float hx = 0.f, hy = 0.f; int i = 0;
+          if (pos != 0xffffffffu) {
+            const uint32_t d = db[gb + (int)pos];                  // (offset in chunk << 6) | count
+            i = (int)(d >> 6) + sub;
+            if (sub < (int)(d & 63u)) {
+              const float4 sg = sb[i];
+              const float num = la * sg.x + lb * sg.y + lc;
+              const float den = la * sg.z + lb * sg.w;
+              if (den != 0) {
+                const float tt = -num / den;
+                if (tt >= 0 && tt <= 1) { hit = true; hx = sg.x + tt * sg.z; hy = sg.y + tt * sg.w; }
               }
-              cnt++;
             }
           }
+          const unsigned hm = __ballot_sync(0xffffffffu, hit);
+          if (FILL && hit) {
+            const uint2 id = sid[i];
+            eg3d_hit h; h.polyline = id.x; h.segment = id.y; h.x = hx; h.y = hy;
+            hits[oj + cj + __popc(hm & ((1u << lane) - 1u))] = h;
+          }
+          cj += __popc(hm);
+#pragma unroll
+          for (int k = 0; k < K1_GPR; k++) gm &= gm - 1;          // drop the groups just handled
         }
       }
+      if (lane == j) cnt = cj;
     }
     __syncthreads();
   }
+  (void)seg0;
   if (sidx < seeds.n) {
     if (sv == t) {  // the starting view holds the seed itself (polyline_matching.cpp:54-55)
       if (FILL) { eg3d_hit h; h.polyline = seeds.pl[sidx]; h.segment = seeds.seg[sidx]; h.x = p.x; h.y = p.y; hits[obase] = h; }
