@@ -72,23 +72,46 @@ struct eg3d_scene {
   int max_view_segs = 0;
 };
 
-template <typename T>
-struct PBuf {  // pinned host buffer (page-locked so D2H runs at full PCIe/C2C rate)
-  T* p = nullptr; size_t n = 0;
-  PBuf() {}
-  PBuf(const PBuf&) = delete; PBuf& operator=(const PBuf&) = delete;
-  ~PBuf() { if (p) cudaFreeHost(p); }
-  cudaError_t alloc(size_t count) { if (p) cudaFreeHost(p); p = nullptr; n = count; return cudaMallocHost((void**)&p, std::max<size_t>(count, 1) * sizeof(T)); }
+// Page-locked host staging for results: one block per result, recycled through a process-wide free list so that the
+// (slow) cudaMallocHost happens once per size class instead of once per call.
+#include <mutex>
+#include <map>
+struct PinnedPool {
+  std::mutex mu; std::multimap<size_t, void*> free_blocks; std::map<void*, size_t> sizes;
+  void* acquire(size_t bytes, cudaError_t& err) {
+    err = cudaSuccess;
+    bytes = std::max<size_t>(bytes, 256);
+    {
+      std::lock_guard<std::mutex> g(mu);
+      auto it = free_blocks.lower_bound(bytes);
+      if (it != free_blocks.end() && it->first <= bytes * 2 + (1 << 20)) { void* p = it->second; free_blocks.erase(it); return p; }
+    }
+    void* p = nullptr;
+    size_t cap = bytes + bytes / 8;
+    err = cudaMallocHost(&p, cap);
+    if (err != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> g(mu);
+    sizes[p] = cap;
+    return p;
+  }
+  void release(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> g(mu);
+    free_blocks.insert({sizes[p], p});
+  }
 };
+static PinnedPool g_pinned;
 
 struct eg3d_points {
   int device = 0; cudaStream_t stream = nullptr;
   int64_t n_points = 0, n_obs = 0;
   // device-resident, ordered by (seed, chain position)
   DBuf<float> d_xyz; DBuf<int> d_seed, d_pos; DBuf<int64_t> d_obs_off; DBuf<int> d_ov; DBuf<uint32_t> d_opl, d_oseg; DBuf<float> d_oxy;
-  // host copies (filled on first eg3d_points_get)
-  bool on_host = false;
-  PBuf<float> xyz; PBuf<int32_t> seed, chain_pos; PBuf<int64_t> obs_off; PBuf<int32_t> obs_view; PBuf<uint32_t> obs_poly, obs_seg; PBuf<float> obs_xy;
+  // host copies (filled on first eg3d_points_get), carved out of one pinned block
+  bool on_host = false; void* hblock = nullptr;
+  float* xyz = nullptr; int32_t *seed = nullptr, *chain_pos = nullptr; int64_t* obs_off = nullptr; int32_t* obs_view = nullptr;
+  uint32_t *obs_poly = nullptr, *obs_seg = nullptr; float* obs_xy = nullptr;
+  ~eg3d_points() { g_pinned.release(hblock); }
 };
 struct eg3d_hits { int64_t n_seeds; int V; std::vector<int64_t> off; std::vector<eg3d_hit> hits; };
 
@@ -361,19 +384,27 @@ static eg3d_status points_to_host(eg3d_points* p) {
   if (p->on_host) return EG3D_OK;
   CK(cudaSetDevice(p->device));
   const int64_t npts = p->n_points, nobs = p->n_obs;
-  CK(p->xyz.alloc(3 * npts)); CK(p->seed.alloc(npts)); CK(p->chain_pos.alloc(npts)); CK(p->obs_off.alloc(npts + 1));
-  CK(p->obs_view.alloc(nobs)); CK(p->obs_poly.alloc(nobs)); CK(p->obs_seg.alloc(nobs)); CK(p->obs_xy.alloc(2 * nobs));
-  p->obs_off.p[0] = 0;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t b_xyz = al(3 * npts * 4), b_seed = al(npts * 4), b_pos = al(npts * 4), b_off = al((npts + 1) * 8), b_ov = al(nobs * 4),
+               b_opl = al(nobs * 4), b_oseg = al(nobs * 4), b_oxy = al(2 * nobs * 4);
+  cudaError_t e;
+  char* base = (char*)g_pinned.acquire(b_xyz + b_seed + b_pos + b_off + b_ov + b_opl + b_oseg + b_oxy, e);
+  if (!base) return fail(EG3D_ERR_OOM, std::string("cudaMallocHost failed: ") + cudaGetErrorString(e));
+  p->hblock = base;
+  p->xyz = (float*)base; base += b_xyz; p->seed = (int32_t*)base; base += b_seed; p->chain_pos = (int32_t*)base; base += b_pos;
+  p->obs_off = (int64_t*)base; base += b_off; p->obs_view = (int32_t*)base; base += b_ov; p->obs_poly = (uint32_t*)base; base += b_opl;
+  p->obs_seg = (uint32_t*)base; base += b_oseg; p->obs_xy = (float*)base;
+  p->obs_off[0] = 0;
   if (npts > 0) {
     cudaStream_t s = p->stream;
-    CK(cudaMemcpyAsync(p->xyz.p, p->d_xyz.p, 3 * npts * sizeof(float), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(p->seed.p, p->d_seed.p, npts * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(p->chain_pos.p, p->d_pos.p, npts * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(p->obs_off.p, p->d_obs_off.p, (npts + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(p->obs_view.p, p->d_ov.p, nobs * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(p->obs_poly.p, p->d_opl.p, nobs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(p->obs_seg.p, p->d_oseg.p, nobs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(p->obs_xy.p, p->d_oxy.p, 2 * nobs * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->xyz, p->d_xyz.p, 3 * npts * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->seed, p->d_seed.p, npts * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->chain_pos, p->d_pos.p, npts * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->obs_off, p->d_obs_off.p, (npts + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->obs_view, p->d_ov.p, nobs * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->obs_poly, p->d_opl.p, nobs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->obs_seg, p->d_oseg.p, nobs * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(p->obs_xy, p->d_oxy.p, 2 * nobs * sizeof(float), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
   }
   p->on_host = true;
@@ -668,8 +699,8 @@ eg3d_status eg3d_points_get(const eg3d_points* pc, eg3d_points_view* v) {
   eg3d_points* p = const_cast<eg3d_points*>(pc);
   eg3d_status st = points_to_host(p); if (st != EG3D_OK) return st;
   v->n_points = p->n_points; v->n_obs = p->n_obs;
-  v->xyz = p->xyz.p; v->seed = p->seed.p; v->chain_pos = p->chain_pos.p; v->obs_off = p->obs_off.p;
-  v->obs_view = p->obs_view.p; v->obs_poly = p->obs_poly.p; v->obs_seg = p->obs_seg.p; v->obs_xy = p->obs_xy.p;
+  v->xyz = p->xyz; v->seed = p->seed; v->chain_pos = p->chain_pos; v->obs_off = p->obs_off;
+  v->obs_view = p->obs_view; v->obs_poly = p->obs_poly; v->obs_seg = p->obs_seg; v->obs_xy = p->obs_xy;
   return EG3D_OK;
 }
 eg3d_status eg3d_points_device_get(const eg3d_points* p, eg3d_points_view* v) {
