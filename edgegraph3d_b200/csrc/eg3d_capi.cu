@@ -324,15 +324,24 @@ static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_o
   DBuf<unsigned long long> prof;
   const bool do_prof = getenv("EG3D_K3_PROF") != nullptr;
   if (do_prof) { CK(prof.alloc(16)); CK(cudaMemsetAsync(prof.p, 0, 16 * sizeof(unsigned long long), sc->stream)); a.prof = prof.p; }
+  // phase A -> phase B hand-over buffers
+  DBuf<PaRec> pa_recs; DBuf<Pt3> pa_pool; DBuf<unsigned long long> pa_cnt; DBuf<int> counter_b;
+  const long long pool_cap = std::max<long long>((long long)n * 12, 1 << 14);
+  CK(pa_recs.alloc(n)); CK(pa_pool.alloc(pool_cap)); CK(pa_cnt.alloc(2)); CK(counter_b.alloc(1));
+  CK(cudaMemsetAsync(pa_cnt.p, 0, 2 * sizeof(unsigned long long), sc->stream));
+  CK(cudaMemsetAsync(counter_b.p, 0, sizeof(int), sc->stream));
+  CK(cudaMemsetAsync(snp.p, 0, (size_t)n * sizeof(int), sc->stream));
+  a.pa_recs = pa_recs.p; a.pa_pool = pa_pool.p; a.pa_pool_cap = pool_cap; a.pa_counters = pa_cnt.p;
   Timer t3(sc->stream), tp(sc->stream);
   t3.start();
-  k3_chain_kernel<<<nblocks, K3_THREADS, 0, sc->stream>>>(sc->dev, a);
+  k3a_hypothesis_kernel<<<nblocks, K3_THREADS, 0, sc->stream>>>(sc->dev, a);
+  K3Args b = a; b.work_counter = counter_b.p;
+  k3b_expand_kernel<<<nblocks, K3_THREADS, 0, sc->stream>>>(sc->dev, b);
   t3.stop();
-  CK(cudaGetLastError());
   unsigned long long cnt[4];
   CK(cudaMemcpyAsync(cnt, oc4.p, sizeof cnt, cudaMemcpyDeviceToHost, sc->stream));
   CK(cudaStreamSynchronize(sc->stream));
-  if (tm) { tm->k3_ms += t3.ms(); tm->kernel_launches += 1; tm->n_capacity_overflows += (int)(cnt[2] + cnt[3]); }
+  if (tm) { tm->k3_ms += t3.ms(); tm->kernel_launches += 2; tm->n_capacity_overflows += (int)(cnt[2] + cnt[3]); }
   if (do_prof) {
     unsigned long long pr[16]; CK(cudaMemcpy(pr, prof.p, sizeof pr, cudaMemcpyDeviceToHost));
     const char* nm[12] = {"A.scan+prune", "A.est3", "A.plg_compatible", "B.epc_prune", "B.epc_gn", "B.add_view_finish(epc)", "B.main_loop", "seed_total", "#est3_lanes", "#est3_rounds", "#plg_compat", "#epc_solved"};

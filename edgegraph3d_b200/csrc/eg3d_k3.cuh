@@ -28,6 +28,7 @@ struct Pt3 {  // a 3-view point of the following phase (64 B)
 };
 struct NTmp { float X[3]; uint32_t seg; float cx, cy; };  // a neighbour candidate (polyline id is implied)
 
+struct PaRec;
 struct K3Args {
   int n_seeds;
   const int* seed_view; const uint32_t* seed_pl; const uint32_t* seed_seg; const float2* seed_xy;
@@ -43,6 +44,15 @@ struct K3Args {
   int* ob_view; uint32_t* ob_pl; uint32_t* ob_seg; float* ob_x; float* ob_y;
   int* seed_npts; int64_t* seed_pbase; int64_t* seed_nobs;
   unsigned long long* prof;   // optional [16] per-phase warp-cycle / event counters (null = off)
+  // phase A -> phase B hand-over: one record per accepted seed + its two 3-view point lists in a pool
+  struct PaRec* pa_recs; Pt3* pa_pool; long long pa_pool_cap;
+  unsigned long long* pa_counters;    // [0] accepted seeds, [1] pool entries used
+};
+struct PaRec {
+  int seed; int sel[3]; int fn1, fn2;
+  uint32_t fd1[3], fd2[3];
+  Pt3 central;
+  long long pool_off;
 };
 
 struct WS {  // per-warp scratch view
@@ -804,7 +814,9 @@ static __device__ __noinline__ void slot_from_pt3(Ctx& c, int slot, const Pt3& p
   }
 }
 
-static __device__ __noinline__ void process_seed(Ctx& c) {
+// Phase A of a seed: view triple, pruned triple enumeration, PLG following.  Returns true when exactly one compatible
+// hypothesis was found; its lists are left in c.w.fD1 / c.w.fD2 and the scalars in `r`.
+static __device__ __noinline__ bool seed_phase_a(Ctx& c, PaRec& r) {
   const DevScene& S = *c.S; const K3Args& A = *c.A;
   const int V = S.V, lane = c.lane;
   const int64_t* off = A.hit_off + (size_t)c.seed * V;
@@ -816,7 +828,7 @@ static __device__ __noinline__ void process_seed(Ctx& c) {
     unsigned m = __ballot_sync(0xffffffffu, nz);
     if (m) { if (minv < 0) minv = base + __ffs(m) - 1; maxv = base + 31 - __clz(m); ne += __popc(m); }
   }
-  if (ne < 3) return;
+  if (ne < 3) return false;
   int mid = 0;
   {
     int want = ne / 2, seen = 0;
@@ -915,9 +927,9 @@ static __device__ __noinline__ void process_seed(Ctx& c) {
       K3P_BEGIN(tp2);
       bool comp = plg_compatible(c, cand, nD1, nD2, d1, d2);
       K3P_END(c, 2, tp2); c.pc[10] += 1;
-      if (c.overflow) return;
+      if (c.overflow) return false;
       if (comp) {
-        if (found) return;  // a second compatible triple: ambiguous, the seed yields nothing (:587-590)
+        if (found) return false;  // a second compatible triple: ambiguous, the seed yields nothing (:587-590)
         found = true;
         fn1 = nD1; fn2 = nD2;
         for (int k = 0; k < 3; k++) { fd1[k] = d1[k]; fd2[k] = d2[k]; fX[k] = Xb[k]; }
@@ -929,18 +941,31 @@ static __device__ __noinline__ void process_seed(Ctx& c) {
       }
     }
   }
-  if (!found) return;
+  if (!found) return false;
+  r.seed = c.seed; r.sel[0] = c.sel[0]; r.sel[1] = c.sel[1]; r.sel[2] = c.sel[2]; r.fn1 = fn1; r.fn2 = fn2;
+  for (int k = 0; k < 3; k++) { r.fd1[k] = fd1[k]; r.fd2[k] = fd2[k]; }
+  store_pt3(&r.central, fcentral, fX);
+  r.pool_off = 0;
+  return true;
+}
+
+// Phase B of an accepted seed: chain = reverse(D1) + central + D2, then expansion to every other view.
+static __device__ __noinline__ void seed_phase_b(Ctx& c, const PaRec& r, const Pt3* l1, const Pt3* l2) {
+  const DevScene& S = *c.S;
+  const int V = S.V, lane = c.lane;
+  const int fn1 = r.fn1, fn2 = r.fn2;
+  c.sel[0] = r.sel[0]; c.sel[1] = r.sel[1]; c.sel[2] = r.sel[2];
   // --- chain = reverse(D1) + central + D2 (polyline_graph_2d.cpp:1298-1306)
   c.len = fn1 + 1 + fn2;
   if (c.len > c.w.capc) { c.overflow = true; return; }
   __syncwarp();
-  for (int i = 0; i < fn1; i++) slot_from_pt3(c, i, c.w.fD1[fn1 - 1 - i]);
-  { Pt3 p; store_pt3(&p, fcentral, fX); slot_from_pt3(c, fn1, p); }
-  for (int i = 0; i < fn2; i++) slot_from_pt3(c, fn1 + 1 + i, c.w.fD2[i]);
+  for (int i = 0; i < fn1; i++) slot_from_pt3(c, i, l1[fn1 - 1 - i]);
+  slot_from_pt3(c, fn1, r.central);
+  for (int i = 0; i < fn2; i++) slot_from_pt3(c, fn1 + 1 + i, l2[i]);
   for (int i = lane; i < c.len; i += 32) c.w.order[i] = i;
   for (int v = lane; v < V; v += 32) { c.w.sdirs[v] = 0; c.w.edirs[v] = 0; }
   __syncwarp();
-  if (lane == 0) for (int k = 0; k < 3; k++) { c.w.sdirs[c.sel[k]] = fd1[k]; c.w.edirs[c.sel[k]] = fd2[k]; }
+  if (lane == 0) for (int k = 0; k < 3; k++) { c.w.sdirs[c.sel[k]] = r.fd1[k]; c.w.edirs[c.sel[k]] = r.fd2[k]; }
   __syncwarp();
   c.nslots = c.len;
   c.central = fn1;
@@ -952,7 +977,7 @@ static __device__ __noinline__ void process_seed(Ctx& c) {
   }
 }
 
-__global__ void __launch_bounds__(K3_THREADS, EG3D_K3_MIN_BLOCKS) k3_chain_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
+__global__ void __launch_bounds__(K3_THREADS, EG3D_K3_MIN_BLOCKS) k3a_hypothesis_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   Ctx c;
@@ -967,7 +992,47 @@ __global__ void __launch_bounds__(K3_THREADS, EG3D_K3_MIN_BLOCKS) k3_chain_kerne
     c.len = 0; c.nslots = 0; c.central = 0; c.overflow = false;
     for (int k = 0; k < 12; k++) c.pc[k] = 0;
     K3P_BEGIN(tall);
-    process_seed(c);
+    PaRec r;
+    const bool found = seed_phase_a(c, r);
+    K3P_END(c, 7, tall);
+    __syncwarp();
+    if (c.overflow) { if (lane == 0) atomicAdd(&A.out_counters[2], 1ull); }
+    else if (found) {
+      unsigned long long ri = 0, po = 0;
+      if (lane == 0) { ri = atomicAdd(&A.pa_counters[0], 1ull); po = atomicAdd(&A.pa_counters[1], (unsigned long long)(r.fn1 + r.fn2)); }
+      ri = __shfl_sync(0xffffffffu, ri, 0); po = __shfl_sync(0xffffffffu, po, 0);
+      if ((long long)po + r.fn1 + r.fn2 > A.pa_pool_cap) { if (lane == 0) atomicAdd(&A.out_counters[3], 1ull); r.fn1 = -1; }
+      r.pool_off = (long long)po;
+      if (lane == 0) A.pa_recs[ri] = r;
+      if (r.fn1 >= 0) {
+        for (int i = lane; i < r.fn1; i += 32) A.pa_pool[po + i] = c.w.fD1[i];
+        for (int i = lane; i < r.fn2; i += 32) A.pa_pool[po + r.fn1 + i] = c.w.fD2[i];
+      }
+    }
+    if (A.prof && lane == 0) for (int k = 0; k < 12; k++) if (c.pc[k]) atomicAdd(&A.prof[k], (unsigned long long)c.pc[k]);
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(K3_THREADS, EG3D_K3_MIN_BLOCKS) k3b_expand_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  Ctx c;
+  c.S = &S; c.A = &A; c.lane = lane;
+  c.w = make_ws(A.scratch + (size_t)warp * A.scratch_per_warp, S.V, A.capf, A.capc, A.oc);
+  const int n_acc = (int)A.pa_counters[0];
+  while (true) {
+    int ri = 0;
+    if (lane == 0) ri = atomicAdd(A.work_counter, 1);
+    ri = __shfl_sync(0xffffffffu, ri, 0);
+    if (ri >= n_acc) break;
+    const PaRec r = A.pa_recs[ri];
+    const int seed = r.seed;
+    c.seed = seed; c.sv = A.seed_view[seed];
+    c.len = 0; c.nslots = 0; c.central = 0; c.overflow = false;
+    for (int k = 0; k < 12; k++) c.pc[k] = 0;
+    K3P_BEGIN(tall);
+    if (r.fn1 >= 0) seed_phase_b(c, r, A.pa_pool + r.pool_off, A.pa_pool + r.pool_off + r.fn1);
     K3P_END(c, 7, tall);
     if (A.prof && lane == 0) {
       for (int k = 0; k < 12; k++) if (c.pc[k]) atomicAdd(&A.prof[k], (unsigned long long)c.pc[k]);
@@ -995,7 +1060,7 @@ __global__ void __launch_bounds__(K3_THREADS, EG3D_K3_MIN_BLOCKS) k3_chain_kerne
       npts = 0; nobs = 0;
     }
     if (lane == 0) { A.seed_npts[seed] = npts; A.seed_pbase[seed] = (int64_t)pbase; A.seed_nobs[seed] = nobs; }
-    // write the chain: point headers by lane 0 sequentially (offsets), observations coalesced
+    // write the chain: point headers by lane 0, observations coalesced
     long long ob = (long long)obase;
     for (int i = 0; i < npts; i++) {
       const int slot = c.w.order[i];
