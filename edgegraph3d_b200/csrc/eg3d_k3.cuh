@@ -15,8 +15,11 @@
 
 namespace eg3d {
 
-#ifndef EG3D_K3_MIN_BLOCKS
-#define EG3D_K3_MIN_BLOCKS 8
+#ifndef EG3D_K3A_MIN_BLOCKS
+#define EG3D_K3A_MIN_BLOCKS 12
+#endif
+#ifndef EG3D_K3B_MIN_BLOCKS
+#define EG3D_K3B_MIN_BLOCKS 8
 #endif
 constexpr int K3_THREADS = 128;  // 4 warps per CTA
 
@@ -977,7 +980,7 @@ static __device__ __noinline__ void seed_phase_b(Ctx& c, const PaRec& r, const P
   }
 }
 
-__global__ void __launch_bounds__(K3_THREADS, EG3D_K3_MIN_BLOCKS) k3a_hypothesis_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
+__global__ void __launch_bounds__(K3_THREADS, EG3D_K3A_MIN_BLOCKS) k3a_hypothesis_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   Ctx c;
@@ -1014,7 +1017,7 @@ __global__ void __launch_bounds__(K3_THREADS, EG3D_K3_MIN_BLOCKS) k3a_hypothesis
   }
 }
 
-__global__ void __launch_bounds__(K3_THREADS, EG3D_K3_MIN_BLOCKS) k3b_expand_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
+__global__ void __launch_bounds__(K3_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   Ctx c;
