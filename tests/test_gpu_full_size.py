@@ -1,0 +1,114 @@
+"""-m gpu: BASELINE-size runs checked through size-independent properties (the oracle is too slow to replay them in full)
+plus oracle spot checks on a stratified sample."""
+import numpy as np
+import pytest
+from edgegraph3d_b200 import lib as E, synthetic as syn
+from tests import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2():
+    sc = syn.make_scene(n_views=200, width=1920, height=1080, focal=1600.0, n_curves=400, segs_per_curve=20, curve_len=0.2,
+                        seed=1234, extent=0.9, closed_frac=0.05)
+    seeds = syn.sample_seeds(E.sample_seeds, sc, per_view=250)
+    return sc, seeds, E.DeviceScene(sc)
+
+
+def test_c2_k1_hits_lie_on_line_and_segment(c2):
+    sc, seeds, dev = c2
+    sub = seeds.take(np.arange(0, len(seeds), 97))
+    off, h, V, tm = dev.epipolar_intersect(sub)
+    assert V == 200 and off[-1] == len(h) > 100000
+    nseg = np.array([sc.n_segments(v) for v in range(200)])
+    assert 7900 <= nseg.min() and nseg.max() == 8000
+    assert tm["n_segment_tests"] == int((nseg.sum() - nseg[sub.view]).sum())
+    # every hit of a non-starting view lies on the seed's epipolar line and inside its segment's bounding box
+    rng = np.random.default_rng(0)
+    for s in rng.choice(len(sub), 40, replace=False):
+        for v in rng.choice(200, 6, replace=False):
+            if v == sub.view[s]:
+                continue
+            F = sc.fundamental[sub.view[s], v].reshape(3, 3)
+            l = F @ np.array([sub.xy[s, 0], sub.xy[s, 1], 1.0]); l /= np.hypot(l[0], l[1])
+            hh = h[off[s * 200 + v]:off[s * 200 + v + 1]]
+            assert np.all(np.diff(hh["polyline"].astype(np.int64) * 100000 + hh["segment"]) >= 0)     # reference order
+            for r in hh:
+                assert abs(l[0] * r["x"] + l[1] * r["y"] + l[2]) < 2e-2
+                pl = sc.polyline(v, r["polyline"])
+                a, b = pl[r["segment"]], pl[r["segment"] + 1]
+                assert min(a[0], b[0]) - 1e-2 <= r["x"] <= max(a[0], b[0]) + 1e-2 and min(a[1], b[1]) - 1e-2 <= r["y"] <= max(a[1], b[1]) + 1e-2
+    # oracle spot check: bit-exact hit lists for a few seeds
+    few = sub.take(np.arange(0, len(sub), 60))
+    g = dev.epipolar_intersect(few)
+    o = O.OracleScene(sc).epipolar_intersect(few)
+    assert np.array_equal(g[0], o[0]) and g[1].tobytes() == o[1].tobytes()
+
+
+def test_c2_full_batch_properties_and_oracle_sample(c2):
+    sc, seeds, dev = c2
+    pts, tm = dev.match_seeds(seeds)
+    assert tm["n_seeds"] == 50000 and tm["n_capacity_overflows"] == 0 and pts.n_points > 50000
+    # output is ordered by (seed, chain position), chains are contiguous
+    assert np.all(np.diff(pts.seed) >= 0)
+    first = np.r_[True, np.diff(pts.seed) > 0]
+    assert np.all(pts.chain_pos[first] == 0) and np.all(np.diff(pts.chain_pos)[~first[1:]] == 1)
+    # every accepted point reprojects consistently on its own observations (GN acceptance is mse < 9)
+    P = sc.cameras.astype(np.float64).reshape(-1, 3, 4)
+    idx = np.random.default_rng(1).choice(pts.n_points, 3000, replace=False)
+    for i in idx:
+        a, b = int(pts.obs_off[i]), int(pts.obs_off[i + 1])
+        assert b - a >= 3
+        Pv = P[pts.obs_view[a:b]]
+        hh = Pv[:, :, :3] @ pts.xyz[i].astype(np.float64) + Pv[:, :, 3]
+        r = pts.obs_xy[a:b] - hh[:, :2] / hh[:, 2:3]
+        assert (r ** 2).sum() / (2 * (b - a)) < 9.5
+    # shard determinism: two halves of the batch concatenate to the full result
+    half = len(seeds) // 2
+    pa, _ = dev.match_seeds(seeds.slice(0, half))
+    pb, _ = dev.match_seeds(seeds.slice(half, len(seeds)))
+    assert pa.n_points + pb.n_points == pts.n_points
+    assert np.array_equal(np.concatenate([pa.xyz, pb.xyz]), pts.xyz)
+    assert np.array_equal(np.concatenate([pa.obs_view, pb.obs_view]), pts.obs_view)
+    # oracle on a stratified sample of the same batch: identical chains
+    sel = np.arange(0, len(seeds), 400)
+    ref = O.OracleScene(sc).match_seeds(seeds.take(sel), n_threads=16)
+    got, _ = dev.match_seeds(seeds.take(sel))
+    assert got.n_points == ref.n_points and np.array_equal(got.obs_off, ref.obs_off)
+    assert np.array_equal(got.obs_view, ref.obs_view) and np.array_equal(got.obs_poly, ref.obs_poly) and np.array_equal(got.obs_seg, ref.obs_seg)
+    assert got.obs_xy.tobytes() == ref.obs_xy.tobytes()
+    assert np.abs(got.xyz - ref.xyz).max() < 1e-4
+
+
+def test_gn_microbench_device_resident(c2):
+    # BASELINE config 5 shape at 1/20 scale: 500k hypotheses x 20 observations, device-resident arrays
+    import torch
+    sc, _, dev = c2
+    n, k = 500_000, 20
+    views, xy, init, truth = syn.gn_microbench_inputs(sc, n, k, seed=99)
+    dv = torch.from_numpy(views).cuda(); dxy = torch.from_numpy(xy).cuda(); di = torch.from_numpy(init).cuda()
+    ox = torch.empty((n, 3), dtype=torch.float32, device="cuda"); om = torch.empty(n, dtype=torch.float32, device="cuda")
+    ok = torch.empty(n, dtype=torch.uint8, device="cuda")
+    res = {}
+    for fp64 in (0, 1):
+        tm = dev.gn_triangulate_device(n, k, dv.data_ptr(), dxy.data_ptr(), di.data_ptr(), fp64, ox.data_ptr(), om.data_ptr(), ok.data_ptr())
+        torch.cuda.synchronize()
+        res[fp64] = (ox.cpu().numpy().copy(), om.cpu().numpy().copy(), ok.cpu().numpy().copy(), tm["gn_ms"])
+        assert tm["gn_ms"] > 0
+    # fp32 filter variant: bit-exact against the oracle on a sample; fp64 variant: same accept flags, X within 2e-6
+    sel = np.arange(0, n, 997)
+    off = np.arange(len(sel) + 1, dtype=np.int64) * k
+    osc = O.OracleScene(sc)
+    for fp64 in (0, 1):
+        x, m, o = osc.gn_triangulate(off, views[sel].reshape(-1), xy[sel].reshape(-1, 2), init[sel], fp64, n_threads=16)
+        gx, gm, go, _ = res[fp64]
+        assert np.array_equal(go[sel], o)
+        good = o == 1
+        if fp64:
+            assert np.abs(gx[sel][good] - x[good]).max() < 2e-6
+        else:
+            assert np.array_equal(gx[sel][good], x[good]) and np.array_equal(gm[sel], m)
+    # most clean hypotheses pass the filter threshold, most of the 10 % with a displaced observation do not
+    assert 0.80 < res[0][2].mean() < 0.97
+    print(f"GN microbench 500k x 20: fp32 {res[0][3]:.3f} ms, fp64 {res[1][3]:.3f} ms")
