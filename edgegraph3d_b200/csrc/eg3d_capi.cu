@@ -332,16 +332,20 @@ static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_o
   CK(cudaMemsetAsync(counter_b.p, 0, sizeof(int), sc->stream));
   CK(cudaMemsetAsync(snp.p, 0, (size_t)n * sizeof(int), sc->stream));
   a.pa_recs = pa_recs.p; a.pa_pool = pa_pool.p; a.pa_pool_cap = pool_cap; a.pa_counters = pa_cnt.p;
-  Timer t3(sc->stream), tp(sc->stream);
+  Timer t3(sc->stream), t3b(sc->stream), tp(sc->stream);
   t3.start();
   k3a_hypothesis_kernel<<<nblocks, K3_THREADS, 0, sc->stream>>>(sc->dev, a);
-  K3Args b = a; b.work_counter = counter_b.p;
-  k3b_expand_kernel<<<nblocks, K3_THREADS, 0, sc->stream>>>(sc->dev, b);
   t3.stop();
+  K3Args b = a; b.work_counter = counter_b.p;
+  t3b.start();
+  k3b_expand_kernel<<<nblocks, K3_THREADS, 0, sc->stream>>>(sc->dev, b);
+  t3b.stop();
   unsigned long long cnt[4];
   CK(cudaMemcpyAsync(cnt, oc4.p, sizeof cnt, cudaMemcpyDeviceToHost, sc->stream));
   CK(cudaStreamSynchronize(sc->stream));
-  if (tm) { tm->k3_ms += t3.ms(); tm->kernel_launches += 2; tm->n_capacity_overflows += (int)(cnt[2] + cnt[3]); }
+  unsigned long long pac[2] = {0, 0};
+  CK(cudaMemcpy(pac, pa_cnt.p, sizeof pac, cudaMemcpyDeviceToHost));
+  if (tm) { tm->k3a_ms += t3.ms(); tm->k3b_ms += t3b.ms(); tm->k3_ms += t3.ms() + t3b.ms(); tm->n_accepted_seeds += (int64_t)pac[0]; tm->kernel_launches += 2; tm->n_capacity_overflows += (int)(cnt[2] + cnt[3]); }
   if (do_prof) {
     unsigned long long pr[16]; CK(cudaMemcpy(pr, prof.p, sizeof pr, cudaMemcpyDeviceToHost));
     const char* nm[12] = {"A.scan+prune", "A.est3", "A.plg_compatible", "B.epc_prune", "B.epc_gn", "B.add_view_finish(epc)", "B.main_loop", "seed_total", "#est3_lanes", "#est3_rounds", "#plg_compat", "#epc_solved"};

@@ -144,13 +144,16 @@ typedef struct eg3d_timing {
   float k1_count_ms;          /* epipolar intersection, counting pass */
   float k1_fill_ms;           /* epipolar intersection, fill pass */
   float scan_ms;              /* prefix sums */
-  float k3_ms;                /* triple enumeration + PLG following + view expansion */
+  float k3_ms;                /* k3a_ms + k3b_ms */
   float pack_ms;              /* ordered compaction of accepted points */
   float gn_ms;                /* stand-alone GN kernel (eg3d_gn_*) */
   int64_t n_seeds, n_hits, n_segment_tests, n_points, n_obs;
   int64_t k1_algorithmic_bytes; /* 16 B x segments swept per (seed, view) + 72 + 8 + 16 B x hits */
   int32_t kernel_launches;
   int32_t n_capacity_overflows; /* seeds dropped because a capacity in eg3d_params was exceeded */
+  float k3a_ms;               /* K3 phase A: view triples, triple enumeration, PLG following (all seeds) */
+  float k3b_ms;               /* K3 phase B: expansion to the remaining views (accepted seeds) */
+  int64_t n_accepted_seeds;
 } eg3d_timing;
 
 typedef struct eg3d_scene  eg3d_scene;   /* opaque, device resident */
