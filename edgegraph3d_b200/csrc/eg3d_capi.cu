@@ -290,7 +290,9 @@ static eg3d_status run_k1(eg3d_scene* sc, const DevSeeds& ds, const DevCand* dc,
 }
 
 // K3 + ordered packing + D2H into an eg3d_points
-static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_off, const eg3d_hit* d_hits, eg3d_points* out, eg3d_timing* tm) {
+static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_off, const eg3d_hit* d_hits, eg3d_points* out, eg3d_timing* tm,
+                               int64_t cap_scale, bool& out_overflow) {
+  out_overflow = false;
   const int V = sc->V; const int n = ds.n;
   out->device = sc->device; out->stream = sc->stream;
   if (n == 0) { CK(out->d_obs_off.alloc(1)); CK(cudaMemsetAsync(out->d_obs_off.p, 0, sizeof(int64_t), sc->stream)); CK(cudaStreamSynchronize(sc->stream)); return EG3D_OK; }
@@ -306,7 +308,8 @@ static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_o
   DBuf<int> counter; CK(counter.alloc(1)); CK(cudaMemsetAsync(counter.p, 0, sizeof(int), sc->stream));
   DBuf<unsigned long long> oc4; CK(oc4.alloc(4)); CK(cudaMemsetAsync(oc4.p, 0, 4 * sizeof(unsigned long long), sc->stream));
   // unordered output capacity: generous typical-case bound; exceeding it is reported, never silently truncated
-  int64_t pt_cap = std::min<int64_t>((int64_t)n * capc, std::max<int64_t>((int64_t)n * 24, 1 << 16));
+  const bool tiny = getenv("EG3D_TEST_TINY_CAPS") != nullptr;   // test knob: start from absurdly small output buffers to exercise the retry
+  int64_t pt_cap = std::min<int64_t>((int64_t)n * capc, (tiny ? (int64_t)64 : std::max<int64_t>((int64_t)n * 24, 1 << 16)) * cap_scale);
   int64_t ob_cap = pt_cap * std::min<int64_t>(oc, 64 + V / 2);
   DBuf<float> uX; DBuf<int> unobs; DBuf<int64_t> uobase; DBuf<int> uv; DBuf<uint32_t> upl, useg; DBuf<float> ux, uy;
   DBuf<int> snp; DBuf<int64_t> spb, sno;
@@ -326,7 +329,7 @@ static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_o
   if (do_prof) { CK(prof.alloc(16)); CK(cudaMemsetAsync(prof.p, 0, 16 * sizeof(unsigned long long), sc->stream)); a.prof = prof.p; }
   // phase A -> phase B hand-over buffers
   DBuf<PaRec> pa_recs; DBuf<Pt3> pa_pool; DBuf<unsigned long long> pa_cnt; DBuf<int> counter_b;
-  const long long pool_cap = std::max<long long>((long long)n * 12, 1 << 14);
+  const long long pool_cap = std::min<long long>((long long)n * 2 * capf, (tiny ? 32ll : std::max<long long>((long long)n * 12, 1 << 14)) * cap_scale);
   CK(pa_recs.alloc(n)); CK(pa_pool.alloc(pool_cap)); CK(pa_cnt.alloc(2)); CK(counter_b.alloc(1));
   CK(cudaMemsetAsync(pa_cnt.p, 0, 2 * sizeof(unsigned long long), sc->stream));
   CK(cudaMemsetAsync(counter_b.p, 0, sizeof(int), sc->stream));
@@ -352,7 +355,7 @@ static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_o
     for (int k = 0; k < 12; k++) fprintf(stderr, "[k3prof] %-26s %14llu%s\n", nm[k], pr[k], k < 8 ? " warp-cycles" : "");
     fprintf(stderr, "[k3prof] max seed cycles %llu (%.1f ms at 1.9 GHz); seeds > 50M cycles: %llu; > 200M cycles: %llu\n", pr[12], pr[12] / 1.9e6, pr[13], pr[14]);
   }
-  if (cnt[3]) return fail(EG3D_ERR_CAPACITY, "accepted-point output buffer exceeded (internal bound); split the seed batch");
+  if (cnt[3]) { out_overflow = true; return EG3D_OK; }   // internal output bound exceeded: the caller retries with larger buffers
   if (cnt[2]) return fail(EG3D_ERR_CAPACITY, "a per-seed capacity (max_chain_points / max_follow_points / observations per point) was exceeded; raise eg3d_params capacities");
   // ordered packing
   tp.start();
@@ -390,6 +393,20 @@ static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_o
   CK(cudaStreamSynchronize(sc->stream));
   if (tm) { tm->pack_ms += tp.ms(); tm->kernel_launches += 4; tm->n_points += npts; tm->n_obs += nobs; }
   return EG3D_OK;
+}
+
+// Output buffers are sized for the typical case; if a batch produces more, K3 is simply run again with larger buffers
+// (nothing is truncated and no result of the short run is used).
+static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_off, const eg3d_hit* d_hits, eg3d_points* out, eg3d_timing* tm) {
+  int64_t scale = 1;
+  for (int attempt = 0; attempt < 7; attempt++, scale *= 4) {
+    eg3d_timing t0; if (tm) t0 = *tm;
+    bool ovf = false;
+    eg3d_status st = run_k3_once(sc, ds, d_off, d_hits, out, tm, scale, ovf);
+    if (st != EG3D_OK || !ovf) return st;
+    if (tm) { const float k3 = tm->k3_ms, k3a = tm->k3a_ms, k3b = tm->k3b_ms; const int kl = tm->kernel_launches; *tm = t0; tm->k3_ms = k3; tm->k3a_ms = k3a; tm->k3b_ms = k3b; tm->kernel_launches = kl; }
+  }
+  return fail(EG3D_ERR_CAPACITY, "accepted-point output exceeds 4096x the typical bound; split the seed batch");
 }
 
 // lazily bring a result to (pinned) host memory

@@ -194,3 +194,25 @@ def test_match_refpoints_parity(small):
     b, _ = dev.match_refpoints(70, sc.n_tracks)
     assert a.n_points + b.n_points == gpu.n_points
     assert np.array_equal(np.concatenate([a.xyz, b.xyz]), gpu.xyz)
+
+
+def test_output_capacity_retry(small, monkeypatch):
+    # the internal output buffers start tiny (test knob) and the call transparently re-runs K3 with larger ones
+    sc, dev, orc = small
+    cands = syn.curve_candidate_sets(sc)
+    ref, _ = dev.match_polyline_sets(cands)
+    monkeypatch.setenv("EG3D_TEST_TINY_CAPS", "1")
+    again, tm = dev.match_polyline_sets(cands)
+    assert again.n_points == ref.n_points > 64 and np.array_equal(again.xyz, ref.xyz) and np.array_equal(again.obs_off, ref.obs_off)
+    assert tm["kernel_launches"] > 10          # more than one K3 attempt
+
+
+def test_per_seed_capacity_is_reported_not_truncated(small):
+    # max_chain_points too small for the chains of this scene: the call fails loudly with EG3D_ERR_CAPACITY
+    from edgegraph3d_b200 import _abi as A
+    sc, _, _ = small
+    cands = syn.curve_candidate_sets(sc)
+    with E.DeviceScene(sc, E.default_params(max_chain_points=3)) as tiny:
+        with pytest.raises(E.Eg3dError) as ei:
+            tiny.match_polyline_sets(cands)
+    assert ei.value.status == A.EG3D_ERR_CAPACITY
