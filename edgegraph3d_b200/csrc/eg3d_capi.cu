@@ -246,39 +246,71 @@ static eg3d_status upload_seeds(eg3d_scene* sc, const eg3d_seeds* s, bool need_c
   return EG3D_OK;
 }
 
-// K1: count -> scan -> fill.  Leaves off (n*V+1) and hits on the device.
+// ---------------------------------------------------------------------------------------------------- K1 driver ----
+static eg3d_status exclusive_scan_i64(eg3d_scene* sc, int64_t* p, size_t n) {
+  size_t tb = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tb, p, p, n, sc->stream);
+  DBuf<unsigned char> tmp; CK(tmp.alloc(tb));
+  cub::DeviceScan::ExclusiveSum(tmp.p, tb, p, p, n, sc->stream);
+  return EG3D_OK;
+}
+
+template <int MODE>
+static void launch_sweep(eg3d_scene* sc, const K1Seeds& ks, const K1Work& w, int64_t* counts, unsigned char* flags, const int64_t* off, eg3d_hit* hits) {
+  if (w.n <= 0) return;
+  dim3 grid((w.n + K1_THREADS - 1) / K1_THREADS, sc->V);
+  k1_sweep_kernel<MODE><<<grid, K1_THREADS, K1_SMEM_BYTES2, sc->stream>>>(sc->dev, ks, w, counts, flags, off, hits);
+}
+
+// Sweep form of K1 for the pairs described by `w` (n_rows result rows): count -> scan -> fill.
+static eg3d_status sweep_lists(eg3d_scene* sc, const K1Seeds& ks, const K1Work& w, size_t n_rows, bool rows_sparse, DBuf<int64_t>& off, DBuf<eg3d_hit>& hits,
+                               int64_t& n_hits, eg3d_timing* tm) {
+  CK(off.alloc(n_rows + 1));
+  if (rows_sparse) CK(cudaMemsetAsync(off.p, 0, (n_rows + 1) * sizeof(int64_t), sc->stream));   // rows no launch writes stay empty
+  else CK(cudaMemsetAsync(off.p + n_rows, 0, sizeof(int64_t), sc->stream));
+  Timer t1(sc->stream), t2(sc->stream), t3(sc->stream);
+  t1.start(); launch_sweep<K1_COUNT>(sc, ks, w, off.p, nullptr, nullptr, nullptr); t1.stop();
+  CK(cudaGetLastError());
+  t2.start();
+  eg3d_status st = exclusive_scan_i64(sc, off.p, n_rows + 1); if (st != EG3D_OK) return st;
+  t2.stop();
+  CK(cudaMemcpyAsync(&n_hits, off.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, sc->stream));
+  CK(cudaStreamSynchronize(sc->stream));
+  CK(hits.alloc((size_t)n_hits));
+  t3.start(); launch_sweep<K1_FILL>(sc, ks, w, nullptr, nullptr, off.p, hits.p); t3.stop();
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(sc->stream));
+  if (tm) { tm->k1_count_ms += t1.ms(); tm->scan_ms += t2.ms(); tm->k1_fill_ms += t3.ms(); tm->n_hits += n_hits; tm->kernel_launches += 4; }
+  return EG3D_OK;
+}
+
+// K1 for every (seed, view) pair: count -> scan -> fill.  Leaves off (n*V+1) and hits on the device.
 static eg3d_status run_k1(eg3d_scene* sc, const DevSeeds& ds, const DevCand* dc, DBuf<int64_t>& off, DBuf<eg3d_hit>& hits,
                           int64_t& n_hits, eg3d_timing* tm) {
   const int V = sc->V; const int64_t nsv = (int64_t)ds.n * V;
+  K1Seeds ks = ds.k1();
+  if (!dc) {
+    K1Work w; w.list = nullptr; w.n = ds.n; w.sel = nullptr;
+    return sweep_lists(sc, ks, w, (size_t)nsv, false, off, hits, n_hits, tm);
+  }
   CK(off.alloc(nsv + 1));
   CK(cudaMemsetAsync(off.p + nsv, 0, sizeof(int64_t), sc->stream));
   Timer t1(sc->stream), t2(sc->stream), t3(sc->stream);
-  K1Seeds ks = ds.k1();
-  dim3 grid((ds.n + K1_THREADS - 1) / K1_THREADS, V);
-  K1Cand kc; kc.off = dc ? dc->off.p : nullptr; kc.pl = dc ? dc->pl.p : nullptr;
-  kc.center = (dc && dc->filtered) ? dc->center.p : nullptr; kc.seed_r2 = (dc && dc->filtered) ? dc->seed_r2.p : nullptr;
+  K1Cand kc; kc.off = dc->off.p; kc.pl = dc->pl.p;
+  kc.center = dc->filtered ? dc->center.p : nullptr; kc.seed_r2 = dc->filtered ? dc->seed_r2.p : nullptr;
   const int cblocks = (int)((nsv + 255) / 256);
   t1.start();
-  if (ds.n > 0) {
-    if (dc) k1_cand_kernel<false><<<cblocks, 256, 0, sc->stream>>>(sc->dev, ks, kc, off.p, nullptr, nullptr);
-    else k1_sweep_kernel<false><<<grid, K1_THREADS, K1_SMEM_BYTES2, sc->stream>>>(sc->dev, ks, 0, off.p, nullptr, nullptr);
-  }
+  if (ds.n > 0) k1_cand_kernel<false><<<cblocks, 256, 0, sc->stream>>>(sc->dev, ks, kc, off.p, nullptr, nullptr);
   t1.stop();
   CK(cudaGetLastError());
   t2.start();
-  size_t tb = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, tb, off.p, off.p, nsv + 1, sc->stream);
-  DBuf<unsigned char> tmp; CK(tmp.alloc(tb));
-  cub::DeviceScan::ExclusiveSum(tmp.p, tb, off.p, off.p, nsv + 1, sc->stream);
+  eg3d_status st = exclusive_scan_i64(sc, off.p, (size_t)nsv + 1); if (st != EG3D_OK) return st;
   t2.stop();
   CK(cudaMemcpyAsync(&n_hits, off.p + nsv, sizeof(int64_t), cudaMemcpyDeviceToHost, sc->stream));
   CK(cudaStreamSynchronize(sc->stream));
   CK(hits.alloc((size_t)n_hits));
   t3.start();
-  if (ds.n > 0) {
-    if (dc) k1_cand_kernel<true><<<cblocks, 256, 0, sc->stream>>>(sc->dev, ks, kc, nullptr, off.p, hits.p);
-    else k1_sweep_kernel<true><<<grid, K1_THREADS, K1_SMEM_BYTES2, sc->stream>>>(sc->dev, ks, 0, nullptr, off.p, hits.p);
-  }
+  if (ds.n > 0) k1_cand_kernel<true><<<cblocks, 256, 0, sc->stream>>>(sc->dev, ks, kc, nullptr, off.p, hits.p);
   t3.stop();
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(sc->stream));
@@ -289,8 +321,65 @@ static eg3d_status run_k1(eg3d_scene* sc, const DevSeeds& ds, const DevCand* dc,
   return EG3D_OK;
 }
 
+// The hit lists K3 reads.  Full form (candidate sets / refpoints): one CSR over every (seed, view) pair.  Lazy form
+// (all-segment sweep): the reference materialises every list (polyline_matching.cpp:45-73) but its per-seed code only
+// ever READS the three selected views unless the seed is accepted, so the sweep is run on demand — an any-hit pass for
+// the view selection, the three selected views of every seed for phase A, and every view of the accepted seeds for
+// phase B.  Same lists, same order, same results; ~5x fewer segment tests and hit bytes on BASELINE configs[1].
+struct HitLists {
+  bool lazy = false;
+  DBuf<unsigned char> flags;                       // lazy: [n*V] list is non-empty
+  DBuf<int> sel;                                   // [n][3]
+  DBuf<int64_t> off_a; DBuf<eg3d_hit> hits_a;      // full: [n*V+1]; lazy: [3n+1]
+  DBuf<int64_t> off_b; DBuf<eg3d_hit> hits_b;      // lazy only: [n_acc*V+1], rebuilt after phase A
+  DBuf<int> acc_seed;                              // [n] accepted seed by phase-A rank
+};
+
+static eg3d_status select_views(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, eg3d_timing* tm) {
+  CK(H.sel.alloc(3 * (size_t)std::max(ds.n, 1)));
+  CK(H.acc_seed.alloc((size_t)std::max(ds.n, 1)));
+  if (ds.n == 0) return EG3D_OK;
+  Timer t(sc->stream);
+  t.start();
+  k3_select_views_kernel<<<(unsigned)(((size_t)ds.n * 32 + 127) / 128), 128, 0, sc->stream>>>(ds.n, sc->V, ds.view.p, H.lazy ? H.flags.p : nullptr,
+                                                                                          H.lazy ? nullptr : H.off_a.p, H.sel.p);
+  t.stop();
+  CK(cudaGetLastError());
+  if (tm) { tm->scan_ms += t.ms(); tm->kernel_launches += 1; }
+  return EG3D_OK;
+}
+
+// Everything phase A needs.  dc != null: candidate form (full CSR).
+static eg3d_status prepare_hits_a(eg3d_scene* sc, const DevSeeds& ds, const DevCand* dc, HitLists& H, eg3d_timing* tm) {
+  int64_t nh = 0;
+  H.lazy = (dc == nullptr) && !getenv("EG3D_K1_FULL");
+  if (!H.lazy) {
+    eg3d_status st = run_k1(sc, ds, dc, H.off_a, H.hits_a, nh, tm); if (st != EG3D_OK) return st;
+    return select_views(sc, ds, H, tm);
+  }
+  const int V = sc->V;
+  K1Seeds ks = ds.k1();
+  CK(H.flags.alloc((size_t)std::max<int64_t>((int64_t)ds.n * V, 1)));
+  Timer t(sc->stream);
+  K1Work w; w.list = nullptr; w.n = ds.n; w.sel = nullptr;
+  t.start(); launch_sweep<K1_ANY>(sc, ks, w, nullptr, H.flags.p, nullptr, nullptr); t.stop();
+  CK(cudaGetLastError());
+  if (tm) { tm->k1_any_ms += t.ms(); tm->kernel_launches += 1; }
+  eg3d_status st = select_views(sc, ds, H, tm); if (st != EG3D_OK) return st;
+  w.sel = H.sel.p;
+  return sweep_lists(sc, ks, w, 3 * (size_t)ds.n, true, H.off_a, H.hits_a, nh, tm);
+}
+
+// lazy form: every view of the accepted seeds (rank order of phase A)
+static eg3d_status prepare_hits_b(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, int64_t n_acc, eg3d_timing* tm) {
+  K1Seeds ks = ds.k1();
+  K1Work w; w.list = H.acc_seed.p; w.n = (int)n_acc; w.sel = nullptr;
+  int64_t nh = 0;
+  return sweep_lists(sc, ks, w, (size_t)n_acc * sc->V, false, H.off_b, H.hits_b, nh, tm);
+}
+
 // K3 + ordered packing + D2H into an eg3d_points
-static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_off, const eg3d_hit* d_hits, eg3d_points* out, eg3d_timing* tm,
+static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, eg3d_points* out, eg3d_timing* tm,
                                int64_t cap_scale, bool& out_overflow) {
   out_overflow = false;
   const int V = sc->V; const int n = ds.n;
@@ -318,7 +407,10 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, const int64_t
   CK(snp.alloc(n)); CK(spb.alloc(n)); CK(sno.alloc(n));
   K3Args a; memset(&a, 0, sizeof a);
   a.n_seeds = n; a.seed_view = ds.view.p; a.seed_pl = ds.pl.p; a.seed_seg = ds.seg.p; a.seed_xy = ds.xy.p;
-  a.hit_off = d_off; a.hits = d_hits; a.capf = capf; a.capc = capc; a.oc = oc;
+  a.hit_off = H.off_a.p; a.hits = H.hits_a.p; a.a_compact = H.lazy ? 1 : 0;
+  a.hit_off_b = H.off_a.p; a.hits_b = H.hits_a.p; a.b_compact = 0;     // lazy form: replaced after phase A
+  a.sel = H.sel.p; a.acc_seed = H.acc_seed.p;
+  a.capf = capf; a.capc = capc; a.oc = oc;
   a.scratch = scratch.p; a.scratch_per_warp = spw; a.work_counter = counter.p;
   a.pt_cap = pt_cap; a.ob_cap = ob_cap; a.out_counters = oc4.p;
   a.o_X = uX.p; a.o_nobs = unobs.p; a.o_obase = uobase.p;
@@ -326,7 +418,11 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, const int64_t
   a.seed_npts = snp.p; a.seed_pbase = spb.p; a.seed_nobs = sno.p;
   DBuf<unsigned long long> prof;
   const bool do_prof = getenv("EG3D_K3_PROF") != nullptr;
-  if (do_prof) { CK(prof.alloc(16)); CK(cudaMemsetAsync(prof.p, 0, 16 * sizeof(unsigned long long), sc->stream)); a.prof = prof.p; }
+  DBuf<unsigned long long> prof_seed;
+  if (do_prof) {
+    CK(prof.alloc(16)); CK(cudaMemsetAsync(prof.p, 0, 16 * sizeof(unsigned long long), sc->stream)); a.prof = prof.p;
+    CK(prof_seed.alloc(2 * (size_t)n)); CK(cudaMemsetAsync(prof_seed.p, 0, 2 * (size_t)n * sizeof(unsigned long long), sc->stream)); a.prof_seed = prof_seed.p;
+  }
   // phase A -> phase B hand-over buffers
   DBuf<PaRec> pa_recs; DBuf<Pt3> pa_pool; DBuf<unsigned long long> pa_cnt; DBuf<int> counter_b;
   const long long pool_cap = std::min<long long>((long long)n * 2 * capf, (tiny ? 32ll : std::max<long long>((long long)n * 12, 1 << 14)) * cap_scale);
@@ -339,21 +435,46 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, const int64_t
   t3.start();
   k3a_hypothesis_kernel<<<nblocks, K3_THREADS, 0, sc->stream>>>(sc->dev, a);
   t3.stop();
+  CK(cudaGetLastError());
+  unsigned long long pac[2] = {0, 0};
+  CK(cudaMemcpyAsync(pac, pa_cnt.p, sizeof pac, cudaMemcpyDeviceToHost, sc->stream));
+  CK(cudaStreamSynchronize(sc->stream));
   K3Args b = a; b.work_counter = counter_b.p;
+  if (H.lazy) {
+    eg3d_status st = prepare_hits_b(sc, ds, H, (int64_t)pac[0], tm); if (st != EG3D_OK) return st;
+    b.hit_off_b = H.off_b.p; b.hits_b = H.hits_b.p; b.b_compact = 1;
+  }
+  // phase-B work order: longest chains first
+  DBuf<unsigned> okeys, okeys2; DBuf<int> ovals, oorder; DBuf<unsigned char> otmp;
+  if (!getenv("EG3D_K3_NO_ORDER")) {
+    CK(okeys.alloc(n)); CK(okeys2.alloc(n)); CK(ovals.alloc(n)); CK(oorder.alloc(n));
+    k3_order_keys_kernel<<<(n + 255) / 256, 256, 0, sc->stream>>>(n, pa_cnt.p, pa_recs.p, okeys.p, ovals.p);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, okeys.p, okeys2.p, ovals.p, oorder.p, n, 0, 32, sc->stream);
+    CK(otmp.alloc(tb));
+    cub::DeviceRadixSort::SortPairs(otmp.p, tb, okeys.p, okeys2.p, ovals.p, oorder.p, n, 0, 32, sc->stream);
+    b.pa_order = oorder.p;
+  }
   t3b.start();
   k3b_expand_kernel<<<nblocks, K3_THREADS, 0, sc->stream>>>(sc->dev, b);
   t3b.stop();
   unsigned long long cnt[4];
   CK(cudaMemcpyAsync(cnt, oc4.p, sizeof cnt, cudaMemcpyDeviceToHost, sc->stream));
   CK(cudaStreamSynchronize(sc->stream));
-  unsigned long long pac[2] = {0, 0};
-  CK(cudaMemcpy(pac, pa_cnt.p, sizeof pac, cudaMemcpyDeviceToHost));
   if (tm) { tm->k3a_ms += t3.ms(); tm->k3b_ms += t3b.ms(); tm->k3_ms += t3.ms() + t3b.ms(); tm->n_accepted_seeds += (int64_t)pac[0]; tm->kernel_launches += 2; tm->n_capacity_overflows += (int)(cnt[2] + cnt[3]); }
   if (do_prof) {
     unsigned long long pr[16]; CK(cudaMemcpy(pr, prof.p, sizeof pr, cudaMemcpyDeviceToHost));
     const char* nm[12] = {"A.scan+prune", "A.est3", "A.plg_compatible", "B.epc_prune", "B.epc_gn", "B.add_view_finish(epc)", "B.main_loop", "seed_total", "#est3_lanes", "#est3_rounds", "#plg_compat", "#epc_solved"};
     for (int k = 0; k < 12; k++) fprintf(stderr, "[k3prof] %-26s %14llu%s\n", nm[k], pr[k], k < 8 ? " warp-cycles" : "");
     fprintf(stderr, "[k3prof] max seed cycles %llu (%.1f ms at 1.9 GHz); seeds > 50M cycles: %llu; > 200M cycles: %llu\n", pr[12], pr[12] / 1.9e6, pr[13], pr[14]);
+    const char* dump = getenv("EG3D_K3_PROF");
+    if (dump && (dump[0] == '/' || strchr(dump, '.'))) {   // EG3D_K3_PROF=<file>: per-seed (cycles, initial length, final length)
+      std::vector<unsigned long long> ps(2 * (size_t)n); CK(cudaMemcpy(ps.data(), prof_seed.p, ps.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      if (FILE* f = fopen(dump, "w")) {
+        for (int i = 0; i < n; i++) if (ps[2 * i]) fprintf(f, "%d %llu %llu %llu\n", i, ps[2 * i], ps[2 * i + 1] & 0xffffffffull, ps[2 * i + 1] >> 32);
+        fclose(f);
+      }
+    }
   }
   if (cnt[3]) { out_overflow = true; return EG3D_OK; }   // internal output bound exceeded: the caller retries with larger buffers
   if (cnt[2]) return fail(EG3D_ERR_CAPACITY, "a per-seed capacity (max_chain_points / max_follow_points / observations per point) was exceeded; raise eg3d_params capacities");
@@ -397,14 +518,15 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, const int64_t
 
 // Output buffers are sized for the typical case; if a batch produces more, K3 is simply run again with larger buffers
 // (nothing is truncated and no result of the short run is used).
-static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, const int64_t* d_off, const eg3d_hit* d_hits, eg3d_points* out, eg3d_timing* tm) {
+static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, eg3d_points* out, eg3d_timing* tm) {
   int64_t scale = 1;
   for (int attempt = 0; attempt < 7; attempt++, scale *= 4) {
     eg3d_timing t0; if (tm) t0 = *tm;
     bool ovf = false;
-    eg3d_status st = run_k3_once(sc, ds, d_off, d_hits, out, tm, scale, ovf);
+    eg3d_status st = run_k3_once(sc, ds, H, out, tm, scale, ovf);
     if (st != EG3D_OK || !ovf) return st;
-    if (tm) { const float k3 = tm->k3_ms, k3a = tm->k3a_ms, k3b = tm->k3b_ms; const int kl = tm->kernel_launches; *tm = t0; tm->k3_ms = k3; tm->k3a_ms = k3a; tm->k3b_ms = k3b; tm->kernel_launches = kl; }
+    if (tm) { const eg3d_timing t1 = *tm; *tm = t0; tm->k3_ms = t1.k3_ms; tm->k3a_ms = t1.k3a_ms; tm->k3b_ms = t1.k3b_ms; tm->kernel_launches = t1.kernel_launches;
+              tm->k1_count_ms = t1.k1_count_ms; tm->k1_fill_ms = t1.k1_fill_ms; tm->scan_ms = t1.scan_ms; }
   }
   return fail(EG3D_ERR_CAPACITY, "accepted-point output exceeds 4096x the typical bound; split the seed batch");
 }
@@ -596,8 +718,9 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   if (tracks) { D.g_corr.cell = sc->hg30.cell; D.g_corr.w = sc->hg30.w; D.g_corr.h = sc->hg30.h; D.g_corr.cell_off = sc->g30_off.p; D.g_corr.ids = sc->g30_ids.p; }
   D.n_tracks = d->n_tracks; D.track_xyz = sc->track_xyz.p; D.track_off = sc->track_off.p; D.track_view = sc->track_view.p; D.track_xy = sc->track_xy.p;
   D.prm = sc->prm;
-  CK(cudaFuncSetAttribute(k1_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
-  CK(cudaFuncSetAttribute(k1_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
   *out = guard.release();
   return EG3D_OK;
 }
@@ -670,6 +793,21 @@ eg3d_status eg3d_epipolar_intersect(eg3d_scene* sc, const eg3d_seeds* seeds, con
   *out = h;
   return EG3D_OK;
 }
+eg3d_status eg3d_epipolar_intersect_device(eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d_candidates* cands, eg3d_timing* tm) {
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  st = check_seeds(sc, seeds, cands); if (st != EG3D_OK) return st;
+  CK(cudaSetDevice(sc->device));
+  g_alloc_stream = sc->stream;
+  eg3d_timing local; memset(&local, 0, sizeof local);
+  DevSeeds ds; st = upload_seeds(sc, seeds, cands != nullptr, ds); if (st != EG3D_OK) return st;
+  DevCand dc; if (cands) { st = upload_cands(sc, cands, dc); if (st != EG3D_OK) return st; }
+  DBuf<int64_t> off; DBuf<eg3d_hit> hits; int64_t nh = 0;
+  st = run_k1(sc, ds, cands ? &dc : nullptr, off, hits, nh, &local); if (st != EG3D_OK) return st;
+  local.n_seeds = seeds->n; local.total_ms = local.k1_count_ms + local.scan_ms + local.k1_fill_ms;
+  k1_accounting(sc, seeds, cands, nh, &local);
+  if (tm) *tm = local;
+  return EG3D_OK;
+}
 eg3d_status eg3d_hits_get(const eg3d_hits* h, int64_t* n_seeds, int32_t* n_views, const int64_t** off, const eg3d_hit** hits) {
   if (!h) return fail(EG3D_ERR_INVALID_ARG, "null hits");
   *n_seeds = h->n_seeds; *n_views = h->V; *off = h->off.data(); *hits = h->hits.data();
@@ -687,13 +825,13 @@ eg3d_status eg3d_match_seeds(eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d
   DevCand dc; if (cands) { st = upload_cands(sc, cands, dc); if (st != EG3D_OK) return st; }
   Timer tall(sc->stream);
   tall.start();
-  DBuf<int64_t> off; DBuf<eg3d_hit> hits; int64_t nh = 0;
-  st = run_k1(sc, ds, cands ? &dc : nullptr, off, hits, nh, &local); if (st != EG3D_OK) return st;
+  HitLists H;
+  st = prepare_hits_a(sc, ds, cands ? &dc : nullptr, H, &local); if (st != EG3D_OK) return st;
   std::unique_ptr<eg3d_points> pts(new eg3d_points());
-  st = run_k3(sc, ds, off.p, hits.p, pts.get(), &local);
+  st = run_k3(sc, ds, H, pts.get(), &local);
   local.n_seeds = seeds->n;
-  local.total_ms = local.k1_count_ms + local.scan_ms + local.k1_fill_ms + local.k3_ms + local.pack_ms;
-  k1_accounting(sc, seeds, cands, nh, &local);
+  local.total_ms = local.k1_any_ms + local.k1_count_ms + local.scan_ms + local.k1_fill_ms + local.k3_ms + local.pack_ms;
+  k1_accounting(sc, seeds, cands, local.n_hits, &local);
   if (tm) *tm = local;
   if (st != EG3D_OK) return st;
   *out = pts.release();
@@ -917,12 +1055,12 @@ eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_po
   DevSeeds ds; st = upload_seeds(sc, &seeds, true, ds); if (st != EG3D_OK) return st;
   DevCand dc; dc.filtered = true;
   CK(dc.off.upload(coff, sc->stream)); CK(dc.pl.upload(cpl, sc->stream)); CK(dc.center.upload(center, sc->stream)); CK(dc.seed_r2.upload(sr2, sc->stream));
-  DBuf<int64_t> off; DBuf<eg3d_hit> hits; int64_t nh = 0;
-  st = run_k1(sc, ds, &dc, off, hits, nh, &local); if (st != EG3D_OK) return st;
+  HitLists H;
+  st = prepare_hits_a(sc, ds, &dc, H, &local); if (st != EG3D_OK) return st;
   std::unique_ptr<eg3d_points> pts(new eg3d_points());
-  st = run_k3(sc, ds, off.p, hits.p, pts.get(), &local);
+  st = run_k3(sc, ds, H, pts.get(), &local);
   local.n_seeds = seeds.n;
-  local.total_ms = local.k1_count_ms + local.scan_ms + local.k1_fill_ms + local.k3_ms + local.pack_ms;
+  local.total_ms = local.k1_any_ms + local.k1_count_ms + local.scan_ms + local.k1_fill_ms + local.k3_ms + local.pack_ms;
   if (tm) *tm = local;
   if (st != EG3D_OK) return st;
   *out = pts.release();

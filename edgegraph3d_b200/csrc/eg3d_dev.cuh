@@ -515,57 +515,62 @@ struct ObsSrc {
 // for FP64 throughput: one reciprocal of the projective depth instead of eight divisions ((p0*z - p8*x)/z^2 ==
 // (p0 - p8*(x/z))/z), explicit fused multiply-adds, cameras pre-widened to double.  Differs from the division form by
 // rounding only (~1e-16 relative); the thresholded 3-view solves use gn3_exact instead.
-EG3D_D void gn_accumulate_fast(const double* __restrict__ P, float px, float py, const double X[3], GnAcc& a) {
+EG3D_D void gn_accumulate_fast(const double* __restrict__ P, float px, float py, double X0, double X1, double X2, GnAcc& a) {
+  // Staged for register pressure (the kernels run at 64 registers/thread): the depth row first, then the x row, then
+  // the y row, each camera row dead before the next one is loaded.  Every accumulator still receives its x term and
+  // then its y term, so the sums round exactly as in the one-shot form.
   const double2* P2 = reinterpret_cast<const double2*>(P);
-  double2 q0 = P2[0], q1 = P2[1], q2 = P2[2], q3 = P2[3], q4 = P2[4], q5 = P2[5];
-  double h0 = fma(q0.x, X[0], fma(q0.y, X[1], fma(q1.x, X[2], q1.y)));
-  double h1 = fma(q2.x, X[0], fma(q2.y, X[1], fma(q3.x, X[2], q3.y)));
-  double h2 = fma(q4.x, X[0], fma(q4.y, X[1], fma(q5.x, X[2], q5.y)));
-  double inv = 1.0 / h2;
-  double u = h0 * inv, v = h1 * inv;
-  double rx = (double)px - u, ry = (double)py - v;
-  a.mse = fma(rx, rx, a.mse); a.mse = fma(ry, ry, a.mse);
-  double jx0 = fma(-q4.x, u, q0.x) * inv, jx1 = fma(-q4.y, u, q0.y) * inv, jx2 = fma(-q5.x, u, q1.x) * inv;
-  double jy0 = fma(-q4.x, v, q2.x) * inv, jy1 = fma(-q4.y, v, q2.y) * inv, jy2 = fma(-q5.x, v, q3.x) * inv;
-  a.h00 = fma(jx0, jx0, a.h00); a.h00 = fma(jy0, jy0, a.h00);
-  a.h01 = fma(jx0, jx1, a.h01); a.h01 = fma(jy0, jy1, a.h01);
-  a.h02 = fma(jx0, jx2, a.h02); a.h02 = fma(jy0, jy2, a.h02);
-  a.h11 = fma(jx1, jx1, a.h11); a.h11 = fma(jy1, jy1, a.h11);
-  a.h12 = fma(jx1, jx2, a.h12); a.h12 = fma(jy1, jy2, a.h12);
-  a.h22 = fma(jx2, jx2, a.h22); a.h22 = fma(jy2, jy2, a.h22);
-  a.g0 = fma(jx0, rx, a.g0); a.g0 = fma(jy0, ry, a.g0);
-  a.g1 = fma(jx1, rx, a.g1); a.g1 = fma(jy1, ry, a.g1);
-  a.g2 = fma(jx2, rx, a.g2); a.g2 = fma(jy2, ry, a.g2);
+  const double2 q4 = P2[4], q5 = P2[5];
+  const double inv = 1.0 / fma(q4.x, X0, fma(q4.y, X1, fma(q5.x, X2, q5.y)));
+  {
+    const double2 q0 = P2[0], q1 = P2[1];
+    const double u = fma(q0.x, X0, fma(q0.y, X1, fma(q1.x, X2, q1.y))) * inv;
+    const double rx = (double)px - u;
+    const double jx0 = fma(-q4.x, u, q0.x) * inv, jx1 = fma(-q4.y, u, q0.y) * inv, jx2 = fma(-q5.x, u, q1.x) * inv;
+    a.mse = fma(rx, rx, a.mse);
+    a.h00 = fma(jx0, jx0, a.h00); a.h01 = fma(jx0, jx1, a.h01); a.h02 = fma(jx0, jx2, a.h02);
+    a.h11 = fma(jx1, jx1, a.h11); a.h12 = fma(jx1, jx2, a.h12); a.h22 = fma(jx2, jx2, a.h22);
+    a.g0 = fma(jx0, rx, a.g0); a.g1 = fma(jx1, rx, a.g1); a.g2 = fma(jx2, rx, a.g2);
+  }
+  {
+    const double2 q2 = P2[2], q3 = P2[3];
+    const double v = fma(q2.x, X0, fma(q2.y, X1, fma(q3.x, X2, q3.y))) * inv;
+    const double ry = (double)py - v;
+    const double jy0 = fma(-q4.x, v, q2.x) * inv, jy1 = fma(-q4.y, v, q2.y) * inv, jy2 = fma(-q5.x, v, q3.x) * inv;
+    a.mse = fma(ry, ry, a.mse);
+    a.h00 = fma(jy0, jy0, a.h00); a.h01 = fma(jy0, jy1, a.h01); a.h02 = fma(jy0, jy2, a.h02);
+    a.h11 = fma(jy1, jy1, a.h11); a.h12 = fma(jy1, jy2, a.h12); a.h22 = fma(jy2, jy2, a.h22);
+    a.g0 = fma(jy0, ry, a.g0); a.g1 = fma(jy1, ry, a.g1); a.g2 = fma(jy2, ry, a.g2);
+  }
 }
 
 // Gauss-Newton (em_GaussNewton, triangulation.cpp:105-176) for up to 32/G independent problems per warp: the warp is
 // split into groups of G lanes (G a power of two, 1..32); group g = lane / G solves the problem described by `o`
-// (identical in all lanes of a group), its lanes stride over the observations and the ten sums are butterfly-reduced
-// inside the group, so every lane of a group holds the same iterate.  Must be called by all 32 lanes; groups without
-// a problem pass active = false.  Returns the accept decision (last_mse < 9) of the caller's group.
+// (identical in all lanes of a group), its lanes stride over the observations (the optional extra observation is index
+// n) and the ten sums are butterfly-reduced inside the group, so every lane of a group holds the same iterate.  Must be
+// called by all 32 lanes; groups without a problem pass active = false.  Returns the accept decision (last_mse < 9) of
+// the caller's group.  Loop-invariant scalars are re-read from the (constant-bank) scene instead of being kept in
+// registers: the observation loop has to stay spill-free at 64 registers.
 static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o, bool active, int G, int lane, double X[3]) {
-  // everything the loop needs is pulled into registers first: the structs live in the callers' stack frames
   const int* __restrict__ ov = o.v;
   const float* __restrict__ ox = o.x;
   const float* __restrict__ oy = o.y;
-  const double* __restrict__ P64 = S.P64;
   const int n = o.n, ntot = o.n + o.has_extra;
   const int sub = lane & (G - 1);
-  const bool mine_extra = o.has_extra && (sub == (n & (G - 1)));
-  const int ev = o.ev; const float ex = o.ex, ey = o.ey;
-  const int max_iters = S.prm.gn_max_iters;
-  const double stop = S.prm.gn_stop, det_min = S.prm.gn_det_min, accept = S.prm.gn_accept_mse;
   double X0 = X[0], X1 = X[1], X2 = X[2];
   double last_mse = 0;
   bool running = active, failed = false;
-  for (int it = 0; it < max_iters; it++) {
+  for (int it = 0; it < S.prm.gn_max_iters; it++) {
     if (!__any_sync(0xffffffffu, running)) break;
     GnAcc a = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (running) {
-      const double Xl[3] = {X0, X1, X2};
+      const double* __restrict__ P64 = S.P64;
 #pragma unroll 1
-      for (int i = sub; i < n; i += G) gn_accumulate_fast(P64 + 12 * ov[i], ox[i], oy[i], Xl, a);
-      if (mine_extra) gn_accumulate_fast(P64 + 12 * ev, ex, ey, Xl, a);
+      for (int i = sub; i < ntot; i += G) {
+        int v; float px, py;
+        if (i < n) { v = ov[i]; px = ox[i]; py = oy[i]; } else { v = o.ev; px = o.ex; py = o.ey; }
+        gn_accumulate_fast(P64 + 12 * v, px, py, X0, X1, X2, a);
+      }
     }
 #pragma unroll 1
     for (int off = G >> 1; off > 0; off >>= 1) {
@@ -578,12 +583,12 @@ static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o,
     }
     if (running) {
       const double cur = a.mse / (ntot * 2);
-      if (fabs(cur - last_mse) < stop) running = false;
+      if (fabs(cur - last_mse) < S.prm.gn_stop) running = false;
       else {
         last_mse = cur;
         const double H[9] = {a.h00, a.h01, a.h02, a.h01, a.h11, a.h12, a.h02, a.h12, a.h22};
         const double d = det3d(H);
-        if (d < det_min) { running = false; failed = true; }
+        if (d < S.prm.gn_det_min) { running = false; failed = true; }
         else {
           double Hi[9]; inv3d(H, d, Hi);
           X0 += Hi[0] * a.g0 + Hi[1] * a.g1 + Hi[2] * a.g2;
@@ -594,7 +599,7 @@ static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o,
     }
   }
   X[0] = X0; X[1] = X1; X[2] = X2;
-  return active && !failed && last_mse < accept;
+  return active && !failed && last_mse < S.prm.gn_accept_mse;
 }
 
 // lanes per problem for `p` (1..32) simultaneous problems

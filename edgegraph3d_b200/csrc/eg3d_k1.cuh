@@ -54,7 +54,7 @@ struct K1Seeds {
   const int* cand_set;  // may be null
 };
 
-// Sweep kernel.  One CTA = one target view x a tile of 256 seeds; the view's staged segments and the bounding boxes of
+// Sweep kernel.  One CTA = one target view x a tile of 256 (seed) entries; the view's staged segments and the bounding boxes of
 // their groups of 32 stream through a double-buffered shared-memory ring (TMA bulk copies, mbarrier complete_tx).
 // Each warp owns 32 seeds of the tile and visits them one after the other; for a seed the 32 lanes
 //   1. test 32 group boxes at a time against the epipolar line (|a cx + b cy + c| <= |a| ex + |b| ey + slack) — a
@@ -70,38 +70,66 @@ constexpr int K1_GPR = 32 / K1_GROUP;          // groups handled per warp step (
 constexpr int K1_GMAX = 4096 / K1_GROUP;       // max groups per chunk
 constexpr int K1_SMEM_BYTES2 = K1_STAGES * (K1_CHUNK * 16 + K1_GMAX * 16 + K1_GMAX * 4) + K1_STAGES * 8;
 
-template <bool FILL>
-__global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K1Seeds seeds, int view_lo,
-                                                              int64_t* __restrict__ counts, const int64_t* __restrict__ off,
-                                                              eg3d_hit* __restrict__ hits) {
+// Which (seed, view) pairs a launch handles and where their results go.  The matching path never reads most of the
+// hit lists the reference materialises (a seed that is not accepted only ever looks at its three selected views), so
+// besides the full sweep there are two targeted forms:
+//   list == null, sel == null : every seed x every view; result row of (seed, t) = seed * V + t        (K1 alone)
+//   sel != null               : only the views sel[seed][0..2] of every seed; row = seed * 3 + k       (phase A)
+//   list != null              : every view of the listed seeds; row = entry * V + t                    (phase B)
+struct K1Work {
+  const int* list;   // entry -> seed index (null: identity)
+  int n;             // number of entries
+  const int* sel;    // [n_seeds][3] wanted views (sel[3*seed] < 0: none), or null
+};
+enum { K1_COUNT = 0, K1_FILL = 1, K1_ANY = 2 };   // K1_ANY: only "is the list non-empty" (stops at a seed's first hit)
+
+template <int MODE>
+__global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K1Seeds seeds, const __grid_constant__ K1Work work,
+                                                              int64_t* __restrict__ counts, unsigned char* __restrict__ flags,
+                                                              const int64_t* __restrict__ off, eg3d_hit* __restrict__ hits) {
+  constexpr bool FILL = MODE == K1_FILL;
   extern __shared__ __align__(128) unsigned char k1_smem[];
   float4 (*sbuf)[K1_CHUNK] = reinterpret_cast<float4 (*)[K1_CHUNK]>(k1_smem);
   float4 (*bbuf)[K1_GMAX] = reinterpret_cast<float4 (*)[K1_GMAX]>(k1_smem + sizeof(float4) * K1_STAGES * K1_CHUNK);
   uint32_t (*dbuf)[K1_GMAX] = reinterpret_cast<uint32_t (*)[K1_GMAX]>(k1_smem + sizeof(float4) * K1_STAGES * (K1_CHUNK + K1_GMAX));
   uint64_t* bars = reinterpret_cast<uint64_t*>(k1_smem + K1_STAGES * (K1_CHUNK * 16 + K1_GMAX * 16 + K1_GMAX * 4));
   const int tid = threadIdx.x, lane = tid & 31;
-  const int t = view_lo + blockIdx.y;                 // target view
-  const int sidx = blockIdx.x * K1_THREADS + tid;     // the seed whose line / counter this lane keeps
-  const int seg0 = S.view_seg_off[t];
+  const int t = blockIdx.y;                           // target view
+  const int entry = blockIdx.x * K1_THREADS + tid;    // the entry whose line / counter this lane keeps
   const int ch0 = S.view_chunk_off[t];
   const int nchunks = S.view_chunk_off[t + 1] - ch0;
 
-  if (tid == 0) {
-    for (int s = 0; s < K1_STAGES; s++) mbar_init(&bars[s], 1);
-    mbar_fence_init();
+  // which pair is this lane's, is it wanted, and where does its result go
+  bool valid = entry < work.n;
+  int sidx = 0; size_t row = 0;
+  if (valid) {
+    sidx = work.list ? work.list[entry] : entry;
+    if (work.sel) {
+      const int* sl = work.sel + 3 * (size_t)sidx;
+      const int k = sl[0] == t ? 0 : sl[1] == t ? 1 : sl[2] == t ? 2 : -1;
+      if (k < 0 || sl[0] < 0) valid = false;
+      row = (size_t)sidx * 3 + (size_t)(k < 0 ? 0 : k);
+    } else row = (size_t)entry * S.V + t;
   }
-  __syncthreads();
-
-  bool active = sidx < seeds.n;
+  bool active = valid;
   int sv = -1; float2 p = make_float2(0.f, 0.f); float3 l = make_float3(0.f, 0.f, 0.f);
-  if (active) {
+  if (valid) {
     sv = seeds.view[sidx]; p = seeds.xy[sidx];
     if (sv == t) active = false;
     else active = epiline(S, sv, t, p, l);
   }
+  // a tile without a single pair to sweep (typical for the targeted forms) leaves before staging anything
+  const bool any_active = __syncthreads_or(active);
+  if (any_active) {
+    if (tid == 0) {
+      for (int s = 0; s < K1_STAGES; s++) mbar_init(&bars[s], 1);
+      mbar_fence_init();
+    }
+    __syncthreads();
+  }
   int cnt = 0;
   int64_t obase = 0;
-  if (FILL && sidx < seeds.n) obase = off[(size_t)sidx * S.V + t];
+  if (FILL && valid) obase = off[row];
   const unsigned amask = __ballot_sync(0xffffffffu, active);
 
   auto issue = [&](int c) {
@@ -112,8 +140,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_const
     tma_bulk_g2s(&bbuf[c % K1_STAGES][0], S.grp_box + ch.z, bbytes, &bars[c % K1_STAGES]);
     tma_bulk_g2s(&dbuf[c % K1_STAGES][0], S.grp_desc + ch.z, dbytes, &bars[c % K1_STAGES]);
   };
-  if (tid == 0 && nchunks > 0) issue(0);
-  for (int c = 0; c < nchunks; c++) {
+  if (any_active && tid == 0 && nchunks > 0) issue(0);
+  for (int c = 0; any_active && c < nchunks; c++) {
     if (tid == 0 && c + 1 < nchunks) issue(c + 1);
     mbar_wait(&bars[c % K1_STAGES], (uint32_t)((c / K1_STAGES) & 1));
     const float4* sb = sbuf[c % K1_STAGES];
@@ -123,6 +151,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_const
     const int ng = ch.w;
     const uint2* sid = S.seg_id + ch.x;
     unsigned am = amask;
+    if (MODE == K1_ANY) am &= ~__ballot_sync(0xffffffffu, cnt > 0);   // seeds that already have a hit are done
     while (am) {                                       // the warp's seeds, one after the other
       const int j = __ffs(am) - 1;
       am &= am - 1;
@@ -167,21 +196,29 @@ __global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_const
             hits[oj + cj + __popc(hm & ((1u << lane) - 1u))] = h;
           }
           cj += __popc(hm);
+          if (MODE == K1_ANY && cj) break;
 #pragma unroll
           for (int k = 0; k < K1_GPR; k++) gm &= gm - 1;          // drop the groups just handled
         }
+        if (MODE == K1_ANY && cj) break;
       }
       if (lane == j) cnt = cj;
     }
-    __syncthreads();
+    if (MODE == K1_ANY) {
+      // every pair of the tile has its answer: drain the copy already in flight and stop staging
+      if (!__syncthreads_or(active && cnt == 0)) {
+        if (c + 1 < nchunks) mbar_wait(&bars[(c + 1) % K1_STAGES], (uint32_t)(((c + 1) / K1_STAGES) & 1));
+        break;
+      }
+    } else __syncthreads();
   }
-  (void)seg0;
-  if (sidx < seeds.n) {
+  if (valid) {
     if (sv == t) {  // the starting view holds the seed itself (polyline_matching.cpp:54-55)
       if (FILL) { eg3d_hit h; h.polyline = seeds.pl[sidx]; h.segment = seeds.seg[sidx]; h.x = p.x; h.y = p.y; hits[obase] = h; }
       cnt = 1;
     }
-    if (!FILL) counts[(size_t)sidx * S.V + t] = cnt;
+    if (MODE == K1_COUNT) counts[row] = cnt;
+    if (MODE == K1_ANY) flags[row] = cnt > 0 ? 1 : 0;
   }
 }
 

@@ -35,8 +35,13 @@ struct PaRec;
 struct K3Args {
   int n_seeds;
   const int* seed_view; const uint32_t* seed_pl; const uint32_t* seed_seg; const float2* seed_xy;
-  const int64_t* hit_off;   // [n_seeds*V + 1]
-  const eg3d_hit* hits;
+  // Hit lists.  Phase A reads the three selected views of a seed: row seed*3 + k of (hit_off, hits) when a_compact, else
+  // row seed*V + sel[k] of the full (seed, view) CSR.  Phase B reads every view of an accepted seed: row
+  // (b_compact ? accepted rank : seed)*V + v of (hit_off_b, hits_b).
+  const int64_t* hit_off; const eg3d_hit* hits; int a_compact;
+  const int64_t* hit_off_b; const eg3d_hit* hits_b; int b_compact;
+  const int* sel;           // [n_seeds][3] selected views (k3_select_views_kernel); sel[3*seed] < 0: fewer than 3 non-empty views
+  int* acc_seed;            // [n_seeds] accepted seed of each phase-A record (rank order)
   int capf, capc, oc;       // capacities: follow points per list, chain points, observations per point
   unsigned char* scratch; size_t scratch_per_warp;
   int* work_counter;
@@ -46,10 +51,12 @@ struct K3Args {
   float* o_X; int* o_nobs; int64_t* o_obase;
   int* ob_view; uint32_t* ob_pl; uint32_t* ob_seg; float* ob_x; float* ob_y;
   int* seed_npts; int64_t* seed_pbase; int64_t* seed_nobs;
-  unsigned long long* prof;   // optional [16] per-phase warp-cycle / event counters (null = off)
+  unsigned long long* prof;   // optional [16] per-phase warp-cycle / event counters (null = off; profile builds only)
+  unsigned long long* prof_seed;  // optional [n_seeds][2]: phase-B warp cycles, initial | final chain length (profile builds only)
   // phase A -> phase B hand-over: one record per accepted seed + its two 3-view point lists in a pool
   struct PaRec* pa_recs; Pt3* pa_pool; long long pa_pool_cap;
   unsigned long long* pa_counters;    // [0] accepted seeds, [1] pool entries used
+  const int* pa_order;                // phase B visits pa_recs[pa_order[i]]: longest chains first (tail balance); null = as produced
 };
 struct PaRec {
   int seed; int sel[3]; int fn1, fn2;
@@ -110,8 +117,11 @@ EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
 // per-seed context (registers; identical in every lane)
 struct Ctx {
   const DevScene* S; const K3Args* A; WS w;
-  long long pc[12];   // profiling accumulators
+#ifdef EG3D_K3_PROFILE
+  long long pc[12];   // profiling accumulators (profile builds only: build.sh -DEG3D_K3_PROFILE)
+#endif
   int lane, seed, sv;
+  long long hrow;  // phase B: first row of this seed in hit_off_b
   int sel[3];
   int len;         // chain length
   int nslots;      // slots in use
@@ -119,8 +129,15 @@ struct Ctx {
   bool overflow;
 };
 
+#ifdef EG3D_K3_PROFILE
 #define K3P_BEGIN(t) long long t = clock64()
 #define K3P_END(c, slot, t) (c).pc[slot] += clock64() - (t)
+#define K3P_ADD(c, slot, v) (c).pc[slot] += (v)
+#else
+#define K3P_BEGIN(t) do {} while (0)
+#define K3P_END(c, slot, t) do {} while (0)
+#define K3P_ADD(c, slot, v) do {} while (0)
+#endif
 
 // 3-view compatible, plg_matching.cpp:51-132.  cur / next: (pl, seg, c) per view a,b,c in sel order.
 struct Cur3 { uint32_t pl[3], seg[3]; float2 c[3]; };
@@ -695,9 +712,9 @@ static __device__ __noinline__ bool add_view_finish(Ctx& c, int v, const Plg& p,
 // expand_allpoints_to_other_view_using_plmap, triangulation.cpp:742-830
 static __device__ __noinline__ void expand_view(Ctx& c, int v) {
   const DevScene& S = *c.S;
-  const int64_t h0 = c.A->hit_off[(size_t)c.seed * S.V + v];
-  const int nh = (int)(c.A->hit_off[(size_t)c.seed * S.V + v + 1] - h0);
-  const eg3d_hit* epcs = c.A->hits + h0;
+  const int64_t h0 = c.A->hit_off_b[c.hrow + v];
+  const int nh = (int)(c.A->hit_off_b[c.hrow + v + 1] - h0);
+  const eg3d_hit* epcs = c.A->hits_b + h0;
   bool matched = false; int iv0 = 0, iv1 = 0;
   // the epipolar hits on the central point: one warm-started GN per lane, first complete success in order wins
   // Exact-safe pruning (pair_cannot_fit): a hit whose 2-view cost against one of the central point's observations
@@ -737,7 +754,7 @@ static __device__ __noinline__ void expand_view(Ctx& c, int v) {
     K3P_END(c, 3, te0);
     if (nq == 0) break;
     const int P = nq < 32 ? nq : 32;
-    c.pc[11] += P;
+    K3P_ADD(c, 11, P);
     const int G = gn_group_width(P);
     const bool active = (c.lane / G) < P;
     const int e = active ? hq[c.lane / G] : 0;
@@ -822,37 +839,16 @@ static __device__ __noinline__ void slot_from_pt3(Ctx& c, int slot, const Pt3& p
 static __device__ __noinline__ bool seed_phase_a(Ctx& c, PaRec& r) {
   const DevScene& S = *c.S; const K3Args& A = *c.A;
   const int V = S.V, lane = c.lane;
-  const int64_t* off = A.hit_off + (size_t)c.seed * V;
-  // --- view triple (triangulation.cpp:1035-1066)
-  int ne = 0, minv = -1, maxv = -1;
-  for (int base = 0; base < V; base += 32) {
-    int v = base + lane;
-    bool nz = v < V && off[v + 1] > off[v];
-    unsigned m = __ballot_sync(0xffffffffu, nz);
-    if (m) { if (minv < 0) minv = base + __ffs(m) - 1; maxv = base + 31 - __clz(m); ne += __popc(m); }
-  }
-  if (ne < 3) return false;
-  int mid = 0;
-  {
-    int want = ne / 2, seen = 0;
-    for (int base = 0; base < V; base += 32) {
-      int v = base + lane;
-      bool nz = v < V && off[v + 1] > off[v];
-      unsigned m = __ballot_sync(0xffffffffu, nz);
-      int pc = __popc(m);
-      if (seen + pc > want) {
-        int r = want - seen;
-        for (int k = 0; k < r; k++) m &= m - 1;
-        mid = base + __ffs(m) - 1;
-        break;
-      }
-      seen += pc;
-    }
-  }
-  c.sel[0] = minv; c.sel[1] = (c.sv == minv || c.sv == maxv) ? mid : c.sv; c.sel[2] = maxv;
-  const eg3d_hit* h0 = A.hits + off[c.sel[0]]; const int n0 = (int)(off[c.sel[0] + 1] - off[c.sel[0]]);
-  const eg3d_hit* h1 = A.hits + off[c.sel[1]]; const int n1h = (int)(off[c.sel[1] + 1] - off[c.sel[1]]);
-  const eg3d_hit* h2 = A.hits + off[c.sel[2]]; const int n2h = (int)(off[c.sel[2] + 1] - off[c.sel[2]]);
+  // --- view triple (triangulation.cpp:1035-1066), chosen by k3_select_views_kernel
+  const int* sl = A.sel + 3 * (size_t)c.seed;
+  if (sl[0] < 0) return false;
+  c.sel[0] = sl[0]; c.sel[1] = sl[1]; c.sel[2] = sl[2];
+  size_t r0, r1, r2;
+  if (A.a_compact) { r0 = (size_t)c.seed * 3; r1 = r0 + 1; r2 = r0 + 2; }
+  else { r0 = (size_t)c.seed * V + c.sel[0]; r1 = (size_t)c.seed * V + c.sel[1]; r2 = (size_t)c.seed * V + c.sel[2]; }
+  const eg3d_hit* h0 = A.hits + A.hit_off[r0]; const int n0 = (int)(A.hit_off[r0 + 1] - A.hit_off[r0]);
+  const eg3d_hit* h1 = A.hits + A.hit_off[r1]; const int n1h = (int)(A.hit_off[r1 + 1] - A.hit_off[r1]);
+  const eg3d_hit* h2 = A.hits + A.hit_off[r2]; const int n2h = (int)(A.hit_off[r2 + 1] - A.hit_off[r2]);
   // --- triple enumeration with the uniqueness test (triangulation.cpp:550-601): one triple per lane
   const long long total = (long long)n0 * n1h * n2h;
   bool found = false;
@@ -898,7 +894,7 @@ static __device__ __noinline__ bool seed_phase_a(Ctx& c, PaRec& r) {
     if (qn == 0) break;
     __syncwarp();
     const int take = qn < 32 ? qn : 32;
-    c.pc[8] += take; c.pc[9] += 1;
+    K3P_ADD(c, 8, take); K3P_ADD(c, 9, 1);
     K3P_BEGIN(tp1);
     bool ok = false; float X[3] = {0, 0, 0};
     int i0 = 0, i1 = 0, i2 = 0;
@@ -929,7 +925,7 @@ static __device__ __noinline__ bool seed_phase_a(Ctx& c, PaRec& r) {
       cand.pl[2] = a2.polyline; cand.seg[2] = a2.segment; cand.c[2] = make_float2(a2.x, a2.y);
       K3P_BEGIN(tp2);
       bool comp = plg_compatible(c, cand, nD1, nD2, d1, d2);
-      K3P_END(c, 2, tp2); c.pc[10] += 1;
+      K3P_END(c, 2, tp2); K3P_ADD(c, 10, 1);
       if (c.overflow) return false;
       if (comp) {
         if (found) return false;  // a second compatible triple: ambiguous, the seed yields nothing (:587-590)
@@ -993,7 +989,9 @@ __global__ void __launch_bounds__(K3_THREADS, EG3D_K3A_MIN_BLOCKS) k3a_hypothesi
     if (seed >= A.n_seeds) break;
     c.seed = seed; c.sv = A.seed_view[seed];
     c.len = 0; c.nslots = 0; c.central = 0; c.overflow = false;
+#ifdef EG3D_K3_PROFILE
     for (int k = 0; k < 12; k++) c.pc[k] = 0;
+#endif
     K3P_BEGIN(tall);
     PaRec r;
     const bool found = seed_phase_a(c, r);
@@ -1006,15 +1004,69 @@ __global__ void __launch_bounds__(K3_THREADS, EG3D_K3A_MIN_BLOCKS) k3a_hypothesi
       ri = __shfl_sync(0xffffffffu, ri, 0); po = __shfl_sync(0xffffffffu, po, 0);
       if ((long long)po + r.fn1 + r.fn2 > A.pa_pool_cap) { if (lane == 0) atomicAdd(&A.out_counters[3], 1ull); r.fn1 = -1; }
       r.pool_off = (long long)po;
-      if (lane == 0) A.pa_recs[ri] = r;
+      if (lane == 0) { A.pa_recs[ri] = r; A.acc_seed[ri] = seed; }
       if (r.fn1 >= 0) {
         for (int i = lane; i < r.fn1; i += 32) A.pa_pool[po + i] = c.w.fD1[i];
         for (int i = lane; i < r.fn2; i += 32) A.pa_pool[po + r.fn1 + i] = c.w.fD2[i];
       }
     }
+#ifdef EG3D_K3_PROFILE
     if (A.prof && lane == 0) for (int k = 0; k < 12; k++) if (c.pc[k]) atomicAdd(&A.prof[k], (unsigned long long)c.pc[k]);
+#endif
     __syncwarp();
   }
+}
+
+// View triple of every seed (triangulation.cpp:1035-1066): first view with hits, the starting view (or, when that is the
+// first or last one, the middle non-empty view), last view with hits.  One warp per seed.  The "has hits" predicate comes
+// from the any-hit flags of the lazy sweep (flags != null) or from the full (seed, view) CSR.
+__global__ void k3_select_views_kernel(int n_seeds, int V, const int* __restrict__ seed_view, const unsigned char* __restrict__ flags,
+                                       const int64_t* __restrict__ off, int* __restrict__ sel) {
+  const int lane = threadIdx.x & 31;
+  const int seed = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (seed >= n_seeds) return;
+  const size_t row = (size_t)seed * V;
+  auto nonempty = [&](int v) { return v < V && (flags ? flags[row + v] != 0 : off[row + v + 1] > off[row + v]); };
+  int ne = 0, minv = -1, maxv = -1;
+  for (int base = 0; base < V; base += 32) {
+    const unsigned m = __ballot_sync(0xffffffffu, nonempty(base + lane));
+    if (m) { if (minv < 0) minv = base + __ffs(m) - 1; maxv = base + 31 - __clz(m); ne += __popc(m); }
+  }
+  int s0 = -1, s1 = -1, s2 = -1;
+  if (ne >= 3) {
+    int mid = 0;
+    const int want = ne / 2;
+    int seen = 0;
+    for (int base = 0; base < V; base += 32) {
+      unsigned m = __ballot_sync(0xffffffffu, nonempty(base + lane));
+      const int pc = __popc(m);
+      if (seen + pc > want) {
+        for (int k = 0; k < want - seen; k++) m &= m - 1;
+        mid = base + __ffs(m) - 1;
+        break;
+      }
+      seen += pc;
+    }
+    const int sv = seed_view[seed];
+    s0 = minv; s1 = (sv == minv || sv == maxv) ? mid : sv; s2 = maxv;
+  }
+  if (lane == 0) { sel[3 * (size_t)seed] = s0; sel[3 * (size_t)seed + 1] = s1; sel[3 * (size_t)seed + 2] = s2; }
+}
+
+// Work order of phase B.  Per-seed cost grows with the chain length (every view is tried against every chain point), and
+// a few hundred seeds are 10-100x the median, so the accepted seeds are visited longest chain first; the order has no
+// effect on the results (pack orders by seed).  Keys for the radix sort: descending length, unused tail entries last.
+__global__ void k3_order_keys_kernel(int n, const unsigned long long* __restrict__ pa_counters, const PaRec* __restrict__ recs,
+                                     unsigned* __restrict__ keys, int* __restrict__ vals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned key = 0xffffffffu;
+  if ((unsigned long long)i < pa_counters[0]) {
+    const PaRec& r = recs[i];
+    const int len = r.fn1 < 0 ? 0 : r.fn1 + r.fn2 + 1;
+    key = 0xffffu - (unsigned)min(len, 0xffff);
+  }
+  keys[i] = key; vals[i] = i;
 }
 
 __global__ void __launch_bounds__(K3_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
@@ -1029,20 +1081,27 @@ __global__ void __launch_bounds__(K3_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_ke
     if (lane == 0) ri = atomicAdd(A.work_counter, 1);
     ri = __shfl_sync(0xffffffffu, ri, 0);
     if (ri >= n_acc) break;
-    const PaRec r = A.pa_recs[ri];
+    const int rank = A.pa_order ? A.pa_order[ri] : ri;
+    const PaRec r = A.pa_recs[rank];
     const int seed = r.seed;
     c.seed = seed; c.sv = A.seed_view[seed];
+    c.hrow = (long long)(A.b_compact ? rank : seed) * S.V;
     c.len = 0; c.nslots = 0; c.central = 0; c.overflow = false;
+#ifdef EG3D_K3_PROFILE
     for (int k = 0; k < 12; k++) c.pc[k] = 0;
+#endif
     K3P_BEGIN(tall);
     if (r.fn1 >= 0) seed_phase_b(c, r, A.pa_pool + r.pool_off, A.pa_pool + r.pool_off + r.fn1);
     K3P_END(c, 7, tall);
+#ifdef EG3D_K3_PROFILE
     if (A.prof && lane == 0) {
       for (int k = 0; k < 12; k++) if (c.pc[k]) atomicAdd(&A.prof[k], (unsigned long long)c.pc[k]);
       atomicMax(&A.prof[12], (unsigned long long)c.pc[7]);
       if (c.pc[7] > 50000000ll) atomicAdd(&A.prof[13], 1ull);
       if (c.pc[7] > 200000000ll) atomicAdd(&A.prof[14], 1ull);
+      if (A.prof_seed) { A.prof_seed[2 * (size_t)seed] = (unsigned long long)c.pc[7]; A.prof_seed[2 * (size_t)seed + 1] = (unsigned long long)(r.fn1 + r.fn2 + 1) | ((unsigned long long)c.len << 32); }
     }
+#endif
     __syncwarp();
     int npts = c.overflow ? 0 : c.len;
     long long nobs = 0;

@@ -15,7 +15,7 @@ _lib = None
 
 EXPORTS = [
     "eg3d_last_error", "eg3d_camera_fundamentals", "eg3d_device_count", "eg3d_params_default", "eg3d_scene_create", "eg3d_scene_destroy",
-    "eg3d_sample_seeds", "eg3d_epipolar_intersect", "eg3d_hits_get", "eg3d_hits_free", "eg3d_match_seeds",
+    "eg3d_sample_seeds", "eg3d_epipolar_intersect", "eg3d_epipolar_intersect_device", "eg3d_hits_get", "eg3d_hits_free", "eg3d_match_seeds",
     "eg3d_match_polyline_sets", "eg3d_match_refpoints", "eg3d_points_get", "eg3d_points_device_get", "eg3d_points_free", "eg3d_gn_triangulate",
     "eg3d_gn_triangulate_device", "eg3d_dedup_close_points", "eg3d_filter",
 ]
@@ -44,6 +44,7 @@ def load():
     L.eg3d_sample_seeds.argtypes = [C.POINTER(A.SceneDesc), A.c_i32p, A.c_u32p, C.c_int64, C.c_float, C.c_int64,
                                     A.c_i32p, A.c_u32p, A.c_u32p, A.c_f32p, A.c_i32p, A.c_i64p]
     L.eg3d_epipolar_intersect.argtypes = [C.c_void_p, C.POINTER(A.Seeds), C.POINTER(A.Candidates), C.POINTER(C.c_void_p), C.POINTER(A.Timing)]
+    L.eg3d_epipolar_intersect_device.argtypes = [C.c_void_p, C.POINTER(A.Seeds), C.POINTER(A.Candidates), C.POINTER(A.Timing)]
     L.eg3d_hits_get.argtypes = [C.c_void_p, A.c_i64p, A.c_i32p, C.POINTER(A.c_i64p), C.POINTER(C.POINTER(A.Hit))]
     L.eg3d_hits_free.argtypes = [C.c_void_p]
     L.eg3d_match_seeds.argtypes = [C.c_void_p, C.POINTER(A.Seeds), C.POINTER(A.Candidates), C.POINTER(C.c_void_p), C.POINTER(A.Timing)]
@@ -204,6 +205,14 @@ class DeviceScene:
             hn = np.zeros(0, dt)
         L.eg3d_hits_free(h)
         return off_np, hn, int(V.value), tm.as_dict()
+
+    def epipolar_intersect_device(self, seeds, cands=None):
+        """K1 alone, result left on the device and released: returns the timing dict (the sweep microbenchmark)."""
+        sd = seeds.desc()
+        cd = cands.desc() if cands is not None else None
+        tm = A.Timing()
+        _check(load().eg3d_epipolar_intersect_device(self.h, C.byref(sd), C.byref(cd) if cd is not None else None, C.byref(tm)))
+        return tm.as_dict()
 
     def match_seeds(self, seeds, cands=None, fetch=True):
         L = load()

@@ -147,13 +147,14 @@ typedef struct eg3d_timing {
   float k3_ms;                /* k3a_ms + k3b_ms */
   float pack_ms;              /* ordered compaction of accepted points */
   float gn_ms;                /* stand-alone GN kernel (eg3d_gn_*) */
-  int64_t n_seeds, n_hits, n_segment_tests, n_points, n_obs;
+  int64_t n_seeds, n_hits /* hit records materialised */, n_segment_tests /* of the reference's full sweep */, n_points, n_obs;
   int64_t k1_algorithmic_bytes; /* 16 B x segments swept per (seed, view) + 72 + 8 + 16 B x hits */
   int32_t kernel_launches;
   int32_t n_capacity_overflows; /* seeds dropped because a capacity in eg3d_params was exceeded */
   float k3a_ms;               /* K3 phase A: view triples, triple enumeration, PLG following (all seeds) */
   float k3b_ms;               /* K3 phase B: expansion to the remaining views (accepted seeds) */
   int64_t n_accepted_seeds;
+  float k1_any_ms;            /* epipolar intersection, any-hit pass of the lazy sweep (eg3d_match_seeds without candidates) */
 } eg3d_timing;
 
 typedef struct eg3d_scene  eg3d_scene;   /* opaque, device resident */
@@ -187,6 +188,10 @@ eg3d_status eg3d_sample_seeds(const eg3d_scene_desc* desc, const int32_t* views,
  * Result: CSR over (seed, view) of eg3d_hit, in the reference's order (polyline id asc, segment asc). */
 eg3d_status eg3d_epipolar_intersect(eg3d_scene*, const eg3d_seeds*, const eg3d_candidates* /* may be NULL */,
                                     eg3d_hits** out, eg3d_timing* timing /* may be NULL */);
+/* Same computation with the result left on (and released from) the device: what BASELINE configs 2-4 measure, the
+ * full sweep itself.  Only `timing` is returned (k1_count_ms, k1_fill_ms, n_hits, n_segment_tests, k1_algorithmic_bytes). */
+eg3d_status eg3d_epipolar_intersect_device(eg3d_scene*, const eg3d_seeds*, const eg3d_candidates* /* may be NULL */,
+                                           eg3d_timing* timing);
 /* host pointers valid until eg3d_hits_free; off has n_seeds*V+1 entries */
 eg3d_status eg3d_hits_get(const eg3d_hits*, int64_t* n_seeds, int32_t* n_views, const int64_t** off, const eg3d_hit** hits);
 void        eg3d_hits_free(eg3d_hits*);
