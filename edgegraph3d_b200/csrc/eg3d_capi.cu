@@ -57,7 +57,7 @@ struct eg3d_scene {
   int device = 0; cudaStream_t stream = nullptr;
   int V = 0, width = 0, height = 0, num_sms = 0;
   eg3d_params prm;
-  DBuf<float> P; DBuf<double> P64; DBuf<double> F; DBuf<double> Fp; DBuf<uint8_t> Fvalid;
+  DBuf<float> P; DBuf<double> P64; DBuf<double> F; DBuf<double> Fp; DBuf<double> Fph; DBuf<uint8_t> Fvalid;
   DBuf<int> view_poly_off, poly_vert_off, view_seg_off, poly_seg_off;
   DBuf<float2> verts; DBuf<uint32_t> poly_start, poly_end;
   DBuf<float4> seg; DBuf<uint2> seg_id; DBuf<float4> grp_box; DBuf<uint32_t> grp_desc; DBuf<int4> chunks; DBuf<int> view_chunk_off;
@@ -392,7 +392,11 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
   const int warps_per_block = K3_THREADS / 32;
   int max_useful = (n + warps_per_block - 1) / warps_per_block;
   if (nblocks > max_useful) nblocks = max_useful;
-  const size_t nwarps = (size_t)nblocks * warps_per_block;
+  // phase B: EG3D_K3B_MIN_BLOCKS CTAs of K3B_THREADS per SM (one CTA per SM in the lock-step form)
+  const int warps_per_block_b = K3B_THREADS / 32;
+  int nblocks_b = sc->num_sms * EG3D_K3B_MIN_BLOCKS;
+  nblocks_b = std::max(1, std::min(nblocks_b, (n + warps_per_block_b - 1) / warps_per_block_b));
+  const size_t nwarps = std::max((size_t)nblocks * warps_per_block, (size_t)nblocks_b * warps_per_block_b);
   DBuf<unsigned char> scratch; CK(scratch.alloc(nwarps * spw));
   DBuf<int> counter; CK(counter.alloc(1)); CK(cudaMemsetAsync(counter.p, 0, sizeof(int), sc->stream));
   DBuf<unsigned long long> oc4; CK(oc4.alloc(4)); CK(cudaMemsetAsync(oc4.p, 0, 4 * sizeof(unsigned long long), sc->stream));
@@ -456,7 +460,7 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
     b.pa_order = oorder.p;
   }
   t3b.start();
-  k3b_expand_kernel<<<nblocks, K3_THREADS, 0, sc->stream>>>(sc->dev, b);
+  k3b_expand_kernel<<<nblocks_b, K3B_THREADS, 0, sc->stream>>>(sc->dev, b);
   t3b.stop();
   unsigned long long cnt[4];
   CK(cudaMemcpyAsync(cnt, oc4.p, sizeof cnt, cudaMemcpyDeviceToHost, sc->stream));
@@ -688,7 +692,12 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   CK(sc->P.upload(d->cameras, (size_t)V * 12, s));
   { std::vector<double> p64((size_t)V * 12); for (size_t i = 0; i < p64.size(); i++) p64[i] = (double)d->cameras[i]; CK(sc->P64.upload(p64, s)); CK(cudaStreamSynchronize(s)); }
   CK(sc->F.upload(d->fundamental, (size_t)V * V * 9, s));
-  { std::vector<double> fp; camera_fundamentals(d->cameras, V, fp); CK(sc->Fp.upload(fp, s)); CK(cudaStreamSynchronize(s)); }
+  {
+    std::vector<double> fp; camera_fundamentals(d->cameras, V, fp);
+    std::vector<double> fph((size_t)V * V);
+    for (size_t i = 0; i < fph.size(); i++) { const double* f = &fp[i * 9]; fph[i] = sqrt(f[0] * f[0] + f[1] * f[1] + f[3] * f[3] + f[4] * f[4]); }
+    CK(sc->Fp.upload(fp, s)); CK(sc->Fph.upload(fph, s)); CK(cudaStreamSynchronize(s));
+  }
   CK(sc->Fvalid.upload(d->fundamental_valid, (size_t)V * V, s));
   CK(sc->view_poly_off.upload(sc->h_view_poly_off, s)); CK(sc->poly_vert_off.upload(sc->h_poly_vert_off, s));
   CK(sc->verts.upload(sc->h_verts, s)); CK(sc->poly_start.upload(sc->h_start, s)); CK(sc->poly_end.upload(sc->h_end, s));
@@ -709,7 +718,7 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   CK(cudaStreamSynchronize(s));
   DevScene& D = sc->dev; memset(&D, 0, sizeof D);
   D.V = V; D.width = sc->width; D.height = sc->height;
-  D.P = sc->P.p; D.P64 = sc->P64.p; D.F = sc->F.p; D.Fp = sc->Fp.p; D.Fvalid = sc->Fvalid.p;
+  D.P = sc->P.p; D.P64 = sc->P64.p; D.F = sc->F.p; D.Fp = sc->Fp.p; D.Fph = sc->Fph.p; D.Fvalid = sc->Fvalid.p;
   D.view_poly_off = sc->view_poly_off.p; D.poly_vert_off = sc->poly_vert_off.p; D.verts = sc->verts.p;
   D.poly_start = sc->poly_start.p; D.poly_end = sc->poly_end.p;
   D.view_seg_off = sc->view_seg_off.p; D.seg = sc->seg.p; D.seg_id = sc->seg_id.p; D.poly_seg_off = sc->poly_seg_off.p;

@@ -32,6 +32,7 @@ struct DevScene {
   const double* F;              // [V*V][9]
   const double* Fp;             // [V*V][9] fundamental matrices derived from the cameras P themselves (exact two-view geometry of
                                 //          the GN problems; the input F may come from LMedS and is NOT used for pruning)
+  const double* Fph;            // [V*V] Frobenius norm of Fp's upper-left 2x2 block (the `h` of pair_cannot_fit)
   const uint8_t* Fvalid;        // [V*V]
   const int* view_poly_off;     // [V+1]
   const int* poly_vert_off;     // [NP+1]
@@ -242,6 +243,67 @@ EG3D_HD_NI float pl_distancesq(const Pl& pl, float2 p, uint32_t& seg, float2& pr
   }
   return md;
 }
+
+#ifdef __CUDACC__
+// Warp-cooperative walk_line for warp-uniform arguments (same result in every lane, identical to walk_line): the walk
+// visits the partial segment from the current point to the next vertex and then whole segments, and stops at the first
+// one that is intersected (or aborts on the first quasi-parallel one, which is tested first).  Lane m takes walk
+// position base + m, so the first lane with a non-zero verdict is the segment the sequential walk would stop at.
+static __device__ __noinline__ bool walk_line_warp(const Pl& pl, PlP init, uint32_t dir, float3 line, const eg3d_params& prm, bool bounded, PlP& next, int lane) {
+  const int n = pl.n;
+  const bool to_start = dir == pl.start;
+  if (!to_start && dir != pl.end) return false;
+  // positions: 0 = partial segment; to_start: m >= 1 <-> i = seg-(m-1) >= 1; to_end: m >= 1 <-> i = seg+m <= n-2
+  const int total = to_start ? (int)init.seg + 1 : n - 1 - (int)init.seg;
+  bool found = false;
+  for (int base = 0; base < total; base += 32) {
+    const int m = base + lane;
+    int r = 0; float2 inter = make_float2(0.f, 0.f); uint32_t sg = 0;
+    if (m < total) {
+      float2 a, b;
+      if (m == 0) { a = init.c; b = to_start ? pl.pc[init.seg] : pl.pc[init.seg + 1]; sg = init.seg; }
+      else if (to_start) { const int i = (int)init.seg - (m - 1); a = pl.pc[i]; b = pl.pc[i - 1]; sg = (uint32_t)(i - 1); }
+      else { const int i = (int)init.seg + m; a = pl.pc[i]; b = pl.pc[i + 1]; sg = (uint32_t)i; }
+      r = isect_seg_line_nqp(a.x, a.y, b.x, b.y, line, prm.quasiparallel_cos, prm.quasiparallel_dist, inter);
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, r != 0);
+    if (any) {
+      const int w = __ffs(any) - 1;
+      if (__shfl_sync(0xffffffffu, r, w) & 2) return false;
+      next.seg = __shfl_sync(0xffffffffu, sg, w);
+      next.c.x = __shfl_sync(0xffffffffu, inter.x, w); next.c.y = __shfl_sync(0xffffffffu, inter.y, w);
+      found = true;
+      break;
+    }
+  }
+  if (found && bounded) {
+    float dsq = sqdist2(next.c, init.c);
+    if (dsq < (prm.follow_corr_min * prm.follow_corr_min) || dsq > (prm.follow_corr_max * prm.follow_corr_max)) found = false;
+  }
+  return found;
+}
+
+// Warp-cooperative pl_distancesq for warp-uniform arguments: the sequential scan keeps the FIRST segment that attains
+// the minimum (strict <), i.e. the arg-min with ties to the lower index; the lanes take segments lane, lane+32, ... and
+// the 32 candidates are reduced with the same ordering.
+static __device__ __noinline__ float pl_distancesq_warp(const Pl& pl, float2 p, uint32_t& seg, float2& proj, int lane) {
+  float md = 0.f; int ms = 0x7fffffff; float2 mp = make_float2(0.f, 0.f);
+  for (int sgi = lane; sgi < pl.n - 1; sgi += 32) {
+    float2 cp;
+    const float cur = min_distsq_seg(p, pl.pc[sgi], pl.pc[sgi + 1], cp);
+    if (ms == 0x7fffffff || cur < md) { md = cur; ms = sgi; mp = cp; }
+  }
+#pragma unroll 1
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, md, o);
+    const int os = __shfl_xor_sync(0xffffffffu, ms, o);
+    const float ox = __shfl_xor_sync(0xffffffffu, mp.x, o), oy = __shfl_xor_sync(0xffffffffu, mp.y, o);
+    if (os != 0x7fffffff && (ms == 0x7fffffff || od < md || (od == md && os < ms))) { md = od; ms = os; mp.x = ox; mp.y = oy; }
+  }
+  seg = (uint32_t)ms; proj = mp;
+  return md;
+}
+#endif
 
 // edge_graph_3d_utilities.cpp:600-629
 EG3D_HD float floor_or_upper_if_close(float v) {
@@ -487,16 +549,22 @@ EG3D_D int gn_update(const GnAcc& a, int n, const eg3d_params& prm, double& last
 // so cost >= min(T^2, ((|s0| - g T)/(n0 + h T))^2) for any T.  If that is >= budget = accept_mse * 2n (with a safety
 // margin for rounding) the solve cannot be accepted and is skipped; a rejected solve has no side effects in the
 // reference, so results are unchanged.  (A first-iteration break needs mse < 3e-6 and cannot occur here.)
-EG3D_D bool pair_cannot_fit(const double* __restrict__ F, float2 pa, float2 pb, double T) {
+// One out-of-line copy (the kernels are bound by instruction-cache refills): h = |F[0:2,0:2]|_F comes precomputed, and
+// the two conditions are compared in squared form, which needs one square root instead of three:
+//   |s0| > g T                       <=>  s0^2 > g^2 T^2
+//   |s0| - g T >= T (n0 + h T)       <=>  B := |s0| - h T^2 > 0  and  B^2 >= T^2 (g^2 + n0^2 + 2 sqrt(g^2 n0^2))
+static __device__ __noinline__ bool pair_cannot_fit(const double* __restrict__ F, double h, float2 pa, float2 pb, double T) {
   const double ax = pa.x, ay = pa.y, bx = pb.x, by = pb.y;
-  const double l0 = F[0] * ax + F[1] * ay + F[2], l1 = F[3] * ax + F[4] * ay + F[5], l2 = F[6] * ax + F[7] * ay + F[8];
-  const double s0 = fabs(bx * l0 + by * l1 + l2);
-  const double n0 = sqrt(l0 * l0 + l1 * l1);
-  const double m0 = F[0] * bx + F[3] * by + F[6], m1 = F[1] * bx + F[4] * by + F[7];
-  const double g = sqrt(m0 * m0 + m1 * m1);
-  const double h = sqrt(F[0] * F[0] + F[1] * F[1] + F[3] * F[3] + F[4] * F[4]);
-  const double num = s0 - g * T;
-  return num > 0 && num >= T * (n0 + h * T);
+  const double l0 = fma(F[0], ax, fma(F[1], ay, F[2])), l1 = fma(F[3], ax, fma(F[4], ay, F[5])), l2 = fma(F[6], ax, fma(F[7], ay, F[8]));
+  const double s0 = fabs(fma(bx, l0, fma(by, l1, l2)));
+  const double n2 = fma(l0, l0, l1 * l1);
+  const double m0 = fma(F[0], bx, fma(F[3], by, F[6])), m1 = fma(F[1], bx, fma(F[4], by, F[7]));
+  const double g2 = fma(m0, m0, m1 * m1);
+  const double T2 = T * T;
+  if (!(s0 * s0 > g2 * T2)) return false;
+  const double B = fma(-h, T2, s0);
+  if (!(B > 0)) return false;
+  return B * B >= T2 * (g2 + n2 + 2.0 * sqrt(g2 * n2));
 }
 EG3D_D double prune_radius(const eg3d_params& prm, int n_obs) {  // T with T^2 = accept_mse * 2n * 1.02
   return sqrt(prm.gn_accept_mse * (double)(2 * n_obs) * 1.02);

@@ -18,10 +18,23 @@ namespace eg3d {
 #ifndef EG3D_K3A_MIN_BLOCKS
 #define EG3D_K3A_MIN_BLOCKS 12
 #endif
-#ifndef EG3D_K3B_MIN_BLOCKS
-#define EG3D_K3B_MIN_BLOCKS 8
+// Phase B is bound by instruction-cache refills, not by occupancy: its hot path is ~65 KB of branchy scalar code, ncu
+// shows the GPC-level instruction cache at 80 % of its peak request rate, and the kernel takes the same time with 8, 16,
+// 28 or 32 resident warps per SM (profiles/r01_k3b_icache.md).  7 CTAs x 4 warps (72 registers) is the measured optimum.
+// EG3D_K3B_SYNC=1 with EG3D_K3B_THREADS=640..1024, EG3D_K3B_MIN_BLOCKS=1 builds the lock-step form (one CTA per SM, a
+// CTA barrier in front of each half of a view's expansion so that the warps share the lines they pull in): 35 % fewer
+// instruction-cache requests but slower overall (barrier idling), kept for experiments.
+#ifndef EG3D_K3B_THREADS
+#define EG3D_K3B_THREADS 128
 #endif
-constexpr int K3_THREADS = 128;  // 4 warps per CTA
+#ifndef EG3D_K3B_MIN_BLOCKS
+#define EG3D_K3B_MIN_BLOCKS 7
+#endif
+#ifndef EG3D_K3B_SYNC
+#define EG3D_K3B_SYNC 0
+#endif
+constexpr int K3_THREADS = 128;  // phase A: 4 warps per CTA
+constexpr int K3B_THREADS = EG3D_K3B_THREADS;
 
 struct Pt3 {  // a 3-view point of the following phase (64 B)
   float X[3];
@@ -615,19 +628,28 @@ static __device__ __noinline__ int walk_dir(Ctx& c, int v, const Plg& p, uint32_
   Pl pl = get_pl(S, v, p.pl);
   PlP q; q.seg = p.seg; q.c = p.c;
   int cnt = 0;
-  int j = towards_start ? cur - 1 : cur + 1;
   __syncwarp();
-  while (towards_start ? (j >= lo) : (j < hi)) {
-    const int slot = slot_of(c, j);
-    const size_t b = (size_t)slot * c.w.oc;
-    float3 l;
-    if (!epiline(S, c.w.ov[b], v, make_float2(c.w.ox[b], c.w.oy[b]), l)) break;   // known_point's first observation (:797-806)
-    PlP nq;
-    if (!walk_line(pl, q, dir, l, S.prm, false, nq)) break;
-    if (c.lane == 0) { tmp[cnt].seg = nq.seg; tmp[cnt].cx = nq.c.x; tmp[cnt].cy = nq.c.y; }
-    cnt++;
-    q = nq;
-    j += towards_start ? -1 : 1;
+  // the chain points in walking order; their epipolar lines (from each point's FIRST observation, :797-806) are
+  // independent of the walk and are computed 32 at a time, the walk itself is sequential with a 32-segment-wide step
+  const int nwalk = towards_start ? cur - lo : hi - cur - 1;
+  bool stop = false;
+  for (int base = 0; base < nwalk && !stop; base += 32) {
+    const int k = base + c.lane;
+    float3 lk = make_float3(0.f, 0.f, 0.f); bool lok = false;
+    if (k < nwalk) {
+      const size_t b = (size_t)slot_of(c, towards_start ? cur - 1 - k : cur + 1 + k) * c.w.oc;
+      lok = epiline(S, c.w.ov[b], v, make_float2(c.w.ox[b], c.w.oy[b]), lk);
+    }
+    const int nb = min(32, nwalk - base);
+    for (int kk = 0; kk < nb; kk++) {
+      if (!__shfl_sync(0xffffffffu, (int)lok, kk)) { stop = true; break; }
+      const float3 l = make_float3(__shfl_sync(0xffffffffu, lk.x, kk), __shfl_sync(0xffffffffu, lk.y, kk), __shfl_sync(0xffffffffu, lk.z, kk));
+      PlP nq;
+      if (!walk_line_warp(pl, q, dir, l, S.prm, false, nq, c.lane)) { stop = true; break; }
+      if (c.lane == 0) { tmp[cnt].seg = nq.seg; tmp[cnt].cx = nq.c.x; tmp[cnt].cy = nq.c.y; }
+      cnt++;
+      q = nq;
+    }
   }
   __syncwarp();
   int keep = cnt;
@@ -709,8 +731,11 @@ static __device__ __noinline__ bool add_view_finish(Ctx& c, int v, const Plg& p,
   return true;
 }
 
-// expand_allpoints_to_other_view_using_plmap, triangulation.cpp:742-830
-static __device__ __noinline__ void expand_view(Ctx& c, int v) {
+// expand_allpoints_to_other_view_using_plmap, triangulation.cpp:742-830, in two halves (the phase-B kernel puts a CTA
+// barrier in front of each): the epipolar hits on the central point (:753-768), then the projection loop over the chain
+// points the first half did not reach (:770-830).
+struct EvState { bool matched; int iv0, iv1; };
+static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) {
   const DevScene& S = *c.S;
   const int64_t h0 = c.A->hit_off_b[c.hrow + v];
   const int nh = (int)(c.A->hit_off_b[c.hrow + v + 1] - h0);
@@ -740,8 +765,8 @@ static __device__ __noinline__ void expand_view(Ctx& c, int v) {
             const int i = probe[k];
             const int vi = c.w.ov[cb + i];
             if (vi == v) continue;
-            const double* F = S.Fp + ((size_t)vi * S.V + v) * 9;
-            if (pair_cannot_fit(F, make_float2(c.w.ox[cb + i], c.w.oy[cb + i]), hp, Tp)) pass = false;
+            const size_t fi = (size_t)vi * S.V + v;
+            if (pair_cannot_fit(S.Fp + fi * 9, S.Fph[fi], make_float2(c.w.ox[cb + i], c.w.oy[cb + i]), hp, Tp)) pass = false;
           }
         }
         const unsigned pm = __ballot_sync(0xffffffffu, pass);
@@ -792,9 +817,15 @@ static __device__ __noinline__ void expand_view(Ctx& c, int v) {
         if (ns > cc) { c.central = ns; iv0 = 0; iv1 = ns + ne; }
         else { iv0 = cc - ns; iv1 = cc + ne; }
       }
-      if (c.overflow) return;
+      if (c.overflow) break;
     }
+    if (c.overflow) break;
   }
+  st.matched = matched; st.iv0 = iv0; st.iv1 = iv1;
+}
+static __device__ __noinline__ void expand_view_main(Ctx& c, int v, const EvState& st) {
+  const DevScene& S = *c.S;
+  const bool matched = st.matched; const int iv0 = st.iv0, iv1 = st.iv1;
   int last = -1;
   K3P_BEGIN(te3);
   for (int cur = 0; cur < c.len; cur++) {
@@ -805,7 +836,7 @@ static __device__ __noinline__ void expand_view(Ctx& c, int v) {
     if (!grid_unique(S.g_expand, v, S.width, S.height, q, pl_id)) continue;
     Pl pl = get_pl(S, v, pl_id);
     Plg init; init.pl = pl_id;
-    if (pl_distancesq(pl, q, init.seg, init.c) > S.prm.max_proj_distsq_expand) return;  // abandons the view
+    if (pl_distancesq_warp(pl, q, init.seg, init.c, c.lane) > S.prm.max_proj_distsq_expand) return;  // abandons the view
     const int hi = matched ? (cur <= iv0 ? iv0 : c.len) : c.len;
     const int n = c.w.snobs[slot];
     double X[3] = {c.w.sX[3 * slot], c.w.sX[3 * slot + 1], c.w.sX[3 * slot + 2]};
@@ -859,9 +890,9 @@ static __device__ __noinline__ bool seed_phase_a(Ctx& c, PaRec& r) {
   // 2-view bound (pair_cannot_fit) to its triple's three view pairs; survivors are queued IN ORDER and solved 32 at a
   // time, so the sequence of GN-valid hypotheses handed to plg_compatible is the reference's.
   const double Tp = prune_radius(S.prm, 3);
-  const double* F01 = S.Fp + ((size_t)c.sel[0] * V + c.sel[1]) * 9;
-  const double* F02 = S.Fp + ((size_t)c.sel[0] * V + c.sel[2]) * 9;
-  const double* F12 = S.Fp + ((size_t)c.sel[1] * V + c.sel[2]) * 9;
+  const size_t i01 = (size_t)c.sel[0] * V + c.sel[1], i02 = (size_t)c.sel[0] * V + c.sel[2], i12 = (size_t)c.sel[1] * V + c.sel[2];
+  const double* F01 = S.Fp + i01 * 9; const double* F02 = S.Fp + i02 * 9; const double* F12 = S.Fp + i12 * 9;
+  const double h01 = S.Fph[i01], h02 = S.Fph[i02], h12 = S.Fph[i12];
   int* tq = c.w.tq;
   long long tnext = 0;
   int qn = 0;
@@ -883,7 +914,7 @@ static __device__ __noinline__ bool seed_phase_a(Ctx& c, PaRec& r) {
           i1 = (int)(rem / n2h); i2 = (int)(rem - (long long)i1 * n2h);
         }
         const float2 q0 = make_float2(h0[i0].x, h0[i0].y), q1 = make_float2(h1[i1].x, h1[i1].y), q2 = make_float2(h2[i2].x, h2[i2].y);
-        pass = !(pair_cannot_fit(F02, q0, q2, Tp) || pair_cannot_fit(F01, q0, q1, Tp) || pair_cannot_fit(F12, q1, q2, Tp));
+        pass = !(pair_cannot_fit(F02, h02, q0, q2, Tp) || pair_cannot_fit(F01, h01, q0, q1, Tp) || pair_cannot_fit(F12, h12, q1, q2, Tp));
       }
       const unsigned pm = __ballot_sync(0xffffffffu, pass);
       if (pass) { const int pos = qn + __popc(pm & ((1u << lane) - 1u)); tq[3 * pos] = i0; tq[3 * pos + 1] = i1; tq[3 * pos + 2] = i2; }
@@ -948,7 +979,8 @@ static __device__ __noinline__ bool seed_phase_a(Ctx& c, PaRec& r) {
   return true;
 }
 
-// Phase B of an accepted seed: chain = reverse(D1) + central + D2, then expansion to every other view.
+// Phase B of an accepted seed, set-up: chain = reverse(D1) + central + D2.  The expansion to every other view
+// (triangulation.cpp:960-973) is the kernel's view loop.
 static __device__ __noinline__ void seed_phase_b(Ctx& c, const PaRec& r, const Pt3* l1, const Pt3* l2) {
   const DevScene& S = *c.S;
   const int V = S.V, lane = c.lane;
@@ -968,12 +1000,6 @@ static __device__ __noinline__ void seed_phase_b(Ctx& c, const PaRec& r, const P
   __syncwarp();
   c.nslots = c.len;
   c.central = fn1;
-  // --- expansion to every other view (triangulation.cpp:960-973)
-  for (int v = 0; v < V; v++) {
-    if (v == c.sel[0] || v == c.sel[1] || v == c.sel[2]) continue;
-    expand_view(c, v);
-    if (c.overflow) return;
-  }
 }
 
 __global__ void __launch_bounds__(K3_THREADS, EG3D_K3A_MIN_BLOCKS) k3a_hypothesis_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
@@ -1069,37 +1095,71 @@ __global__ void k3_order_keys_kernel(int n, const unsigned long long* __restrict
   keys[i] = key; vals[i] = i;
 }
 
-__global__ void __launch_bounds__(K3_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
+__global__ void __launch_bounds__(K3B_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   Ctx c;
   c.S = &S; c.A = &A; c.lane = lane;
   c.w = make_ws(A.scratch + (size_t)warp * A.scratch_per_warp, S.V, A.capf, A.capc, A.oc);
   const int n_acc = (int)A.pa_counters[0];
+  const int V = S.V;
   while (true) {
     int ri = 0;
     if (lane == 0) ri = atomicAdd(A.work_counter, 1);
     ri = __shfl_sync(0xffffffffu, ri, 0);
-    if (ri >= n_acc) break;
-    const int rank = A.pa_order ? A.pa_order[ri] : ri;
-    const PaRec r = A.pa_recs[rank];
-    const int seed = r.seed;
-    c.seed = seed; c.sv = A.seed_view[seed];
-    c.hrow = (long long)(A.b_compact ? rank : seed) * S.V;
+    const bool has = ri < n_acc;
+#if EG3D_K3B_SYNC
+    if (!__syncthreads_or(has)) break;       // the CTA's warps take their seeds together and leave together
+#else
+    if (!has) break;
+#endif
+    int seed = 0;
     c.len = 0; c.nslots = 0; c.central = 0; c.overflow = false;
+    c.sel[0] = c.sel[1] = c.sel[2] = -1;
 #ifdef EG3D_K3_PROFILE
     for (int k = 0; k < 12; k++) c.pc[k] = 0;
 #endif
     K3P_BEGIN(tall);
-    if (r.fn1 >= 0) seed_phase_b(c, r, A.pa_pool + r.pool_off, A.pa_pool + r.pool_off + r.fn1);
+    bool live = false;
+#ifdef EG3D_K3_PROFILE
+    int len0 = 0;
+#endif
+    if (has) {
+      const int rank = A.pa_order ? A.pa_order[ri] : ri;
+      const PaRec& r = A.pa_recs[rank];
+      seed = r.seed;
+      c.seed = seed; c.sv = A.seed_view[seed];
+      c.hrow = (long long)(A.b_compact ? rank : seed) * V;
+      if (r.fn1 >= 0) {
+        seed_phase_b(c, r, A.pa_pool + r.pool_off, A.pa_pool + r.pool_off + r.fn1);
+        live = !c.overflow;
+#ifdef EG3D_K3_PROFILE
+        len0 = r.fn1 + r.fn2 + 1;
+#endif
+      }
+    }
+    // --- expansion to every other view (triangulation.cpp:960-973), the CTA's seeds view by view
+    for (int v = 0; v < V; v++) {
+      const bool run = live && !c.overflow && v != c.sel[0] && v != c.sel[1] && v != c.sel[2];
+      EvState st; st.matched = false; st.iv0 = 0; st.iv1 = 0;
+#if EG3D_K3B_SYNC
+      __syncthreads();
+#endif
+      if (run) expand_view_epc(c, v, st);
+#if EG3D_K3B_SYNC
+      __syncthreads();
+#endif
+      if (run && !c.overflow) expand_view_main(c, v, st);
+    }
     K3P_END(c, 7, tall);
+    if (!has) continue;
 #ifdef EG3D_K3_PROFILE
     if (A.prof && lane == 0) {
       for (int k = 0; k < 12; k++) if (c.pc[k]) atomicAdd(&A.prof[k], (unsigned long long)c.pc[k]);
       atomicMax(&A.prof[12], (unsigned long long)c.pc[7]);
       if (c.pc[7] > 50000000ll) atomicAdd(&A.prof[13], 1ull);
       if (c.pc[7] > 200000000ll) atomicAdd(&A.prof[14], 1ull);
-      if (A.prof_seed) { A.prof_seed[2 * (size_t)seed] = (unsigned long long)c.pc[7]; A.prof_seed[2 * (size_t)seed + 1] = (unsigned long long)(r.fn1 + r.fn2 + 1) | ((unsigned long long)c.len << 32); }
+      if (A.prof_seed) { A.prof_seed[2 * (size_t)seed] = (unsigned long long)c.pc[7]; A.prof_seed[2 * (size_t)seed + 1] = (unsigned long long)len0 | ((unsigned long long)c.len << 32); }
     }
 #endif
     __syncwarp();
