@@ -68,15 +68,29 @@ def _bezier(cp, t):
 
 def make_scene(n_views=6, width=640, height=480, focal=520.0, n_curves=24, segs_per_curve=24, curve_len=0.9,
                seed=0, n_tracks=0, track_cap=30, closed_frac=0.1, vertex_jitter=0.3, vertex_noise_px=0.03,
-               extent=0.75, per_ring=50, track_noise_px=0.3, drop_view_frac=0.0):
+               extent=0.75, per_ring=50, track_noise_px=0.3, drop_view_frac=0.0,
+               cameras=None, fundamental=None, fundamental_valid=None, real_tracks=None, centers=None):
+    """`cameras` ([V,12] f32, e.g. from openmvg_io.load_sfm_data) replaces the synthetic rig; `fundamental` /
+    `fundamental_valid` replace the analytic F (e.g. LMedS matrices estimated from the tracks, as the reference does);
+    `real_tracks` = (xyz, off, view, xy) replaces the generated tracks; `centers` ([K,3]) are the 3D positions the
+    curves are scattered around (the SfM points of a real scene) instead of the uniform box."""
     rng = np.random.default_rng(seed)
-    P32 = make_cameras(n_views, width, height, focal, rng, per_ring=per_ring)
+    if cameras is not None:
+        P32 = np.ascontiguousarray(cameras, np.float32).reshape(-1, 3, 4)
+        n_views = P32.shape[0]
+    else:
+        P32 = make_cameras(n_views, width, height, focal, rng, per_ring=per_ring)
     P = P32.astype(np.float64)
     F, Fv = fundamental_from_cameras(P32)
+    if fundamental is not None:
+        F, Fv = np.asarray(fundamental, np.float64).reshape(n_views, n_views, 9), np.asarray(fundamental_valid, np.uint8).reshape(n_views, n_views)
     n = segs_per_curve
     curves = []
     for c in range(n_curves):
-        ctr = rng.uniform(-extent, extent, 3) * np.array([1.0, 0.6, 1.0])
+        if centers is not None:
+            ctr = np.asarray(centers[rng.integers(len(centers))], np.float64) + rng.normal(0, 0.3 * curve_len, 3)
+        else:
+            ctr = rng.uniform(-extent, extent, 3) * np.array([1.0, 0.6, 1.0])
         if rng.uniform() < closed_frac:
             a = rng.normal(size=3); a /= np.linalg.norm(a)
             b = np.cross(a, rng.normal(size=3)); b /= np.linalg.norm(b)
@@ -129,7 +143,9 @@ def make_scene(n_views=6, width=640, height=480, focal=520.0, n_curves=24, segs_
     verts = np.concatenate(verts) if verts else np.zeros((0, 2), np.float32)
 
     tr = dict(track_xyz=None, track_off=None, track_view=None, track_xy=None)
-    if n_tracks > 0:
+    if real_tracks is not None:
+        tr = dict(track_xyz=real_tracks[0], track_off=real_tracks[1], track_view=real_tracks[2], track_xy=real_tracks[3])
+    elif n_tracks > 0:
         xyz, off, tv, txy = [], [0], [], []
         for _ in range(n_tracks):
             c = rng.integers(n_curves)
