@@ -259,7 +259,8 @@ template <int MODE>
 static void launch_sweep(eg3d_scene* sc, const K1Seeds& ks, const K1Work& w, int64_t* counts, unsigned char* flags, const int64_t* off, eg3d_hit* hits) {
   if (w.n <= 0) return;
   dim3 grid((w.n + K1_THREADS - 1) / K1_THREADS, sc->V);
-  k1_sweep_kernel<MODE><<<grid, K1_THREADS, K1_SMEM_BYTES2, sc->stream>>>(sc->dev, ks, w, counts, flags, off, hits);
+  if (!w.list && !w.sel) k1_sweep_kernel<MODE, true><<<grid, K1_THREADS, K1_SMEM_BYTES2, sc->stream>>>(sc->dev, ks, w, counts, flags, off, hits);
+  else k1_sweep_kernel<MODE, false><<<grid, K1_THREADS, K1_SMEM_BYTES2, sc->stream>>>(sc->dev, ks, w, counts, flags, off, hits);
 }
 
 // Sweep form of K1 for the pairs described by `w` (n_rows result rows): count -> scan -> fill.
@@ -396,7 +397,9 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
   const int warps_per_block_b = K3B_THREADS / 32;
   int nblocks_b = sc->num_sms * EG3D_K3B_MIN_BLOCKS;
   nblocks_b = std::max(1, std::min(nblocks_b, (n + warps_per_block_b - 1) / warps_per_block_b));
-  const size_t nwarps = std::max((size_t)nblocks * warps_per_block, (size_t)nblocks_b * warps_per_block_b);
+  const int batch_b = EG3D_K3B_BATCH > 0 ? EG3D_K3B_BATCH : 1;     // arenas per phase-B warp
+  if (EG3D_K3B_BATCH > 0) nblocks_b = std::max(1, std::min(sc->num_sms, (n + warps_per_block_b * batch_b - 1) / (warps_per_block_b * batch_b)));
+  const size_t nwarps = std::max((size_t)nblocks * warps_per_block, (size_t)nblocks_b * warps_per_block_b * batch_b);
   DBuf<unsigned char> scratch; CK(scratch.alloc(nwarps * spw));
   DBuf<int> counter; CK(counter.alloc(1)); CK(cudaMemsetAsync(counter.p, 0, sizeof(int), sc->stream));
   DBuf<unsigned long long> oc4; CK(oc4.alloc(4)); CK(cudaMemsetAsync(oc4.p, 0, 4 * sizeof(unsigned long long), sc->stream));
@@ -727,9 +730,12 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   if (tracks) { D.g_corr.cell = sc->hg30.cell; D.g_corr.w = sc->hg30.w; D.g_corr.h = sc->hg30.h; D.g_corr.cell_off = sc->g30_off.p; D.g_corr.ids = sc->g30_ids.p; }
   D.n_tracks = d->n_tracks; D.track_xyz = sc->track_xyz.p; D.track_off = sc->track_off.p; D.track_view = sc->track_view.p; D.track_xy = sc->track_xy.p;
   D.prm = sc->prm;
-  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
-  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
-  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_ANY>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_COUNT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_FILL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_ANY, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_COUNT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_FILL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
+  CK(cudaFuncSetAttribute(k1_sweep_kernel<K1_ANY, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES2));
   *out = guard.release();
   return EG3D_OK;
 }

@@ -83,7 +83,7 @@ struct K1Work {
 };
 enum { K1_COUNT = 0, K1_FILL = 1, K1_ANY = 2 };   // K1_ANY: only "is the list non-empty" (stops at a seed's first hit)
 
-template <int MODE>
+template <int MODE, bool ALL_PAIRS>   // ALL_PAIRS: list == null && sel == null resolved at compile time (the full sweep)
 __global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K1Seeds seeds, const __grid_constant__ K1Work work,
                                                               int64_t* __restrict__ counts, unsigned char* __restrict__ flags,
                                                               const int64_t* __restrict__ off, eg3d_hit* __restrict__ hits) {
@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_const
   // which pair is this lane's, is it wanted, and where does its result go
   bool valid = entry < work.n;
   int sidx = 0; size_t row = 0;
-  if (valid) {
+  if (ALL_PAIRS) { sidx = entry; row = (size_t)entry * S.V + t; }
+  else if (valid) {
     sidx = work.list ? work.list[entry] : entry;
     if (work.sel) {
       const int* sl = work.sel + 3 * (size_t)sidx;

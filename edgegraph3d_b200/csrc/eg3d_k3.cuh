@@ -33,6 +33,9 @@ namespace eg3d {
 #ifndef EG3D_K3B_SYNC
 #define EG3D_K3B_SYNC 0
 #endif
+#ifndef EG3D_K3B_BATCH
+#define EG3D_K3B_BATCH 0   // > 0: lock-step form with this many seeds per warp (k3b_expand_kernel, batched variant)
+#endif
 constexpr int K3_THREADS = 128;  // phase A: 4 warps per CTA
 constexpr int K3B_THREADS = EG3D_K3B_THREADS;
 
@@ -1079,6 +1082,49 @@ __global__ void k3_select_views_kernel(int n_seeds, int V, const int* __restrict
   if (lane == 0) { sel[3 * (size_t)seed] = s0; sel[3 * (size_t)seed + 1] = s1; sel[3 * (size_t)seed + 2] = s2; }
 }
 
+// Hands a finished chain to the unordered output: one contiguous range of points / observations per seed.
+static __device__ __noinline__ void emit_chain(Ctx& c, int seed) {
+  const K3Args& A = *c.A;
+  const int lane = c.lane;
+  __syncwarp();
+  int npts = c.overflow ? 0 : c.len;
+  long long nobs = 0;
+  for (int i = lane; i < npts; i += 32) nobs += c.w.snobs[c.w.order[i]];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nobs += __shfl_xor_sync(0xffffffffu, nobs, o);
+  unsigned long long pbase = 0, obase = 0;
+  if (lane == 0) {
+    if (c.overflow) atomicAdd(&A.out_counters[2], 1ull);
+    if (npts > 0) {
+      pbase = atomicAdd(&A.out_counters[0], (unsigned long long)npts);
+      obase = atomicAdd(&A.out_counters[1], (unsigned long long)nobs);
+    }
+  }
+  pbase = __shfl_sync(0xffffffffu, pbase, 0); obase = __shfl_sync(0xffffffffu, obase, 0);
+  if (npts > 0 && ((long long)pbase + npts > A.pt_cap || (long long)obase + nobs > A.ob_cap)) {
+    if (lane == 0) atomicAdd(&A.out_counters[3], 1ull);
+    npts = 0; nobs = 0;
+  }
+  if (lane == 0) { A.seed_npts[seed] = npts; A.seed_pbase[seed] = (int64_t)pbase; A.seed_nobs[seed] = nobs; }
+  // write the chain: point headers by lane 0, observations coalesced
+  long long ob = (long long)obase;
+  for (int i = 0; i < npts; i++) {
+    const int slot = c.w.order[i];
+    const int n = c.w.snobs[slot];
+    if (lane == 0) {
+      A.o_X[3 * (pbase + i)] = c.w.sX[3 * slot]; A.o_X[3 * (pbase + i) + 1] = c.w.sX[3 * slot + 1]; A.o_X[3 * (pbase + i) + 2] = c.w.sX[3 * slot + 2];
+      A.o_nobs[pbase + i] = n; A.o_obase[pbase + i] = ob;
+    }
+    const size_t b = (size_t)slot * c.w.oc;
+    for (int k = lane; k < n; k += 32) {
+      A.ob_view[ob + k] = c.w.ov[b + k]; A.ob_pl[ob + k] = c.w.opl[b + k]; A.ob_seg[ob + k] = c.w.oseg[b + k];
+      A.ob_x[ob + k] = c.w.ox[b + k]; A.ob_y[ob + k] = c.w.oy[b + k];
+    }
+    ob += n;
+  }
+  __syncwarp();
+}
+
 // Work order of phase B.  Per-seed cost grows with the chain length (every view is tried against every chain point), and
 // a few hundred seeds are 10-100x the median, so the accepted seeds are visited longest chain first; the order has no
 // effect on the results (pack orders by seed).  Keys for the radix sort: descending length, unused tail entries last.
@@ -1095,6 +1141,103 @@ __global__ void k3_order_keys_kernel(int n, const unsigned long long* __restrict
   keys[i] = key; vals[i] = i;
 }
 
+#if EG3D_K3B_BATCH > 0
+// Lock-step phase B with EG3D_K3B_BATCH seeds per warp: one CTA per SM, every warp owns a small batch of accepted seeds
+// (one scratch arena each, the few per-seed scalars parked in shared memory) and runs one half of a view's expansion for
+// all of them before the CTA-wide barrier.  The warps of an SM then execute the same ~half of the hot code at the same
+// time and every line they pull in is used by batch x warps seeds, instead of each warp cycling through the whole
+// ~65 KB path on its own (profiles/r01_k3b_icache.md).
+struct SeedState { int seed, sv, sel0, sel1, sel2, len, nslots, central, overflow, live, ran, matched, iv0, iv1, has; long long hrow; };
+__global__ void __launch_bounds__(K3B_THREADS, 1) k3b_expand_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
+  constexpr int KB = EG3D_K3B_BATCH;
+  __shared__ SeedState ss[K3B_THREADS / 32][KB];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  Ctx c;
+  c.S = &S; c.A = &A; c.lane = lane;
+  const int n_acc = (int)A.pa_counters[0];
+  const int V = S.V;
+  auto load = [&](int j) {
+    const SeedState& q = ss[wib][j];
+    c.seed = q.seed; c.sv = q.sv; c.sel[0] = q.sel0; c.sel[1] = q.sel1; c.sel[2] = q.sel2;
+    c.len = q.len; c.nslots = q.nslots; c.central = q.central; c.overflow = q.overflow != 0; c.hrow = q.hrow;
+    c.w = make_ws(A.scratch + ((size_t)warp * KB + j) * A.scratch_per_warp, V, A.capf, A.capc, A.oc);
+  };
+  auto store = [&](int j) {
+    __syncwarp();
+    if (lane == 0) { SeedState& q = ss[wib][j]; q.len = c.len; q.nslots = c.nslots; q.central = c.central; q.overflow = c.overflow ? 1 : 0; }
+    __syncwarp();
+  };
+#ifdef EG3D_K3_PROFILE
+  for (int k = 0; k < 12; k++) c.pc[k] = 0;
+#endif
+  while (true) {
+    bool any = false;
+    for (int j = 0; j < KB; j++) {
+      int ri = 0;
+      if (lane == 0) ri = atomicAdd(A.work_counter, 1);
+      ri = __shfl_sync(0xffffffffu, ri, 0);
+      const bool has = ri < n_acc;
+      any |= has;
+      __syncwarp();
+      if (lane == 0) { SeedState& q = ss[wib][j]; q.has = has ? 1 : 0; q.live = 0; q.overflow = 0; q.len = 0; q.nslots = 0; q.central = 0; q.seed = 0; q.sel0 = q.sel1 = q.sel2 = -1; }
+      __syncwarp();
+      if (!has) continue;
+      const int rank = A.pa_order ? A.pa_order[ri] : ri;
+      const PaRec& r = A.pa_recs[rank];
+      c.seed = r.seed; c.sv = A.seed_view[r.seed];
+      c.hrow = (long long)(A.b_compact ? rank : r.seed) * V;
+      c.len = 0; c.nslots = 0; c.central = 0; c.overflow = false;
+      c.sel[0] = c.sel[1] = c.sel[2] = -1;
+      c.w = make_ws(A.scratch + ((size_t)warp * KB + j) * A.scratch_per_warp, V, A.capf, A.capc, A.oc);
+      bool live = false;
+      if (r.fn1 >= 0) { seed_phase_b(c, r, A.pa_pool + r.pool_off, A.pa_pool + r.pool_off + r.fn1); live = !c.overflow; }
+      __syncwarp();
+      if (lane == 0) {
+        SeedState& q = ss[wib][j];
+        q.seed = c.seed; q.sv = c.sv; q.sel0 = c.sel[0]; q.sel1 = c.sel[1]; q.sel2 = c.sel[2]; q.hrow = c.hrow; q.live = live ? 1 : 0;
+        q.len = c.len; q.nslots = c.nslots; q.central = c.central; q.overflow = c.overflow ? 1 : 0;
+      }
+      __syncwarp();
+    }
+    if (!__syncthreads_or(any)) break;
+    // --- expansion to every other view (triangulation.cpp:960-973): the CTA's seeds, view by view, half by half
+    for (int v = 0; v < V; v++) {
+      __syncthreads();
+      for (int j = 0; j < KB; j++) {
+        const SeedState& q = ss[wib][j];
+        const bool run = q.live && !q.overflow && v != q.sel0 && v != q.sel1 && v != q.sel2;
+        if (run) {
+          load(j);
+          EvState st; st.matched = false; st.iv0 = 0; st.iv1 = 0;
+          expand_view_epc(c, v, st);
+          store(j);
+          if (lane == 0) { SeedState& w = ss[wib][j]; w.matched = st.matched ? 1 : 0; w.iv0 = st.iv0; w.iv1 = st.iv1; }
+        }
+        __syncwarp();
+        if (lane == 0) ss[wib][j].ran = run ? 1 : 0;
+        __syncwarp();
+      }
+      __syncthreads();
+      for (int j = 0; j < KB; j++) {
+        const SeedState& q = ss[wib][j];
+        if (q.ran && !q.overflow) {
+          load(j);
+          EvState st; st.matched = q.matched != 0; st.iv0 = q.iv0; st.iv1 = q.iv1;
+          expand_view_main(c, v, st);
+          store(j);
+        }
+      }
+    }
+    for (int j = 0; j < KB; j++) {
+      if (!ss[wib][j].has) continue;
+      load(j);
+      emit_chain(c, c.seed);
+    }
+    __syncwarp();
+  }
+}
+#else
 __global__ void __launch_bounds__(K3B_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1162,44 +1305,10 @@ __global__ void __launch_bounds__(K3B_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_k
       if (A.prof_seed) { A.prof_seed[2 * (size_t)seed] = (unsigned long long)c.pc[7]; A.prof_seed[2 * (size_t)seed + 1] = (unsigned long long)len0 | ((unsigned long long)c.len << 32); }
     }
 #endif
-    __syncwarp();
-    int npts = c.overflow ? 0 : c.len;
-    long long nobs = 0;
-    for (int i = lane; i < npts; i += 32) nobs += c.w.snobs[c.w.order[i]];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nobs += __shfl_xor_sync(0xffffffffu, nobs, o);
-    unsigned long long pbase = 0, obase = 0;
-    if (lane == 0) {
-      if (c.overflow) atomicAdd(&A.out_counters[2], 1ull);
-      if (npts > 0) {
-        pbase = atomicAdd(&A.out_counters[0], (unsigned long long)npts);
-        obase = atomicAdd(&A.out_counters[1], (unsigned long long)nobs);
-      }
-    }
-    pbase = __shfl_sync(0xffffffffu, pbase, 0); obase = __shfl_sync(0xffffffffu, obase, 0);
-    if (npts > 0 && ((long long)pbase + npts > A.pt_cap || (long long)obase + nobs > A.ob_cap)) {
-      if (lane == 0) atomicAdd(&A.out_counters[3], 1ull);
-      npts = 0; nobs = 0;
-    }
-    if (lane == 0) { A.seed_npts[seed] = npts; A.seed_pbase[seed] = (int64_t)pbase; A.seed_nobs[seed] = nobs; }
-    // write the chain: point headers by lane 0, observations coalesced
-    long long ob = (long long)obase;
-    for (int i = 0; i < npts; i++) {
-      const int slot = c.w.order[i];
-      const int n = c.w.snobs[slot];
-      if (lane == 0) {
-        A.o_X[3 * (pbase + i)] = c.w.sX[3 * slot]; A.o_X[3 * (pbase + i) + 1] = c.w.sX[3 * slot + 1]; A.o_X[3 * (pbase + i) + 2] = c.w.sX[3 * slot + 2];
-        A.o_nobs[pbase + i] = n; A.o_obase[pbase + i] = ob;
-      }
-      const size_t b = (size_t)slot * c.w.oc;
-      for (int k = lane; k < n; k += 32) {
-        A.ob_view[ob + k] = c.w.ov[b + k]; A.ob_pl[ob + k] = c.w.opl[b + k]; A.ob_seg[ob + k] = c.w.oseg[b + k];
-        A.ob_x[ob + k] = c.w.ox[b + k]; A.ob_y[ob + k] = c.w.oy[b + k];
-      }
-      ob += n;
-    }
-    __syncwarp();
+    emit_chain(c, seed);
   }
 }
+
+#endif  // EG3D_K3B_BATCH
 
 }  // namespace eg3d
