@@ -354,6 +354,37 @@ EG3D_HD_NI bool grid_unique(const DevGrid& g, int view, int img_w, int img_h, fl
   return cnt == 1 && !multi;
 }
 
+#ifdef __CUDACC__
+// Warp-cooperative grid_unique for warp-uniform arguments: the (up to) nine cells of the clipped 3x3 neighbourhood are
+// read by nine lanes at once; the union holds exactly one polyline id iff every non-empty cell holds only that id.
+static __device__ __noinline__ bool grid_unique_warp(const DevGrid& g, int view, int img_w, int img_h, float2 c, uint32_t& pl_id, int lane) {
+  if (c.x <= 0 || c.x >= img_w || c.y <= 0 || c.y >= img_h) return false;
+  const bool on_row = is_multiple_of(c.x, g.cell);
+  const bool on_col = is_multiple_of(c.y, g.cell);
+  int cx = (int)floor_or_upper_if_close(c.x / g.cell), cy = (int)floor_or_upper_if_close(c.y / g.cell);
+  if (cx >= g.w) cx = g.w - 1;
+  if (cy >= g.h) cy = g.h - 1;
+  const int i0 = cy > 0 ? -1 : 0, i1 = on_row ? 0 : (cy < g.h - 1 ? 1 : 0);
+  const int j0 = cx > 0 ? -1 : 0, j1 = on_col ? 0 : (cx < g.w - 1 ? 1 : 0);
+  const int i = lane / 3 - 1, j = lane % 3 - 1;            // lanes 0..8 <-> (i, j) in {-1,0,1}^2
+  int cnt = 0; uint32_t first = 0; bool multi = false;
+  if (lane < 9 && i >= i0 && i <= i1 && j >= j0 && j <= j1) {
+    const int* off = g.cell_off + (size_t)view * g.w * g.h;
+    const int cidx = (cy + i) * g.w + (cx + j);
+    const int k0 = off[cidx], k1 = off[cidx + 1];
+    cnt = k1 - k0;
+    if (cnt > 0) first = g.ids[k0];
+    for (int k = k0 + 1; k < k1; k++) if (g.ids[k] != first) multi = true;
+  }
+  const unsigned have = __ballot_sync(0xffffffffu, cnt > 0);
+  if (__any_sync(0xffffffffu, multi) || have == 0) { pl_id = 0; return false; }
+  const uint32_t f0 = __shfl_sync(0xffffffffu, first, __ffs(have) - 1);
+  const bool same = __all_sync(0xffffffffu, cnt == 0 || first == f0);
+  pl_id = f0;
+  return same;
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------
 // 2-view DLT initialiser = cv::triangulatePoints (triangulation.cpp:216,290): null vector of the 4x4 DLT matrix by
 // one-sided Jacobi SVD in double, cast to float.  Same operation sequence as the oracle's restatement.

@@ -836,7 +836,7 @@ static __device__ __noinline__ void expand_view_main(Ctx& c, int v, const EvStat
     const int slot = slot_of(c, cur);
     float2 q = project(S.P + 12 * v, c.w.sX[3 * slot], c.w.sX[3 * slot + 1], c.w.sX[3 * slot + 2]);
     uint32_t pl_id;
-    if (!grid_unique(S.g_expand, v, S.width, S.height, q, pl_id)) continue;
+    if (!grid_unique_warp(S.g_expand, v, S.width, S.height, q, pl_id, c.lane)) continue;
     Pl pl = get_pl(S, v, pl_id);
     Plg init; init.pl = pl_id;
     if (pl_distancesq_warp(pl, q, init.seg, init.c, c.lane) > S.prm.max_proj_distsq_expand) return;  // abandons the view
@@ -856,17 +856,6 @@ static __device__ __noinline__ void expand_view_main(Ctx& c, int v, const EvStat
   K3P_END(c, 6, te3);
 }
 
-// materialise a 3-view point as a chain slot
-static __device__ __noinline__ void slot_from_pt3(Ctx& c, int slot, const Pt3& p) {
-  if (c.lane == 0) {
-    size_t b = (size_t)slot * c.w.oc;
-    for (int i = 0; i < 3; i++) {
-      c.w.ov[b + i] = c.sel[p.perm[i]]; c.w.opl[b + i] = p.pl[i]; c.w.oseg[b + i] = p.seg[i]; c.w.ox[b + i] = p.cx[i]; c.w.oy[b + i] = p.cy[i];
-    }
-    c.w.snobs[slot] = 3;
-    c.w.sX[3 * slot] = p.X[0]; c.w.sX[3 * slot + 1] = p.X[1]; c.w.sX[3 * slot + 2] = p.X[2];
-  }
-}
 
 // Phase A of a seed: view triple, pruned triple enumeration, PLG following.  Returns true when exactly one compatible
 // hypothesis was found; its lists are left in c.w.fD1 / c.w.fD2 and the scalars in `r`.
@@ -993,9 +982,15 @@ static __device__ __noinline__ void seed_phase_b(Ctx& c, const PaRec& r, const P
   c.len = fn1 + 1 + fn2;
   if (c.len > c.w.capc) { c.overflow = true; return; }
   __syncwarp();
-  for (int i = 0; i < fn1; i++) slot_from_pt3(c, i, l1[fn1 - 1 - i]);
-  slot_from_pt3(c, fn1, r.central);
-  for (int i = 0; i < fn2; i++) slot_from_pt3(c, fn1 + 1 + i, l2[i]);
+  for (int i = lane; i < c.len; i += 32) {     // one chain point per lane
+    const Pt3& p = i < fn1 ? l1[fn1 - 1 - i] : (i == fn1 ? r.central : l2[i - fn1 - 1]);
+    const size_t b = (size_t)i * c.w.oc;
+    for (int k = 0; k < 3; k++) {
+      c.w.ov[b + k] = c.sel[p.perm[k]]; c.w.opl[b + k] = p.pl[k]; c.w.oseg[b + k] = p.seg[k]; c.w.ox[b + k] = p.cx[k]; c.w.oy[b + k] = p.cy[k];
+    }
+    c.w.snobs[i] = 3;
+    c.w.sX[3 * i] = p.X[0]; c.w.sX[3 * i + 1] = p.X[1]; c.w.sX[3 * i + 2] = p.X[2];
+  }
   for (int i = lane; i < c.len; i += 32) c.w.order[i] = i;
   for (int v = lane; v < V; v += 32) { c.w.sdirs[v] = 0; c.w.edirs[v] = 0; }
   __syncwarp();
