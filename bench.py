@@ -254,6 +254,17 @@ def workload_name(name, cfg, per_view, n):
 
 
 def main():
+    # Only the JSON line may reach stdout: library banners (NCCL prints its version there) are sent to stderr by
+    # pointing fd 1 at fd 2 for the rest of the process and keeping the real stdout for the one line.
+    global print
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*a, **k):  # noqa: A001
+        k.setdefault("file", real_stdout)
+        _print(*a, **k)
+        real_stdout.flush()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
