@@ -10,7 +10,7 @@ the lists nobody reads are not materialised); `roofline_k1` therefore times the 
 through eg3d_epipolar_intersect_device, after the timed steps.
 N = 1 runs BASELINE configs[1]: the synthetic 200-view rig, 1920x1080, 8 000 polyline segments per view, 50 000 seeds.
 N > 1 is weak scaling on the same rig: every rank keeps 50 000 seeds (seed spacing 20/N px => 250*N seeds per view) and
-owns a contiguous block of starting views (the reference's outer loop, polyline_matching.cpp:162).
+owns the starting views r, r+N, ... (the reference's outer loop over starting views, polyline_matching.cpp:162, dealt round-robin).
 
 `value` = accepted (pre-dedup) 3D edge-points of all ranks / max-over-ranks device time of a step (CUDA events on the
 library's stream; inputs already resident).  `e2e` = the same count / wall time of the C-ABI call sequence a user makes
@@ -57,10 +57,11 @@ def build_workload(name, n_gpus):
 
 
 def make_seeds(scene, sampler, per_view, n_gpus, rank):
-    """250*N seeds per view at spacing 20/N px, first polylines first; rank r owns starting views [r*V/N, (r+1)*V/N)."""
-    V = scene.n_views
-    lo, hi = (rank * V) // n_gpus, ((rank + 1) * V) // n_gpus
-    return syn.sample_seeds(sampler, scene, per_view=per_view * n_gpus, spacing=20.0 / n_gpus, views=range(lo, hi))
+    """250*N seeds per view at spacing 20/N px, first polylines first; rank r owns the starting views r, r+N, r+2N, ...
+    (multigpu.view_round_robin: better balanced than contiguous blocks; the merged result is put back into the
+    reference's loop order by global seed ordinal, multigpu.all_gather_points(order_keys=...))."""
+    from edgegraph3d_b200 import multigpu as mg
+    return syn.sample_seeds(sampler, scene, per_view=per_view * n_gpus, spacing=20.0 / n_gpus, views=mg.view_round_robin(scene.n_views, n_gpus, rank))
 
 
 class ClockSampler:
@@ -419,7 +420,7 @@ def main():
         "config": {"workload": workload_name(args.workload, cfg, per_view, n_gpus),
                    "l2": "flushed between iterations (256 MiB write); per-step hit lists (GBs) exceed L2 anyway",
                    "seeds_per_gpu": len(seeds), "points_per_step": job_points, "scene_upload_ms": scene_ms,
-                   "parallelism": f"starting views block-sharded over {n_gpus} GPU(s); one NCCL all-gather of accepted records" if n_gpus > 1 else "1 GPU"},
+                   "parallelism": f"starting views dealt round-robin to {n_gpus} GPU(s); one NCCL all-gather of accepted records" if n_gpus > 1 else "1 GPU"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": seeds.nbytes(), "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": 1e3 * e2e_total_s / args.steps,
                 "note": "eg3d_match_seeds (pinned seeds H2D + kernels) + eg3d_points_get (D2H into pinned memory); the scene handle "

@@ -15,6 +15,14 @@ def view_block(n_views, world_size, rank):
     return (rank * n_views) // world_size, ((rank + 1) * n_views) // world_size
 
 
+def view_round_robin(n_views, world_size, rank):
+    """Starting views rank, rank + world_size, ...: per-view cost varies slowly with the view index (neighbouring cameras
+    see similar geometry), so interleaving balances the ranks better than contiguous blocks (measured at N=8: the slowest
+    block rank is ~20 % above the fastest).  The merged result is put back into the reference's loop order with
+    `order_keys` (global seed ordinals) in all_gather_points."""
+    return list(range(rank, n_views, world_size))
+
+
 def balanced_view_blocks(seeds_per_view, world_size):
     """Contiguous view blocks with (nearly) equal seed counts: prefix sums over the per-view seed counts."""
     c = np.concatenate([[0], np.cumsum(np.asarray(seeds_per_view, np.int64))])
@@ -31,12 +39,13 @@ _FIELDS = (("xyz", np.float32, 3), ("seed", np.int32, 1), ("chain_pos", np.int32
            ("obs_poly", np.uint32, 1), ("obs_seg", np.uint32, 1), ("obs_xy", np.float32, 2))
 
 
-def all_gather_points(local, dist, device=None, seed_offset_by_rank=True):
+def all_gather_points(local, dist, device=None, seed_offset_by_rank=True, order_keys=None):
     """All-gather a PointSet over the default process group; returns the concatenation in rank order on every rank.
 
     `local` holds this rank's accepted points (host numpy arrays); tensors are staged on `device` (cuda for NCCL, cpu for
-    gloo).  Seed ordinals are made global by adding the number of seeds... callers that need global ordinals pass seeds
-    already offset; here only the point records travel.  One count all-gather + one padded all-gather per field.
+    gloo).  One count all-gather + one padded all-gather per field.  `order_keys` (int64 per local SEED: its ordinal in
+    the unsharded seed list) makes the merged result independent of the shard plan: points are sorted by (global seed
+    ordinal, chain position) = the reference's loop order, and `seed` is rewritten to the global ordinal.
     """
     import torch
     world = dist.get_world_size()
@@ -62,10 +71,20 @@ def all_gather_points(local, dist, device=None, seed_offset_by_rank=True):
         rows = maxm if name.startswith("obs_") else maxn
         got[name] = gather(getattr(local, name), rows, w, dt)
     got_len = gather(lens, maxn, 1, np.int64)
+    got_key = None
+    if order_keys is not None:
+        pk = np.asarray(order_keys, np.int64)[local.seed] if local.n_points else np.zeros(0, np.int64)
+        got_key = gather(pk, maxn, 1, np.int64)
     parts = []
     for r in range(world):
         n, m = int(cnts[r, 0]), int(cnts[r, 1])
         off = np.concatenate([[0], np.cumsum(got_len[r][:n, 0])]).astype(np.int64)
         parts.append(PointSet(got["xyz"][r][:n], got["seed"][r][:n, 0], got["chain_pos"][r][:n, 0], off,
                               got["obs_view"][r][:m, 0], got["obs_poly"][r][:m, 0], got["obs_seg"][r][:m, 0], got["obs_xy"][r][:m]))
-    return PointSet.concat(parts), cnts
+    merged = PointSet.concat(parts)
+    if got_key is not None and merged.n_points:
+        keys = np.concatenate([got_key[r][:int(cnts[r, 0]), 0] for r in range(world)])
+        order = np.lexsort((merged.chain_pos, keys))
+        merged = merged.take(order)
+        merged.seed = keys[order].astype(np.int64)
+    return merged, cnts

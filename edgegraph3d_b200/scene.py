@@ -224,6 +224,14 @@ class PointSet:
                          tuple(zip(self.obs_view[a:b].tolist(), self.obs_poly[a:b].tolist(), self.obs_seg[a:b].tolist()))))
         return keys
 
+    def take(self, idx):
+        """Points `idx` (in that order) with their observation lists."""
+        idx = np.asarray(idx, np.int64)
+        lens = (self.obs_off[idx + 1] - self.obs_off[idx]).astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        o = np.concatenate([np.arange(self.obs_off[i], self.obs_off[i + 1]) for i in idx]).astype(np.int64) if len(idx) else np.zeros(0, np.int64)
+        return PointSet(self.xyz[idx], self.seed[idx], self.chain_pos[idx], off, self.obs_view[o], self.obs_poly[o], self.obs_seg[o], self.obs_xy[o])
+
     @staticmethod
     def concat(parts):
         parts = [p for p in parts]

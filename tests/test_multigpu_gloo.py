@@ -17,6 +17,7 @@ def _free_port():
 
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
+    import numpy as np
     import torch.distributed as dist
     from edgegraph3d_b200 import synthetic as syn, multigpu as mg
     from tests import oracle_lib as O
@@ -36,6 +37,15 @@ def _worker(rank, world, port, q):
     start = int(cnts[:rank, 0].sum())
     ok = ok and np.array_equal(merged.xyz[start:start + local.n_points], local.xyz)
     ok = ok and np.array_equal(merged.obs_off[start:start + local.n_points + 1] - merged.obs_off[start], local.obs_off)
+    # round-robin shard plan on the all-segment sweep form + keyed merge: exactly the unsharded result, in its order
+    seeds_all = syn.sample_seeds(O.sample_seeds, sc, per_view=10)
+    mine = np.where(np.isin(seeds_all.view, mg.view_round_robin(sc.n_views, world, rank)))[0]
+    loc2 = osc.match_seeds(seeds_all.take(mine), n_threads=2)
+    m2, _ = mg.all_gather_points(loc2, dist, order_keys=mine)
+    full2 = osc.match_seeds(seeds_all, n_threads=2)
+    ok = ok and m2.n_points == full2.n_points and full2.n_points > 0 and np.array_equal(m2.seed, full2.seed)
+    ok = ok and np.array_equal(m2.chain_pos, full2.chain_pos) and np.array_equal(m2.obs_off, full2.obs_off)
+    ok = ok and np.array_equal(m2.xyz, full2.xyz) and np.array_equal(m2.obs_seg, full2.obs_seg) and np.array_equal(m2.obs_xy, full2.obs_xy)
     q.put((rank, bool(ok), merged.n_points, int(cnts[:, 0].sum())))
     dist.barrier()
     dist.destroy_process_group()
@@ -61,3 +71,4 @@ def test_balanced_view_blocks():
     assert blocks[0][0] == 0 and blocks[-1][1] == 8
     assert all(b[0] <= b[1] for b in blocks) and all(blocks[i][1] == blocks[i + 1][0] for i in range(3))
     assert mg.view_block(200, 8, 7) == (175, 200) and mg.view_block(6, 2, 0) == (0, 3)
+    assert mg.view_round_robin(10, 4, 1) == [1, 5, 9] and sorted(sum((mg.view_round_robin(7, 3, r) for r in range(3)), [])) == list(range(7))
