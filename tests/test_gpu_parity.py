@@ -216,3 +216,34 @@ def test_per_seed_capacity_is_reported_not_truncated(small):
         with pytest.raises(E.Eg3dError) as ei:
             tiny.match_polyline_sets(cands)
     assert ei.value.status == A.EG3D_ERR_CAPACITY
+
+
+def test_lazy_sweep_equals_full_sweep(small):
+    """eg3d_match_seeds materialises only the hit lists its per-seed code reads (any-hit pass, the three selected views,
+    every view of the accepted seeds); EG3D_K1_FULL=1 makes it run the reference's full sweep first.  Same result,
+    bit for bit, from far fewer hit records — and both equal the oracle."""
+    import os
+    sc, dev, orc = small
+    seeds = syn.sample_seeds(E.sample_seeds, sc)
+    lazy, tm_lazy = dev.match_seeds(seeds)
+    os.environ["EG3D_K1_FULL"] = "1"
+    try:
+        full, tm_full = dev.match_seeds(seeds)
+    finally:
+        del os.environ["EG3D_K1_FULL"]
+    assert lazy.n_points == full.n_points > 0
+    for f in ("seed", "chain_pos", "obs_off", "obs_view", "obs_poly", "obs_seg"):
+        assert np.array_equal(getattr(lazy, f), getattr(full, f)), f
+    assert lazy.obs_xy.tobytes() == full.obs_xy.tobytes() and lazy.xyz.tobytes() == full.xyz.tobytes()
+    assert tm_lazy["k1_any_ms"] > 0 and tm_full["k1_any_ms"] == 0
+    assert 0 < tm_lazy["n_hits"] < tm_full["n_hits"]
+    assert_points_parity(sc, lazy, orc.match_seeds(seeds))
+
+
+def test_k1_device_only_entry_point_counts_the_same_hits(small):
+    sc, dev, _ = small
+    seeds = syn.sample_seeds(E.sample_seeds, sc)
+    off, hits, V, tm = dev.epipolar_intersect(seeds)
+    tm_dev = dev.epipolar_intersect_device(seeds)
+    assert tm_dev["n_hits"] == hits.shape[0] == int(off[-1])
+    assert tm_dev["n_segment_tests"] == tm["n_segment_tests"] and tm_dev["k1_algorithmic_bytes"] == tm["k1_algorithmic_bytes"]
