@@ -623,10 +623,10 @@ static __device__ __noinline__ int follow_big(Ctx& c, const uint32_t* dirs, bool
   return added;
 }
 
-// compatible_direction_noupdate_vector, plg_matching.cpp:866-914.  The polyline walk is sequential and cheap; the
-// warm-started GNs of the visited chain points are independent, so they run one per lane and the list is truncated at
-// the first failure.  Returns the number of accepted neighbours (entries of tmp[]).
-static __device__ __noinline__ int walk_dir(Ctx& c, int v, const Plg& p, uint32_t dir, bool towards_start, int lo, int cur, int hi, NTmp* tmp) {
+// compatible_direction_noupdate_vector, plg_matching.cpp:866-914, in two parts.  walk_geo: the polyline walk over the
+// chain points on one side of `cur` (sequential, cheap, warp-cooperative steps); fills tmp[] with the new view's
+// observation of every chain point reached and returns their number.
+static __device__ __noinline__ int walk_geo(Ctx& c, int v, const Plg& p, uint32_t dir, bool towards_start, int lo, int cur, int hi, NTmp* tmp) {
   const DevScene& S = *c.S;
   Pl pl = get_pl(S, v, p.pl);
   PlP q; q.seg = p.seg; q.c = p.c;
@@ -655,33 +655,56 @@ static __device__ __noinline__ int walk_dir(Ctx& c, int v, const Plg& p, uint32_
     }
   }
   __syncwarp();
-  int keep = cnt;
-  for (int base = 0; base < cnt;) {
-    const int P = min(32, cnt - base);
+  return cnt;
+}
+
+// walk_solve: the warm-started GNs of the chain points reached by walk_geo are independent, so the cnt1 points towards
+// the start (tmp1) and the cnt2 points towards the end (tmp2) are solved together, up to 32 problems per gn_group call;
+// each side's list is cut at its first failure (keep1 / keep2 = accepted neighbours, their X written to tmp[].X).
+static __device__ __noinline__ void walk_solve(Ctx& c, int v, int cur, NTmp* tmp1, int cnt1, NTmp* tmp2, int cnt2, int& keep1, int& keep2) {
+  const DevScene& S = *c.S;
+  keep1 = cnt1; keep2 = cnt2;
+  const int total = cnt1 + cnt2;
+  for (int base = 0; base < total;) {
+    const int P = min(32, total - base);
     const int G = gn_group_width(P);
-    const int k = base + c.lane / G;
+    const int q = base + c.lane / G;                     // problem index in the concatenated list
     const bool active = (c.lane / G) < P;
+    const bool side1 = q < cnt1;
+    const int k = side1 ? q : q - cnt1;
+    NTmp* tmp = side1 ? tmp1 : tmp2;
     bool fail = false;
     int slot = 0, n = 0; float ex = 0.f, ey = 0.f;
     double X[3] = {0, 0, 0};
     if (active) {
-      const int jj = towards_start ? cur - 1 - k : cur + 1 + k;
-      slot = slot_of(c, jj);
+      slot = slot_of(c, side1 ? cur - 1 - k : cur + 1 + k);
       n = c.w.snobs[slot];
       X[0] = c.w.sX[3 * slot]; X[1] = c.w.sX[3 * slot + 1]; X[2] = c.w.sX[3 * slot + 2];
       ex = tmp[k].cx; ey = tmp[k].cy;
     }
-    bool ok = gn_group(S, slot_obs(c, slot, n, true, v, ex, ey), active, G, c.lane, X);
+    const bool ok = gn_group(S, slot_obs(c, slot, n, true, v, ex, ey), active, G, c.lane, X);
     if (active) {
       if (ok) { if ((c.lane & (G - 1)) == 0) { tmp[k].X[0] = (float)X[0]; tmp[k].X[1] = (float)X[1]; tmp[k].X[2] = (float)X[2]; } }
       else fail = true;
     }
-    unsigned fm = __ballot_sync(0xffffffffu, fail);
-    if (fm) { keep = base + (__ffs(fm) - 1) / G; break; }
+    const unsigned f1 = __ballot_sync(0xffffffffu, fail && side1), f2 = __ballot_sync(0xffffffffu, fail && !side1);
+    if (f1) keep1 = min(keep1, base + (__ffs(f1) - 1) / G);
+    if (f2) keep2 = min(keep2, base + (__ffs(f2) - 1) / G - cnt1);
     base += P;
+    if (keep1 < cnt1 && (keep2 < cnt2 || cnt2 == 0) ) break;          // both lists are already cut
+    if (keep1 < cnt1 && base < cnt1) base = cnt1;                      // the rest of side 1 is moot
+    if (keep2 < cnt2 && base >= cnt1) break;                           // the rest of side 2 is moot
   }
   __syncwarp();
-  return keep;
+}
+
+static __device__ __noinline__ int walk_dir(Ctx& c, int v, const Plg& p, uint32_t dir, bool towards_start, int lo, int cur, int hi, NTmp* tmp) {
+  const int cnt = walk_geo(c, v, p, dir, towards_start, lo, cur, hi, tmp);
+  if (cnt == 0) return 0;
+  int k1 = 0, k2 = 0;
+  if (towards_start) walk_solve(c, v, cur, tmp, cnt, tmp, 0, k1, k2);
+  else walk_solve(c, v, cur, tmp, 0, tmp, cnt, k1, k2);
+  return towards_start ? k1 : k2;
 }
 
 // add_view_to_3dpoint_and_sides_plgp_matches_vector after its first GN succeeded (plg_matching.cpp:1345-1412;
@@ -691,10 +714,18 @@ static __device__ __noinline__ bool add_view_finish(Ctx& c, int v, const Plg& p,
   Pl pl = get_pl(S, v, p.pl);
   int n1 = 0, n2 = 0; uint32_t nd1 = 0, nd2 = 0;
   if (cur > lo) {
-    n1 = walk_dir(c, v, p, pl.start, true, lo, cur, hi, c.w.tmp1);
+    // Common case first: the start side follows pl.start and the end side pl.end.  Both walks are done before any solve,
+    // and their neighbours are solved in ONE batch (a failed solve has no side effects, and when the start side yields
+    // nothing the end-side work is simply discarded and the reference's order of attempts resumes below).
+    const int g1 = walk_geo(c, v, p, pl.start, true, lo, cur, hi, c.w.tmp1);
+    if (g1 > 0) {
+      const int g2 = cur < hi ? walk_geo(c, v, p, pl.end, false, lo, cur, hi, c.w.tmp2) : 0;
+      int k2 = 0;
+      walk_solve(c, v, cur, c.w.tmp1, g1, c.w.tmp2, g2, n1, k2);
+      if (n1 > 0) n2 = k2;
+    }
     if (n1 > 0) {
       nd1 = pl.start; nd2 = pl.end;
-      if (cur < hi) n2 = walk_dir(c, v, p, pl.end, false, lo, cur, hi, c.w.tmp2);
     } else {
       n1 = walk_dir(c, v, p, pl.end, true, lo, cur, hi, c.w.tmp1);
       if (n1 > 0) {
@@ -715,8 +746,21 @@ static __device__ __noinline__ bool add_view_finish(Ctx& c, int v, const Plg& p,
   // success: commit
   __syncwarp();
   slot_append(c, slot_of(c, cur), v, p.pl, p.seg, p.c.x, p.c.y, Xc);
-  for (int k = 0; k < n1; k++) { NTmp t = c.w.tmp1[k]; slot_append(c, slot_of(c, cur - 1 - k), v, p.pl, t.seg, t.cx, t.cy, t.X); }
-  for (int k = 0; k < n2; k++) { NTmp t = c.w.tmp2[k]; slot_append(c, slot_of(c, cur + 1 + k), v, p.pl, t.seg, t.cx, t.cy, t.X); }
+  // the neighbours sit in distinct slots: one append per lane
+  for (int q = c.lane; q < n1 + n2; q += 32) {
+    const bool s1 = q < n1;
+    const NTmp t = s1 ? c.w.tmp1[q] : c.w.tmp2[q - n1];
+    const int slot = slot_of(c, s1 ? cur - 1 - q : cur + 1 + (q - n1));
+    const int n = c.w.snobs[slot];
+    if (n >= c.w.oc) c.overflow = true;
+    else {
+      const size_t b = (size_t)slot * c.w.oc + n;
+      c.w.ov[b] = v; c.w.opl[b] = p.pl; c.w.oseg[b] = t.seg; c.w.ox[b] = t.cx; c.w.oy[b] = t.cy;
+      c.w.snobs[slot] = n + 1;
+      c.w.sX[3 * slot] = t.X[0]; c.w.sX[3 * slot + 1] = t.X[1]; c.w.sX[3 * slot + 2] = t.X[2];
+    }
+  }
+  c.overflow = __any_sync(0xffffffffu, c.overflow);
   __syncwarp();
   if (c.overflow) return false;
   ns = n1; ne = n2;
