@@ -247,3 +247,54 @@ def test_k1_device_only_entry_point_counts_the_same_hits(small):
     tm_dev = dev.epipolar_intersect_device(seeds)
     assert tm_dev["n_hits"] == hits.shape[0] == int(off[-1])
     assert tm_dev["n_segment_tests"] == tm["n_segment_tests"] and tm_dev["k1_algorithmic_bytes"] == tm["k1_algorithmic_bytes"]
+
+
+@pytest.mark.parametrize("overrides", [dict(dlt_wellposed=0), dict(filter_abs_int=1), dict(split_interval_distance=7.0, follow_first_image_distance=6.0),
+                                        dict(max_proj_distsq_expand=4.0, quasiparallel_cos=0.9)])
+def test_parameter_variants_parity(overrides):
+    """The policy switches and a few of the reference's compile-time constants (eg3d_params) away from their defaults:
+    sweep form, candidate form and the outlier filter still equal the oracle run with the same parameters."""
+    sc = syn.make_scene(n_views=7, n_curves=20, seed=11, n_tracks=80)
+    prm_g, prm_o = E.default_params(**overrides), O.default_params(**overrides)
+    orc = O.OracleScene(sc, prm_o)
+    with E.DeviceScene(sc, prm_g) as dev:
+        seeds = syn.sample_seeds(E.sample_seeds, sc, per_view=40, spacing=prm_g.split_interval_distance)
+        assert_points_parity(sc, dev.match_seeds(seeds)[0], orc.match_seeds(seeds))
+        cands = syn.curve_candidate_sets(sc, seed=11)
+        g = dev.match_polyline_sets(cands)[0]
+        r = orc.match_polyline_sets(cands)
+        assert_points_parity(sc, g, r)
+        if g.n_points:
+            fx, inl, _ = dev.filter(g.xyz, g.obs_off, g.obs_view, g.obs_xy, 0)
+            ox, oinl = orc.filter(r.xyz, r.obs_off, r.obs_view, r.obs_xy, 0)
+            assert np.array_equal(inl, oinl) and np.array_equal(fx[inl == 1], ox[oinl == 1])
+
+
+def test_degenerate_scenes():
+    """Three views (the minimum for a hypothesis), every fundamental matrix but one pair invalid, and a view without
+    polylines: no crash, results equal to the oracle (mostly empty)."""
+    sc = syn.make_scene(n_views=3, n_curves=10, seed=5)
+    seeds = syn.sample_seeds(E.sample_seeds, sc)
+    with E.DeviceScene(sc) as dev:
+        assert_points_parity(sc, dev.match_seeds(seeds)[0], O.OracleScene(sc).match_seeds(seeds))
+    sc2 = syn.make_scene(n_views=5, n_curves=10, seed=6)
+    sc2.fundamental_valid[:] = 0
+    sc2.fundamental_valid[0, 1] = sc2.fundamental_valid[1, 0] = 1
+    seeds2 = syn.sample_seeds(E.sample_seeds, sc2)
+    with E.DeviceScene(sc2) as dev:
+        g = dev.match_seeds(seeds2)[0]
+        assert_points_parity(sc2, g, O.OracleScene(sc2).match_seeds(seeds2))
+        assert g.n_points == 0          # fewer than three views can ever hold hits
+    # a view whose polylines are all invalidated (empty vertex ranges keep their ids)
+    sc3 = syn.make_scene(n_views=5, n_curves=10, seed=7)
+    g0, g1 = int(sc3.view_poly_off[2]), int(sc3.view_poly_off[3])
+    lens = np.diff(sc3.poly_vert_off)
+    keep = np.ones(len(sc3.verts), bool)
+    keep[int(sc3.poly_vert_off[g0]):int(sc3.poly_vert_off[g1])] = False
+    lens[g0:g1] = 0
+    sc3 = FlatScene(sc3.width, sc3.height, sc3.cameras, sc3.fundamental, sc3.fundamental_valid, sc3.view_poly_off,
+                    np.concatenate([[0], np.cumsum(lens)]).astype(np.int64), sc3.verts[keep], sc3.poly_start, sc3.poly_end)
+    seeds3 = syn.sample_seeds(E.sample_seeds, sc3)
+    assert not (seeds3.view == 2).any()
+    with E.DeviceScene(sc3) as dev:
+        assert_points_parity(sc3, dev.match_seeds(seeds3)[0], O.OracleScene(sc3).match_seeds(seeds3))
