@@ -404,6 +404,10 @@ def main():
     t_k1 = [tr.get("k1_sweep_kernel<count>"), tr.get("k1_sweep_kernel<fill>")]
     traffic_k3b = (t_k3b["dram_read_bytes"] + t_k3b["dram_write_bytes"]) if (t_k3b and args.workload == "c2" and not args.seeds_limit) else None
     traffic_k1 = (sum(x["dram_read_bytes"] + x["dram_write_bytes"] for x in t_k1) / 2) if (all(t_k1) and args.workload == "c2" and not args.seeds_limit) else None
+    icache = {}
+    ip = os.path.join(ROOT, "profiles", "r01_icache.json")
+    if os.path.exists(ip) and args.workload == "c2" and not args.seeds_limit:
+        icache = json.load(open(ip))
     k1c = float(np.mean([a for a, _ in k1_ms])); k1f = float(np.mean([b for _, b in k1_ms])); k3 = float(np.mean(k3_ms)); k3a = float(np.mean(k3a_ms)); k3b = float(np.mean(k3b_ms))
     step_ms = dev_total_ms / args.steps
     k1_bytes = sweep["k1_algorithmic_bytes"] if sweep else last_tm["k1_algorithmic_bytes"]
@@ -446,6 +450,11 @@ def main():
                                 "the step K1 is lazy (kernel_ms.k1_*; share_of_step is that lazy K1).  Algorithmic (streaming) bytes per "
                                 "SURVEY 8(d); a view's segments are staged once per CTA in shared memory, so real DRAM traffic is far "
                                 "lower and the fraction exceeds 1"},
+        "roofline_icache": ({"kernel": "k3b_expand_kernel", "bound": "GPC instruction-cache request rate (what actually limits K3, profiles/r01_k3b_icache.md)",
+                             "achieved": icache["k3b_expand_kernel"]["instruction_requests"] / (k3b * 1e-3), "peak": icache["gcc_peak_requests_per_s"],
+                             "unit": "instruction-line requests/s", "frac": icache["k3b_expand_kernel"]["instruction_requests"] / (k3b * 1e-3) / icache["gcc_peak_requests_per_s"],
+                             "note": "request count per launch from the committed ncu counter capture (profiles/r01_icache.json), divided by the "
+                                     "kernel time measured live in this run; ncu itself reports 77 % (k3b) and 92 % (k3a) of peak"} if icache else None),
         "kernel_ms": {"k1_any": float(np.mean(k1any_ms)), "k1_count": k1c, "k1_fill": k1f, "scan_select": float(np.mean(scan_ms)), "k3a_hypothesis": k3a, "k3b_expand": k3b,
                       "pack": float(np.mean(pack_ms)), "allgather": float(np.mean(ag_all))},
         "clocks": clocks,
