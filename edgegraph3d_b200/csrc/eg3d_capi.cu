@@ -14,6 +14,7 @@
 #include "eg3d_k1.cuh"
 #include "eg3d_k3.cuh"
 #include "eg3d_gn.cuh"
+#include "eg3d_a6.cuh"
 
 using namespace eg3d;
 
@@ -63,6 +64,7 @@ struct eg3d_scene {
   DBuf<float4> seg; DBuf<uint2> seg_id; DBuf<float4> grp_box; DBuf<uint32_t> grp_desc; DBuf<int4> chunks; DBuf<int> view_chunk_off;
   DBuf<int> g4_off, g30_off; DBuf<uint32_t> g4_ids, g30_ids;
   DBuf<float> track_xyz; DBuf<int64_t> track_off; DBuf<int32_t> track_view; DBuf<float2> track_xy;
+  DBuf<int> obs_track;          // [NO] track id of every observation (pipeline-3 seeding, one warp per observation)
   DevScene dev;
   // host copies needed by host-side steps (seed sampler, refpoint seeding)
   std::vector<int> h_view_poly_off, h_poly_vert_off; std::vector<float2> h_verts; std::vector<uint32_t> h_start, h_end;
@@ -715,6 +717,11 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
     CK(sc->track_xyz.upload(d->track_xyz, (size_t)d->n_tracks * 3, s)); CK(sc->track_off.upload(d->track_off, (size_t)d->n_tracks + 1, s));
     CK(sc->track_view.upload(d->track_view, (size_t)NO, s)); CK(sc->track_xy.upload((const float2*)d->track_xy, (size_t)NO, s));
     sc->h_track_off.assign(d->track_off, d->track_off + d->n_tracks + 1);
+    {
+      std::vector<int> ot((size_t)NO);
+      for (int64_t t = 0; t < d->n_tracks; t++) for (int64_t o = d->track_off[t]; o < d->track_off[t + 1]; o++) ot[(size_t)o] = (int)t;
+      CK(sc->obs_track.upload(ot, s));
+    }
     sc->h_track_view.assign(d->track_view, d->track_view + NO);
     sc->h_track_xy.assign((const float2*)d->track_xy, (const float2*)d->track_xy + NO);
   }
@@ -1006,9 +1013,9 @@ eg3d_status eg3d_filter(eg3d_scene* sc, int64_t n, float* xyz, const int64_t* ob
 }
 
 // B2 / a6: plg_matching_from_refpoints (plg_matching_from_refpoints.cpp:64-104).  Seeding — the polylines within 30 px of
-// every observation (30 px grid), the seeds within 10 px (projection onto the polyline) and the per-seed radius — is
-// O(#observations x few polylines) and runs on the host (plg_edge_manager.cpp:261-288); the epipolar intersections with
-// the radius filter (:191-259) run in k1_cand_kernel, then K3 exactly as for pipelines 1-2
+// every observation (30 px grid), the seeds within 10 px (projection onto the polyline) and the per-seed radius
+// (plg_edge_manager.cpp:261-288) — runs on the device, one warp per observation (eg3d_a6.cuh); the epipolar
+// intersections with the radius filter (:191-259) run in k1_cand_kernel, then K3 exactly as for pipelines 1-2
 // (plgpcm_3views_plg_following.cpp:40-50 scatters the per-observing-view lists into a V-vector = the CSR rows).
 eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_points** out, eg3d_timing* tm) {
   eg3d_status st = require_device(); if (st != EG3D_OK) return st;
@@ -1018,63 +1025,57 @@ eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_po
   CK(cudaSetDevice(sc->device));
   g_alloc_stream = sc->stream;
   const int V = sc->V;
-  const eg3d_params& prm = sc->prm;
-  DevScene hs; memset(&hs, 0, sizeof hs);
-  hs.V = V; hs.view_poly_off = sc->h_view_poly_off.data(); hs.poly_vert_off = sc->h_poly_vert_off.data();
-  hs.verts = sc->h_verts.data(); hs.poly_start = sc->h_start.data(); hs.poly_end = sc->h_end.data();
-  DevGrid g; g.cell = sc->hg30.cell; g.w = sc->hg30.w; g.h = sc->hg30.h; g.cell_off = sc->hg30.off.data(); g.ids = sc->hg30.ids.data();
-  const float start_dsq = prm.detection_starting_radius * prm.detection_starting_radius;
-  const float corr_d = prm.detection_starting_radius * prm.detection_mult;
-  const float corr_dsq = corr_d * corr_d;
-  const int64_t nt = te - tb;
-  std::vector<int64_t> coff((size_t)nt * V + 1, 0); std::vector<uint32_t> cpl; std::vector<float2> center((size_t)nt * V, make_float2(0.f, 0.f));
-  std::vector<int32_t> sv, scs; std::vector<uint32_t> spl, sseg; std::vector<float> sxy, sr2;
-  struct SeedTmp { uint32_t pl, seg; float2 c; };
-  for (int64_t rp = tb; rp < te; rp++) {
-    const int64_t o0 = sc->h_track_off[rp], no = sc->h_track_off[rp + 1] - o0;
-    const int32_t* views = sc->h_track_view.data() + o0; const float2* xy = sc->h_track_xy.data() + o0;
-    std::vector<std::vector<uint32_t>> pcp(no); std::vector<std::vector<SeedTmp>> sni(no);
-    auto coords_on = [&](int img) { float2 p = make_float2(0.f, 0.f); for (int64_t i = 0; i < no; i++) if (views[i] == img) p = xy[i]; return p; };  // last match wins
-    for (int64_t i = 0; i < no; i++) {
-      const float2 sp = coords_on(views[i]);
-      std::set<uint32_t> ids;
-      grid_visit(g, views[i], sc->width, sc->height, sp, [&](uint32_t id) { ids.insert(id); });
-      for (uint32_t id : ids) {
-        Pl pl = get_pl(hs, views[i], id);
-        uint32_t cs; float2 proj;
-        const float dsq = pl_distancesq(pl, sp, cs, proj);
-        if (dsq <= start_dsq) { pcp[i].push_back(id); sni[i].push_back(SeedTmp{id, cs, proj}); }
-        else if (dsq <= corr_dsq) pcp[i].push_back(id);
-      }
-    }
-    // candidate CSR rows of this refpoint: (refpoint, view) -> pcp of the observation in that view
-    const size_t row0 = (size_t)(rp - tb) * V;
-    std::vector<const std::vector<uint32_t>*> byview(V, nullptr);
-    for (int64_t j = 0; j < no; j++) { byview[views[j]] = &pcp[j]; center[row0 + views[j]] = xy[j]; }
-    for (int v = 0; v < V; v++) {
-      if (byview[v]) cpl.insert(cpl.end(), byview[v]->begin(), byview[v]->end());
-      coff[row0 + v + 1] = (int64_t)cpl.size();
-    }
-    for (int64_t i = 0; i < no; i++) {
-      const float2 init = coords_on(views[i]);
-      for (const auto& sd : sni[i]) {
-        const float radius = dist2(init, sd.c) * prm.detection_mult;   // plg_edge_manager.cpp:254
-        sv.push_back(views[i]); scs.push_back((int32_t)(rp - tb)); spl.push_back(sd.pl); sseg.push_back(sd.seg);
-        sxy.push_back(sd.c.x); sxy.push_back(sd.c.y); sr2.push_back(radius * radius);
-      }
-    }
-  }
   eg3d_timing local; memset(&local, 0, sizeof local);
-  eg3d_seeds seeds; seeds.n = (int64_t)sv.size(); seeds.view = sv.data(); seeds.polyline = spl.data(); seeds.segment = sseg.data();
-  seeds.xy = sxy.data(); seeds.cand_set = scs.data();
-  DevSeeds ds; st = upload_seeds(sc, &seeds, true, ds); if (st != EG3D_OK) return st;
+  const int64_t nt = te - tb, o_begin = sc->h_track_off[tb], o_end = sc->h_track_off[te], n_o = o_end - o_begin;
+  const size_t n_rows = (size_t)nt * V;
+  DBuf<A6Rec> recs; DBuf<int> n_ids, n_cand, n_seed, ovf; DBuf<unsigned char> is_last; DBuf<int64_t> seed_off, coff;
+  CK(recs.alloc((size_t)n_o * A6_IDS)); CK(n_ids.alloc(n_o)); CK(n_cand.alloc(n_o)); CK(n_seed.alloc(n_o + 1)); CK(is_last.alloc(n_o)); CK(ovf.alloc(1));
+  CK(seed_off.alloc(n_o + 1)); CK(coff.alloc(n_rows + 1));
+  CK(cudaMemsetAsync(ovf.p, 0, sizeof(int), sc->stream));
+  CK(cudaMemsetAsync(n_seed.p, 0, (size_t)(n_o + 1) * sizeof(int), sc->stream));
+  CK(cudaMemsetAsync(coff.p, 0, (n_rows + 1) * sizeof(int64_t), sc->stream));
+  A6Args a; memset(&a, 0, sizeof a);
+  a.o_begin = o_begin; a.o_end = o_end; a.tb = tb; a.obs_track = sc->obs_track.p;
+  a.recs = recs.p; a.n_ids = n_ids.p; a.n_cand = n_cand.p; a.n_seed = n_seed.p; a.is_last = is_last.p; a.overflow = ovf.p; a.row_cnt = coff.p;
+  Timer ts(sc->stream);
+  ts.start();
+  const unsigned blocks = (unsigned)(((size_t)n_o * 32 + A6_THREADS - 1) / A6_THREADS);
+  if (n_o > 0) a6_classify_kernel<<<blocks, A6_THREADS, 0, sc->stream>>>(sc->dev, a);
+  CK(cudaGetLastError());
+  {
+    size_t tb1 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb1, n_seed.p, seed_off.p, n_o + 1, sc->stream);
+    DBuf<unsigned char> tmp; CK(tmp.alloc(tb1));
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb1, n_seed.p, seed_off.p, n_o + 1, sc->stream);
+  }
+  st = exclusive_scan_i64(sc, coff.p, n_rows + 1); if (st != EG3D_OK) return st;
+  int64_t n_seeds = 0, n_cands = 0; int h_ovf = 0;
+  CK(cudaMemcpyAsync(&n_seeds, seed_off.p + n_o, sizeof(int64_t), cudaMemcpyDeviceToHost, sc->stream));
+  CK(cudaMemcpyAsync(&n_cands, coff.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, sc->stream));
+  CK(cudaMemcpyAsync(&h_ovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, sc->stream));
+  CK(cudaStreamSynchronize(sc->stream));
+  if (h_ovf) return fail(EG3D_ERR_CAPACITY, "an observation has more polylines in its 30 px neighbourhood than the device seeding holds (A6_RAW / A6_IDS)");
+  if (n_seeds > 0x7fffffff) return fail(EG3D_ERR_CAPACITY, "too many seeds in one call; split the track range");
+  DevSeeds ds; ds.n = (int)n_seeds;
+  CK(ds.view.alloc(n_seeds)); CK(ds.pl.alloc(n_seeds)); CK(ds.seg.alloc(n_seeds)); CK(ds.xy.alloc(n_seeds)); CK(ds.cand_set.alloc(n_seeds));
   DevCand dc; dc.filtered = true;
-  CK(dc.off.upload(coff, sc->stream)); CK(dc.pl.upload(cpl, sc->stream)); CK(dc.center.upload(center, sc->stream)); CK(dc.seed_r2.upload(sr2, sc->stream));
+  CK(dc.pl.alloc(n_cands)); CK(dc.center.alloc(n_rows)); CK(dc.seed_r2.alloc(n_seeds));
+  CK(cudaMemsetAsync(dc.center.p, 0, std::max<size_t>(n_rows, 1) * sizeof(float2), sc->stream));
+  a.seed_off = seed_off.p; a.coff = coff.p;
+  a.s_view = ds.view.p; a.s_pl = ds.pl.p; a.s_seg = ds.seg.p; a.s_xy = ds.xy.p; a.s_set = ds.cand_set.p; a.s_r2 = dc.seed_r2.p;
+  a.cpl = dc.pl.p; a.center = dc.center.p;
+  if (n_o > 0) a6_fill_kernel<<<blocks, A6_THREADS, 0, sc->stream>>>(sc->dev, a);
+  ts.stop();
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(sc->stream));
+  local.scan_ms += ts.ms(); local.kernel_launches += 5;
+  // hand the CSR offsets to the candidate descriptor (the buffer changes owner)
+  dc.off.p = coff.p; dc.off.n = coff.n; dc.off.s = coff.s; coff.p = nullptr;
   HitLists H;
   st = prepare_hits_a(sc, ds, &dc, H, &local); if (st != EG3D_OK) return st;
   std::unique_ptr<eg3d_points> pts(new eg3d_points());
   st = run_k3(sc, ds, H, pts.get(), &local);
-  local.n_seeds = seeds.n;
+  local.n_seeds = n_seeds;
   local.total_ms = local.k1_any_ms + local.k1_count_ms + local.scan_ms + local.k1_fill_ms + local.k3_ms + local.pack_ms;
   if (tm) *tm = local;
   if (st != EG3D_OK) return st;
