@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_sweep_kernel(const __grid_const
     else active = epiline(S, sv, t, p, l);
   }
   // a tile without a single pair to sweep (typical for the targeted forms) leaves before staging anything
-  const bool any_active = __syncthreads_or(active);
+  const bool any_active = ALL_PAIRS ? true : __syncthreads_or(active);   // the full sweep always has work
   if (any_active) {
     if (tid == 0) {
       for (int s = 0; s < K1_STAGES; s++) mbar_init(&bars[s], 1);
