@@ -302,3 +302,78 @@ def test_polyline_grid_build_and_lookup(which, cell):
             assert got == want, (view, p, got, want)
             nonempty += bool(want)
         assert nonempty > 30
+
+
+def ref_minimum_distancesq(p, v, w):
+    """geometric_utilities.cpp:940-954 -> (distance squared, projection)."""
+    l2 = ref_squared_2d_distance(v, w)
+    if l2 == 0.0:
+        return ref_squared_2d_distance(p, v), (v[0], v[1])
+    pv, wv = (f32(p[0] - v[0]), f32(p[1] - v[1])), (f32(w[0] - v[0]), f32(w[1] - v[1]))
+    q = f32(f32(f32(pv[0] * wv[0]) + f32(pv[1] * wv[1])) / l2)
+    m = q if q < f32(1) else f32(1)                  # std::min<float>(1, q)
+    t = m if f32(0) < m else f32(0)                  # std::max<float>(0, m)
+    proj = (f32(v[0] + f32(t * wv[0])), f32(v[1] + f32(t * wv[1])))
+    return ref_squared_2d_distance(p, proj), proj
+
+
+def ref_compute_distancesq(pc, p):
+    """polyline::compute_distancesq, polyline_graph_2d.cpp:845-862: the FIRST closest segment wins (strict <)."""
+    md, proj = ref_minimum_distancesq(p, pc[0], pc[1])
+    seg = 0
+    for i in range(2, len(pc)):
+        d, cp = ref_minimum_distancesq(p, pc[i - 1], pc[i])
+        if d < md:
+            md, proj, seg = d, cp, i - 1
+    return md, seg, proj
+
+
+def test_point_to_polyline_distance_bit_exact():
+    L = O.lib()
+    L.eg3d_oracle_polyline_distancesq.restype = C.c_float
+    L.eg3d_oracle_polyline_distancesq.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.c_float, C.c_float, C.POINTER(C.c_uint32), A.c_f32p]
+    sc = syn.make_scene(n_views=2, n_curves=14, seed=17, closed_frac=0.2)
+    osc = O.OracleScene(sc)
+    rng = np.random.default_rng(8)
+    seg = C.c_uint32(); proj = np.zeros(2, f32)
+    n = 0
+    for view in range(2):
+        for pl in range(sc.n_polylines(view)):
+            pc = sc.polyline(view, pl)
+            if len(pc) < 2:
+                continue
+            for _ in range(12):
+                k = int(rng.integers(0, len(pc)))
+                p = (pc[k] + rng.normal(0, rng.choice([0.0, 0.5, 6.0, 60.0]), 2)).astype(f32)
+                d = L.eg3d_oracle_polyline_distancesq(osc.h, view, pl, p[0], p[1], C.byref(seg), A.ptr(proj, A.c_f32p))
+                rd, rs, rp = ref_compute_distancesq(pc, p)
+                assert (f32(d), seg.value, proj[0], proj[1]) == (rd, rs, rp[0], rp[1]), (view, pl, p)
+                n += 1
+    assert n > 200
+
+
+def test_density_limiter_second_reading():
+    """filter_3d_points_close_2d_array, filtering_close_plgps.cpp:75-124: a point is kept iff at least one of its
+    observations falls in a still-empty 3 px cell of its view; a kept point marks all its cells."""
+    from edgegraph3d_b200.scene import PointSet
+    sc = syn.make_scene(n_views=4, n_curves=6, seed=3)
+    rng = np.random.default_rng(12)
+    npts = 600
+    lens = rng.integers(2, 5, npts)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    views = np.concatenate([rng.choice(4, k, replace=False) for k in lens]).astype(np.int32)
+    base = rng.uniform(20, 200, (npts, 2))
+    xy = np.concatenate([base[i] + rng.normal(0, 2.0, (lens[i], 2)) for i in range(npts)]).astype(f32)
+    ps = PointSet(np.zeros((npts, 3), f32), np.arange(npts, dtype=np.int32), np.zeros(npts, np.int32), off, views,
+                  np.zeros(len(views), np.uint32), np.zeros(len(views), np.uint32), xy)
+    got = O.OracleScene(sc).dedup_close_points(ps)
+    gw, gh = int(np.ceil(f32(sc.width) / 3)), int(np.ceil(f32(sc.height) / 3))
+    bm = np.zeros((4, gh, gw), bool)
+    want = np.zeros(npts, np.uint8)
+    for i in range(npts):
+        cells = [(int(views[o]), int(f32(xy[o, 1] / f32(3))), int(f32(xy[o, 0] / f32(3)))) for o in range(off[i], off[i + 1])]
+        if any(not bm[c] for c in cells):
+            want[i] = 1
+            for c in cells:
+                bm[c] = True
+    assert np.array_equal(got, want) and 0 < want.sum() < npts
