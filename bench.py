@@ -433,8 +433,9 @@ def main():
         "roofline": {"kernel": "k3b_expand_kernel (view expansion of the accepted seeds: warm-started FP64 Gauss-Newton + polyline walks)",
                      "bound": "hbm", "achieved": k3b_bytes / (k3b * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": k3b_bytes / (k3b * 1e-3) / 1e9 / peak, "traffic": traffic_k3b, "peak_source": peak_src, "share_of_step": k3b / step_ms,
-                     "traffic_note": "bytes per launch from the committed ncu capture (profiles/r01_traffic.json); far above the algorithmic "
-                                     "bytes: per-lane stack frames and the per-warp scratch arena of the scalar walk thrash L1/L2",
+                     "traffic_note": "bytes per launch from the committed ncu capture (profiles/r01_traffic.json); above the algorithmic "
+                                     "bytes because the per-lane stack frames and per-warp scratch arenas of the scalar walk spill past L1 "
+                                     "(16 warps/SM keep them inside the L2: 21 GB; at 28 warps/SM the same kernel moved 93 GB at the same speed)",
                      "algorithmic_bytes_per_launch": k3b_bytes, "avg_launch_ms": k3b,
                      "note": "dominant kernel of the step; bound by INSTRUCTION-CACHE refills, not by bandwidth or occupancy (ncu: GPC "
                              "instruction-cache request rate at 78-80 % of peak, same kernel time with 8..32 resident warps/SM, "
