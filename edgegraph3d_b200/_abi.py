@@ -69,6 +69,15 @@ class Timing(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class PlgView(C.Structure):
+    _fields_ = [("n_polylines", C.c_int64), ("poly_vert_off", c_i64p), ("verts", c_f32p), ("poly_start", c_u32p),
+                ("poly_end", c_u32p), ("poly_length", c_f32p), ("n_nodes", C.c_int64), ("node_xy", c_f32p),
+                ("n_pixel_nodes", C.c_int64), ("pixel_node_xy", c_f32p), ("pixel_adj_off", c_i64p), ("pixel_adj", c_u32p)]
+
+
+PLG_STAGE_FULL, PLG_STAGE_PIXEL_GRAPH, PLG_STAGE_RAW, PLG_STAGE_MERGED, PLG_STAGE_SIMPLIFIED, PLG_STAGE_CONNECTED = range(6)
+
+
 def ptr(arr, ctype_ptr):
     """numpy array -> typed ctypes pointer (None -> NULL). The caller keeps `arr` alive."""
     if arr is None:

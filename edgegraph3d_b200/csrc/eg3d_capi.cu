@@ -20,6 +20,7 @@ using namespace eg3d;
 
 static thread_local std::string g_err;
 static eg3d_status fail(eg3d_status s, const std::string& m) { g_err = m; return s; }
+eg3d_status eg3d_internal_fail(eg3d_status s, const char* msg) { return fail(s, msg); }  // for the host-only translation units
 #define CK(call)                                                                                              \
   do {                                                                                                        \
     cudaError_t e_ = (call);                                                                                  \

@@ -18,6 +18,7 @@ EXPORTS = [
     "eg3d_sample_seeds", "eg3d_epipolar_intersect", "eg3d_epipolar_intersect_device", "eg3d_hits_get", "eg3d_hits_free", "eg3d_match_seeds",
     "eg3d_match_polyline_sets", "eg3d_match_refpoints", "eg3d_points_get", "eg3d_points_device_get", "eg3d_points_free", "eg3d_gn_triangulate",
     "eg3d_gn_triangulate_device", "eg3d_dedup_close_points", "eg3d_filter",
+    "eg3d_plg_from_edge_image", "eg3d_plg_get", "eg3d_plg_free",
 ]
 
 
@@ -60,6 +61,9 @@ def load():
     L.eg3d_dedup_close_points.argtypes = [C.c_void_p, C.POINTER(A.PointsView), A.c_u8p]
     L.eg3d_filter.argtypes = [C.c_void_p, C.c_int64, A.c_f32p, A.c_i64p, A.c_i32p, A.c_f32p, C.c_int64, C.c_float, C.c_int32,
                               A.c_u8p, C.POINTER(A.Timing)]
+    L.eg3d_plg_from_edge_image.argtypes = [A.c_u8p, C.c_int32, C.c_int32, C.c_int32, A.c_u8p, C.c_int32, C.POINTER(C.c_void_p)]
+    L.eg3d_plg_get.argtypes = [C.c_void_p, C.POINTER(A.PlgView)]
+    L.eg3d_plg_free.argtypes = [C.c_void_p]
     _lib = L
     return L
 

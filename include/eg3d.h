@@ -246,6 +246,49 @@ eg3d_status eg3d_filter(eg3d_scene*, int64_t n, float* xyz, const int64_t* obs_o
                         const float* obs_xy, int64_t first_edgepoint, float gn_max_mse, int32_t forced_min_filter,
                         uint8_t* inliers, eg3d_timing* timing);
 
+/* ------------------------------------------------------------------------- */
+/* Row f1 (host, upstream of the path): edge image -> optimized polyline graph */
+/* ------------------------------------------------------------------------- */
+/*
+ * Replaces convertEdgeImagePolyLineGraph_optimized(const Mat& img, const Vec3b& edge_color)
+ * (src/edgegraph3d/io/input/convert_edge_images_pixel_to_segment.cpp:880-883, called per view by
+ * convert_edge_images_to_optimized_polyline_graphs :885-892 from edge_matcher.cpp:83): pixel graph without
+ * short cycles (:294-426), polyline extraction (:428-626) and PolyLineGraph2DHMapImpl::optimize
+ * (src/edgegraph3d/plgs/polyline_graph_2d_hmap_impl.cpp:255-266).  Order-dependent graph surgery: host code, no
+ * device needed.  The result lists EVERY polyline id the reference's graph holds; removed polylines have an empty
+ * vertex range, exactly what eg3d_scene_desc expects.
+ */
+typedef struct eg3d_plg eg3d_plg;  /* opaque, host resident */
+typedef enum eg3d_plg_stage {      /* stop_after: intermediate graphs for tests and debugging */
+  EG3D_PLG_STAGE_FULL = 0,         /* the reference's result */
+  EG3D_PLG_STAGE_PIXEL_GRAPH = 1,  /* convertEdgeImagePixelToGraph_NoCycles only (no polylines) */
+  EG3D_PLG_STAGE_RAW = 2,          /* + convert_EdgeGraph_to_PolyLineGraph */
+  EG3D_PLG_STAGE_MERGED = 3,       /* + remove_invalid_polylines, remove_degenerate_loops, remove_2connection_nodes */
+  EG3D_PLG_STAGE_SIMPLIFIED = 4,   /* + PolyLineGraph2D::optimize (1 px simplification) */
+  EG3D_PLG_STAGE_CONNECTED = 5     /* + connect_close_extremes (6 px) and the second simplification */
+} eg3d_plg_stage;
+typedef struct eg3d_plg_view {
+  int64_t         n_polylines;
+  const int64_t*  poly_vert_off;   /* [NP+1] */
+  const float*    verts;           /* [NVERT][2] polyline_coords */
+  const uint32_t* poly_start;      /* [NP] */
+  const uint32_t* poly_end;        /* [NP] */
+  const float*    poly_length;     /* [NP] polyline::length (-1 = invalidated) */
+  int64_t         n_nodes;
+  const float*    node_xy;         /* [NN][2] nodes_coords; (-1,-1) = invalidated node */
+  int64_t         n_pixel_nodes;   /* the intermediate pixel graph (GraphAdjacencySetUndirectedNoType + node coords) */
+  const float*    pixel_node_xy;   /* [NPIX][2] */
+  const int64_t*  pixel_adj_off;   /* [NPIX+1] */
+  const uint32_t* pixel_adj;       /* ascending neighbour ids */
+} eg3d_plg_view;
+/* img: rows x cols x channels, continuous (cv::imread layout); a pixel is an edge pixel iff all its channels equal
+ * edge_color[c] (EDGE_COLOR = (255,255,255), include/edgegraph3d/utils/globals/global_defines.hpp:47).
+ * The caller's image is not modified (the reference clears "useless hub" pixels in place). */
+eg3d_status eg3d_plg_from_edge_image(const uint8_t* img, int32_t rows, int32_t cols, int32_t channels,
+                                     const uint8_t* edge_color, int32_t stop_after, eg3d_plg** out);
+eg3d_status eg3d_plg_get(const eg3d_plg*, eg3d_plg_view* view);   /* pointers valid until eg3d_plg_free */
+void        eg3d_plg_free(eg3d_plg*);
+
 #ifdef __cplusplus
 }
 #endif

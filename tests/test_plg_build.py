@@ -1,0 +1,148 @@
+"""Row f1 (edge image -> optimized polyline graph, host C++ behind the C-ABI) against the second reading in
+oracle/plg_build_ref.py, stage by stage and bit for bit: pixel graph (node coordinates, adjacency), polyline ids,
+vertex lists, start/end node ids, lengths, node table.  CPU only — this stage needs no device.
+
+The reference ships no expected outputs for this stage (parity unpinned by the reference itself); inputs are synthetic
+rasters built to hit its special cases and crops of the real dtu006 edge maps (tests/golden/dtu006_edges.npz)."""
+import ctypes as C
+import hashlib
+import json
+import os
+import numpy as np
+import pytest
+from edgegraph3d_b200 import _abi as A, lib as E, plg_build as PB
+from oracle import plg_build_ref as R
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+STAGES = [A.PLG_STAGE_PIXEL_GRAPH, A.PLG_STAGE_RAW, A.PLG_STAGE_MERGED, A.PLG_STAGE_SIMPLIFIED, A.PLG_STAGE_CONNECTED, A.PLG_STAGE_FULL]
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def assert_same_graph(mask, stage):
+    g = PB.polyline_graph_from_edge_image(mask.astype(np.uint8) * 255, edge_color=255, stop_after=stage)
+    plg, pg, coords = R.polyline_graph_from_mask(mask, stage)
+    assert len(coords) == len(g.pixel_node_xy)
+    assert np.array_equal(bits(np.array(coords, np.float32).reshape(-1, 2)), bits(g.pixel_node_xy))
+    for n in range(len(coords)):
+        assert sorted(pg.adj[n]) == g.pixel_adj[g.pixel_adj_off[n]:g.pixel_adj_off[n + 1]].tolist(), n
+    assert len(plg.polylines) == g.n_polylines
+    for i, p in enumerate(plg.polylines):
+        assert np.array_equal(bits(np.array(p.coords, np.float32).reshape(-1, 2)), bits(g.polyline(i))), i
+        assert (p.start, p.end) == (int(g.poly_start[i]), int(g.poly_end[i])), i
+        assert bits(np.float32(p.length)) == bits(g.poly_length[i]), i
+    assert np.array_equal(bits(np.array(plg.nodes, np.float32).reshape(-1, 2)), bits(g.node_xy))
+    return g
+
+
+def synthetic_raster(seed, size=80):
+    """Curves, junctions, thick strokes (squares / triangles of pixels), small and large loops, border pixels."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(seed)
+    im = np.zeros((size, size), np.uint8)
+    for _ in range(rng.integers(3, 8)):
+        pts = rng.integers(2, size - 2, (rng.integers(2, 6), 2)).astype(np.int32)
+        cv2.polylines(im, [pts.reshape(-1, 1, 2)], bool(rng.integers(0, 2)), 255, int(rng.integers(1, 3)))
+    for _ in range(rng.integers(1, 4)):
+        c = rng.integers(8, size - 8, 2)
+        cv2.circle(im, (int(c[0]), int(c[1])), int(rng.integers(1, 9)), 255, 1)
+    for _ in range(rng.integers(0, 4)):                      # 2x2 / L-shaped blobs: the "useless hub" patterns
+        y, x = rng.integers(1, size - 3, 2)
+        im[y:y + 2, x:x + 2] = 255
+        im[y + rng.integers(0, 2), x + rng.integers(0, 2)] = 0 if rng.integers(0, 2) else 255
+    if seed % 3 == 0:                                        # strokes on the image border: the unchecked neighbour reads
+        im[0, 3:size // 2] = 255
+        im[size - 1, size // 3:size - 2] = 255
+        im[2:size // 2, 0] = 255
+        im[size // 4:size - 1, size - 1] = 255
+        im[1, 1] = 255
+    if seed % 4 == 1:                                        # salt noise: isolated pixels and short stubs
+        im[rng.random((size, size)) < 0.02] = 255
+    return im > 0
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_product_equals_second_reading_on_synthetic_rasters(seed):
+    mask = synthetic_raster(seed)
+    for st in STAGES:
+        g = assert_same_graph(mask, st)
+    assert g.n_polylines > 0
+
+
+def test_tiny_and_degenerate_images():
+    for mask in (np.zeros((5, 7), bool), np.ones((1, 1), bool), np.ones((2, 2), bool), np.ones((6, 6), bool),
+                 np.eye(9, dtype=bool), np.eye(9, dtype=bool)[::-1], np.pad(np.ones((1, 5), bool), 2)):
+        for st in STAGES:
+            assert_same_graph(mask, st)
+    g = PB.polyline_graph_from_edge_image(np.zeros((4, 4, 3), np.uint8))
+    assert g.n_polylines == 0 and len(g.pixel_node_xy) == 0
+
+
+def dtu006_masks():
+    z = np.load(os.path.join(HERE, "golden", "dtu006_edges.npz"))
+    shape = tuple(int(x) for x in z["shape"])
+    return np.unpackbits(z["packed"], axis=2)[:, :, :shape[2]].astype(bool)
+
+
+def test_product_equals_second_reading_on_dtu006_crops():
+    masks = dtu006_masks()
+    rng = np.random.default_rng(5)
+    done = 0
+    while done < 6:
+        v, y, x = rng.integers(0, 25), rng.integers(0, 1200 - 160), rng.integers(0, 1600 - 160)
+        m = masks[v, y:y + 160, x:x + 160]
+        if m.sum() < 500:
+            continue
+        for st in STAGES:
+            assert_same_graph(m, st)
+        done += 1
+
+
+def test_dtu006_views_full_size():
+    """All 25 real edge maps at 1600x1200 through the library: structural properties that hold for any input, determinism,
+    and the per-view counts recorded when this stage was written (regression only: made by this code, not by the reference)."""
+    masks = dtu006_masks()
+    imgs = [np.repeat((m.astype(np.uint8) * 255)[:, :, None], 3, axis=2) for m in masks]     # BGR, as cv2.imread gives
+    plgs = PB.polyline_graphs_from_edge_images(imgs)
+    again = PB.polyline_graph_from_edge_image(imgs[3])
+    assert again.verts.tobytes() == plgs[3].verts.tobytes() and np.array_equal(again.poly_vert_off, plgs[3].poly_vert_off)
+    counts = []
+    for g in plgs:
+        nv = np.diff(g.poly_vert_off)
+        assert ((nv == 0) | (nv >= 2)).all()                              # removed polylines are empty, live ones have a segment
+        live = np.where(nv >= 2)[0]
+        first, last = g.verts[g.poly_vert_off[live]], g.verts[g.poly_vert_off[live + 1] - 1]
+        assert np.array_equal(first, g.node_xy[g.poly_start[live]]) and np.array_equal(last, g.node_xy[g.poly_end[live]])  # is_valid_polyline
+        assert (g.verts > 0).all() and (g.verts[:, 0] < 1600).all() and (g.verts[:, 1] < 1200).all()
+        assert np.array_equal(g.verts * 4, np.round(g.verts * 4))        # pixel centres (x.5) or midpoints of two of them
+        # (a thin closed loop may legitimately simplify to [p, p]: compute_2dline(p, p) is the vertical line through p)
+        assert (g.poly_length[live] >= 0).all() and (g.poly_length[nv == 0] == -1).all()
+        deg = np.diff(g.pixel_adj_off)
+        assert deg.max() <= 8 and (g.pixel_adj < len(g.pixel_node_xy)).all()
+        # every live polyline vertex is a node of the pixel graph (simplification only drops vertices) or a 2-point stub's midpoint
+        pix = set(map(tuple, (g.pixel_node_xy * 2).astype(np.int64).tolist()))
+        stray = [tuple(v) for v in (g.verts * 2).astype(np.int64).tolist() if tuple(v) not in pix]
+        assert len(stray) <= 0.01 * len(g.verts)
+        counts.append([g.n_polylines, g.n_valid(), g.n_segments(), len(g.node_xy), len(g.pixel_node_xy), int(len(g.pixel_adj) // 2)])
+    sha = hashlib.sha256(b"".join(g.verts.tobytes() + g.poly_vert_off.tobytes() + g.poly_start.tobytes() + g.poly_end.tobytes() for g in plgs)).hexdigest()
+    path = os.path.join(HERE, "golden", "dtu006_plg_counts.json")
+    if os.environ.get("EG3D_WRITE_GOLDEN"):
+        json.dump({"columns": ["polylines", "live", "segments", "nodes", "pixel_nodes", "pixel_edges"], "counts": counts, "sha256": sha,
+                   "note": "regression record written by tests/test_plg_build.py with EG3D_WRITE_GOLDEN=1 (this repo's own output)"}, open(path, "w"))
+    rec = json.load(open(path))
+    assert rec["counts"] == counts and rec["sha256"] == sha
+
+
+def test_cabi_argument_errors():
+    L = E.load()
+    h = C.c_void_p()
+    img = np.zeros((4, 4), np.uint8)
+    col = np.array([255], np.uint8)
+    assert L.eg3d_plg_from_edge_image(None, 4, 4, 1, A.ptr(col, A.c_u8p), 0, C.byref(h)) == A.EG3D_ERR_INVALID_ARG
+    assert L.eg3d_plg_from_edge_image(A.ptr(img, A.c_u8p), 0, 4, 1, A.ptr(col, A.c_u8p), 0, C.byref(h)) == A.EG3D_ERR_INVALID_ARG
+    assert L.eg3d_plg_from_edge_image(A.ptr(img, A.c_u8p), 4, 4, 7, A.ptr(col, A.c_u8p), 0, C.byref(h)) == A.EG3D_ERR_INVALID_ARG
+    assert b"image" in L.eg3d_last_error()
+    assert L.eg3d_plg_get(None, C.byref(A.PlgView())) == A.EG3D_ERR_INVALID_ARG
+    L.eg3d_plg_free(None)
