@@ -9,6 +9,7 @@
 #include <set>
 #include <algorithm>
 #include <memory>
+#include <limits>
 #include <cub/cub.cuh>
 #include "eg3d_dev.cuh"
 #include "eg3d_k1.cuh"
@@ -778,6 +779,126 @@ eg3d_status eg3d_sample_seeds(const eg3d_scene_desc* d, const int32_t* views, co
   *n_out = n;
   return n <= capacity ? EG3D_OK : fail(EG3D_ERR_CAPACITY, "seed capacity too small");
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row f2 (host, upstream of pipeline 2): polyline_matching_closeness_to_refpoints,
+// src/edgegraph3d/matching/polyline_matching/polyline_matcher.cpp:75-168.  Works on the caller's host arrays only.
+// ---------------------------------------------------------------------------------------------------------------
+struct eg3d_polyline_sets { int32_t n_sets = 0, V = 0; std::vector<int64_t> off; std::vector<uint32_t> ids; std::vector<int64_t> refpoints; };
+
+struct CollectIds {   // grid_visit visitor usable from the host (count with cap = 0, then fill)
+  uint32_t* buf; int* n; int cap;
+  EG3D_HD void operator()(uint32_t id) const { if (*n < cap) buf[*n] = id; (*n)++; }
+};
+static void fill_host_plg(const eg3d_scene_desc* d, eg3d_scene& sc) {
+  const int V = sc.V = d->n_views; sc.width = d->width; sc.height = d->height;
+  const int64_t NP = d->view_poly_off[V], NV = d->poly_vert_off[NP];
+  sc.h_view_poly_off.resize(V + 1); for (int i = 0; i <= V; i++) sc.h_view_poly_off[i] = (int)d->view_poly_off[i];
+  sc.h_poly_vert_off.resize(NP + 1); for (int64_t i = 0; i <= NP; i++) sc.h_poly_vert_off[i] = (int)d->poly_vert_off[i];
+  sc.h_verts.assign((const float2*)d->verts, (const float2*)d->verts + NV);
+  sc.h_start.assign(d->poly_start, d->poly_start + NP); sc.h_end.assign(d->poly_end, d->poly_end + NP);
+}
+
+eg3d_status eg3d_polyline_sets_from_refpoints(const eg3d_scene_desc* d, float find_within_dist, float mult, eg3d_polyline_sets** out) {
+  if (!d || !out) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  if (d->n_tracks <= 0 || !d->track_off || !d->track_view || !d->track_xy) return fail(EG3D_ERR_INVALID_ARG, "the scene has no SfM tracks");
+  if (!(find_within_dist > 0)) return fail(EG3D_ERR_INVALID_ARG, "find_within_dist must be positive");
+  const int64_t NVtot = d->poly_vert_off[d->view_poly_off[d->n_views]];
+  if (NVtot > 0x7fffffff) return fail(EG3D_ERR_INVALID_ARG, "too many vertices");
+  eg3d_scene tmp;                       // host copies only: no device buffer is ever allocated in it
+  fill_host_plg(d, tmp);
+  const int V = tmp.V;
+  HostGrid hg; build_grid(tmp, find_within_dist, hg);   // PolyLine2DMapSearch(plg, img_sz, FIND_WITHIN_DIST), :80-81
+  DevScene hs; memset(&hs, 0, sizeof hs);
+  hs.V = V; hs.view_poly_off = tmp.h_view_poly_off.data(); hs.poly_vert_off = tmp.h_poly_vert_off.data();
+  hs.verts = tmp.h_verts.data(); hs.poly_start = tmp.h_start.data(); hs.poly_end = tmp.h_end.data();
+  DevGrid g; g.cell = hg.cell; g.w = hg.w; g.h = hg.h; g.cell_off = hg.off.data(); g.ids = hg.ids.data();
+  const float search_dist_sq = find_within_dist * find_within_dist;
+  // polyline-match graph: nodes = (view, polyline) in first-seen order, undirected set adjacency (:62-73, graph_adjacency_set_*.cpp)
+  std::map<std::pair<int, uint32_t>, int64_t> node_of;
+  std::vector<std::pair<int, uint32_t>> nodes;
+  std::vector<std::set<int64_t>> adj;
+  std::unique_ptr<eg3d_polyline_sets> r(new eg3d_polyline_sets());
+  r->V = V;
+  std::vector<uint32_t> near_ids;
+  for (int64_t t = 0; t < d->n_tracks; t++) {
+    const int64_t o0 = d->track_off[t], o1 = d->track_off[t + 1], n_obs = o1 - o0;
+    size_t maxpl = 0;
+    // per observing view: the polylines within find_within_dist of the observation (find_polylines_within_search_dist_with_reprojections,
+    // polyLine_2d_map_search.cpp:119-135); only lists of length 1 are ever read, so (count, id, distance) is enough
+    std::vector<size_t> cnt((size_t)n_obs, 0); std::vector<uint32_t> first_id((size_t)n_obs, 0); std::vector<float> first_d((size_t)n_obs, 0.f);
+    for (int64_t k = 0; k < n_obs; k++) {
+      const int cam = d->track_view[o0 + k];
+      if (cam < 0 || cam >= V) return fail(EG3D_ERR_INVALID_ARG, "track_view out of range");
+      // get_2d_coordinates_of_point_on_image returns the LAST observation of that camera (edge_graph_3d_utilities.cpp:382-393)
+      float2 c = make_float2(0.f, 0.f);
+      for (int64_t m = 0; m < n_obs; m++) if (d->track_view[o0 + m] == cam) c = make_float2(d->track_xy[2 * (o0 + m)], d->track_xy[2 * (o0 + m) + 1]);
+      int n_near = 0;
+      grid_visit(g, cam, tmp.width, tmp.height, c, CollectIds{nullptr, &n_near, 0});
+      near_ids.resize((size_t)n_near);
+      n_near = 0;
+      grid_visit(g, cam, tmp.width, tmp.height, c, CollectIds{near_ids.data(), &n_near, (int)near_ids.size()});
+      std::sort(near_ids.begin(), near_ids.end());
+      near_ids.erase(std::unique(near_ids.begin(), near_ids.end()), near_ids.end());
+      for (uint32_t id : near_ids) {
+        Pl pl = get_pl(hs, cam, id);
+        uint32_t seg; float2 proj;
+        const float dsq = pl_distancesq(pl, c, seg, proj);
+        if (dsq <= search_dist_sq) { if (cnt[k] == 0) { first_id[k] = id; first_d[k] = sqrtf(dsq); } cnt[k]++; }
+      }
+      maxpl = std::max(maxpl, cnt[k]);
+    }
+    if (maxpl != 1) continue;
+    std::set<std::pair<int, uint32_t>> cams_pls;
+    float min_dist = std::numeric_limits<float>::max(), max_dist = std::numeric_limits<float>::min();   // sic: min() is the smallest positive float
+    for (int64_t k = 0; k < n_obs; k++) {
+      if (cnt[k] == 0) continue;
+      min_dist = min_dist <= first_d[k] ? min_dist : first_d[k];
+      max_dist = max_dist >= first_d[k] ? max_dist : first_d[k];
+      cams_pls.insert({d->track_view[o0 + k], first_id[k]});
+    }
+    if ((double)cams_pls.size() < (double)n_obs * 0.7) continue;
+    if (min_dist < (max_dist / mult)) continue;
+    if (max_dist > (min_dist * mult)) continue;
+    if (cams_pls.size() < 2) continue;
+    std::vector<int64_t> ids;
+    for (const auto& cp : cams_pls) {
+      auto it = node_of.find(cp);
+      if (it == node_of.end()) { it = node_of.insert({cp, (int64_t)nodes.size()}).first; nodes.push_back(cp); adj.emplace_back(); }
+      ids.push_back(it->second);
+    }
+    for (size_t i = 0; i < ids.size(); i++)
+      for (size_t j = i + 1; j < ids.size(); j++) { adj[ids[i]].insert(ids[j]); adj[ids[j]].insert(ids[i]); }
+    r->refpoints.push_back(t);
+  }
+  // GraphAdjacencySetUndirectedNoType::get_components (graph_adjacency_set_undirected_no_type.cpp:44-69): one candidate set
+  // per connected component, in order of the component's lowest node id; per view an ascending set of polyline ids
+  std::vector<uint8_t> visited(nodes.size(), 0);
+  r->off.push_back(0);
+  for (size_t s = 0; s < nodes.size(); s++) {
+    if (visited[s]) continue;
+    std::vector<std::set<uint32_t>> per_view(V);
+    std::vector<int64_t> st{(int64_t)s};
+    visited[s] = 1;
+    while (!st.empty()) {
+      const int64_t c = st.back(); st.pop_back();
+      per_view[nodes[c].first].insert(nodes[c].second);
+      for (int64_t nb : adj[c]) if (!visited[nb]) { visited[nb] = 1; st.push_back(nb); }
+    }
+    for (int v = 0; v < V; v++) { r->ids.insert(r->ids.end(), per_view[v].begin(), per_view[v].end()); r->off.push_back((int64_t)r->ids.size()); }
+    r->n_sets++;
+  }
+  *out = r.release();
+  return EG3D_OK;
+}
+eg3d_status eg3d_polyline_sets_get(const eg3d_polyline_sets* p, eg3d_candidates* view, int64_t* n_refpoints, const int64_t** refpoints) {
+  if (!p || !view) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  view->n_sets = p->n_sets; view->off = p->off.data(); view->polyline = p->ids.data();
+  if (n_refpoints) *n_refpoints = (int64_t)p->refpoints.size();
+  if (refpoints) *refpoints = p->refpoints.data();
+  return EG3D_OK;
+}
+void eg3d_polyline_sets_free(eg3d_polyline_sets* p) { delete p; }
 
 static eg3d_status check_seeds(const eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d_candidates* cands) {
   if (!sc || !seeds) return fail(EG3D_ERR_INVALID_ARG, "null argument");

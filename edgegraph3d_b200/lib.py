@@ -19,6 +19,7 @@ EXPORTS = [
     "eg3d_match_polyline_sets", "eg3d_match_refpoints", "eg3d_points_get", "eg3d_points_device_get", "eg3d_points_free", "eg3d_gn_triangulate",
     "eg3d_gn_triangulate_device", "eg3d_dedup_close_points", "eg3d_filter",
     "eg3d_plg_from_edge_image", "eg3d_plg_get", "eg3d_plg_free",
+    "eg3d_polyline_sets_from_refpoints", "eg3d_polyline_sets_get", "eg3d_polyline_sets_free",
 ]
 
 
@@ -64,6 +65,9 @@ def load():
     L.eg3d_plg_from_edge_image.argtypes = [A.c_u8p, C.c_int32, C.c_int32, C.c_int32, A.c_u8p, C.c_int32, C.POINTER(C.c_void_p)]
     L.eg3d_plg_get.argtypes = [C.c_void_p, C.POINTER(A.PlgView)]
     L.eg3d_plg_free.argtypes = [C.c_void_p]
+    L.eg3d_polyline_sets_from_refpoints.argtypes = [C.POINTER(A.SceneDesc), C.c_float, C.c_float, C.POINTER(C.c_void_p)]
+    L.eg3d_polyline_sets_get.argtypes = [C.c_void_p, C.POINTER(A.Candidates), A.c_i64p, C.POINTER(A.c_i64p)]
+    L.eg3d_polyline_sets_free.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -88,6 +92,26 @@ def camera_fundamentals(cameras):
     out = np.zeros((V, V, 9), np.float64)
     load().eg3d_camera_fundamentals(A.ptr(cams, A.c_f32p), V, A.ptr(out, A.c_f64p))
     return out
+
+
+def polyline_sets_from_refpoints(scene, find_within_dist=10.0, mult=3.0):
+    """f2 (host C++): polyline_matching_closeness_to_refpoints (polyline_matcher.cpp:75-168), the producer of pipeline 2's
+    candidate sets.  -> (CandidateSets, ids of the contributing SfM points)."""
+    from .scene import CandidateSets
+    L = load()
+    d = scene.desc()
+    h = C.c_void_p()
+    _check(L.eg3d_polyline_sets_from_refpoints(C.byref(d), find_within_dist, mult, C.byref(h)))
+    try:
+        c = A.Candidates(); n = C.c_int64(); rp = A.c_i64p()
+        _check(L.eg3d_polyline_sets_get(h, C.byref(c), C.byref(n), C.byref(rp)))
+        n_off = int(c.n_sets) * scene.n_views + 1
+        off = np.ctypeslib.as_array(c.off, shape=(n_off,)).copy()
+        ids = np.ctypeslib.as_array(c.polyline, shape=(int(off[-1]),)).copy() if off[-1] > 0 else np.zeros(0, np.uint32)
+        ref = np.ctypeslib.as_array(rp, shape=(int(n.value),)).copy() if n.value > 0 else np.zeros(0, np.int64)
+        return CandidateSets(int(c.n_sets), off, ids), ref
+    finally:
+        L.eg3d_polyline_sets_free(h)
 
 
 def sample_seeds(scene, views, polylines, spacing):

@@ -289,6 +289,26 @@ eg3d_status eg3d_plg_from_edge_image(const uint8_t* img, int32_t rows, int32_t c
 eg3d_status eg3d_plg_get(const eg3d_plg*, eg3d_plg_view* view);   /* pointers valid until eg3d_plg_free */
 void        eg3d_plg_free(eg3d_plg*);
 
+/* ------------------------------------------------------------------------- */
+/* Row f2 (host, producer of pipeline 2's candidate sets)                    */
+/* ------------------------------------------------------------------------- */
+/*
+ * Replaces polyline_matching_closeness_to_refpoints(plgs, sfmd, img_sz)
+ * (src/edgegraph3d/matching/polyline_matching/polyline_matcher.cpp:75-168, called from pipelines.cpp:118): an SfM point
+ * whose observations each lie within FIND_WITHIN_DIST (10 px, polyline_matcher.hpp:45) of at most one polyline, in >= 70 %
+ * of its views and at comparable distances (ratio <= DETECTION_CORRESPONDENCES_MULTIPLICATION_FACTOR = 3), links those
+ * (view, polyline) pairs; every connected component of that graph is one `vector<set<ulong>>` candidate set, i.e. one
+ * eg3d_match_polyline_sets input.  Host code over the caller's arrays (the polyline-to-polyline similarity graph +
+ * Louvain producer of pipeline 1, :222-336, is not built: its community detection is vendored third-party code).
+ */
+typedef struct eg3d_polyline_sets eg3d_polyline_sets;  /* opaque, host resident */
+eg3d_status eg3d_polyline_sets_from_refpoints(const eg3d_scene_desc* desc, float find_within_dist, float mult,
+                                              eg3d_polyline_sets** out);
+/* view->off has n_sets*V+1 entries; refpoints = ids of the SfM points that contributed (the function's first result). */
+eg3d_status eg3d_polyline_sets_get(const eg3d_polyline_sets*, eg3d_candidates* view, int64_t* n_refpoints,
+                                   const int64_t** refpoints);
+void        eg3d_polyline_sets_free(eg3d_polyline_sets*);
+
 #ifdef __cplusplus
 }
 #endif

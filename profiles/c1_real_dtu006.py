@@ -1,6 +1,8 @@
-"""Documentation run (not a bench line): the reference's packaged example end to end on real data — the 25 real edge
-maps (tests/golden/dtu006_edges.npz) -> polyline graphs (row f1, host) -> pipeline 3 (refpoint-seeded matching) on the
-device, checked against the CPU oracle.  Usage: python profiles/c1_real_dtu006.py [out.json]"""
+"""Documentation run (not a bench line): the reference's packaged example end to end on REAL data — the 25 real edge
+maps (tests/golden/dtu006_edges.npz) -> polyline graphs (row f1, host) -> candidate sets from the SfM points (row f2,
+host) -> pipeline 2 (eg3d_match_polyline_sets) + pipeline 3 (eg3d_match_refpoints) on the device -> density limiter ->
+outlier filter, every stage checked against the CPU oracle.  Pipeline 1 (similarity graph + Louvain communities) is not
+built.  Usage: python profiles/c1_real_dtu006.py [out.json]"""
 import json
 import os
 import sys
@@ -10,22 +12,50 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from edgegraph3d_b200 import lib as E, real_scene  # noqa: E402
+from edgegraph3d_b200.scene import PointSet  # noqa: E402
 from tests import oracle_lib as O  # noqa: E402
 
-if __name__ == "__main__":
-    t = time.time(); sc, plgs = real_scene.dtu006_scene(os.path.join(ROOT, "tests", "golden")); t_plg = time.time() - t
-    res = {"views": sc.n_views, "tracks": sc.n_tracks, "segments_per_view": [sc.n_segments(v) for v in range(sc.n_views)], "plg_build_s": t_plg}
-    prm = E.default_params(max_chain_points=256, max_follow_points=320)
+
+def same(g, r):
+    return bool(g.n_points == r.n_points and np.array_equal(g.obs_off, r.obs_off) and np.array_equal(g.obs_view, r.obs_view)
+                and np.array_equal(g.obs_poly, r.obs_poly) and np.array_equal(g.obs_seg, r.obs_seg) and g.obs_xy.tobytes() == r.obs_xy.tobytes())
+
+
+def run(golden_dir, threads):
+    t = time.time(); sc, plgs = real_scene.dtu006_scene(golden_dir); t_plg = time.time() - t
+    t = time.time(); cands, ref = E.polyline_sets_from_refpoints(sc); t_sets = time.time() - t
+    res = {"views": sc.n_views, "tracks": sc.n_tracks, "segments_per_view": [sc.n_segments(v) for v in range(sc.n_views)],
+           "host_s": {"polyline_graphs_25_views": t_plg, "candidate_sets": t_sets}, "candidate_sets": cands.n_sets, "contributing_sfm_points": len(ref)}
+    prm = E.default_params(max_chain_points=256, max_follow_points=320)   # real chains reach 136 points (default capacity 96)
+    osc = O.OracleScene(sc, prm)
     with E.DeviceScene(sc, prm) as dev:
-        g3, tm = dev.match_refpoints(0, sc.n_tracks)
-        g3b, tm = dev.match_refpoints(0, sc.n_tracks)
-    res["gpu"] = {"points": g3.n_points, "obs": g3.n_obs, "timing": tm}
-    t = time.time(); r3 = O.OracleScene(sc, prm).match_refpoints(0, sc.n_tracks, n_threads=os.cpu_count()); res["oracle_s"] = time.time() - t
-    res["oracle"] = {"points": r3.n_points, "obs": r3.n_obs, "threads": os.cpu_count()}
-    same = (g3.n_points == r3.n_points and np.array_equal(g3.obs_off, r3.obs_off) and np.array_equal(g3.obs_view, r3.obs_view)
-            and np.array_equal(g3.obs_poly, r3.obs_poly) and np.array_equal(g3.obs_seg, r3.obs_seg) and g3.obs_xy.tobytes() == r3.obs_xy.tobytes())
-    res["identical_chains_and_observations"] = bool(same)
-    res["max_abs_xyz_diff"] = float(np.abs(g3.xyz - r3.xyz).max()) if same and g3.n_points else None
+        for _ in range(2):   # second pass = warm
+            t = time.time(); g2, tm2 = dev.match_polyline_sets(cands); g3, tm3 = dev.match_refpoints(0, sc.n_tracks); wall = time.time() - t
+        t = time.time(); r2 = osc.match_polyline_sets(cands, n_threads=threads); r3 = osc.match_refpoints(0, sc.n_tracks, n_threads=threads); t_or = time.time() - t
+        res["pipeline2"] = {"points": g2.n_points, "obs": g2.n_obs, "device_ms": tm2["total_ms"], "seeds": tm2["n_seeds"], "identical": same(g2, r2),
+                            "max_abs_xyz_diff": float(np.abs(g2.xyz - r2.xyz).max()) if same(g2, r2) and g2.n_points else None}
+        res["pipeline3"] = {"points": g3.n_points, "obs": g3.n_obs, "device_ms": tm3["total_ms"], "seeds": tm3["n_seeds"], "identical": same(g3, r3),
+                            "max_abs_xyz_diff": float(np.abs(g3.xyz - r3.xyz).max()) if same(g3, r3) and g3.n_points else None}
+        res["e2e_wall_ms_pipelines_2_3"] = wall * 1e3
+        res["oracle"] = {"seconds_pipelines_2_3": t_or, "threads": threads}
+        allp = PointSet.concat([g2, g3])
+        keep_g = dev.dedup_close_points(allp); keep_o = osc.dedup_close_points(allp)
+        kept = np.where(keep_g)[0]
+        xyz = np.concatenate([sc.track_xyz, allp.xyz[kept]])
+        lens = allp.obs_off[kept + 1] - allp.obs_off[kept]
+        obs_off = np.concatenate([sc.track_off, int(sc.track_off[-1]) + np.cumsum(lens)])
+        idx = np.concatenate([np.arange(allp.obs_off[i], allp.obs_off[i + 1]) for i in kept])
+        obs_view = np.concatenate([sc.track_view, allp.obs_view[idx]]); obs_xy = np.concatenate([sc.track_xy, allp.obs_xy[idx]])
+        fx, inl, tmf = dev.filter(xyz, obs_off, obs_view, obs_xy, sc.n_tracks)
+        ox, oinl = osc.filter(xyz, obs_off, obs_view, obs_xy, sc.n_tracks, n_threads=threads)[:2]
+        res["density_limiter"] = {"in": allp.n_points, "kept": int(keep_g.sum()), "identical": bool(np.array_equal(keep_g, keep_o))}
+        res["filter"] = {"points_in": len(xyz), "inliers": int(inl.sum()), "edge_point_inliers": int(inl[sc.n_tracks:].sum()),
+                         "identical_inlier_sets": bool(np.array_equal(inl, oinl)), "identical_refined_xyz": bool(np.array_equal(fx[inl == 1], ox[oinl == 1]))}
+    return res
+
+
+if __name__ == "__main__":
+    res = run(os.path.join(ROOT, "tests", "golden"), os.cpu_count())
     print(json.dumps(res))
     if len(sys.argv) > 1:
         json.dump(res, open(sys.argv[1], "w"))
