@@ -218,4 +218,53 @@ inline void filter(Eg3dScene& scene, SfMData& sfmd, int first_edgepoint, float g
   sfmd = res;
 }
 
+// f1: convertEdgeImagePolyLineGraph_optimized / convert_edge_images_to_optimized_polyline_graphs
+// (convert_edge_images_pixel_to_segment.hpp:98-101).  img = the pixels of a continuous CV_8UC3 Mat (img.data, img.rows,
+// img.cols); with EG3D_REF_USE_REFERENCE_TYPES the cv::Mat overloads below forward to it.  Only the fields the matching
+// path reads are filled (polyline start / end / coords); removed polylines keep their id with empty coords, as in the
+// reference (polyline_graph_2d.cpp:1035-1038).
+inline PolyLineGraph2DHMapImpl convertEdgeImagePolyLineGraph_optimized(const uint8_t* bgr, int rows, int cols, const uint8_t edge_color[3]) {
+  eg3d_plg* h = nullptr;
+  check(eg3d_plg_from_edge_image(bgr, rows, cols, 3, edge_color, EG3D_PLG_STAGE_FULL, &h));
+  eg3d_plg_view v; check(eg3d_plg_get(h, &v));
+  PolyLineGraph2DHMapImpl plg;
+  plg.polylines.resize((size_t)v.n_polylines);
+  for (int64_t i = 0; i < v.n_polylines; i++) {
+    auto& pl = plg.polylines[(size_t)i];
+    pl.start = v.poly_start[i]; pl.end = v.poly_end[i];
+    for (int64_t k = v.poly_vert_off[i]; k < v.poly_vert_off[i + 1]; k++) pl.polyline_coords.push_back(vec2(v.verts[2 * k], v.verts[2 * k + 1]));
+  }
+  eg3d_plg_free(h);
+  return plg;
+}
+#ifdef EG3D_REF_USE_REFERENCE_TYPES
+inline PolyLineGraph2DHMapImpl convertEdgeImagePolyLineGraph_optimized(const cv::Mat& img, const cv::Vec3b& edge_color) {
+  const cv::Mat c = img.isContinuous() ? img : img.clone();
+  const uint8_t col[3] = {edge_color[0], edge_color[1], edge_color[2]};
+  return convertEdgeImagePolyLineGraph_optimized(c.data, c.rows, c.cols, col);
+}
+inline std::vector<PolyLineGraph2DHMapImpl> convert_edge_images_to_optimized_polyline_graphs(const std::vector<cv::Mat>& imgs, const cv::Vec3b& edge_color) {
+  std::vector<PolyLineGraph2DHMapImpl> res;
+  for (const auto& img : imgs) res.push_back(convertEdgeImagePolyLineGraph_optimized(img, edge_color));
+  return res;
+}
+#endif
+
+// f2: polyline_matching_closeness_to_refpoints (polyline_matcher.hpp:64): pair(refpoint ids, one vector<set<ulong>> per match)
+inline std::pair<std::vector<ulong_t>, std::vector<std::vector<std::set<ulong_t>>>> polyline_matching_closeness_to_refpoints(const Eg3dScene& scene) {
+  eg3d_polyline_sets* h = nullptr;
+  check(eg3d_polyline_sets_from_refpoints(&scene.desc(), 10.0f /* FIND_WITHIN_DIST */, 3.0f /* DETECTION_CORRESPONDENCES_MULTIPLICATION_FACTOR */, &h));
+  eg3d_candidates c; int64_t n_ref = 0; const int64_t* ref = nullptr;
+  check(eg3d_polyline_sets_get(h, &c, &n_ref, &ref));
+  std::pair<std::vector<ulong_t>, std::vector<std::vector<std::set<ulong_t>>>> res;
+  res.first.assign(ref, ref + n_ref);
+  const int V = scene.n_views();
+  res.second.assign((size_t)c.n_sets, std::vector<std::set<ulong_t>>((size_t)V));
+  for (int i = 0; i < c.n_sets; i++)
+    for (int v = 0; v < V; v++)
+      for (int64_t k = c.off[(size_t)i * V + v]; k < c.off[(size_t)i * V + v + 1]; k++) res.second[(size_t)i][(size_t)v].insert(c.polyline[k]);
+  eg3d_polyline_sets_free(h);
+  return res;
+}
+
 }  // namespace eg3d_shim
