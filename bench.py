@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — triangulated 3D edge-points/sec on the BASELINE.json workload (see DESIGN.md "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|small]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|small|c1|c1real]
 
 A "step" is one pass of the hot path (K1 epipolar intersection -> K3 triple enumeration / PLG following / view expansion
 -> ordered packing [-> NCCL all-gather of the accepted points when N > 1]) over the whole seed batch of the workload.
@@ -293,6 +293,13 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
 
+    if args.workload == "c1real":
+        # BASELINE configs[0] on the packaged files: real edge maps -> polyline graphs -> candidate sets -> pipelines 2+3 ->
+        # density limiter -> filter, every stage checked against the oracle (documentation line, not the headline configuration)
+        sys.path.insert(0, os.path.join(ROOT, "profiles"))
+        import c1_real_dtu006
+        print(json.dumps(c1_real_dtu006.run(os.path.join(ROOT, "tests", "golden"), os.cpu_count())))
+        return
     scene, cfg, per_view = build_workload(args.workload, n_gpus)
     if args.workload == "c1":
         return run_c1(args, scene, cfg, E)

@@ -1,11 +1,11 @@
 """Development aid (not a bench): run the C2 batch through one build of the library and print kernel times plus a
 checksum of the result, so that A/B builds (EG3D_LIB=<path>) can be compared for speed AND identical output.
-  EG3D_LIB=edgegraph3d_b200/libeg3d_x.so python _ab.py [reps] [seeds_limit]"""
+  EG3D_LIB=edgegraph3d_b200/libeg3d_x.so python profiles/ab_compare.py [reps] [seeds_limit]"""
 import os
 import sys
 import zlib
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from edgegraph3d_b200 import synthetic as syn, lib as E
 
