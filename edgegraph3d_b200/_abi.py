@@ -75,6 +75,11 @@ class PlgView(C.Structure):
                 ("n_pixel_nodes", C.c_int64), ("pixel_node_xy", c_f32p), ("pixel_adj_off", c_i64p), ("pixel_adj", c_u32p)]
 
 
+class SimilarityGraphView(C.Structure):
+    _fields_ = [("n_views", C.c_int32), ("n_nodes", C.c_int64), ("node_view", c_i32p), ("node_polyline", c_u32p), ("n_edges", C.c_int64),
+                ("edge_a", c_i64p), ("edge_b", c_i64p), ("edge_weight", c_f32p), ("dimacs", C.c_char_p), ("dimacs_len", C.c_int64)]
+
+
 PLG_STAGE_FULL, PLG_STAGE_PIXEL_GRAPH, PLG_STAGE_RAW, PLG_STAGE_MERGED, PLG_STAGE_SIMPLIFIED, PLG_STAGE_CONNECTED = range(6)
 
 

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <memory>
 #include <limits>
+#include <sstream>
 #include <cub/cub.cuh>
 #include "eg3d_dev.cuh"
 #include "eg3d_k1.cuh"
@@ -899,6 +900,216 @@ eg3d_status eg3d_polyline_sets_get(const eg3d_polyline_sets* p, eg3d_candidates*
   return EG3D_OK;
 }
 void eg3d_polyline_sets_free(eg3d_polyline_sets* p) { delete p; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row f2, pipeline 1's producer: polyline_matching_similarity_graph, polyline_matcher.cpp:222-336.  The weighted
+// (view, polyline) compatibility graph is the reference's, number for number; its communities are found here by a
+// deterministic sequential Louvain (the reference hands the graph to the vendored multi-threaded Grappolo, whose result
+// depends on the thread count and interleaving and which returns nothing on one thread).
+// ---------------------------------------------------------------------------------------------------------------
+struct eg3d_similarity_graph {
+  int32_t V = 0;
+  std::vector<int32_t> node_view; std::vector<uint32_t> node_pl;
+  std::vector<int64_t> ea, eb; std::vector<float> ew;      // node a < node b, in the reference's insertion order
+  std::string dimacs;                                      // GraphAdjacencySetUndirectedNoTypeWeighted::write_to_file
+};
+
+// the polylines within find_within_dist of point c in view cam, ascending id (polyLine_2d_map_search.cpp:119-135)
+static void near_polylines(const DevGrid& g, const DevScene& hs, int cam, int width, int height, float2 c, float dsq_max,
+                           std::vector<uint32_t>& scratch, std::vector<std::pair<uint32_t, float>>& out) {
+  out.clear();
+  int n_near = 0;
+  grid_visit(g, cam, width, height, c, CollectIds{nullptr, &n_near, 0});
+  scratch.resize((size_t)n_near);
+  n_near = 0;
+  grid_visit(g, cam, width, height, c, CollectIds{scratch.data(), &n_near, (int)scratch.size()});
+  std::sort(scratch.begin(), scratch.end());
+  scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
+  for (uint32_t id : scratch) {
+    Pl pl = get_pl(hs, cam, id);
+    uint32_t seg; float2 proj;
+    const float dsq = pl_distancesq(pl, c, seg, proj);
+    if (dsq <= dsq_max) out.push_back({id, sqrtf(dsq)});
+  }
+}
+
+eg3d_status eg3d_polyline_similarity_graph(const eg3d_scene_desc* d, float find_within_dist, eg3d_similarity_graph** out) {
+  if (!d || !out) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  if (d->n_tracks <= 0 || !d->track_off || !d->track_view || !d->track_xy) return fail(EG3D_ERR_INVALID_ARG, "the scene has no SfM tracks");
+  if (!(find_within_dist > 0)) return fail(EG3D_ERR_INVALID_ARG, "find_within_dist must be positive");
+  if (d->poly_vert_off[d->view_poly_off[d->n_views]] > 0x7fffffff) return fail(EG3D_ERR_INVALID_ARG, "too many vertices");
+  eg3d_scene tmp; fill_host_plg(d, tmp);
+  const int V = tmp.V; const int64_t NT = d->n_tracks;
+  HostGrid hg; build_grid(tmp, find_within_dist, hg);
+  DevScene hs; memset(&hs, 0, sizeof hs);
+  hs.V = V; hs.view_poly_off = tmp.h_view_poly_off.data(); hs.poly_vert_off = tmp.h_poly_vert_off.data();
+  hs.verts = tmp.h_verts.data(); hs.poly_start = tmp.h_start.data(); hs.poly_end = tmp.h_end.data();
+  DevGrid g; g.cell = hg.cell; g.w = hg.w; g.h = hg.h; g.cell_off = hg.off.data(); g.ids = hg.ids.data();
+  const float dsq_max = find_within_dist * find_within_dist;
+  std::unique_ptr<eg3d_similarity_graph> r(new eg3d_similarity_graph()); r->V = V;
+  std::map<std::pair<int, uint32_t>, int64_t> node_of;
+  std::vector<std::set<int64_t>> adj;
+  // close_refpoints[(view, polyline)] (ascending point ids), refpoint weights, visibility (:236-300)
+  std::map<std::pair<int, uint32_t>, std::vector<int64_t>> close_refpoints;
+  std::vector<float> weight((size_t)NT, 0.f);
+  std::vector<std::vector<uint8_t>> visible((size_t)V, std::vector<uint8_t>((size_t)NT, 0));   // pointsVisibleFromCamN_ as a bitmap
+  std::vector<uint32_t> scratch; std::vector<std::pair<uint32_t, float>> near;
+  for (int64_t t = 0; t < NT; t++) {
+    const int64_t o0 = d->track_off[t], o1 = d->track_off[t + 1];
+    std::set<std::pair<int, uint32_t>> cams_pls;
+    for (int64_t k = o0; k < o1; k++) {
+      const int cam = d->track_view[k];
+      if (cam < 0 || cam >= V) return fail(EG3D_ERR_INVALID_ARG, "track_view out of range");
+      visible[cam][t] = 1;
+      float2 c = make_float2(0.f, 0.f);   // the LAST observation of that camera (edge_graph_3d_utilities.cpp:382-393)
+      for (int64_t m = o0; m < o1; m++) if (d->track_view[m] == cam) c = make_float2(d->track_xy[2 * m], d->track_xy[2 * m + 1]);
+      near_polylines(g, hs, cam, tmp.width, tmp.height, c, dsq_max, scratch, near);
+      for (const auto& q : near) cams_pls.insert({cam, q.first});
+    }
+    // compute_refpoint_weight (:196-205): views with close polylines / close polylines
+    int non_empty = 0, sum_pls = 0, last_cam = -1;
+    for (const auto& cp : cams_pls) { if (cp.first != last_cam) { non_empty++; last_cam = cp.first; } sum_pls++; }
+    weight[t] = non_empty == 0 ? 0.0f : non_empty / ((float)sum_pls);
+    std::vector<int64_t> ids;
+    for (const auto& cp : cams_pls) {
+      close_refpoints[cp].push_back(t);
+      auto it = node_of.find(cp);
+      if (it == node_of.end()) { it = node_of.insert({cp, (int64_t)r->node_view.size()}).first; r->node_view.push_back(cp.first); r->node_pl.push_back(cp.second); adj.emplace_back(); }
+      ids.push_back(it->second);
+    }
+    for (size_t i = 0; i < ids.size(); i++)
+      for (size_t j = i + 1; j < ids.size(); j++) { adj[ids[i]].insert(ids[j]); adj[ids[j]].insert(ids[i]); }
+  }
+  // compute_compatibility (:171-194): weighted Jaccard index of the two polylines' close SfM points, each list restricted
+  // to the points that are also visible in the OTHER polyline's view
+  const int64_t N = (int64_t)r->node_view.size();
+  std::vector<std::map<int64_t, float>> wadj((size_t)N);
+  std::vector<int64_t> la, lb, tmpv;
+  for (int64_t n1 = 0; n1 < N; n1++)
+    for (int64_t n2 : adj[n1]) {
+      if (!(n1 < n2)) continue;
+      const std::pair<int, uint32_t> m1{r->node_view[n1], r->node_pl[n1]}, m2{r->node_view[n2], r->node_pl[n2]};
+      la.clear(); lb.clear();
+      for (int64_t t : close_refpoints[m1]) if (visible[m2.first][t]) la.push_back(t);
+      for (int64_t t : close_refpoints[m2]) if (visible[m1.first][t]) lb.push_back(t);
+      tmpv.resize(la.size() + lb.size());
+      auto e = std::set_intersection(la.begin(), la.end(), lb.begin(), lb.end(), tmpv.begin());
+      float inter = 0.0f; for (auto it = tmpv.begin(); it != e; ++it) inter += weight[*it];
+      float w = 0.0f;
+      if (inter != 0.0f) {
+        e = std::set_union(la.begin(), la.end(), lb.begin(), lb.end(), tmpv.begin());
+        float uni = 0.0f; for (auto it = tmpv.begin(); it != e; ++it) uni += weight[*it];
+        w = inter / uni;
+      }
+      if (w > 0.0f) { r->ea.push_back(n1); r->eb.push_back(n2); r->ew.push_back(w); wadj[n1][n2] = w; wadj[n2][n1] = w; }
+    }
+  // write_to_file (graph_adjacency_set_undirected_no_type_weighted.cpp:54-73): every edge appears in both directions and
+  // the header counts both; weights in the stream's default float format
+  {
+    std::ostringstream f;
+    int64_t m2 = 0; for (const auto& a : wadj) m2 += (int64_t)a.size();
+    f << "p sp " << (unsigned long)N << " " << (unsigned long)m2 << "\n";
+    for (int64_t n1 = 0; n1 < N; n1++) for (const auto& kv : wadj[n1]) f << "a " << (unsigned long)(n1 + 1) << " " << (unsigned long)(kv.first + 1) << " " << kv.second << "\n";
+    r->dimacs = f.str();
+  }
+  *out = r.release();
+  return EG3D_OK;
+}
+
+eg3d_status eg3d_similarity_graph_get(const eg3d_similarity_graph* p, eg3d_similarity_graph_view* v) {
+  if (!p || !v) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  v->n_views = p->V; v->n_nodes = (int64_t)p->node_view.size(); v->node_view = p->node_view.data(); v->node_polyline = p->node_pl.data();
+  v->n_edges = (int64_t)p->ew.size(); v->edge_a = p->ea.data(); v->edge_b = p->eb.data(); v->edge_weight = p->ew.data();
+  v->dimacs = p->dimacs.c_str(); v->dimacs_len = (int64_t)p->dimacs.size();
+  return EG3D_OK;
+}
+void eg3d_similarity_graph_free(eg3d_similarity_graph* p) { delete p; }
+
+// Deterministic sequential Louvain (Blondel et al. 2008) on the weighted graph: nodes are visited in ascending id, a node
+// moves to the neighbouring community with the largest modularity gain (ties: the lowest community id), levels are
+// aggregated until a level makes no move.  Nodes without an edge get -1 (no community), the others ids 0..n-1 in order
+// of first appearance.  *modularity (may be NULL) receives Q of the returned partition.
+eg3d_status eg3d_similarity_graph_communities(const eg3d_similarity_graph* p, int64_t* community, double* modularity) {
+  if (!p || !community) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  const int64_t N0 = (int64_t)p->node_view.size();
+  std::vector<std::map<int64_t, double>> adj((size_t)N0);        // current level graph (self loops allowed after aggregation)
+  for (size_t e = 0; e < p->ew.size(); e++) { adj[p->ea[e]][p->eb[e]] += (double)p->ew[e]; adj[p->eb[e]][p->ea[e]] += (double)p->ew[e]; }
+  double m2 = 0; for (const auto& a : adj) for (const auto& kv : a) m2 += kv.second;   // 2m (a self loop {i: w} counts w, stored as 2*w below)
+  std::vector<int64_t> owner((size_t)N0); for (int64_t i = 0; i < N0; i++) owner[i] = i;   // original node -> node of the current level
+  int64_t N = N0;
+  while (true) {
+    std::vector<double> k((size_t)N, 0.0), tot((size_t)N, 0.0);
+    std::vector<int64_t> com((size_t)N);
+    for (int64_t i = 0; i < N; i++) { for (const auto& kv : adj[i]) k[i] += kv.second; tot[i] = k[i]; com[i] = i; }
+    bool moved_any = false, moved = true;
+    int sweeps = 0;
+    while (moved && m2 > 0 && sweeps++ < 100) {
+      moved = false;
+      for (int64_t i = 0; i < N; i++) {
+        std::map<int64_t, double> to;                                  // weight from i to each neighbouring community
+        for (const auto& kv : adj[i]) if (kv.first != i) to[com[kv.first]] += kv.second;
+        const int64_t old = com[i];
+        tot[old] -= k[i];
+        int64_t best = old; double best_gain = (to.count(old) ? to[old] : 0.0) - tot[old] * k[i] / m2;
+        for (const auto& kv : to) {
+          const double gain = kv.second - tot[kv.first] * k[i] / m2;
+          if (gain > best_gain || (gain == best_gain && kv.first < best)) { best = kv.first; best_gain = gain; }
+        }
+        tot[best] += k[i];
+        if (best != old) { com[i] = best; moved = true; moved_any = true; }
+      }
+    }
+    // renumber the communities of this level in order of first appearance and aggregate
+    std::vector<int64_t> renum((size_t)N, -1); int64_t nc = 0;
+    for (int64_t i = 0; i < N; i++) if (renum[com[i]] < 0) renum[com[i]] = nc++;
+    for (int64_t i = 0; i < N0; i++) owner[i] = renum[com[owner[i]]];
+    if (!moved_any) break;
+    std::vector<std::map<int64_t, double>> nadj((size_t)nc);
+    for (int64_t i = 0; i < N; i++) for (const auto& kv : adj[i]) nadj[renum[com[i]]][renum[com[kv.first]]] += kv.second;
+    adj.swap(nadj); N = nc;
+  }
+  // nodes without any edge belong to no community (-1), as in Grappolo's output; the others are renumbered 0..n-1 in
+  // order of first appearance
+  {
+    std::vector<uint8_t> has_edge((size_t)N0, 0);
+    for (size_t e = 0; e < p->ew.size(); e++) { has_edge[p->ea[e]] = 1; has_edge[p->eb[e]] = 1; }
+    std::map<int64_t, int64_t> ren;
+    for (int64_t i = 0; i < N0; i++) {
+      if (!has_edge[i]) { owner[i] = -1; continue; }
+      auto it = ren.find(owner[i]);
+      if (it == ren.end()) it = ren.insert({owner[i], (int64_t)ren.size()}).first;
+      owner[i] = it->second;
+    }
+  }
+  for (int64_t i = 0; i < N0; i++) community[i] = owner[i];
+  if (modularity) {
+    // Q = sum_c [ in_c / 2m - (tot_c / 2m)^2 ] on the original graph
+    std::map<int64_t, double> in, tot; double mm = 0;
+    for (size_t e = 0; e < p->ew.size(); e++) {
+      const double w = (double)p->ew[e]; mm += 2 * w;
+      tot[owner[p->ea[e]]] += w; tot[owner[p->eb[e]]] += w;
+      if (owner[p->ea[e]] == owner[p->eb[e]]) in[owner[p->ea[e]]] += 2 * w;
+    }
+    double q = 0; if (mm > 0) for (const auto& kv : tot) q += (in.count(kv.first) ? in[kv.first] : 0.0) / mm - (kv.second / mm) * (kv.second / mm);
+    *modularity = q;
+  }
+  return EG3D_OK;
+}
+
+// compute_polyline_matches_from_nodes_component_ids (polyline_matcher.cpp:207-219): one candidate set per community id in
+// [0, max id]; nodes with a negative id belong to none
+eg3d_status eg3d_polyline_sets_from_communities(const eg3d_similarity_graph* p, const int64_t* community, eg3d_polyline_sets** out) {
+  if (!p || !community || !out) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  const int64_t N = (int64_t)p->node_view.size(); const int V = p->V;
+  int64_t maxc = -1; for (int64_t i = 0; i < N; i++) maxc = std::max(maxc, community[i]);
+  std::vector<std::vector<std::set<uint32_t>>> sets((size_t)(maxc + 1), std::vector<std::set<uint32_t>>((size_t)V));
+  for (int64_t i = 0; i < N; i++) if (community[i] >= 0) sets[(size_t)community[i]][(size_t)p->node_view[i]].insert(p->node_pl[i]);
+  std::unique_ptr<eg3d_polyline_sets> r(new eg3d_polyline_sets()); r->V = V; r->n_sets = (int32_t)(maxc + 1);
+  r->off.push_back(0);
+  for (const auto& s : sets) for (int v = 0; v < V; v++) { r->ids.insert(r->ids.end(), s[v].begin(), s[v].end()); r->off.push_back((int64_t)r->ids.size()); }
+  *out = r.release();
+  return EG3D_OK;
+}
 
 static eg3d_status check_seeds(const eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d_candidates* cands) {
   if (!sc || !seeds) return fail(EG3D_ERR_INVALID_ARG, "null argument");

@@ -20,6 +20,8 @@ EXPORTS = [
     "eg3d_gn_triangulate_device", "eg3d_dedup_close_points", "eg3d_filter",
     "eg3d_plg_from_edge_image", "eg3d_plg_get", "eg3d_plg_free",
     "eg3d_polyline_sets_from_refpoints", "eg3d_polyline_sets_get", "eg3d_polyline_sets_free",
+    "eg3d_polyline_similarity_graph", "eg3d_similarity_graph_get", "eg3d_similarity_graph_communities", "eg3d_polyline_sets_from_communities",
+    "eg3d_similarity_graph_free",
 ]
 
 
@@ -68,6 +70,11 @@ def load():
     L.eg3d_polyline_sets_from_refpoints.argtypes = [C.POINTER(A.SceneDesc), C.c_float, C.c_float, C.POINTER(C.c_void_p)]
     L.eg3d_polyline_sets_get.argtypes = [C.c_void_p, C.POINTER(A.Candidates), A.c_i64p, C.POINTER(A.c_i64p)]
     L.eg3d_polyline_sets_free.argtypes = [C.c_void_p]
+    L.eg3d_polyline_similarity_graph.argtypes = [C.POINTER(A.SceneDesc), C.c_float, C.POINTER(C.c_void_p)]
+    L.eg3d_similarity_graph_get.argtypes = [C.c_void_p, C.POINTER(A.SimilarityGraphView)]
+    L.eg3d_similarity_graph_communities.argtypes = [C.c_void_p, A.c_i64p, A.c_f64p]
+    L.eg3d_polyline_sets_from_communities.argtypes = [C.c_void_p, A.c_i64p, C.POINTER(C.c_void_p)]
+    L.eg3d_similarity_graph_free.argtypes = [C.c_void_p]
     _lib = L
     return L
 
@@ -112,6 +119,66 @@ def polyline_sets_from_refpoints(scene, find_within_dist=10.0, mult=3.0):
         return CandidateSets(int(c.n_sets), off, ids), ref
     finally:
         L.eg3d_polyline_sets_free(h)
+
+
+def _candidate_sets_from_handle(h, n_views):
+    from .scene import CandidateSets
+    L = load()
+    c = A.Candidates(); n = C.c_int64(); rp = A.c_i64p()
+    _check(L.eg3d_polyline_sets_get(h, C.byref(c), C.byref(n), C.byref(rp)))
+    off = np.ctypeslib.as_array(c.off, shape=(int(c.n_sets) * n_views + 1,)).copy()
+    ids = np.ctypeslib.as_array(c.polyline, shape=(int(off[-1]),)).copy() if off[-1] > 0 else np.zeros(0, np.uint32)
+    return CandidateSets(int(c.n_sets), off, ids)
+
+
+class SimilarityGraph:
+    """f2, pipeline 1's producer (host C++): the weighted (view, polyline) compatibility graph of
+    polyline_matching_similarity_graph (polyline_matcher.cpp:222-336) + its communities + the candidate sets they give."""
+
+    def __init__(self, scene, find_within_dist=10.0):
+        L = load()
+        self.n_views = scene.n_views
+        d = scene.desc()
+        self.h = C.c_void_p()
+        _check(L.eg3d_polyline_similarity_graph(C.byref(d), find_within_dist, C.byref(self.h)))
+        v = A.SimilarityGraphView()
+        _check(L.eg3d_similarity_graph_get(self.h, C.byref(v)))
+        n, m = int(v.n_nodes), int(v.n_edges)
+        self.node_view = np.ctypeslib.as_array(v.node_view, shape=(n,)).copy() if n else np.zeros(0, np.int32)
+        self.node_polyline = np.ctypeslib.as_array(v.node_polyline, shape=(n,)).copy() if n else np.zeros(0, np.uint32)
+        self.edge_a = np.ctypeslib.as_array(v.edge_a, shape=(m,)).copy() if m else np.zeros(0, np.int64)
+        self.edge_b = np.ctypeslib.as_array(v.edge_b, shape=(m,)).copy() if m else np.zeros(0, np.int64)
+        self.edge_weight = np.ctypeslib.as_array(v.edge_weight, shape=(m,)).copy() if m else np.zeros(0, np.float32)
+        self.dimacs = C.string_at(v.dimacs, int(v.dimacs_len)).decode()
+
+    def communities(self):
+        """The library's deterministic sequential Louvain -> (community id per node, modularity)."""
+        com = np.zeros(len(self.node_view), np.int64)
+        q = C.c_double()
+        _check(load().eg3d_similarity_graph_communities(self.h, A.ptr(com, A.c_i64p), C.cast(C.byref(q), A.c_f64p)))
+        return com, q.value
+
+    def candidate_sets(self, community):
+        L = load()
+        com = np.ascontiguousarray(community, np.int64)
+        assert len(com) == len(self.node_view)
+        h = C.c_void_p()
+        _check(L.eg3d_polyline_sets_from_communities(self.h, A.ptr(com, A.c_i64p), C.byref(h)))
+        try:
+            return _candidate_sets_from_handle(h, self.n_views)
+        finally:
+            L.eg3d_polyline_sets_free(h)
+
+    def close(self):
+        if self.h:
+            load().eg3d_similarity_graph_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def sample_seeds(scene, views, polylines, spacing):

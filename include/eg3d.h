@@ -309,6 +309,39 @@ eg3d_status eg3d_polyline_sets_get(const eg3d_polyline_sets*, eg3d_candidates* v
                                    const int64_t** refpoints);
 void        eg3d_polyline_sets_free(eg3d_polyline_sets*);
 
+/*
+ * Pipeline 1's producer: polyline_matching_similarity_graph (polyline_matcher.cpp:222-336, called from pipelines.cpp:72).
+ * eg3d_polyline_similarity_graph builds the reference's weighted compatibility graph: nodes = (view, polyline) pairs
+ * within FIND_WITHIN_DIST of an SfM observation, in first-seen order; an edge joins two pairs close to the same SfM point;
+ * its weight is the weighted Jaccard index of the two polylines' close SfM points (compute_compatibility :171-194, point
+ * weights compute_refpoint_weight :196-205); edges of weight 0 are dropped.  `dimacs` is, byte for byte, the file
+ * GraphAdjacencySetUndirectedNoTypeWeighted::write_to_file (graph_adjacency_set_undirected_no_type_weighted.cpp:54-73)
+ * hands to Grappolo.  The reference then takes Grappolo's communities (community_detection_interface.cpp:57-73); that code
+ * is multi-threaded only and not reproducible run to run, so eg3d_similarity_graph_communities is this library's own
+ * deterministic sequential Louvain, and eg3d_polyline_sets_from_communities
+ * (compute_polyline_matches_from_nodes_component_ids :207-219) accepts ids from either.  Host code.
+ */
+typedef struct eg3d_similarity_graph eg3d_similarity_graph;  /* opaque, host resident */
+typedef struct eg3d_similarity_graph_view {
+  int32_t         n_views;
+  int64_t         n_nodes;
+  const int32_t*  node_view;      /* [n_nodes] */
+  const uint32_t* node_polyline;  /* [n_nodes] */
+  int64_t         n_edges;
+  const int64_t*  edge_a;         /* [n_edges] edge_a < edge_b */
+  const int64_t*  edge_b;
+  const float*    edge_weight;
+  const char*     dimacs;         /* NUL-terminated text of the compatibility-graph file */
+  int64_t         dimacs_len;
+} eg3d_similarity_graph_view;
+eg3d_status eg3d_polyline_similarity_graph(const eg3d_scene_desc* desc, float find_within_dist, eg3d_similarity_graph** out);
+eg3d_status eg3d_similarity_graph_get(const eg3d_similarity_graph*, eg3d_similarity_graph_view* view);
+eg3d_status eg3d_similarity_graph_communities(const eg3d_similarity_graph*, int64_t* community /* [n_nodes] */,
+                                              double* modularity /* may be NULL */);
+eg3d_status eg3d_polyline_sets_from_communities(const eg3d_similarity_graph*, const int64_t* community /* [n_nodes] */,
+                                                eg3d_polyline_sets** out);
+void        eg3d_similarity_graph_free(eg3d_similarity_graph*);
+
 #ifdef __cplusplus
 }
 #endif
