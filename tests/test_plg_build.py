@@ -3,7 +3,8 @@ oracle/plg_build_ref.py, stage by stage and bit for bit: pixel graph (node coord
 vertex lists, start/end node ids, lengths, node table.  CPU only — this stage needs no device.
 
 The reference ships no expected outputs for this stage (parity unpinned by the reference itself); inputs are synthetic
-rasters built to hit its special cases and crops of the real dtu006 edge maps (tests/golden/dtu006_edges.npz)."""
+rasters built to hit its special cases and crops of the real dtu006 edge maps (tests/golden/dtu006_edges.npz).  The same
+comparison on all 25 complete 1600x1200 views was run by hand (70-130 s per view for the Python reading): identical."""
 import ctypes as C
 import hashlib
 import json
