@@ -35,6 +35,26 @@ def balanced_view_blocks(seeds_per_view, world_size):
     return [(int(cuts[r]), int(cuts[r + 1])) for r in range(world_size)]
 
 
+def polyline_set_seed_views(scene, cands, spacing, sampler):
+    """Starting view of every seed of eg3d_match_polyline_sets(cands) in the reference's loop order (candidate set,
+    starting view, candidate polyline, 20 px steps: pipelines.cpp:92-100 around polyline_matching.cpp:162-190).  A rank that
+    owns the starting views [lo, hi) computes the sub-sequence with lo <= view < hi, so
+    `np.where((views >= lo) & (views < hi))[0]` are that rank's `order_keys` for all_gather_points: with several candidate
+    sets a plain rank-order concatenation would be view-major, not set-major, and the order-dependent density limiter
+    (filtering_close_plgps.cpp:75-124) would see a different sequence.  `sampler` = lib.sample_seeds (host C++)."""
+    V = scene.n_views
+    counts = np.diff(cands.off).astype(np.int64)                      # per (set, view) range, already in (set, view) order
+    views = np.repeat(np.tile(np.arange(V, dtype=np.int32), cands.n_sets), counts)
+    sv = sampler(scene, views, cands.polyline, spacing)[0]
+    return np.asarray(sv, np.int32)
+
+
+def track_block(n_tracks, world_size, rank):
+    """Contiguous block of SfM point ids owned by `rank` (plg_matching_from_refpoints.cpp:90): rank-order concatenation of
+    the blocks is the reference's loop order."""
+    return (rank * n_tracks) // world_size, ((rank + 1) * n_tracks) // world_size
+
+
 _FIELDS = (("xyz", np.float32, 3), ("seed", np.int32, 1), ("chain_pos", np.int32, 1), ("obs_view", np.int32, 1),
            ("obs_poly", np.uint32, 1), ("obs_seg", np.uint32, 1), ("obs_xy", np.float32, 2))
 

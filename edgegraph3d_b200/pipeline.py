@@ -44,14 +44,37 @@ def candidate_sets(scene):
     return c1, c2, info
 
 
-def run_pipelines(matcher, scene, cands1, cands2):
+def run_pipelines(matcher, scene, cands1, cands2, dist=None, device=None, spacing=20.0):
     """Pipelines 1-3 in the reference's order (pipelines.cpp:217-229).  `matcher` is a lib.DeviceScene (or any object with the
-    same match_polyline_sets / match_refpoints methods, e.g. the test oracle).  -> ([points1, points2, points3], [timing...])"""
+    same match_polyline_sets / match_refpoints methods, e.g. the test oracle).  -> ([points1, points2, points3], [timing...])
+
+    With `dist` (an initialised torch.distributed, world size N > 1) every rank computes its shard — starting views
+    [lo, hi) for pipelines 1-2, SfM points [tb, te) for pipeline 3 — and ONE all-gather per pipeline puts the accepted
+    points of all ranks back into the reference's loop order on every rank, so what follows (density limiter, filter) sees
+    exactly the single-GPU sequence.  `spacing` = eg3d_params.split_interval_distance of the scene."""
+    world = dist.get_world_size() if dist is not None else 1
     out, tms = [], []
-    for call in (lambda: matcher.match_polyline_sets(cands1), lambda: matcher.match_polyline_sets(cands2), lambda: matcher.match_refpoints(0, scene.n_tracks)):
-        r = call()
+    if world == 1:
+        for call in (lambda: matcher.match_polyline_sets(cands1), lambda: matcher.match_polyline_sets(cands2), lambda: matcher.match_refpoints(0, scene.n_tracks)):
+            r = call()
+            pts, tm = r if isinstance(r, tuple) else (r, None)
+            out.append(pts); tms.append(tm)
+        return out, tms
+    from . import multigpu as mg
+    rank = dist.get_rank()
+    lo, hi = mg.view_block(scene.n_views, world, rank)
+    for cands in (cands1, cands2):
+        views = mg.polyline_set_seed_views(scene, cands, spacing, E.sample_seeds)
+        keys = np.where((views >= lo) & (views < hi))[0]
+        r = matcher.match_polyline_sets(cands, lo, hi)
         pts, tm = r if isinstance(r, tuple) else (r, None)
-        out.append(pts); tms.append(tm)
+        merged, _ = mg.all_gather_points(pts, dist, device=device, order_keys=keys)
+        out.append(merged); tms.append(tm)
+    tb, te = mg.track_block(scene.n_tracks, world, rank)
+    r = matcher.match_refpoints(tb, te)
+    pts, tm = r if isinstance(r, tuple) else (r, None)
+    merged, _ = mg.all_gather_points(pts, dist, device=device)
+    out.append(merged); tms.append(tm)
     return out, tms
 
 
@@ -65,9 +88,11 @@ def add_points_to_tracks(scene, pts, keep):
     return xyz, obs_off, np.concatenate([scene.track_view, pts.obs_view[idx]]), np.concatenate([scene.track_xy, pts.obs_xy[idx]])
 
 
-def edge_reconstruction(dev, scene, cands1, cands2):
-    """edge_reconstruction_pipeline + filter on a device scene -> dict with every intermediate the reference writes out."""
-    parts, tms = run_pipelines(dev, scene, cands1, cands2)
+def edge_reconstruction(dev, scene, cands1, cands2, dist=None, device=None, spacing=20.0):
+    """edge_reconstruction_pipeline + filter on a device scene -> dict with every intermediate the reference writes out.
+    Multi-GPU (`dist`): the matching is sharded (run_pipelines); the density limiter is order dependent and the filter is
+    cheap, so every rank runs both on the gathered points and ends with the same result."""
+    parts, tms = run_pipelines(dev, scene, cands1, cands2, dist=dist, device=device, spacing=spacing)
     allp = PointSet.concat(parts)
     keep = dev.dedup_close_points(allp)                                   # pipelines.cpp:236
     xyz, obs_off, obs_view, obs_xy = add_points_to_tracks(scene, allp, keep)

@@ -22,29 +22,18 @@ def same(g, r):
                 and np.array_equal(g.obs_poly, r.obs_poly) and np.array_equal(g.obs_seg, r.obs_seg) and g.obs_xy.tobytes() == r.obs_xy.tobytes())
 
 
-class OracleMatcher:
-    """The CPU oracle behind the two method names pipeline.run_pipelines calls."""
-    def __init__(self, osc, threads):
-        self.osc, self.threads = osc, threads
-
-    def match_polyline_sets(self, cands):
-        return self.osc.match_polyline_sets(cands, n_threads=self.threads)
-
-    def match_refpoints(self, tb, te):
-        return self.osc.match_refpoints(tb, te, n_threads=self.threads)
-
-
 def run(golden_dir, threads):
     t = time.time(); sc, plgs = real_scene.dtu006_scene(golden_dir); t_plg = time.time() - t
     cands1, cands2, res = P.candidate_sets(sc)
     res.update(views=sc.n_views, tracks=sc.n_tracks, segments_per_view=[sc.n_segments(v) for v in range(sc.n_views)])
     res["host_s"]["polyline_graphs_25_views"] = t_plg
     prm = E.default_params(**P.REAL_DATA_CAPACITIES)   # real chains reach 140 points (default capacity 96)
-    osc = O.OracleScene(sc, prm)
+    odev = O.OracleDevice(sc, prm, n_threads=threads)
+    osc = odev.osc
     with E.DeviceScene(sc, prm) as dev:
         P.run_pipelines(dev, sc, cands1, cands2)       # warm-up pass
         t = time.time(); r = P.edge_reconstruction(dev, sc, cands1, cands2); wall = time.time() - t
-        t = time.time(); oparts, _ = P.run_pipelines(OracleMatcher(osc, threads), sc, cands1, cands2); t_or = time.time() - t
+        t = time.time(); oparts, _ = P.run_pipelines(odev, sc, cands1, cands2); t_or = time.time() - t
         for k, (g, tm, o) in enumerate(zip(r["parts"], r["timings"], oparts)):
             res["pipeline%d" % (k + 1)] = {"points": g.n_points, "obs": g.n_obs, "device_ms": tm["total_ms"], "seeds": tm["n_seeds"], "identical": same(g, o),
                                            "max_abs_xyz_diff": float(np.abs(g.xyz - o.xyz).max()) if same(g, o) and g.n_points else None}

@@ -183,6 +183,35 @@ class OracleScene:
         return out[:min(n, cap)].tolist()
 
 
+class OracleDevice:
+    """Tests-only stand-in for edgegraph3d_b200.lib.DeviceScene: the same method names and return shapes, answered by the
+    CPU oracle, so that host-side drivers (edgegraph3d_b200/pipeline.py, the multi-rank merge) can be exercised without a GPU
+    and so that a GPU run can be compared with the oracle call for call."""
+
+    def __init__(self, scene, params=None, n_threads=4):
+        self.scene, self.params, self.n_threads = scene, params, n_threads
+        self.osc = OracleScene(scene, params)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.osc.close()
+
+    def match_polyline_sets(self, cands, view_begin=0, view_end=None):
+        return self.osc.match_polyline_sets(cands, view_begin, view_end, n_threads=self.n_threads), {"total_ms": 0.0, "n_seeds": 0}
+
+    def match_refpoints(self, tb=0, te=None):
+        return self.osc.match_refpoints(tb, te, n_threads=self.n_threads), {"total_ms": 0.0, "n_seeds": 0}
+
+    def dedup_close_points(self, pts):
+        return self.osc.dedup_close_points(pts)
+
+    def filter(self, xyz, obs_off, obs_view, obs_xy, first_edgepoint):
+        fx, inl = self.osc.filter(xyz, obs_off, obs_view, obs_xy, first_edgepoint, n_threads=self.n_threads)[:2]
+        return fx, inl, {"gn_ms": 0.0}
+
+
 def sample_seeds(scene, views, polylines, spacing):
     """a3 seed sampler through the oracle (same contract as eg3d_sample_seeds)."""
     d = scene.desc()

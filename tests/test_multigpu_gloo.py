@@ -72,3 +72,58 @@ def test_balanced_view_blocks():
     assert all(b[0] <= b[1] for b in blocks) and all(blocks[i][1] == blocks[i + 1][0] for i in range(3))
     assert mg.view_block(200, 8, 7) == (175, 200) and mg.view_block(6, 2, 0) == (0, 3)
     assert mg.view_round_robin(10, 4, 1) == [1, 5, 9] and sorted(sum((mg.view_round_robin(7, 3, r) for r in range(3)), [])) == list(range(7))
+
+
+def _pipeline_worker(rank, world, port, q):
+    """pipeline.edge_reconstruction with two ranks: view-sharded pipelines 1-2 over SEVERAL candidate sets (merged back into
+    the reference's set-major order by seed-ordinal keys), track-sharded pipeline 3, then the order-dependent density
+    limiter and the filter — every array must equal the single-process run."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import torch.distributed as dist
+    from edgegraph3d_b200 import synthetic as syn, pipeline as P
+    from edgegraph3d_b200.scene import CandidateSets
+    from tests import oracle_lib as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = syn.make_scene(n_views=6, n_curves=12, seed=21, n_tracks=60)
+    c1 = syn.curve_candidate_sets(sc, seed=21)
+    V = sc.n_views
+    # a second family of sets: the first one regrouped two by two (still several sets, other boundaries)
+    groups = [[sorted(set(c1.polyline[c1.off[i * V + v]:c1.off[i * V + v + 1]].tolist()) |
+                      (set(c1.polyline[c1.off[(i + 1) * V + v]:c1.off[(i + 1) * V + v + 1]].tolist()) if i + 1 < c1.n_sets else set()))
+               for v in range(V)] for i in range(0, c1.n_sets, 2)]
+    c2 = CandidateSets.from_lists(groups, V)
+    dev = O.OracleDevice(sc, n_threads=2)
+    single = P.edge_reconstruction(dev, sc, c1, c2)
+    sharded = P.edge_reconstruction(dev, sc, c1, c2, dist=dist)
+    ok = c1.n_sets > 2 and c2.n_sets > 1 and single["points"].n_points > 50
+    a, b = single["points"], sharded["points"]
+    ok = ok and a.n_points == b.n_points and np.array_equal(a.xyz, b.xyz) and np.array_equal(a.obs_off, b.obs_off)
+    ok = ok and np.array_equal(a.obs_view, b.obs_view) and np.array_equal(a.obs_poly, b.obs_poly) and np.array_equal(a.obs_seg, b.obs_seg)
+    ok = ok and np.array_equal(a.obs_xy, b.obs_xy) and np.array_equal(a.chain_pos, b.chain_pos)
+    ok = ok and np.array_equal(single["keep"], sharded["keep"]) and np.array_equal(single["inliers"], sharded["inliers"])
+    ok = ok and np.array_equal(single["filtered_xyz"], sharded["filtered_xyz"])
+    # the plain rank-order concatenation would NOT have been the reference order for the multi-set pipelines
+    lo, hi = (rank * V) // world, ((rank + 1) * V) // world
+    local = dev.match_polyline_sets(c1, lo, hi)[0]
+    from edgegraph3d_b200 import multigpu as mg
+    naive, _ = mg.all_gather_points(local, dist)
+    differs = naive.n_points == single["parts"][0].n_points and not np.array_equal(naive.xyz, single["parts"][0].xyz)
+    q.put((rank, bool(ok), bool(differs), a.n_points))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_pipeline_equals_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res
+    assert all(r[2] for r in res), res      # the keyed merge is doing real work on this input

@@ -11,31 +11,6 @@ from edgegraph3d_b200 import pipeline as P, openmvg_io as io
 from tests import oracle_lib as O
 
 
-class OracleDevice:
-    """tests-only stand-in for lib.DeviceScene: same methods, answered by the oracle."""
-    def __init__(self, scene, params):
-        self.osc = O.OracleScene(scene, params)
-
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *a):
-        self.osc.close()
-
-    def match_polyline_sets(self, cands):
-        return self.osc.match_polyline_sets(cands, n_threads=4), {"total_ms": 0.0, "n_seeds": 0}
-
-    def match_refpoints(self, tb, te):
-        return self.osc.match_refpoints(tb, te, n_threads=4), {"total_ms": 0.0, "n_seeds": 0}
-
-    def dedup_close_points(self, pts):
-        return self.osc.dedup_close_points(pts)
-
-    def filter(self, xyz, obs_off, obs_view, obs_xy, first):
-        fx, inl = self.osc.filter(xyz, obs_off, obs_view, obs_xy, first, n_threads=4)[:2]
-        return fx, inl, {"gn_ms": 0.0}
-
-
 def write_scene(tmp, V=6, W=640, H=480):
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(2)
@@ -83,7 +58,7 @@ def write_scene(tmp, V=6, W=640, H=480):
 
 def test_edge_matching_host_glue(tmp_path):
     doc = write_scene(tmp_path)
-    info = P.edge_matching(str(tmp_path / "sfm_data.json"), str(tmp_path / "edges"), str(tmp_path / "out"), _scene_factory=OracleDevice)
+    info = P.edge_matching(str(tmp_path / "sfm_data.json"), str(tmp_path / "edges"), str(tmp_path / "out"), _scene_factory=O.OracleDevice)
     assert info["candidate_sets_pipeline1"] > 0 and info["candidate_sets_pipeline2"] >= 0
     assert sum(info["points_per_pipeline"]) > 100 and 0 < info["kept_after_density_limiter"] < sum(info["points_per_pipeline"])
     n_sfm = len(doc["structure"])
