@@ -267,4 +267,28 @@ inline std::pair<std::vector<ulong_t>, std::vector<std::vector<std::set<ulong_t>
   return res;
 }
 
+// f2, pipeline 1: polyline_matching_similarity_graph (polyline_matcher.hpp:47).  The reference returns
+// tuple(close_polylines, close_refpoints, matches); only the third element is consumed (pipelines.cpp:77), so that is what
+// this returns: one vector<set<ulong>> per community.  compatibility_graph_file, when given, receives the text the
+// reference writes for Grappolo (byte for byte); the communities themselves come from the library's deterministic Louvain.
+inline std::vector<std::vector<std::set<ulong_t>>> polyline_matching_similarity_graph(const Eg3dScene& scene, std::string* compatibility_graph_file = nullptr) {
+  eg3d_similarity_graph* g = nullptr;
+  check(eg3d_polyline_similarity_graph(&scene.desc(), 10.0f /* FIND_WITHIN_DIST */, &g));
+  eg3d_similarity_graph_view gv; check(eg3d_similarity_graph_get(g, &gv));
+  if (compatibility_graph_file) compatibility_graph_file->assign(gv.dimacs, (size_t)gv.dimacs_len);
+  std::vector<int64_t> com((size_t)gv.n_nodes);
+  check(eg3d_similarity_graph_communities(g, com.data(), nullptr));
+  eg3d_polyline_sets* h = nullptr;
+  check(eg3d_polyline_sets_from_communities(g, com.data(), &h));
+  eg3d_candidates c; check(eg3d_polyline_sets_get(h, &c, nullptr, nullptr));
+  const int V = scene.n_views();
+  std::vector<std::vector<std::set<ulong_t>>> res((size_t)c.n_sets, std::vector<std::set<ulong_t>>((size_t)V));
+  for (int i = 0; i < c.n_sets; i++)
+    for (int v = 0; v < V; v++)
+      for (int64_t k = c.off[(size_t)i * V + v]; k < c.off[(size_t)i * V + v + 1]; k++) res[(size_t)i][(size_t)v].insert(c.polyline[k]);
+  eg3d_polyline_sets_free(h);
+  eg3d_similarity_graph_free(g);
+  return res;
+}
+
 }  // namespace eg3d_shim

@@ -52,6 +52,8 @@ int main() {
     auto kept = filter_3d_points_close_2d_array(scene, pts);
     auto sets = polyline_matching_closeness_to_refpoints;   // f2: needs SfM tracks, this toy scene has none (compile check only)
     (void)sets;
+    auto sets1 = polyline_matching_similarity_graph;    // f2, pipeline 1: likewise
+    (void)sets1;
     std::printf("shim ok: %zu points, %zu after the density limiter\n", pts.size(), kept.size());
     return pts.empty() ? 2 : 0;
   } catch (const std::exception& e) {
