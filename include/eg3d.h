@@ -13,8 +13,12 @@
  * library-owned outputs released with the matching *_free / *_destroy, int
  * status codes, no exceptions across the boundary.  A scene handle is bound to
  * the CUDA device that was current when it was created.  Thread-compatible,
- * not thread-safe.  All entry points fail with EG3D_ERR_NO_DEVICE when no CUDA
- * device is usable: there is no CPU fallback in this library.
+ * not thread-safe.  Every entry point of the hot path (scene creation, matching,
+ * Gauss-Newton, filtering) fails with EG3D_ERR_NO_DEVICE when no CUDA device is
+ * usable: there is no CPU fallback in this library.  The entry points marked
+ * "host" (seed sampler, camera fundamentals, and the stages upstream of the path:
+ * polyline graphs from edge images, candidate polyline sets) are order-dependent
+ * host code in the reference's design too and need no device.
  */
 #ifndef EG3D_H_
 #define EG3D_H_
