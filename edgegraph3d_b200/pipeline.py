@@ -20,7 +20,7 @@ import numpy as np
 from . import lib as E
 from . import openmvg_io as io
 from . import real_scene
-from .scene import PointSet
+from .scene import PointSet, ranges
 
 # chains on real polyline graphs are longer than on the synthetic rigs the defaults are sized for
 REAL_DATA_CAPACITIES = dict(max_chain_points=256, max_follow_points=320)
@@ -84,7 +84,7 @@ def add_points_to_tracks(scene, pts, keep):
     xyz = np.concatenate([scene.track_xyz, pts.xyz[kept]])
     lens = pts.obs_off[kept + 1] - pts.obs_off[kept]
     obs_off = np.concatenate([scene.track_off, int(scene.track_off[-1]) + np.cumsum(lens)]).astype(np.int64)
-    idx = np.concatenate([np.arange(pts.obs_off[i], pts.obs_off[i + 1]) for i in kept]) if len(kept) else np.zeros(0, np.int64)
+    idx = ranges(pts.obs_off[kept], lens)
     return xyz, obs_off, np.concatenate([scene.track_view, pts.obs_view[idx]]), np.concatenate([scene.track_xy, pts.obs_xy[idx]])
 
 

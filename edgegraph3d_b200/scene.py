@@ -164,6 +164,16 @@ class CandidateSets:
         return c
 
 
+def ranges(starts, lens):
+    """Concatenation of arange(starts[i], starts[i] + lens[i]) without a Python loop."""
+    starts, lens = np.asarray(starts, np.int64), np.asarray(lens, np.int64)
+    total = int(lens.sum())
+    if total == 0:
+        return np.zeros(0, np.int64)
+    first = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    return np.repeat(starts - first, lens) + np.arange(total, dtype=np.int64)
+
+
 @dataclass
 class PointSet:
     """Flattened `vector<new_3dpoint_plgp_matches>` (polyline_graph_2d.hpp:451)."""
@@ -229,7 +239,7 @@ class PointSet:
         idx = np.asarray(idx, np.int64)
         lens = (self.obs_off[idx + 1] - self.obs_off[idx]).astype(np.int64)
         off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-        o = np.concatenate([np.arange(self.obs_off[i], self.obs_off[i + 1]) for i in idx]).astype(np.int64) if len(idx) else np.zeros(0, np.int64)
+        o = ranges(self.obs_off[idx], lens)
         return PointSet(self.xyz[idx], self.seed[idx], self.chain_pos[idx], off, self.obs_view[o], self.obs_poly[o], self.obs_seg[o], self.obs_xy[o])
 
     @staticmethod
