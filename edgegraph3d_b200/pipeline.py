@@ -118,8 +118,20 @@ def edge_matching(sfm_json, edges_folder, out_folder, params=None, _scene_factor
     scene, _ = real_scene.scene_from_parts(sfm, imgs)
     cands1, cands2, info = candidate_sets(scene)
     prm = params if params is not None else E.default_params(**REAL_DATA_CAPACITIES)
-    with (_scene_factory or E.DeviceScene)(scene, prm) as dev:      # _scene_factory: test hook (the CPU oracle behind the same methods)
-        r = edge_reconstruction(dev, scene, cands1, cands2)
+    for attempt in range(4):
+        try:
+            with (_scene_factory or E.DeviceScene)(scene, prm) as dev:      # _scene_factory: test hook (the CPU oracle behind the same methods)
+                r = edge_reconstruction(dev, scene, cands1, cands2)
+            break
+        except E.Eg3dError as e:
+            # a per-seed capacity was too small for this input (the library reports it, it never truncates): double both and
+            # run again on a fresh scene handle
+            from . import _abi as A
+            if e.status != A.EG3D_ERR_CAPACITY or attempt == 3:
+                raise
+            prm.max_chain_points *= 2
+            prm.max_follow_points *= 2
+    info["max_chain_points"], info["max_follow_points"] = int(prm.max_chain_points), int(prm.max_follow_points)
     os.makedirs(out_folder, exist_ok=True)
     n_before = io.save_sfm_data(os.path.join(out_folder, "before_filtering.json"), doc, r["xyz"], r["obs_off"], r["obs_view"], r["obs_xy"], view_keys=sfm["view_keys"])
     n_after = io.save_sfm_data(os.path.join(out_folder, "output.json"), doc, r["filtered_xyz"], r["obs_off"], r["obs_view"], r["obs_xy"], inliers=r["inliers"],

@@ -77,3 +77,29 @@ def test_edge_matching_host_glue(tmp_path):
         assert len(v) >= 3 and len(set(v.tolist())) == len(v)
         h = P12[v] @ np.append(before["track_xyz"][i].astype(np.float64), 1)
         assert (((h[:, :2] / h[:, 2:3]) - before["track_xy"][o]) ** 2).sum(1).mean() < 18.0    # em_GaussNewton accepts mse/(2n) < 9 per coordinate (triangulation.cpp:150-168)
+
+
+def test_edge_matching_grows_capacities_on_demand(tmp_path):
+    """EG3D_ERR_CAPACITY from the library (a chain longer than max_chain_points) makes the driver double the capacities and
+    run again; any other error is passed on."""
+    from edgegraph3d_b200 import lib as E, _abi as A
+    write_scene(tmp_path)
+    seen = []
+
+    class Stingy(O.OracleDevice):
+        def match_polyline_sets(self, cands, view_begin=0, view_end=None):
+            seen.append(int(self.params.max_chain_points))
+            if self.params.max_chain_points < 1000:
+                raise E.Eg3dError(A.EG3D_ERR_CAPACITY, "a per-seed capacity was exceeded")
+            return super().match_polyline_sets(cands, view_begin, view_end)
+
+    info = P.edge_matching(str(tmp_path / "sfm_data.json"), str(tmp_path / "edges"), str(tmp_path / "out"), _scene_factory=Stingy)
+    assert seen[:3] == [256, 512, 1024] and info["max_chain_points"] == 1024 and info["max_follow_points"] == 1280
+
+    class Broken(O.OracleDevice):
+        def match_polyline_sets(self, cands, view_begin=0, view_end=None):
+            raise E.Eg3dError(A.EG3D_ERR_CUDA, "boom")
+
+    with pytest.raises(E.Eg3dError) as ei:
+        P.edge_matching(str(tmp_path / "sfm_data.json"), str(tmp_path / "edges"), str(tmp_path / "out2"), _scene_factory=Broken)
+    assert ei.value.status == A.EG3D_ERR_CUDA
