@@ -1,0 +1,154 @@
+"""Row a6 (pipeline-3 seeding: PLGEdgeManager::detect_nearby_intersections_and_correspondences_plgp,
+src/edgegraph3d/edge_managers/plg_edge_manager.cpp:191-300) — a second reading composed of the numpy re-derivations of
+the primitives (30 px grid, point-to-polyline distance, segment/line intersection, double-intermediate distance) and REAL
+cv2.computeCorrespondEpilines calls for the epipolar lines, against the oracle's seeds and per-view hit lists
+(eg3d_oracle_refpoint_hits), bit for bit.  The GPU path is compared with the same oracle lists in test_gpu_parity.py.  CPU only."""
+import os
+import numpy as np
+import pytest
+from edgegraph3d_b200 import synthetic as syn, real_scene
+from tests import oracle_lib as O
+from tests.test_oracle_primitives import (f32, ref_build_grid, ref_grid_query, ref_compute_distancesq, ref_intersect_segment_line,
+                                          ref_squared_2d_distance)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def ref_refpoint_hits(sc, tb, te, start_dist=10.0, mult=3.0):
+    """-> list over seeds of [V lists of (polyline, segment, x, y)] in the order plg_matching_from_refpoint consumes them
+    (plg_matching_from_refpoints.cpp:64-81 -> plgpcm_3views_plg_following.cpp:40-50 scatters to a V-vector)."""
+    cv2 = pytest.importorskip("cv2")
+    V = sc.n_views
+    cell = start_dist * mult                                              # plg_edge_manager.cpp:73-74: 30 px grid
+    grids = {}
+    start_dsq, corr_dsq = f32(f32(start_dist) * f32(start_dist)), f32(f32(cell) * f32(cell))
+    F = sc.fundamental.reshape(V, V, 3, 3)
+    out = []
+    for t in range(tb, te):
+        o0, o1 = int(sc.track_off[t]), int(sc.track_off[t + 1])
+        cams = [int(c) for c in sc.track_view[o0:o1]]
+        obs = [sc.track_xy[k] for k in range(o0, o1)]
+
+        def coords_on(cam):                                               # get_2d_coordinates_of_point_on_image: the last match
+            return obs[max(i for i, c in enumerate(cams) if c == cam)]
+        pcps, snis = [], []
+        for cam in cams:                                                  # :272-288
+            if cam not in grids:
+                grids[cam] = ref_build_grid(sc, cam, cell, sc.width, sc.height)
+            grid, gw, gh = grids[cam]
+            p = coords_on(cam)
+            cur_pcps, cur_sni = [], []
+            for pl in ref_grid_query(grid, gw, gh, cell, sc.width, sc.height, p):
+                d, seg, proj = ref_compute_distancesq(sc.polyline(cam, pl), p)
+                if d <= start_dsq:
+                    cur_pcps.append(pl)
+                    cur_sni.append((pl, seg, proj))
+                elif d <= corr_dsq:
+                    cur_pcps.append(pl)
+            pcps.append(cur_pcps)
+            snis.append(cur_sni)
+        for i, start in enumerate(cams):                                  # :290-297
+            init = coords_on(start)
+            for (pl, seg, proj) in snis[i]:                               # :246-259
+                radius = f32(np.sqrt(ref_squared_2d_distance(init, proj)) * f32(mult))
+                rsq = f32(radius * radius)
+                rows = [[] for _ in range(V)]
+                for j, cur in enumerate(cams):                            # :208-243
+                    if cur == start:
+                        rows[cur] = [(pl, seg, f32(proj[0]), f32(proj[1]))]   # a later duplicate of the same camera overwrites (scatter)
+                        continue
+                    if not sc.fundamental_valid[start, cur]:
+                        rows[cur] = []
+                        continue
+                    line = cv2.computeCorrespondEpilines(np.array([[proj]], np.float32), 1, F[start, cur]).reshape(3)
+                    hits = []
+                    for cpl in pcps[j]:                                   # :191-205
+                        pc = sc.polyline(cur, cpl)
+                        for k in range(1, len(pc)):
+                            found, q = ref_intersect_segment_line((pc[k][0], pc[k][1], pc[k - 1][0], pc[k - 1][1]), line)
+                            if found and ref_squared_2d_distance(obs[j], q) <= rsq:
+                                hits.append((cpl, k - 1, q[0], q[1]))
+                    rows[cur] = hits
+                out.append(rows)
+    return out
+
+
+def assert_same(sc, tb, te):
+    off, hits, V = O.OracleScene(sc).refpoint_hits(tb, te)
+    want = ref_refpoint_hits(sc, tb, te)
+    assert len(off) == len(want) * V + 1
+    n_hits = 0
+    for s, rows in enumerate(want):
+        for v in range(V):
+            got = hits[off[s * V + v]:off[s * V + v + 1]]
+            assert len(got) == len(rows[v]), (s, v)
+            for g, w in zip(got, rows[v]):
+                assert (int(g["polyline"]), int(g["segment"])) == (int(w[0]), int(w[1])), (s, v)
+                assert np.float32(g["x"]).tobytes() == np.float32(w[2]).tobytes() and np.float32(g["y"]).tobytes() == np.float32(w[3]).tobytes(), (s, v)
+            n_hits += len(got)
+    return len(want), n_hits
+
+
+def test_refpoint_seeding_second_reading_synthetic():
+    sc = syn.make_scene(n_views=5, n_curves=14, seed=8, closed_frac=0.15, n_tracks=80)
+    n_seeds, n_hits = assert_same(sc, 0, sc.n_tracks)
+    assert n_seeds > 50 and n_hits > 200
+
+
+def test_refpoint_seeding_second_reading_real_dtu006():
+    """Real polyline graphs, real tracks, LMedS fundamental matrices (some pairs invalid): the first 60 SfM points."""
+    sc, _ = real_scene.dtu006_scene(os.path.join(HERE, "golden"))
+    n_seeds, n_hits = assert_same(sc, 0, 60)
+    assert n_seeds > 100 and n_hits > 300
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Row a5: find_epipolar_correspondences (src/edgegraph3d/matching/plg_matching/polyline_matching.cpp:45-73)
+# ------------------------------------------------------------------------------------------------------------------
+def ref_epipolar_correspondences(sc, seeds, cands=None):
+    """Per seed, V lists of (polyline, segment, x, y): every other view with a valid F, the candidate polylines of that view
+    (or all of them in the sweep form) in ascending id, polyline::intersect_line segment by segment (polyline_graph_2d.cpp:312-327)."""
+    cv2 = pytest.importorskip("cv2")
+    V = sc.n_views
+    F = sc.fundamental.reshape(V, V, 3, 3)
+    out = []
+    for s in range(len(seeds)):
+        start = int(seeds.view[s])
+        rows = [[] for _ in range(V)]
+        for cur in range(V):
+            if cur == start:                                              # :54-55: the starting view holds the seed itself
+                rows[cur] = [(int(seeds.polyline[s]), int(seeds.segment[s]), seeds.xy[s][0], seeds.xy[s][1])]
+                continue
+            if not sc.fundamental_valid[start, cur]:
+                continue
+            line = cv2.computeCorrespondEpilines(seeds.xy[s].reshape(1, 1, 2), 1, F[start, cur]).reshape(3)
+            if cands is None:
+                pls = range(sc.n_polylines(cur))
+            else:
+                k = int(seeds.cand_set[s]) * V + cur
+                pls = cands.polyline[cands.off[k]:cands.off[k + 1]].tolist()
+            for pl in pls:
+                pc = sc.polyline(cur, pl)
+                for k in range(1, len(pc)):
+                    found, q = ref_intersect_segment_line((pc[k][0], pc[k][1], pc[k - 1][0], pc[k - 1][1]), line)
+                    if found:
+                        rows[cur].append((pl, k - 1, q[0], q[1]))
+        out.append(rows)
+    return out
+
+
+@pytest.mark.parametrize("mode", ["sweep", "candidates"])
+def test_epipolar_correspondences_second_reading(mode):
+    sc = syn.make_scene(n_views=5, n_curves=12, seed=5, closed_frac=0.2, drop_view_frac=0.1)
+    cands = syn.curve_candidate_sets(sc, seed=5) if mode == "candidates" else None
+    seeds = syn.sample_seeds(O.sample_seeds, sc, per_view=6, cand_set=0 if cands is not None else None)
+    off, hits, V = O.OracleScene(sc).epipolar_intersect(seeds, cands)
+    want = ref_epipolar_correspondences(sc, seeds, cands)
+    total = 0
+    for s, rows in enumerate(want):
+        for v in range(V):
+            got = hits[off[s * V + v]:off[s * V + v + 1]]
+            assert [(int(g["polyline"]), int(g["segment"])) for g in got] == [(int(w[0]), int(w[1])) for w in rows[v]], (s, v)
+            assert np.array([[g["x"], g["y"]] for g in got], np.float32).tobytes() == np.array([[w[2], w[3]] for w in rows[v]], np.float32).tobytes()
+            total += len(got)
+    assert total > 50
