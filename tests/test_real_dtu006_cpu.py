@@ -55,3 +55,35 @@ def test_real_dtu006_oracle_results_satisfy_the_references_invariants():
     for pts in (p2, p3):
         med = check_invariants(sc, pts)
         assert med < 2.0           # typical accepted point: about a pixel
+
+
+def test_filter_view_count_rule_second_reading():
+    """compute_ray_stats + compute_inliers (src/edgegraph3d/filtering/outliers_filtering.cpp:14-64) written out again in numpy on top of
+    the per-point Gauss-Newton verdicts (those are pinned bit for bit against cv2 in test_oracle_golden.py): the median
+    track length is read off a histogram with the `>= count/2` integer rule, and edge points need more than
+    max(3, median/2 - 1) observations.  Input: the real dtu006 tracks + the oracle's pipeline-2 points after the density limiter."""
+    sc, _ = real_scene.dtu006_scene(os.path.join(HERE, "golden"))
+    c2, _ = E.polyline_sets_from_refpoints(sc)
+    dev = O.OracleDevice(sc, E.default_params(**P.REAL_DATA_CAPACITIES), n_threads=8)
+    pts = dev.match_polyline_sets(c2)[0]
+    keep = dev.dedup_close_points(pts)
+    xyz, obs_off, obs_view, obs_xy = P.add_points_to_tracks(sc, pts, keep)
+    first = sc.n_tracks
+    for forced in (-1, 5):
+        _, inl = dev.osc.filter(xyz, obs_off, obs_view, obs_xy, first, forced_min_filter=forced, n_threads=8)
+        _, _, gn_ok = dev.osc.gn_triangulate(obs_off, obs_view, obs_xy, xyz, fp64=0, n_threads=8)      # GaussNewton of the filter, per point
+        lens = np.diff(obs_off)
+        hist = np.bincount(lens[gn_ok == 1] - 1, minlength=sc.n_views)                                   # point_rays_amount_distribution
+        count = int((gn_ok == 1).sum())
+        acc, median = 0, 0
+        for median in range(sc.n_views):
+            acc += int(hist[median])
+            if acc >= count // 2:
+                break
+        intended = 3 if 3 >= median // 2 - 1 else median // 2 - 1
+        if forced > -1:
+            intended = forced
+        want = gn_ok.astype(bool).copy()
+        want[first:] &= lens[first:] > intended
+        assert np.array_equal(inl.astype(bool), want)
+        assert 0 < want[first:].sum() < (gn_ok[first:] == 1).sum() or forced == -1
