@@ -152,3 +152,32 @@ def test_epipolar_correspondences_second_reading(mode):
             assert np.array([[g["x"], g["y"]] for g in got], np.float32).tobytes() == np.array([[w[2], w[3]] for w in rows[v]], np.float32).tobytes()
             total += len(got)
     assert total > 50
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Row a8: the view triple of compute_3D_point_multiple_views_plg_following_expandallviews_vector (triangulation.cpp:1035-1066)
+# ------------------------------------------------------------------------------------------------------------------
+def test_view_triple_selection_is_visible_in_the_output():
+    """The three views a hypothesis is built from are (first view with hits, the starting view — or, if that is the first or
+    the last one, the middle non-empty view —, last view with hits).  Every chain point that came out of the 3-view stage
+    lists them first, in that order (view expansion only appends); points appended later by all-view following
+    (follow_direction_vector_start/end) carry whichever views could be followed.  Checked on the oracle's output from hit
+    lists computed independently: every accepted seed's chain holds at least two such points, and they are the large majority."""
+    sc = syn.make_scene(n_views=7, n_curves=14, seed=9, closed_frac=0.1, drop_view_frac=0.15)
+    seeds = syn.sample_seeds(O.sample_seeds, sc, per_view=40)
+    osc = O.OracleScene(sc)
+    off, hits, V = osc.epipolar_intersect(seeds)
+    pts = osc.match_seeds(seeds)
+    assert pts.n_points > 100
+    with_triple = {}
+    for i in range(pts.n_points):
+        s = int(pts.seed[i])
+        nonempty = [v for v in range(V) if off[s * V + v + 1] > off[s * V + v]]     # the starting view holds the seed itself
+        assert len(nonempty) >= 3
+        start = int(seeds.view[s])
+        want = [nonempty[0], nonempty[len(nonempty) // 2] if start in (nonempty[0], nonempty[-1]) else start, nonempty[-1]]
+        views = pts.obs_view[pts.obs_off[i]:pts.obs_off[i + 1]].tolist()
+        with_triple[s] = with_triple.get(s, 0) + (views[:3] == want)
+    # compatible_new_plg_point needs >= 2 points in a direction (plg_matching.cpp:1276-1287), all of them 3-view points
+    assert all(n >= 2 for n in with_triple.values()), with_triple
+    assert sum(with_triple.values()) > 0.8 * pts.n_points        # points appended by later all-view following are the exception
