@@ -1,8 +1,12 @@
-"""Row a6 (pipeline-3 seeding: PLGEdgeManager::detect_nearby_intersections_and_correspondences_plgp,
-src/edgegraph3d/edge_managers/plg_edge_manager.cpp:191-300) — a second reading composed of the numpy re-derivations of
-the primitives (30 px grid, point-to-polyline distance, segment/line intersection, double-intermediate distance) and REAL
-cv2.computeCorrespondEpilines calls for the epipolar lines, against the oracle's seeds and per-view hit lists
-(eg3d_oracle_refpoint_hits), bit for bit.  The GPU path is compared with the same oracle lists in test_gpu_parity.py.  CPU only."""
+"""Second readings one level above the primitives, CPU only.
+
+Row a6 (pipeline-3 seeding: PLGEdgeManager::detect_nearby_intersections_and_correspondences_plgp,
+src/edgegraph3d/edge_managers/plg_edge_manager.cpp:191-300) and row a5 (find_epipolar_correspondences,
+polyline_matching.cpp:45-73): the numpy re-derivations of the primitives (grids, point-to-polyline distance, segment/line
+intersection, double-intermediate distance) composed with REAL cv2.computeCorrespondEpilines calls, against the oracle's
+seeds and per-view hit lists, bit for bit.  Rows a8 / a10: rules that the reference text fixes and that are visible in the
+output (the view triple a hypothesis is built from; 10 px steps on the driving view), checked on the oracle's result from
+independently computed inputs.  The GPU path is compared with the same oracle in test_gpu_parity.py."""
 import os
 import numpy as np
 import pytest
@@ -181,3 +185,24 @@ def test_view_triple_selection_is_visible_in_the_output():
     # compatible_new_plg_point needs >= 2 points in a direction (plg_matching.cpp:1276-1287), all of them 3-view points
     assert all(n >= 2 for n in with_triple.values()), with_triple
     assert sum(with_triple.values()) > 0.8 * pts.n_points        # points appended by later all-view following are the exception
+
+
+def test_following_steps_ten_pixels_on_the_driving_view():
+    """PLG following advances 10 px (Euclidean, FOLLOW_FIRST_IMAGE_DISTANCE, plg_matching.hpp:39) along the polyline of the
+    first selected view and finds the other views by epipolar intersection (plg_matching.cpp:51-132): consecutive chain points
+    of the 3-view stage are therefore 10 px apart on that view (linear interpolation on the crossing segment), on one polyline."""
+    sc = syn.make_scene(n_views=7, n_curves=14, seed=9, closed_frac=0.1, drop_view_frac=0.15)
+    seeds = syn.sample_seeds(O.sample_seeds, sc, per_view=40)
+    pts = O.OracleScene(sc).match_seeds(seeds)
+    d, same_pl = [], []
+    for i in range(pts.n_points - 1):
+        a, b = int(pts.obs_off[i]), int(pts.obs_off[i + 1])
+        if pts.seed[i] != pts.seed[i + 1] or pts.obs_view[a:a + 3].tolist() != pts.obs_view[b:b + 3].tolist():
+            continue
+        d.append(float(np.linalg.norm(pts.obs_xy[a].astype(np.float64) - pts.obs_xy[b].astype(np.float64))))
+        same_pl.append(pts.obs_poly[a] == pts.obs_poly[b])
+    d = np.array(d)
+    assert len(d) > 500
+    ok = np.abs(d - 10.0) < 0.05
+    assert ok.mean() > 0.97, ok.mean()               # the rest: joints between the 3-view stage and later all-view following
+    assert np.mean(same_pl) > 0.99
