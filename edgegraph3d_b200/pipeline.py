@@ -46,7 +46,7 @@ def candidate_sets(scene):
 
 def run_pipelines(matcher, scene, cands1, cands2, dist=None, device=None, spacing=20.0):
     """Pipelines 1-3 in the reference's order (pipelines.cpp:217-229).  `matcher` is a lib.DeviceScene (or any object with the
-    same match_polyline_sets / match_refpoints methods, e.g. the test oracle).  -> ([points1, points2, points3], [timing...])
+    same match_polyline_sets / match_refpoints methods; the tests pass a stand-in to exercise this glue without a GPU).  -> ([points1, points2, points3], [timing...])
 
     With `dist` (an initialised torch.distributed, world size N > 1) every rank computes its shard — starting views
     [lo, hi) for pipelines 1-2, SfM points [tb, te) for pipeline 3 — and ONE all-gather per pipeline puts the accepted
@@ -120,7 +120,7 @@ def edge_matching(sfm_json, edges_folder, out_folder, params=None, _scene_factor
     prm = params if params is not None else E.default_params(**REAL_DATA_CAPACITIES)
     for attempt in range(4):
         try:
-            with (_scene_factory or E.DeviceScene)(scene, prm) as dev:      # _scene_factory: test hook (the CPU oracle behind the same methods)
+            with (_scene_factory or E.DeviceScene)(scene, prm) as dev:      # _scene_factory: injection point for the tests only; the product always runs E.DeviceScene (no CPU path here)
                 r = edge_reconstruction(dev, scene, cands1, cands2)
             break
         except E.Eg3dError as e:
