@@ -233,3 +233,39 @@ def test_view_expansion_appends_views_in_ascending_order():
         owner = np.repeat(np.arange(pts.n_points), lens)[rest]
         # (repeats exist only as the duplicated observations described in tests/test_real_dtu006_cpu.py)
         assert (v[rest][:, None] == first3[owner]).any(1).sum() <= 0.002 * pts.n_obs
+
+
+def test_three_view_points_are_epipolar_consistent():
+    """`compatible` (plg_matching.cpp:51-132) builds every followed point from a 10 px step on the driving view a and the
+    intersections of a's epipolar lines (F[a][b], F[a][c]) with the polylines of b and c; the central hypothesis is built
+    from the hits of the SEED's epipolar lines (polyline_matching.cpp:45-73).  So every 3-view-stage point of the output lies,
+    in views b and c, on the real cv2 epipolar line of its own observation in a — or, for the central point, of the seed."""
+    cv2 = pytest.importorskip("cv2")
+    sc = syn.make_scene(n_views=7, n_curves=14, seed=9, closed_frac=0.1, drop_view_frac=0.15)
+    seeds = syn.sample_seeds(O.sample_seeds, sc, per_view=40)
+    osc = O.OracleScene(sc)
+    off, hits, V = osc.epipolar_intersect(seeds)
+    pts = osc.match_seeds(seeds)
+    F = sc.fundamental.reshape(V, V, 3, 3)
+
+    def dist(x, src, a, b):            # distance of x (view b) to the epipolar line of src (view a); the line is normalised
+        l = cv2.computeCorrespondEpilines(src.reshape(1, 1, 2), 1, F[a, b]).reshape(3).astype(np.float64)
+        return abs(l[0] * float(x[0]) + l[1] * float(x[1]) + l[2])
+
+    followed = central = 0
+    for i in range(pts.n_points):
+        s, o = int(pts.seed[i]), int(pts.obs_off[i])
+        nonempty = [v for v in range(V) if off[s * V + v + 1] > off[s * V + v]]
+        start = int(seeds.view[s])
+        a, b, c = nonempty[0], nonempty[len(nonempty) // 2] if start in (nonempty[0], nonempty[-1]) else start, nonempty[-1]
+        if pts.obs_view[o:o + 3].tolist() != [a, b, c]:
+            continue                                           # appended later by all-view following
+        xa, xb, xc = pts.obs_xy[o], pts.obs_xy[o + 1], pts.obs_xy[o + 2]
+        if max(dist(xb, xa, a, b), dist(xc, xa, a, c)) < 0.01:
+            followed += 1
+            continue
+        sx = seeds.xy[s]
+        d = max(np.abs(x - sx).max() if vw == start else dist(x, sx, start, vw) for vw, x in ((a, xa), (b, xb), (c, xc)))
+        assert d < 0.01, (i, s, d)
+        central += 1
+    assert followed > 500 and central > 10
