@@ -291,4 +291,36 @@ inline std::vector<std::vector<std::set<ulong_t>>> polyline_matching_similarity_
   return res;
 }
 
+// add_3dpoints_to_sfmd (src/edgegraph3d/io/output/output_utilities.cpp:96-111)
+inline void add_3dpoints_to_sfmd(SfMData& sfmd, const std::vector<new_3dpoint_plgp_matches>& p3ds) {
+  if ((int)sfmd.pointsVisibleFromCamN_.size() < sfmd.numCameras_) sfmd.pointsVisibleFromCamN_.resize((size_t)sfmd.numCameras_);
+  for (const auto& p : p3ds) {
+    const int id = (int)sfmd.points_.size();
+    sfmd.points_.push_back(std::get<0>(p));
+    for (int cam : std::get<2>(p)) sfmd.pointsVisibleFromCamN_[(size_t)cam].push_back(id);
+    std::vector<vec2> coords;
+    for (const auto& q : std::get<1>(p)) coords.push_back(q.plp.coords);
+    sfmd.point2DoncamViewingPoint_.push_back(coords);
+    sfmd.camViewingPointN_.push_back(std::get<2>(p));
+  }
+  sfmd.numPoints_ = (int)sfmd.points_.size();
+}
+
+// edge_reconstruction_pipeline (src/edgegraph3d/matching/plg_matching/pipelines.cpp:201-246) without its image / timing /
+// serialisation arguments: pipelines 1-3 in the reference's order, the density limiter, add_3dpoints_to_sfmd.
+// `scene` must have been built from the same sfmd and plgs.  Returns first_edgepoint (the number of SfM points before the
+// edge points were appended), the argument filter() takes next (edge_matcher.cpp:118-132).
+inline int edge_reconstruction_pipeline(Eg3dScene& scene, SfMData& sfmd) {
+  const int first_edgepoint = (int)sfmd.points_.size();
+  std::vector<new_3dpoint_plgp_matches> p3ds =
+      find_new_3d_points_from_compatible_polylines_expandallviews_parallel(scene, polyline_matching_similarity_graph(scene));
+  const auto pmctr = polyline_matching_closeness_to_refpoints(scene);
+  const auto p2 = find_new_3d_points_from_compatible_polylines_expandallviews_parallel(scene, pmctr.second);
+  p3ds.insert(p3ds.end(), p2.begin(), p2.end());
+  const auto p3 = plg_matching_from_refpoints_parallel(scene);
+  p3ds.insert(p3ds.end(), p3.begin(), p3.end());
+  add_3dpoints_to_sfmd(sfmd, filter_3d_points_close_2d_array(scene, p3ds));
+  return first_edgepoint;
+}
+
 }  // namespace eg3d_shim

@@ -54,6 +54,8 @@ int main() {
     (void)sets;
     auto sets1 = polyline_matching_similarity_graph;    // f2, pipeline 1: likewise
     (void)sets1;
+    auto whole = edge_reconstruction_pipeline;          // pipelines.cpp:201-246 under its own name (needs tracks: compile check only)
+    (void)whole;
     std::printf("shim ok: %zu points, %zu after the density limiter\n", pts.size(), kept.size());
     return pts.empty() ? 2 : 0;
   } catch (const std::exception& e) {
