@@ -269,3 +269,34 @@ def test_three_view_points_are_epipolar_consistent():
         assert d < 0.01, (i, s, d)
         central += 1
     assert followed > 500 and central > 10
+
+
+def test_all_view_followed_points_are_epipolar_consistent_with_their_driving_view():
+    """The all-view `compatible` (plg_matching.cpp:633-759) steps 10 px on ONE of the point's views (the new list starts with
+    it) and finds every other view by intersecting that observation's epipolar line, so a point appended to a chain by
+    all-view following has its next observations on the real cv2 epipolar lines of its FIRST observation (views that view
+    expansion appends afterwards need not be)."""
+    cv2 = pytest.importorskip("cv2")
+    sc = syn.make_scene(n_views=7, n_curves=14, seed=9, closed_frac=0.1, drop_view_frac=0.15)
+    seeds = syn.sample_seeds(O.sample_seeds, sc, per_view=40)
+    osc = O.OracleScene(sc)
+    off, hits, V = osc.epipolar_intersect(seeds)
+    pts = osc.match_seeds(seeds)
+    F = sc.fundamental.reshape(V, V, 3, 3)
+    n = full = 0
+    for i in range(pts.n_points):
+        s, o, e = int(pts.seed[i]), int(pts.obs_off[i]), int(pts.obs_off[i + 1])
+        nonempty = [v for v in range(V) if off[s * V + v + 1] > off[s * V + v]]
+        start = int(seeds.view[s])
+        triple = [nonempty[0], nonempty[len(nonempty) // 2] if start in (nonempty[0], nonempty[-1]) else start, nonempty[-1]]
+        views = pts.obs_view[o:e].tolist()
+        if views[:3] == triple:
+            continue                                                  # 3-view stage: covered above
+        ok = []
+        for k in range(1, len(views)):
+            l = cv2.computeCorrespondEpilines(pts.obs_xy[o].reshape(1, 1, 2), 1, F[views[0], views[k]]).reshape(3).astype(np.float64)
+            ok.append(abs(l[0] * float(pts.obs_xy[o + k][0]) + l[1] * float(pts.obs_xy[o + k][1]) + l[2]) < 0.01)
+        assert ok[0] and ok[1], (i, views, ok)                        # a followed point needs >= 3 views: the first two others came from following
+        n += 1
+        full += all(ok)
+    assert n > 100 and full > 0.8 * n
