@@ -1,10 +1,15 @@
 """Oracle vs the cv2-generated known-answer vectors (tests/golden/make_golden_cv2.py): pins the oracle at the
 OpenCV boundary — the only third-party arithmetic on the hot path."""
 import ctypes as C
+import os
 import numpy as np
+import pytest
 from edgegraph3d_b200 import _abi as A
 from edgegraph3d_b200.scene import FlatScene
 from tests import oracle_lib as O
+
+
+HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _scene_with_cameras(cams):
@@ -61,3 +66,34 @@ def test_gn32_matches_cv2_rebuild(golden):
     sel = golden["gn32_ok"] == 1
     assert np.array_equal(xyz[sel], golden["gn32_X"][sel].astype(np.float32))
     assert np.array_equal(mse, golden["gn32_mse"].astype(np.float32))
+
+
+def test_degenerate_dlt_is_a_point_on_the_ray_not_a_defined_value():
+    """Why eg3d_params.dlt_wellposed exists.  get_min_max's "last index" quirk (edge_graph_3d_utilities.hpp:86-88) can hand
+    cv::triangulatePoints the SAME camera and the SAME observation twice (triangulation.cpp:290).  The DLT system then has
+    rank 2: its null space is the whole back-projected ray, and the vector an SVD returns from it depends on the SVD
+    implementation (and on how the library builds the system).  Real cv2 and the oracle's Jacobi SVD both return a point that
+    reprojects onto the observation — but at unrelated depths, in front of or behind the camera."""
+    cv2 = pytest.importorskip("cv2")
+    L = O.lib()
+    z = np.load(os.path.join(HERE, "golden", "dtu006_sfm.npz"))
+    P = z["cameras"].reshape(-1, 3, 4).astype(np.float32)
+    rng = np.random.default_rng(0)
+    out = np.zeros(4, np.float32)
+    depth_ratio = []
+    for _ in range(40):
+        v = int(rng.integers(0, len(P)))
+        x = rng.uniform([200, 200], [1400, 1000]).astype(np.float32)
+        Pv = np.ascontiguousarray(P[v])
+        X = cv2.triangulatePoints(Pv, Pv, x.reshape(2, 1), x.reshape(2, 1)).reshape(4).astype(np.float64)
+        L.eg3d_oracle_triangulate_dlt(A.ptr(Pv.reshape(-1), A.c_f32p), A.ptr(Pv.reshape(-1), A.c_f32p), A.ptr(x, A.c_f32p), A.ptr(x, A.c_f32p),
+                                      A.ptr(out, A.c_f32p))
+        d = []
+        for Y in (X, out.astype(np.float64)):
+            h = Pv.astype(np.float64) @ Y
+            assert np.abs(h[:2] / h[2] - x).max() < 0.5          # on the ray of the observation ...
+            d.append(h[2] / Y[3])
+        depth_ratio.append(d[0] / d[1])
+    r = np.abs(np.array(depth_ratio))
+    assert (r > 3).sum() + (r < 1 / 3).sum() > 20               # ... at depths that have nothing to do with each other
+    assert (np.array(depth_ratio) < 0).any()                     # sometimes on opposite sides of the camera
