@@ -164,3 +164,19 @@ def test_cabi_argument_errors():
     assert b"image" in L.eg3d_last_error()
     assert L.eg3d_plg_get(None, C.byref(A.PlgView())) == A.EG3D_ERR_INVALID_ARG
     L.eg3d_plg_free(None)
+
+
+def test_edge_colour_must_match_on_every_channel():
+    """img.at<Vec3b>(i,j) == edge_color compares all three channels (convert_edge_images_pixel_to_segment.cpp:205-207): an
+    almost-white pixel is background, and another edge colour selects other pixels."""
+    img = np.zeros((20, 20, 3), np.uint8)
+    img[5, 2:18] = 255
+    img[10, 2:18] = (255, 255, 254)
+    img[15, 2:18] = (0, 0, 255)
+    white = PB.polyline_graph_from_edge_image(img)
+    assert white.n_valid() == 1 and np.allclose(white.polyline(int(np.argmax(np.diff(white.poly_vert_off) > 1)))[:, 1], 5.5)
+    red = PB.polyline_graph_from_edge_image(img, edge_color=(0, 0, 255))
+    assert red.n_valid() == 1 and np.allclose(red.polyline(int(np.argmax(np.diff(red.poly_vert_off) > 1)))[:, 1], 15.5)
+    before = img.copy()
+    PB.polyline_graph_from_edge_image(img)
+    assert np.array_equal(img, before)          # the caller's pixels are left alone (the reference clears pixels in place)
