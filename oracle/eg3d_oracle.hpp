@@ -94,6 +94,11 @@ void em_estimate3Dpositions(const Scene& s, const std::vector<V2>& coords, const
 void em_add_new_observation_to_3Dpositions(const Scene& s, const V3& X0, const std::vector<V2>& coords, const std::vector<int>& ids,
                                            const V2& new_coords, int new_view, V3& X, bool& valid);
 
+} // namespace eg3d_oracle
+#include <atomic>
+namespace eg3d_oracle {
+extern std::atomic<long long> g_dlt_calls, g_dlt_degenerate; /* test statistics, eg3d_oracle_match.cpp */
+
 /* --- the per-seed path --- */
 std::vector<std::vector<PlgPoint>> find_epipolar_correspondences(const Scene& s, const std::vector<std::vector<ulong_t>>* cand,
                                                                  int starting_plg_id, const PlgPoint& starting_plgp);

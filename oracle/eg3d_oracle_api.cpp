@@ -248,6 +248,11 @@ int eg3d_oracle_epiline(const double* F9, float x, float y, float* out3) {
   V3 l; bool ok = computeCorrespondEpilineSinglePoint(V2{x, y}, F9, true, l);
   out3[0] = l.x; out3[1] = l.y; out3[2] = l.z; return ok;
 }
+/* (calls, degenerate calls) of the 2-view DLT since the last reset; reset = 1 clears the counters after reading */
+void eg3d_oracle_dlt_stats(long long* calls, long long* degenerate, int reset) {
+  *calls = g_dlt_calls.load(); *degenerate = g_dlt_degenerate.load();
+  if (reset) { g_dlt_calls = 0; g_dlt_degenerate = 0; }
+}
 void eg3d_oracle_triangulate_dlt(const float* P1, const float* P2, const float* x1, const float* x2, float* out4) {
   triangulate_dlt(P1, P2, V2{x1[0], x1[1]}, V2{x2[0], x2[1]}, out4);
 }

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <tuple>
 
+#include <atomic>
 namespace eg3d_oracle {
 
 /* ============================================================ 2-view DLT initialiser ====================== */
@@ -129,10 +130,15 @@ int em_GaussNewton(const Scene& s, const std::vector<int>& views, const std::vec
 
 /* triangulation.cpp:178-250 / 252-323.  get_min_max (edge_graph_3d_utilities.hpp:69-92): min = first arg-min,
  * "max" = ALWAYS the last index (missing braces). */
+/* statistics for the tests: how often the quirk hands the DLT the same camera twice (eg3d_oracle_dlt_stats) */
+std::atomic<long long> g_dlt_calls{0}, g_dlt_degenerate{0};
+
 void em_estimate3Dpositions(const Scene& s, const std::vector<V2>& coords, const std::vector<int>& ids, V3& Xo, bool& valid) {
   int min_index = 0;
   for (int i = 0; i < (int)ids.size(); i++) if (ids[i] < ids[min_index]) min_index = i;
   int max_index = (int)ids.size() - 1;
+  g_dlt_calls.fetch_add(1, std::memory_order_relaxed);
+  if (ids[max_index] == ids[min_index]) g_dlt_degenerate.fetch_add(1, std::memory_order_relaxed);
   if (s.prm.dlt_wellposed && ids[max_index] == ids[min_index]) {
     for (int j = (int)ids.size() - 1; j >= 0; j--) if (ids[j] != ids[min_index]) { max_index = j; break; }
   }

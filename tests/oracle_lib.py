@@ -36,6 +36,7 @@ def lib():
         L.eg3d_oracle_match_polyline_sets.argtypes = [C.c_void_p, C.POINTER(A.Candidates), C.c_int32, C.c_int32, C.c_int]
         L.eg3d_oracle_match_refpoints.restype = C.c_void_p
         L.eg3d_oracle_match_refpoints.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int]
+        L.eg3d_oracle_dlt_stats.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_int]
         L.eg3d_oracle_refpoint_hits.restype = C.c_void_p
         L.eg3d_oracle_refpoint_hits.argtypes = [C.c_void_p, C.c_int64, C.c_int64, A.c_i64p]
         L.eg3d_oracle_hits_get.argtypes = [C.c_void_p, A.c_i64p, A.c_i32p, C.POINTER(A.c_i64p), C.POINTER(C.POINTER(A.Hit))]
@@ -181,6 +182,13 @@ class OracleScene:
         out = np.zeros(cap, np.uint32)
         n = lib().eg3d_oracle_grid_query(self.h, view, which, x, y, A.ptr(out, A.c_u32p), cap)
         return out[:min(n, cap)].tolist()
+
+
+def dlt_stats(reset=True):
+    """(fresh 2-view DLT calls, calls that got the same camera twice) since the last reset — statistics of the oracle."""
+    a, b = C.c_longlong(), C.c_longlong()
+    lib().eg3d_oracle_dlt_stats(C.byref(a), C.byref(b), int(reset))
+    return a.value, b.value
 
 
 class OracleDevice:

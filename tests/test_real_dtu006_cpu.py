@@ -50,7 +50,10 @@ def test_real_dtu006_oracle_results_satisfy_the_references_invariants():
     sc, _ = real_scene.dtu006_scene(os.path.join(HERE, "golden"))
     c2, ref = E.polyline_sets_from_refpoints(sc)
     dev = O.OracleDevice(sc, E.default_params(**P.REAL_DATA_CAPACITIES), n_threads=8)
+    O.dlt_stats()
     p2 = dev.match_polyline_sets(c2)[0]
+    calls, degenerate = O.dlt_stats()
+    assert calls > 100000 and 0.05 < degenerate / calls < 0.25      # the get_min_max quirk is not a corner case
     p3 = dev.match_refpoints(0, 1500)[0]
     for pts in (p2, p3):
         med = check_invariants(sc, pts)
