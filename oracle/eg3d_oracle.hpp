@@ -88,6 +88,7 @@ V2 compute_projection(const float P12[12], const V3& X);
 
 /* --- triangulation (triangulation.cpp) --- */
 void triangulate_dlt(const float P1[12], const float P2[12], const V2& x1, const V2& x2, float out4[4]);
+void triangulate_dlt_opencv(const float P1[12], const float P2[12], const V2& x1, const V2& x2, float out4[4]);
 int em_GaussNewton(const Scene& s, const std::vector<int>& views, const std::vector<V2>& pts, const double init[3],
                    double out[3], double* last_mse_out);
 void em_estimate3Dpositions(const Scene& s, const std::vector<V2>& coords, const std::vector<int>& ids, V3& X, bool& valid);

@@ -256,6 +256,9 @@ void eg3d_oracle_dlt_stats(long long* calls, long long* degenerate, int reset) {
 void eg3d_oracle_triangulate_dlt(const float* P1, const float* P2, const float* x1, const float* x2, float* out4) {
   triangulate_dlt(P1, P2, V2{x1[0], x1[1]}, V2{x2[0], x2[1]}, out4);
 }
+void eg3d_oracle_triangulate_dlt_opencv(const float* P1, const float* P2, const float* x1, const float* x2, float* out4) {
+  triangulate_dlt_opencv(P1, P2, V2{x1[0], x1[1]}, V2{x2[0], x2[1]}, out4);
+}
 int eg3d_oracle_intersect_segment_line(const float* segm4, const float* line3, float* inter2) {
   bool f; V2 p{0, 0}; intersect_segment_line(segm4, V3{line3[0], line3[1], line3[2]}, f, p);
   inter2[0] = p.x; inter2[1] = p.y; return f;

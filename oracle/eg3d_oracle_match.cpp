@@ -56,6 +56,78 @@ void triangulate_dlt(const float P1[12], const float P2[12], const V2& x1, const
   for (int i = 0; i < 4; i++) out4[i] = (float)Vm[i][best];
 }
 
+/* The same initialiser with OpenCV's own SVD restated: cv::triangulatePoints (OpenCV 4.x, modules/calib3d/src/triangulate.cpp:
+ * the 4x4 system above in double) -> cv::SVD::compute -> JacobiSVDImpl_<double> (modules/core/src/lapack.cpp) run on the
+ * TRANSPOSED matrix: rows = columns of A, squared norms cached in W, pairs (i<j) skipped when |p| <= eps*sqrt(a*b) with
+ * eps = DBL_EPSILON*10, rotation from hypot(2p, a-b), at most max(m,30) sweeps, singular values sorted descending by
+ * selection sort with the rows of Vt swapped along; result = last row of Vt, narrowed to float.  OpenCV is not vendored in
+ * the reference; this is the published algorithm, pinned against REAL cv2 4.13 calls: bit-identical (sign included) on the
+ * 400 golden cases and on live degenerate inputs (same camera twice), where the null space is a whole ray and every other
+ * SVD returns a different point of it (tests/test_oracle_golden.py).  eg3d_params.dlt_wellposed == 2 selects it. */
+void triangulate_dlt_opencv(const float P1[12], const float P2[12], const V2& x1, const V2& x2, float out4[4]) {
+  double At[4][4], Vt[4][4], W[4];   /* At[i][k] = A[k][i] */
+  const float* Ps[2] = {P1, P2};
+  const V2 xs[2] = {x1, x2};
+  for (int j = 0; j < 2; j++) {
+    const double x = xs[j].x, y = xs[j].y;
+    for (int k = 0; k < 4; k++) {
+      At[k][j * 2 + 0] = x * (double)Ps[j][8 + k] - (double)Ps[j][k];
+      At[k][j * 2 + 1] = y * (double)Ps[j][8 + k] - (double)Ps[j][4 + k];
+    }
+  }
+  const int n = 4, m = 4;
+  const double eps = 2.220446049250313e-16 * 10;
+  for (int i = 0; i < n; i++) {
+    double sd = 0;
+    for (int k = 0; k < m; k++) sd += At[i][k] * At[i][k];
+    W[i] = sd;
+    for (int k = 0; k < n; k++) Vt[i][k] = 0;
+    Vt[i][i] = 1;
+  }
+  for (int iter = 0; iter < 30; iter++) {
+    bool changed = false;
+    for (int i = 0; i < n - 1; i++)
+      for (int j = i + 1; j < n; j++) {
+        double a = W[i], p = 0, b = W[j];
+        for (int k = 0; k < m; k++) p += At[i][k] * At[j][k];
+        if (std::fabs(p) <= eps * std::sqrt(a * b)) continue;
+        p *= 2;
+        const double beta = a - b, gamma = std::hypot(p, beta);
+        double c, sn;
+        if (beta < 0) { const double delta = (gamma - beta) * 0.5; sn = std::sqrt(delta / gamma); c = p / (gamma * sn * 2); }
+        else { c = std::sqrt((gamma + beta) / (gamma * 2)); sn = p / (gamma * c * 2); }
+        a = b = 0;
+        for (int k = 0; k < m; k++) {
+          const double t0 = c * At[i][k] + sn * At[j][k], t1 = -sn * At[i][k] + c * At[j][k];
+          At[i][k] = t0; At[j][k] = t1;
+          a += t0 * t0; b += t1 * t1;
+        }
+        W[i] = a; W[j] = b;
+        changed = true;
+        for (int k = 0; k < n; k++) {
+          const double t0 = c * Vt[i][k] + sn * Vt[j][k], t1 = -sn * Vt[i][k] + c * Vt[j][k];
+          Vt[i][k] = t0; Vt[j][k] = t1;
+        }
+      }
+    if (!changed) break;
+  }
+  for (int i = 0; i < n; i++) {
+    double sd = 0;
+    for (int k = 0; k < m; k++) sd += At[i][k] * At[i][k];
+    W[i] = std::sqrt(sd);
+  }
+  for (int i = 0; i < n - 1; i++) {
+    int j = i;
+    for (int k = i + 1; k < n; k++) if (W[j] < W[k]) j = k;
+    if (i != j) {
+      std::swap(W[i], W[j]);
+      for (int k = 0; k < m; k++) std::swap(At[i][k], At[j][k]);
+      for (int k = 0; k < n; k++) std::swap(Vt[i][k], Vt[j][k]);
+    }
+  }
+  for (int k = 0; k < 4; k++) out4[k] = (float)Vt[3][k];
+}
+
 /* ============================================================ em_GaussNewton (FP64) ======================= */
 static inline void cam4(const Scene& s, int view, double P[12]) {
   for (int i = 0; i < 12; i++) P[i] = (double)s.P[view][i]; /* float -> CV_64F, triangulation.cpp:301-306 */
@@ -139,11 +211,14 @@ void em_estimate3Dpositions(const Scene& s, const std::vector<V2>& coords, const
   int max_index = (int)ids.size() - 1;
   g_dlt_calls.fetch_add(1, std::memory_order_relaxed);
   if (ids[max_index] == ids[min_index]) g_dlt_degenerate.fetch_add(1, std::memory_order_relaxed);
-  if (s.prm.dlt_wellposed && ids[max_index] == ids[min_index]) {
+  if (s.prm.dlt_wellposed == 1 && ids[max_index] == ids[min_index]) {
     for (int j = (int)ids.size() - 1; j >= 0; j--) if (ids[j] != ids[min_index]) { max_index = j; break; }
   }
   float t4[4];
-  triangulate_dlt(s.P[ids[min_index]].data(), s.P[ids[max_index]].data(), coords[min_index], coords[max_index], t4);
+  if (s.prm.dlt_wellposed == 2)   /* the reference linked against OpenCV 4.x, quirk and all */
+    triangulate_dlt_opencv(s.P[ids[min_index]].data(), s.P[ids[max_index]].data(), coords[min_index], coords[max_index], t4);
+  else
+    triangulate_dlt(s.P[ids[min_index]].data(), s.P[ids[max_index]].data(), coords[min_index], coords[max_index], t4);
   double init[3] = {(double)(t4[0] / t4[3]), (double)(t4[1] / t4[3]), (double)(t4[2] / t4[3])}; /* Vec4f / float */
   double out[3];
   if (em_GaussNewton(s, ids, coords, init, out, nullptr) != -1) {

@@ -44,6 +44,35 @@ def test_dlt_matches_triangulatePoints(golden):
     assert worst < 5e-6, worst
 
 
+def test_opencv_faithful_dlt_is_bit_identical_to_triangulatePoints(golden):
+    """The restatement of OpenCV's own Jacobi SVD (triangulate_dlt_opencv, eg3d_params.dlt_wellposed == 2 in the oracle)
+    reproduces cv2.triangulatePoints BIT FOR BIT, sign included: on the 400 golden cases and — live, when cv2 is importable —
+    on degenerate inputs (the same camera twice, with the same or with another observation), where the null space is not a
+    single direction and only the same algorithm in the same operation order lands on the same vector."""
+    L = O.lib()
+    cams = golden["dlt_cams"]
+    out = np.zeros(4, np.float32)
+    for va, vb, x1, x2, ref in zip(golden["dlt_va"], golden["dlt_vb"], golden["dlt_x1"], golden["dlt_x2"], golden["dlt_X4"]):
+        P1, P2 = np.ascontiguousarray(cams[va]), np.ascontiguousarray(cams[vb])
+        x1, x2 = np.ascontiguousarray(x1), np.ascontiguousarray(x2)
+        L.eg3d_oracle_triangulate_dlt_opencv(A.ptr(P1, A.c_f32p), A.ptr(P2, A.c_f32p), A.ptr(x1, A.c_f32p), A.ptr(x2, A.c_f32p), A.ptr(out, A.c_f32p))
+        assert out.tobytes() == np.ascontiguousarray(ref, np.float32).tobytes()
+    cv2 = pytest.importorskip("cv2")
+    z = np.load(os.path.join(HERE, "golden", "dtu006_sfm.npz"))
+    P = z["cameras"].reshape(-1, 3, 4).astype(np.float32)
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        a, b = rng.choice(len(P), 2, replace=False)
+        x1 = rng.uniform([0, 0], [1600, 1200]).astype(np.float32)
+        x2 = rng.uniform([0, 0], [1600, 1200]).astype(np.float32)
+        for pa, pb, xa, xb in ((P[a], P[b], x1, x2), (P[a], P[a], x1, x1), (P[a], P[a], x1, x2)):
+            pa, pb = np.ascontiguousarray(pa), np.ascontiguousarray(pb)
+            ref = cv2.triangulatePoints(pa, pb, xa.reshape(2, 1), xb.reshape(2, 1)).reshape(4).astype(np.float32)
+            L.eg3d_oracle_triangulate_dlt_opencv(A.ptr(pa.reshape(-1), A.c_f32p), A.ptr(pb.reshape(-1), A.c_f32p), A.ptr(xa, A.c_f32p), A.ptr(xb, A.c_f32p),
+                                                 A.ptr(out, A.c_f32p))
+            assert out.tobytes() == ref.tobytes()
+
+
 def _run_gn(golden, name, fp64):
     sc = _scene_with_cameras(golden["cams"])
     osc = O.OracleScene(sc)
