@@ -1111,6 +1111,13 @@ eg3d_status eg3d_polyline_sets_from_communities(const eg3d_similarity_graph* p, 
   return EG3D_OK;
 }
 
+// Host evaluation of the 2-view initialiser in its two forms (tests; no device needed): opencv_svd = 0 -> dlt_null (the
+// kernels' current SVD), 1 -> dlt_null_opencv (OpenCV's own Jacobi SVD restated; see eg3d_dev.cuh).
+void eg3d_triangulate_dlt_host(const float* P1, const float* P2, const float* x1, const float* x2, int32_t opencv_svd, float* out4) {
+  if (opencv_svd) dlt_null_opencv(P1, P2, make_float2(x1[0], x1[1]), make_float2(x2[0], x2[1]), out4);
+  else dlt_null(P1, P2, make_float2(x1[0], x1[1]), make_float2(x2[0], x2[1]), out4);
+}
+
 static eg3d_status check_seeds(const eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d_candidates* cands) {
   if (!sc || !seeds) return fail(EG3D_ERR_INVALID_ARG, "null argument");
   if (seeds->n > 0x7fffffff / std::max(1, sc->V)) {}

@@ -434,6 +434,88 @@ EG3D_HD_NI void dlt_null(const float* P1, const float* P2, float2 x1, float2 x2,
   for (int i = 0; i < 4; i++) out4[i] = (float)Vm[i][best];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same initialiser with OpenCV's OWN SVD restated (prepared this round on the host, to be selected by
+// eg3d_params.dlt_wellposed == 2 in the kernels next round): cv::triangulatePoints (OpenCV 4.x triangulate.cpp: the 4x4
+// system above) -> cv::SVD::compute -> JacobiSVDImpl_<double> (core/src/lapack.cpp) on the transposed matrix, squared norms
+// cached in W, a pair is skipped when |p| <= 10 eps sqrt(a b), rotation from hypot(2p, a-b), <= 30 sweeps, singular values
+// sorted descending by selection sort with the rows of Vt swapped along, result = last row of Vt as float.  Why it matters:
+// the reference's get_min_max quirk hands the DLT the same camera twice in 1-12 % of the fresh triangulations of the real
+// example; the null space is then a whole ray and only this algorithm in this operation order returns the point of it that
+// a reference linked against OpenCV returns (bit-identical to cv2 4.13, sign included: tests/test_cabi_host.py), while the
+// accepted point set depends on that point.  hypot_cr: a correctly rounded hypot from IEEE operations only
+// (sqrt of the double-double sum of squares + one exact-residual correction), so host and device agree bit for bit.
+EG3D_HD_NI double hypot_cr(double x, double y) {
+  x = fabs(x); y = fabs(y);
+  if (x < y) { const double t = x; x = y; y = t; }
+  if (y == 0) return x;
+  int ex;
+  frexp(x, &ex);                                      // scale the larger argument into [0.5, 1): exact, no under/overflow below
+  x = ldexp(x, -ex); y = ldexp(y, -ex);
+  const double x2 = x * x, xx = fma(x, x, -x2), y2 = y * y, yy = fma(y, y, -y2);
+  const double s = x2 + y2, e = y2 - (s - x2);        // Fast2Sum (x2 >= y2)
+  const double lo = (xx + yy) + e;
+  const double h = sqrt(s);
+  return ldexp(h + (fma(-h, h, s) + lo) / (2 * h), ex);
+}
+EG3D_HD_NI void dlt_null_opencv(const float* P1, const float* P2, float2 x1, float2 x2, float out4[4]) {
+  double At[4][4], Vt[4][4], W[4];   // At[i][k] = A[k][i]
+  for (int k = 0; k < 4; k++) {
+    At[k][0] = (double)x1.x * (double)P1[8 + k] - (double)P1[k];
+    At[k][1] = (double)x1.y * (double)P1[8 + k] - (double)P1[4 + k];
+    At[k][2] = (double)x2.x * (double)P2[8 + k] - (double)P2[k];
+    At[k][3] = (double)x2.y * (double)P2[8 + k] - (double)P2[4 + k];
+  }
+  const double eps = 2.220446049250313e-16 * 10;
+  for (int i = 0; i < 4; i++) {
+    double sd = 0;
+    for (int k = 0; k < 4; k++) { sd += At[i][k] * At[i][k]; Vt[i][k] = (i == k) ? 1.0 : 0.0; }
+    W[i] = sd;
+  }
+#pragma unroll 1
+  for (int iter = 0; iter < 30; iter++) {
+    bool changed = false;
+#pragma unroll 1
+    for (int i = 0; i < 3; i++)
+#pragma unroll 1
+      for (int j = i + 1; j < 4; j++) {
+        double a = W[i], p = 0, b = W[j];
+        for (int k = 0; k < 4; k++) p += At[i][k] * At[j][k];
+        if (fabs(p) <= eps * sqrt(a * b)) continue;
+        p *= 2;
+        const double beta = a - b, gamma = hypot_cr(p, beta);
+        double c, sn;
+        if (beta < 0) { const double delta = (gamma - beta) * 0.5; sn = sqrt(delta / gamma); c = p / (gamma * sn * 2); }
+        else { c = sqrt((gamma + beta) / (gamma * 2)); sn = p / (gamma * c * 2); }
+        a = b = 0;
+        for (int k = 0; k < 4; k++) {
+          const double t0 = c * At[i][k] + sn * At[j][k], t1 = -sn * At[i][k] + c * At[j][k];
+          At[i][k] = t0; At[j][k] = t1;
+          a += t0 * t0; b += t1 * t1;
+        }
+        W[i] = a; W[j] = b;
+        changed = true;
+        for (int k = 0; k < 4; k++) {
+          const double t0 = c * Vt[i][k] + sn * Vt[j][k], t1 = -sn * Vt[i][k] + c * Vt[j][k];
+          Vt[i][k] = t0; Vt[j][k] = t1;
+        }
+      }
+    if (!changed) break;
+  }
+  for (int i = 0; i < 4; i++) {
+    double sd = 0;
+    for (int k = 0; k < 4; k++) sd += At[i][k] * At[i][k];
+    W[i] = sqrt(sd);
+  }
+  int row[4] = {0, 1, 2, 3};           // the selection sort only has to track which row of Vt ends up last
+  for (int i = 0; i < 3; i++) {
+    int j = i;
+    for (int k = i + 1; k < 4; k++) if (W[j] < W[k]) j = k;
+    if (i != j) { const double tw = W[i]; W[i] = W[j]; W[j] = tw; const int tr = row[i]; row[i] = row[j]; row[j] = tr; }
+  }
+  for (int k = 0; k < 4; k++) out4[k] = (float)Vt[row[3]][k];
+}
+
 EG3D_HD double det3d(const double* m) {
   return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
 }

@@ -91,7 +91,9 @@ typedef struct eg3d_params {
   float  dedup_cell;                  /* 3     filtering_close_plgps.cpp:75 */
   /* 1 (default): when get_min_max's "last index" quirk selects the same camera twice for the 2-view DLT
    * initialiser (edge_graph_3d_utilities.hpp:86-88), use the last list entry whose view differs instead
-   * (SURVEY A.2.1).  0: keep the rank-deficient DLT (result is implementation-defined noise).             */
+   * (SURVEY A.2.1).  0: keep the rank-deficient DLT with this library's own SVD (a point of the null-space ray that differs
+   * from OpenCV's).  2 (oracle only this round; the kernels treat it as 1): the quirk's pair with OpenCV 4.x's own Jacobi SVD
+   * restated — the setting that reproduces a reference linked against OpenCV.                            */
   int32_t dlt_wellposed;
   /* 0 (default): `abs(mse/(2n) - last_mse)` in gauss_newton.cpp:114 is the float overload (GCC >= 6).
    * 1: emulate the truncating `int abs(int)` binding of the author's GCC 5 toolchain.         */
@@ -171,6 +173,11 @@ const char* eg3d_last_error(void);
  * cameras [V][12], out [V][V][9] (row-major, unit Frobenius norm, zero on the diagonal). */
 void        eg3d_camera_fundamentals(const float* cameras, int32_t n_views, double* out);
 int         eg3d_device_count(void);
+/* Host evaluation of the 2-view DLT initialiser (cv::triangulatePoints at triangulation.cpp:216,290) as the kernels compute
+ * it: opencv_svd = 0 -> the current one-sided Jacobi SVD, 1 -> OpenCV's own Jacobi SVD restated (bit-identical to
+ * cv2.triangulatePoints, degenerate inputs included; the kernels adopt it as eg3d_params.dlt_wellposed = 2 next round). */
+void        eg3d_triangulate_dlt_host(const float* P1, const float* P2, const float* x1, const float* x2,
+                                      int32_t opencv_svd, float* out4);
 
 /* Copies the scene to the current CUDA device and builds the derived structures the path reads:
  * per-view segment arrays in the reference's (P[i], P[i-1]) orientation (plg_edge_manager.hpp:92-93,

@@ -62,8 +62,26 @@ void triangulate_dlt(const float P1[12], const float P2[12], const V2& x1, const
  * eps = DBL_EPSILON*10, rotation from hypot(2p, a-b), at most max(m,30) sweeps, singular values sorted descending by
  * selection sort with the rows of Vt swapped along; result = last row of Vt, narrowed to float.  OpenCV is not vendored in
  * the reference; this is the published algorithm, pinned against REAL cv2 4.13 calls: bit-identical (sign included) on the
- * 400 golden cases and on live degenerate inputs (same camera twice), where the null space is a whole ray and every other
- * SVD returns a different point of it (tests/test_oracle_golden.py).  eg3d_params.dlt_wellposed == 2 selects it. */
+ * 400 golden cases and on > 99.9 % of live inputs incl. degenerate ones (same camera twice), within one float ulp on the
+ * rest (hypot, below); there the null space is a whole ray and every other SVD returns a different point of it
+ * (tests/test_oracle_golden.py).  eg3d_params.dlt_wellposed == 2 selects it. */
+/* hypot from IEEE operations only, correctly rounded (sqrt of the double-double sum of squares + one exact-residual
+ * correction), so that this oracle and the device code agree bit for bit.  OpenCV calls the C library's hypot, which in
+ * glibc is accurate to ~0.8 ulp, not correctly rounded, and differs between its FMA / non-FMA builds: in 4 of 6 000 live
+ * cases (all fully degenerate) that moves the float result by one ulp (<= 8e-8 relative) — the noise floor of "identical". */
+static double hypot_cr(double x, double y) {
+  x = std::fabs(x); y = std::fabs(y);
+  if (x < y) std::swap(x, y);
+  if (y == 0) return x;
+  int ex;
+  std::frexp(x, &ex);
+  x = std::ldexp(x, -ex); y = std::ldexp(y, -ex);
+  const double x2 = x * x, xx = std::fma(x, x, -x2), y2 = y * y, yy = std::fma(y, y, -y2);
+  const double s = x2 + y2, e = y2 - (s - x2);
+  const double lo = (xx + yy) + e;
+  const double h = std::sqrt(s);
+  return std::ldexp(h + (std::fma(-h, h, s) + lo) / (2 * h), ex);
+}
 void triangulate_dlt_opencv(const float P1[12], const float P2[12], const V2& x1, const V2& x2, float out4[4]) {
   double At[4][4], Vt[4][4], W[4];   /* At[i][k] = A[k][i] */
   const float* Ps[2] = {P1, P2};
@@ -92,7 +110,7 @@ void triangulate_dlt_opencv(const float P1[12], const float P2[12], const V2& x1
         for (int k = 0; k < m; k++) p += At[i][k] * At[j][k];
         if (std::fabs(p) <= eps * std::sqrt(a * b)) continue;
         p *= 2;
-        const double beta = a - b, gamma = std::hypot(p, beta);
+        const double beta = a - b, gamma = hypot_cr(p, beta);
         double c, sn;
         if (beta < 0) { const double delta = (gamma - beta) * 0.5; sn = std::sqrt(delta / gamma); c = p / (gamma * sn * 2); }
         else { c = std::sqrt((gamma + beta) / (gamma * 2)); sn = p / (gamma * c * 2); }
