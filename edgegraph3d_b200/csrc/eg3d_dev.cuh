@@ -15,6 +15,11 @@
 #ifndef EG3D_GN_UNROLL
 #define EG3D_GN_UNROLL 1
 #endif
+// 1: eg3d_params.dlt_wellposed == 2 selects dlt_null_opencv (OpenCV's own SVD, the quirk's camera pair) in the kernels.
+// Prepared in round 1 without a GPU to verify it, hence off: with 0 the kernels are byte-identical to the measured build.
+#ifndef EG3D_DLT_OPENCV
+#define EG3D_DLT_OPENCV 0
+#endif
 
 namespace eg3d {
 constexpr int kGnUnroll = EG3D_GN_UNROLL;
@@ -592,7 +597,11 @@ EG3D_HD_NI bool est3(const DevScene& S, const int v[3], const float2 pt[3], floa
   if (v[1] < v[mi]) mi = 1;
   if (v[2] < v[mi]) mi = 2;
   int ma = 2;
+#if EG3D_DLT_OPENCV
+  if (S.prm.dlt_wellposed == 1 && v[ma] == v[mi]) {
+#else
   if (S.prm.dlt_wellposed && v[ma] == v[mi]) {
+#endif
     if (v[2] != v[mi]) ma = 2; else if (v[1] != v[mi]) ma = 1; else if (v[0] != v[mi]) ma = 0;
   }
   float2 pmi = pt[0], pma = pt[0];
@@ -600,6 +609,9 @@ EG3D_HD_NI bool est3(const DevScene& S, const int v[3], const float2 pt[3], floa
   if (mi == 1) { pmi = pt[1]; vmi = v[1]; } else if (mi == 2) { pmi = pt[2]; vmi = v[2]; }
   if (ma == 1) { pma = pt[1]; vma = v[1]; } else if (ma == 2) { pma = pt[2]; vma = v[2]; }
   float t4[4];
+#if EG3D_DLT_OPENCV
+  if (S.prm.dlt_wellposed == 2) dlt_null_opencv(S.P + 12 * vmi, S.P + 12 * vma, pmi, pma, t4); else
+#endif
   dlt_null(S.P + 12 * vmi, S.P + 12 * vma, pmi, pma, t4);
   double X[3] = {(double)(t4[0] / t4[3]), (double)(t4[1] / t4[3]), (double)(t4[2] / t4[3])};
   if (!gn3_exact(S, v, pt, X)) return false;

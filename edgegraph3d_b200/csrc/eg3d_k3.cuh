@@ -440,10 +440,19 @@ static __device__ __noinline__ bool est_slot(Ctx& c, int slot, int n, float Xo[3
     if (ov2 < bestv || (ov2 == bestv && oi2 < besti)) { bestv = ov2; besti = oi2; }
   }
   int mi = besti, ma = n - 1;
+#if EG3D_DLT_OPENCV
+  if (S.prm.dlt_wellposed == 1 && ov[ma] == ov[mi]) {
+#else
   if (S.prm.dlt_wellposed && ov[ma] == ov[mi]) {
+#endif
     for (int j = n - 1; j >= 0; j--) if (ov[j] != ov[mi]) { ma = j; break; }
   }
   float t4[4];
+#if EG3D_DLT_OPENCV
+  if (S.prm.dlt_wellposed == 2)
+    dlt_null_opencv(S.P + 12 * ov[mi], S.P + 12 * ov[ma], make_float2(c.w.ox[b + mi], c.w.oy[b + mi]), make_float2(c.w.ox[b + ma], c.w.oy[b + ma]), t4);
+  else
+#endif
   dlt_null(S.P + 12 * ov[mi], S.P + 12 * ov[ma], make_float2(c.w.ox[b + mi], c.w.oy[b + mi]), make_float2(c.w.ox[b + ma], c.w.oy[b + ma]), t4);
   double X[3] = {(double)(t4[0] / t4[3]), (double)(t4[1] / t4[3]), (double)(t4[2] / t4[3])};
   if (!gn_group(S, slot_obs(c, slot, n, false, 0, 0.f, 0.f), true, 32, c.lane, X)) return false;
