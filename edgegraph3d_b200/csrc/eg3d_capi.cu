@@ -1111,6 +1111,15 @@ eg3d_status eg3d_polyline_sets_from_communities(const eg3d_similarity_graph* p, 
   return EG3D_OK;
 }
 
+#define EG3D_STR2(x) #x
+#define EG3D_STR(x) EG3D_STR2(x)
+// compile-time switches of this build (A/B variants are told apart by it; tests gate on it)
+const char* eg3d_build_info(void) {
+  return "EG3D_DLT_OPENCV=" EG3D_STR(EG3D_DLT_OPENCV) " EG3D_K3A_MIN_BLOCKS=" EG3D_STR(EG3D_K3A_MIN_BLOCKS) " EG3D_K3B_MIN_BLOCKS=" EG3D_STR(EG3D_K3B_MIN_BLOCKS)
+         " EG3D_K3B_THREADS=" EG3D_STR(EG3D_K3B_THREADS) " EG3D_K3B_SYNC=" EG3D_STR(EG3D_K3B_SYNC) " EG3D_K3B_BATCH=" EG3D_STR(EG3D_K3B_BATCH)
+         " EG3D_GN_UNROLL=" EG3D_STR(EG3D_GN_UNROLL) " EG3D_K1_GROUP=" EG3D_STR(EG3D_K1_GROUP);
+}
+
 // Host evaluation of the 2-view initialiser in its two forms (tests; no device needed): opencv_svd = 0 -> dlt_null (the
 // kernels' current SVD), 1 -> dlt_null_opencv (OpenCV's own Jacobi SVD restated; see eg3d_dev.cuh).
 void eg3d_triangulate_dlt_host(const float* P1, const float* P2, const float* x1, const float* x2, int32_t opencv_svd, float* out4) {

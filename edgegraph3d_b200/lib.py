@@ -21,7 +21,7 @@ EXPORTS = [
     "eg3d_plg_from_edge_image", "eg3d_plg_get", "eg3d_plg_free",
     "eg3d_polyline_sets_from_refpoints", "eg3d_polyline_sets_get", "eg3d_polyline_sets_free",
     "eg3d_polyline_similarity_graph", "eg3d_similarity_graph_get", "eg3d_similarity_graph_communities", "eg3d_polyline_sets_from_communities",
-    "eg3d_similarity_graph_free", "eg3d_triangulate_dlt_host",
+    "eg3d_similarity_graph_free", "eg3d_triangulate_dlt_host", "eg3d_build_info",
 ]
 
 
@@ -75,6 +75,7 @@ def load():
     L.eg3d_similarity_graph_communities.argtypes = [C.c_void_p, A.c_i64p, A.c_f64p]
     L.eg3d_polyline_sets_from_communities.argtypes = [C.c_void_p, A.c_i64p, C.POINTER(C.c_void_p)]
     L.eg3d_similarity_graph_free.argtypes = [C.c_void_p]
+    L.eg3d_build_info.restype = C.c_char_p
     L.eg3d_triangulate_dlt_host.argtypes = [A.c_f32p, A.c_f32p, A.c_f32p, A.c_f32p, C.c_int32, A.c_f32p]
     _lib = L
     return L
@@ -83,6 +84,11 @@ def load():
 def _check(st):
     if st != A.EG3D_OK:
         raise Eg3dError(st, load().eg3d_last_error().decode(errors="replace"))
+
+
+def build_info():
+    """{'EG3D_DLT_OPENCV': '0', ...}: the compile-time switches of the loaded library."""
+    return dict(kv.split("=", 1) for kv in load().eg3d_build_info().decode().split())
 
 
 def default_params(**overrides):
