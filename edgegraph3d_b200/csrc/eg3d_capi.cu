@@ -1111,6 +1111,10 @@ eg3d_status eg3d_polyline_sets_from_communities(const eg3d_similarity_graph* p, 
   return EG3D_OK;
 }
 
+// Host evaluation of compute_projection as the kernels compute it (eg3d::project; tests)
+void eg3d_project_host(const float* cam12, const float* x3, float* out2) {
+  const float2 q = project(cam12, x3[0], x3[1], x3[2]); out2[0] = q.x; out2[1] = q.y;
+}
 #define EG3D_STR2(x) #x
 #define EG3D_STR(x) EG3D_STR2(x)
 // compile-time switches of this build (A/B variants are told apart by it; tests gate on it)

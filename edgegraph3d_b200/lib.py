@@ -21,7 +21,7 @@ EXPORTS = [
     "eg3d_plg_from_edge_image", "eg3d_plg_get", "eg3d_plg_free",
     "eg3d_polyline_sets_from_refpoints", "eg3d_polyline_sets_get", "eg3d_polyline_sets_free",
     "eg3d_polyline_similarity_graph", "eg3d_similarity_graph_get", "eg3d_similarity_graph_communities", "eg3d_polyline_sets_from_communities",
-    "eg3d_similarity_graph_free", "eg3d_triangulate_dlt_host", "eg3d_build_info",
+    "eg3d_similarity_graph_free", "eg3d_triangulate_dlt_host", "eg3d_build_info", "eg3d_project_host",
 ]
 
 
@@ -76,6 +76,7 @@ def load():
     L.eg3d_polyline_sets_from_communities.argtypes = [C.c_void_p, A.c_i64p, C.POINTER(C.c_void_p)]
     L.eg3d_similarity_graph_free.argtypes = [C.c_void_p]
     L.eg3d_build_info.restype = C.c_char_p
+    L.eg3d_project_host.argtypes = [A.c_f32p, A.c_f32p, A.c_f32p]
     L.eg3d_triangulate_dlt_host.argtypes = [A.c_f32p, A.c_f32p, A.c_f32p, A.c_f32p, C.c_int32, A.c_f32p]
     _lib = L
     return L

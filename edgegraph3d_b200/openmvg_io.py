@@ -14,6 +14,27 @@ def _f32(x):
     return np.asarray(x, dtype=np.float64).astype(np.float32)          # JSON doubles narrowed with GetFloat
 
 
+def glm_camera_matrix(R, C, K):
+    """translation = -center * rotation (OpenMvgParser.cpp:289) and cameraMatrix = eMatrix * kMatrix (:107-125) in float32, in
+    the operation order of the reference's vendored glm 0.9.6 (vec3 * mat3: m[i][0] v.x + m[i][1] v.y + m[i][2] v.z;
+    mat4 * mat4: column c = m1[0] m2[c][0] + m1[1] m2[c][1] + m1[2] m2[c][2] + m1[3] m2[c][3], left to right, the zero terms
+    included).  A BLAS product rounds differently in the last bit of some entries (17 of dtu006's 25 cameras); this form is
+    bit-identical to real glm (tests/golden/glm_golden.npz, made by the probe oracle/glm_probe.cpp).  -> (P [3,4], t [3])"""
+    f32 = np.float32
+    R = np.asarray(R, f32).reshape(3, 3)
+    nc = -np.asarray(C, f32)
+    t = np.array([f32(f32(f32(R[i, 0] * nc[0]) + f32(R[i, 1] * nc[1])) + f32(R[i, 2] * nc[2])) for i in range(3)], f32)
+    E = np.zeros((4, 4), f32); E[:3, :3] = R; E[:3, 3] = t; E[3, 3] = 1        # glm object: E[r][c]
+    Km = np.zeros((4, 4), f32); Km[:3, :3] = np.asarray(K, f32).reshape(3, 3)
+    res = np.zeros((4, 4), f32)
+    for c in range(4):
+        acc = (E[0] * Km[c, 0]).astype(f32)
+        for k in (1, 2, 3):
+            acc = (acc + (E[k] * Km[c, k]).astype(f32)).astype(f32)
+        res[c] = acc
+    return res[:3].copy(), t
+
+
 def load_sfm_data(path_or_dict):
     """-> dict(width, height, cameras [V,12] f32 = P = K[R|t] (rows 0..2 of cameraMatrix), K, R, center, t,
     track_xyz [N,3] f32, track_off [N+1] i64, track_view [M] i32, track_xy [M,2] f32, view_keys)."""
@@ -33,9 +54,8 @@ def load_sfm_data(path_or_dict):
         pos_of_pose[key] = pos
         R = _f32(ex["value"]["rotation"]).reshape(3, 3)
         C = _f32(ex["value"]["center"])
-        t = -(R @ C)                                               # float32: translation = -center * rotation (:289)
         K, w, h = intr[views[key]["id_intrinsic"]] if key in views else next(iter(intr.values()))
-        P = (K @ np.concatenate([R, t[:, None]], axis=1)).astype(np.float32)   # float32 products: cameraMatrix = eMatrix * kMatrix
+        P, t = glm_camera_matrix(R, C, K)
         cams.append(P.reshape(12)); Ks.append(K); Rs.append(R); Cs.append(C); ts.append(t); keys.append(key)
     xyz, off, tv, txy = [], [0], [], []
     for pt in d["structure"]:

@@ -173,6 +173,8 @@ const char* eg3d_last_error(void);
  * cameras [V][12], out [V][V][9] (row-major, unit Frobenius norm, zero on the diagonal). */
 void        eg3d_camera_fundamentals(const float* cameras, int32_t n_views, double* out);
 int         eg3d_device_count(void);
+/* Host evaluation of compute_projection (geometric_utilities.cpp:973-977) as the kernels compute it (tests). */
+void        eg3d_project_host(const float* cam12, const float* x3, float* out2);
 const char* eg3d_build_info(void);   /* the compile-time switches of this build, "NAME=value ..." */
 /* Host evaluation of the 2-view DLT initialiser (cv::triangulatePoints at triangulation.cpp:216,290) as the kernels compute
  * it: opencv_svd = 0 -> the current one-sided Jacobi SVD, 1 -> OpenCV's own Jacobi SVD restated (bit-identical to

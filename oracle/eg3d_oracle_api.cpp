@@ -256,6 +256,9 @@ void eg3d_oracle_dlt_stats(long long* calls, long long* degenerate, int reset) {
 void eg3d_oracle_triangulate_dlt(const float* P1, const float* P2, const float* x1, const float* x2, float* out4) {
   triangulate_dlt(P1, P2, V2{x1[0], x1[1]}, V2{x2[0], x2[1]}, out4);
 }
+void eg3d_oracle_compute_projection(const float* cam12, const float* x3, float* out2) {
+  V2 q = compute_projection(cam12, V3{x3[0], x3[1], x3[2]}); out2[0] = q.x; out2[1] = q.y;
+}
 void eg3d_oracle_triangulate_dlt_opencv(const float* P1, const float* P2, const float* x1, const float* x2, float* out4) {
   triangulate_dlt_opencv(P1, P2, V2{x1[0], x1[1]}, V2{x2[0], x2[1]}, out4);
 }

@@ -62,13 +62,13 @@ void triangulate_dlt(const float P1[12], const float P2[12], const V2& x1, const
  * eps = DBL_EPSILON*10, rotation from hypot(2p, a-b), at most max(m,30) sweeps, singular values sorted descending by
  * selection sort with the rows of Vt swapped along; result = last row of Vt, narrowed to float.  OpenCV is not vendored in
  * the reference; this is the published algorithm, pinned against REAL cv2 4.13 calls: bit-identical (sign included) on the
- * 400 golden cases and on > 99.9 % of live inputs incl. degenerate ones (same camera twice), within one float ulp on the
+ * 400 golden cases and on > 99.9 % of live inputs incl. degenerate ones (same camera twice), within a few float ulps on the
  * rest (hypot, below); there the null space is a whole ray and every other SVD returns a different point of it
  * (tests/test_oracle_golden.py).  eg3d_params.dlt_wellposed == 2 selects it. */
 /* hypot from IEEE operations only, correctly rounded (sqrt of the double-double sum of squares + one exact-residual
  * correction), so that this oracle and the device code agree bit for bit.  OpenCV calls the C library's hypot, which in
  * glibc is accurate to ~0.8 ulp, not correctly rounded, and differs between its FMA / non-FMA builds: in 4 of 6 000 live
- * cases (all fully degenerate) that moves the float result by one ulp (<= 8e-8 relative) — the noise floor of "identical". */
+ * cases (all fully degenerate) that moves the float result by a few ulps (<= 3e-7 relative) — the noise floor of "identical". */
 static double hypot_cr(double x, double y) {
   x = std::fabs(x); y = std::fabs(y);
   if (x < y) std::swap(x, y);

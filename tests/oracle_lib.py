@@ -53,6 +53,7 @@ def lib():
         L.eg3d_oracle_epiline.argtypes = [A.c_f64p, C.c_float, C.c_float, A.c_f32p]
         L.eg3d_oracle_triangulate_dlt.argtypes = [A.c_f32p] * 5
         L.eg3d_oracle_triangulate_dlt_opencv.argtypes = [A.c_f32p] * 5
+        L.eg3d_oracle_compute_projection.argtypes = [A.c_f32p] * 3
         L.eg3d_oracle_intersect_segment_line.argtypes = [A.c_f32p] * 3
         L.eg3d_oracle_intersect_segment_line_nqp.argtypes = [A.c_f32p, A.c_f32p, C.c_float, C.c_float, A.c_f32p]
         L.eg3d_oracle_squared_2d_distance.restype = C.c_float
