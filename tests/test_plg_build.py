@@ -180,3 +180,89 @@ def test_edge_colour_must_match_on_every_channel():
     before = img.copy()
     PB.polyline_graph_from_edge_image(img)
     assert np.array_equal(img, before)          # the caller's pixels are left alone (the reference clears pixels in place)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The pixel graph against the reference's OWN compiled graph class (oracle/_ref/libref_graph.so: graph_no_type.cpp,
+# graph_adjacency_set_no_type.cpp, graph_adjacency_set_undirected_no_type.cpp compiled unmodified from /root/reference)
+# ------------------------------------------------------------------------------------------------------------------
+def _ref_graph_lib():
+    so = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libref_graph.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libref_graph.so not built (needs /root/reference: make -C oracle ref)")
+    L = C.CDLL(so)
+    L.eg3d_ref_graph_new.restype = C.c_void_p
+    L.eg3d_ref_graph_new.argtypes = [C.c_ulong]
+    L.eg3d_ref_graph_free.argtypes = [C.c_void_p]
+    L.eg3d_ref_graph_link.argtypes = [C.c_void_p, C.c_ulong, C.c_ulong, C.c_ulong]
+    L.eg3d_ref_graph_degree.restype = C.c_ulong
+    L.eg3d_ref_graph_degree.argtypes = [C.c_void_p, C.c_ulong]
+    L.eg3d_ref_graph_neighbours.argtypes = [C.c_void_p, C.c_ulong, C.POINTER(C.c_ulong)]
+    return L
+
+
+def link_attempts(mask):
+    """Node ids and the (P, C) pairs convertEdgeImagePixelToGraph_NoCycles hands to is_connected / add_edge, in its order
+    (convert_edge_images_pixel_to_segment.cpp:294-343 for the nodes, :361-421 for the pairs)."""
+    rows, cols = mask.shape
+    flat = mask.astype(bool).ravel().copy()
+
+    def e(i, j):
+        k = i * cols + j
+        return 0 <= k < flat.size and bool(flat[k])
+    ids, n = {}, 0
+    for i in range(rows):
+        for j in range(cols):
+            if e(i, j):
+                if ((i > 1 and j > 1 and e(i - 1, j) and e(i, j - 1) and not e(i + 1, j + 1)) or
+                        (i > 1 and j < cols - 1 and e(i - 1, j) and e(i, j + 1) and not e(i + 1, j - 1)) or
+                        (i < rows - 1 and j < cols - 1 and e(i + 1, j) and e(i, j + 1) and not e(i - 1, j - 1)) or
+                        (i < rows - 1 and j > 1 and e(i + 1, j) and e(i, j - 1) and not e(i - 1, j + 1))):
+                    flat[i * cols + j] = False
+                else:
+                    ids[(i, j)] = n
+                    n += 1
+    pairs = []
+    for i in range(rows - 1):
+        for j in range(cols - 1):
+            if flat[i * cols + j]:
+                for ci, cj in [(i, j + 1), (i + 1, j), (i + 1, j + 1)] + ([(i + 1, j - 1)] if j > 1 else []):
+                    if flat[ci * cols + cj]:
+                        pairs.append((ids[(i, j)], ids[(ci, cj)]))
+    return n, pairs
+
+
+def assert_pixel_graph_equals_reference_class(mask, L):
+    n, pairs = link_attempts(mask)
+    g = PB.polyline_graph_from_edge_image(mask.astype(np.uint8) * 255, edge_color=255, stop_after=A.PLG_STAGE_PIXEL_GRAPH)
+    assert len(g.pixel_node_xy) == n
+    h = L.eg3d_ref_graph_new(n)
+    try:
+        for p, c in pairs:
+            L.eg3d_ref_graph_link(h, p, c, 8)                      # LOOP_CHECK_DIST
+        buf = (C.c_ulong * 16)()
+        for node in range(n):
+            d = int(L.eg3d_ref_graph_degree(h, node))
+            L.eg3d_ref_graph_neighbours(h, node, buf)
+            assert list(buf[:d]) == g.pixel_adj[g.pixel_adj_off[node]:g.pixel_adj_off[node + 1]].tolist(), node
+    finally:
+        L.eg3d_ref_graph_free(h)
+    return n, len(pairs)
+
+
+def test_pixel_graph_equals_the_references_own_graph_class():
+    """The bounded loop check (is_connected with max_dist 8, whose `visited` flags survive between calls because the undo list
+    is a vector<bool>) is the strangest rule of this stage; here it is not restated but EXECUTED: the reference's compiled
+    class receives the same sequence of neighbour pairs and must end with the adjacency the product computes."""
+    L = _ref_graph_lib()
+    total = 0
+    for seed in range(12):
+        total += assert_pixel_graph_equals_reference_class(synthetic_raster(seed), L)[1]
+    rng = np.random.default_rng(3)
+    for _ in range(60):
+        h, w = rng.integers(3, 48, 2)
+        total += assert_pixel_graph_equals_reference_class(rng.random((h, w)) < rng.choice([0.08, 0.25, 0.4, 0.6, 0.85]), L)[1]
+    masks = dtu006_masks()
+    for v, y, x in ((0, 300, 400), (7, 500, 900), (19, 200, 1000)):
+        total += assert_pixel_graph_equals_reference_class(masks[v, y:y + 256, x:x + 256], L)[1]
+    assert total > 20000

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 FLT_MAX, FLT_MIN = np.finfo(np.float32).max, np.finfo(np.float32).tiny
 
 
-def ref_polyline_sets(sc, find_within_dist=10.0, mult=3.0):
+def ref_polyline_sets(sc, find_within_dist=10.0, mult=3.0, return_graph=False):
     V = sc.n_views
     grids = [ref_build_grid(sc, v, find_within_dist, sc.width, sc.height) for v in range(V)]
     dsq_max = f32(f32(find_within_dist) * f32(find_within_dist))
@@ -70,6 +70,8 @@ def ref_polyline_sets(sc, find_within_dist=10.0, mult=3.0):
                     seen[nb] = True
                     stack.append(nb)
         sets.append([sorted(x) for x in comp])
+    if return_graph:
+        return sets, refpoints, nodes, adj
     return sets, refpoints
 
 
@@ -278,3 +280,40 @@ def test_communities_against_the_references_own_grappolo(tmp_path):
     assert ((ref < 0) == (com < 0)).all()                    # the same nodes (those without an edge) are left out by both
     q_ref = modularity(g, ref)
     assert q >= q_ref - 1e-3 and q > 0.9, (q, q_ref)
+
+
+def test_component_order_equals_the_references_own_get_components():
+    """GraphAdjacencySetUndirectedNoType::get_components (graph_adjacency_set_undirected_no_type.cpp:44-69) decides the ORDER of
+    pipeline 2's candidate sets; here the reference's compiled class (oracle/_ref/libref_graph.so) gets the polyline-match
+    graph of a synthetic scene and must number the components as the product does."""
+    import ctypes as C
+    so = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libref_graph.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref/libref_graph.so not built (needs /root/reference: make -C oracle ref)")
+    L = C.CDLL(so)
+    L.eg3d_ref_graph_new.restype = C.c_void_p
+    L.eg3d_ref_graph_new.argtypes = [C.c_ulong]
+    L.eg3d_ref_graph_free.argtypes = [C.c_void_p]
+    L.eg3d_ref_graph_add_edge.argtypes = [C.c_void_p, C.c_ulong, C.c_ulong]
+    L.eg3d_ref_graph_components.argtypes = [C.c_void_p, C.POINTER(C.c_ulong)]
+    sc = syn.make_scene(n_views=5, n_curves=14, seed=8, closed_frac=0.15, n_tracks=120)
+    cs, _ = E.polyline_sets_from_refpoints(sc)
+    V = sc.n_views
+    _, _, order, adj = ref_polyline_sets(sc, return_graph=True)          # nodes in first-seen order + adjacency of the second reading
+    edges = [(a, b) for a in range(len(order)) for b in sorted(adj[a]) if a < b]
+    g = L.eg3d_ref_graph_new(len(order))
+    try:
+        for a, b in edges:
+            L.eg3d_ref_graph_add_edge(g, a, b)
+        comp = (C.c_ulong * len(order))()
+        L.eg3d_ref_graph_components(g, comp)
+    finally:
+        L.eg3d_ref_graph_free(g)
+    # every node's component number (the reference's own numbering) = index of the product's candidate set that holds it
+    covered = 0
+    for k, cp in enumerate(order):
+        i = int(comp[k])
+        ids_v = cs.polyline[cs.off[i * V + cp[0]]:cs.off[i * V + cp[0] + 1]].tolist()
+        assert cp[1] in ids_v, (k, cp, i)
+        covered += 1
+    assert covered >= 6 and len(set(comp)) == cs.n_sets
