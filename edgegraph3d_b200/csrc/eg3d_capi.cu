@@ -57,7 +57,16 @@ struct DBuf {  // owning device buffer
 
 struct HostGrid { float cell; int w, h; std::vector<int> off; std::vector<uint32_t> ids; };
 
+// The library's stream is shared by a scene and by every result produced from it (their device buffers are freed on it):
+// it is destroyed when the last of them goes, so an eg3d_points may outlive its scene.  Declared FIRST in both structs, i.e.
+// destroyed after their buffers.
+struct StreamHolder {
+  int device = 0; cudaStream_t s = nullptr;
+  ~StreamHolder() { if (s) { cudaSetDevice(device); cudaStreamSynchronize(s); cudaStreamDestroy(s); } }
+};
+
 struct eg3d_scene {
+  std::shared_ptr<StreamHolder> sh;
   int device = 0; cudaStream_t stream = nullptr;
   int V = 0, width = 0, height = 0, num_sms = 0;
   eg3d_params prm;
@@ -108,6 +117,7 @@ struct PinnedPool {
 static PinnedPool g_pinned;
 
 struct eg3d_points {
+  std::shared_ptr<StreamHolder> sh;
   int device = 0; cudaStream_t stream = nullptr;
   int64_t n_points = 0, n_obs = 0;
   // device-resident, ordered by (seed, chain position)
@@ -389,7 +399,7 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
                                int64_t cap_scale, bool& out_overflow) {
   out_overflow = false;
   const int V = sc->V; const int n = ds.n;
-  out->device = sc->device; out->stream = sc->stream;
+  out->sh = sc->sh; out->device = sc->device; out->stream = sc->stream;
   if (n == 0) { CK(out->d_obs_off.alloc(1)); CK(cudaMemsetAsync(out->d_obs_off.p, 0, sizeof(int64_t), sc->stream)); CK(cudaStreamSynchronize(sc->stream)); return EG3D_OK; }
   const int capf = sc->prm.max_follow_points, capc = sc->prm.max_chain_points, oc = V + 16;
   const size_t spw = k3_scratch_bytes(V, capf, capc, oc);
@@ -432,7 +442,7 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
   const bool do_prof = getenv("EG3D_K3_PROF") != nullptr;
   DBuf<unsigned long long> prof_seed;
   if (do_prof) {
-    CK(prof.alloc(16)); CK(cudaMemsetAsync(prof.p, 0, 16 * sizeof(unsigned long long), sc->stream)); a.prof = prof.p;
+    CK(prof.alloc(48)); CK(cudaMemsetAsync(prof.p, 0, 48 * sizeof(unsigned long long), sc->stream)); a.prof = prof.p;
     CK(prof_seed.alloc(2 * (size_t)n)); CK(cudaMemsetAsync(prof_seed.p, 0, 2 * (size_t)n * sizeof(unsigned long long), sc->stream)); a.prof_seed = prof_seed.p;
   }
   // phase A -> phase B hand-over buffers
@@ -466,6 +476,7 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
     CK(otmp.alloc(tb));
     cub::DeviceRadixSort::SortPairs(otmp.p, tb, okeys.p, okeys2.p, ovals.p, oorder.p, n, 0, 32, sc->stream);
     b.pa_order = oorder.p;
+    if (tm) tm->kernel_launches += 1;
   }
   t3b.start();
   k3b_expand_kernel<<<nblocks_b, K3B_THREADS, 0, sc->stream>>>(sc->dev, b);
@@ -475,10 +486,18 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
   CK(cudaStreamSynchronize(sc->stream));
   if (tm) { tm->k3a_ms += t3.ms(); tm->k3b_ms += t3b.ms(); tm->k3_ms += t3.ms() + t3b.ms(); tm->n_accepted_seeds += (int64_t)pac[0]; tm->kernel_launches += 2; tm->n_capacity_overflows += (int)(cnt[2] + cnt[3]); }
   if (do_prof) {
-    unsigned long long pr[16]; CK(cudaMemcpy(pr, prof.p, sizeof pr, cudaMemcpyDeviceToHost));
-    const char* nm[12] = {"A.scan+prune", "A.est3", "A.plg_compatible", "B.epc_prune", "B.epc_gn", "B.add_view_finish(epc)", "B.main_loop", "seed_total", "#est3_lanes", "#est3_rounds", "#plg_compat", "#epc_solved"};
-    for (int k = 0; k < 12; k++) fprintf(stderr, "[k3prof] %-26s %14llu%s\n", nm[k], pr[k], k < 8 ? " warp-cycles" : "");
-    fprintf(stderr, "[k3prof] max seed cycles %llu (%.1f ms at 1.9 GHz); seeds > 50M cycles: %llu; > 200M cycles: %llu\n", pr[12], pr[12] / 1.9e6, pr[13], pr[14]);
+    unsigned long long pr[48]; CK(cudaMemcpy(pr, prof.p, sizeof pr, cudaMemcpyDeviceToHost));
+    const char* nm[32] = {"A.scan+prune", "A.est3", "A.plg_compatible", "B.epc_prune", "B.epc_gn", "B.add_view_finish(epc)", "B.main_loop", "seed_total", "#est3_lanes", "#est3_rounds", "#plg_compat", "#epc_solved",
+                          "#epc_gn_calls", "#main_first_gn", "#avf_calls(main)", "#avf_ok(main)", "#walk_solve_calls", "#walk_solve_problems", "#main_points_visited", "#main_grid_unique_ok", "", "#follow_big", "#est_slot", "#combos_slot",
+                          "#views_run", "#epc_matched", "#sum_len_at_view", "#walk_geo_calls", "#walk_geo_nwalk", "", "", ""};
+    for (int k = 0; k < 32; k++) if (nm[k][0]) fprintf(stderr, "[k3prof] %-26s %14llu%s\n", nm[k], pr[k], k < 8 ? " warp-cycles" : "");
+    fprintf(stderr, "[k3prof] max seed cycles %llu (%.1f ms at 1.9 GHz); seeds > 50M cycles: %llu; > 200M cycles: %llu\n", pr[40], pr[40] / 1.9e6, pr[41], pr[42]);
+#ifdef EG3D_K3_PROFILE
+    {
+      unsigned long long g[8]; CK(cudaMemcpyFromSymbol(g, g_gnprof, sizeof g));
+      fprintf(stderr, "[k3prof] gn_group: calls %llu, iterations %llu, obs-loop passes %llu, running-lane-iterations %llu (cumulative over K3a+K3b of this process)\n", g[0], g[1], g[2], g[3]);
+    }
+#endif
     const char* dump = getenv("EG3D_K3_PROF");
     if (dump && (dump[0] == '/' || strchr(dump, '.'))) {   // EG3D_K3_PROF=<file>: per-seed (cycles, initial length, final length)
       std::vector<unsigned long long> ps(2 * (size_t)n); CK(cudaMemcpy(ps.data(), prof_seed.p, ps.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -620,7 +639,7 @@ void eg3d_params_default(eg3d_params* p) {
   p->detection_starting_radius = 10.0f; p->detection_mult = 3.0f;
   p->gn_max_iters = 30; p->gn_stop = 0.0000005; p->gn_det_min = 0.00001; p->gn_accept_mse = 9;
   p->filter_gn_stop = 0.0000000005; p->filter_gn_det_min = 0.0000000001; p->filter_gn_max_mse = 2.25f;
-  p->filter_3views_amount = 3; p->dedup_cell = 3.0f; p->dlt_wellposed = 1; p->filter_abs_int = 0;
+  p->filter_3views_amount = 3; p->dedup_cell = 3.0f; p->dlt_wellposed = 2; p->filter_abs_int = 0;
   p->max_chain_points = 96; p->max_follow_points = 160;
 }
 
@@ -632,7 +651,9 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
   CK(cudaGetDevice(&sc->device));
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, sc->device));
   sc->num_sms = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+  sc->sh = std::make_shared<StreamHolder>(); sc->sh->device = sc->device;
+  CK(cudaStreamCreateWithFlags(&sc->sh->s, cudaStreamNonBlocking));
+  sc->stream = sc->sh->s;
   g_alloc_stream = sc->stream;
   {
     cudaMemPool_t pool; CK(cudaDeviceGetDefaultMemPool(&pool, sc->device));
@@ -753,10 +774,8 @@ eg3d_status eg3d_scene_create(const eg3d_scene_desc* d, const eg3d_params* param
 void eg3d_scene_destroy(eg3d_scene* sc) {
   if (!sc) return;
   cudaSetDevice(sc->device);
-  cudaStream_t st = sc->stream;
-  if (st) cudaStreamSynchronize(st);
-  delete sc;   // buffers are returned to the pool on the (still live) stream
-  if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+  if (sc->stream) cudaStreamSynchronize(sc->stream);
+  delete sc;   // buffers are returned to the pool on the stream, which lives until the last result of this scene is freed
 }
 
 eg3d_status eg3d_sample_seeds(const eg3d_scene_desc* d, const int32_t* views, const uint32_t* polylines, int64_t n_pl, float spacing,
@@ -1119,7 +1138,7 @@ void eg3d_project_host(const float* cam12, const float* x3, float* out2) {
 #define EG3D_STR(x) EG3D_STR2(x)
 // compile-time switches of this build (A/B variants are told apart by it; tests gate on it)
 const char* eg3d_build_info(void) {
-  return "EG3D_DLT_OPENCV=" EG3D_STR(EG3D_DLT_OPENCV) " EG3D_K3A_MIN_BLOCKS=" EG3D_STR(EG3D_K3A_MIN_BLOCKS) " EG3D_K3B_MIN_BLOCKS=" EG3D_STR(EG3D_K3B_MIN_BLOCKS)
+  return "EG3D_DLT_OPENCV=1 EG3D_K3A_MIN_BLOCKS=" EG3D_STR(EG3D_K3A_MIN_BLOCKS) " EG3D_K3B_MIN_BLOCKS=" EG3D_STR(EG3D_K3B_MIN_BLOCKS)
          " EG3D_K3B_THREADS=" EG3D_STR(EG3D_K3B_THREADS) " EG3D_K3B_SYNC=" EG3D_STR(EG3D_K3B_SYNC) " EG3D_K3B_BATCH=" EG3D_STR(EG3D_K3B_BATCH)
          " EG3D_GN_UNROLL=" EG3D_STR(EG3D_GN_UNROLL) " EG3D_K1_GROUP=" EG3D_STR(EG3D_K1_GROUP);
 }
@@ -1204,8 +1223,9 @@ eg3d_status eg3d_match_seeds(eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d
   st = prepare_hits_a(sc, ds, cands ? &dc : nullptr, H, &local); if (st != EG3D_OK) return st;
   std::unique_ptr<eg3d_points> pts(new eg3d_points());
   st = run_k3(sc, ds, H, pts.get(), &local);
+  tall.stop();
   local.n_seeds = seeds->n;
-  local.total_ms = local.k1_any_ms + local.k1_count_ms + local.scan_ms + local.k1_fill_ms + local.k3_ms + local.pack_ms;
+  local.total_ms = tall.ms();   // first kernel launch .. last kernel end, everything in between included
   k1_accounting(sc, seeds, cands, local.n_hits, &local);
   if (tm) *tm = local;
   if (st != EG3D_OK) return st;
@@ -1390,7 +1410,8 @@ eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_po
   A6Args a; memset(&a, 0, sizeof a);
   a.o_begin = o_begin; a.o_end = o_end; a.tb = tb; a.obs_track = sc->obs_track.p;
   a.recs = recs.p; a.n_ids = n_ids.p; a.n_cand = n_cand.p; a.n_seed = n_seed.p; a.is_last = is_last.p; a.overflow = ovf.p; a.row_cnt = coff.p;
-  Timer ts(sc->stream);
+  Timer ts(sc->stream), tall(sc->stream);
+  tall.start();
   ts.start();
   const unsigned blocks = (unsigned)(((size_t)n_o * 32 + A6_THREADS - 1) / A6_THREADS);
   if (n_o > 0) a6_classify_kernel<<<blocks, A6_THREADS, 0, sc->stream>>>(sc->dev, a);
@@ -1428,8 +1449,9 @@ eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_po
   st = prepare_hits_a(sc, ds, &dc, H, &local); if (st != EG3D_OK) return st;
   std::unique_ptr<eg3d_points> pts(new eg3d_points());
   st = run_k3(sc, ds, H, pts.get(), &local);
+  tall.stop();
   local.n_seeds = n_seeds;
-  local.total_ms = local.k1_any_ms + local.k1_count_ms + local.scan_ms + local.k1_fill_ms + local.k3_ms + local.pack_ms;
+  local.total_ms = tall.ms();
   if (tm) *tm = local;
   if (st != EG3D_OK) return st;
   *out = pts.release();

@@ -15,11 +15,6 @@
 #ifndef EG3D_GN_UNROLL
 #define EG3D_GN_UNROLL 1
 #endif
-// 1: eg3d_params.dlt_wellposed == 2 selects dlt_null_opencv (OpenCV's own SVD, the quirk's camera pair) in the kernels.
-// Prepared in round 1 without a GPU to verify it, hence off: with 0 the kernels are byte-identical to the measured build.
-#ifndef EG3D_DLT_OPENCV
-#define EG3D_DLT_OPENCV 0
-#endif
 
 namespace eg3d {
 constexpr int kGnUnroll = EG3D_GN_UNROLL;
@@ -597,11 +592,7 @@ EG3D_HD_NI bool est3(const DevScene& S, const int v[3], const float2 pt[3], floa
   if (v[1] < v[mi]) mi = 1;
   if (v[2] < v[mi]) mi = 2;
   int ma = 2;
-#if EG3D_DLT_OPENCV
   if (S.prm.dlt_wellposed == 1 && v[ma] == v[mi]) {
-#else
-  if (S.prm.dlt_wellposed && v[ma] == v[mi]) {
-#endif
     if (v[2] != v[mi]) ma = 2; else if (v[1] != v[mi]) ma = 1; else if (v[0] != v[mi]) ma = 0;
   }
   float2 pmi = pt[0], pma = pt[0];
@@ -609,10 +600,7 @@ EG3D_HD_NI bool est3(const DevScene& S, const int v[3], const float2 pt[3], floa
   if (mi == 1) { pmi = pt[1]; vmi = v[1]; } else if (mi == 2) { pmi = pt[2]; vmi = v[2]; }
   if (ma == 1) { pma = pt[1]; vma = v[1]; } else if (ma == 2) { pma = pt[2]; vma = v[2]; }
   float t4[4];
-#if EG3D_DLT_OPENCV
-  if (S.prm.dlt_wellposed == 2) dlt_null_opencv(S.P + 12 * vmi, S.P + 12 * vma, pmi, pma, t4); else
-#endif
-  dlt_null(S.P + 12 * vmi, S.P + 12 * vma, pmi, pma, t4);
+  dlt_null_opencv(S.P + 12 * vmi, S.P + 12 * vma, pmi, pma, t4);
   double X[3] = {(double)(t4[0] / t4[3]), (double)(t4[1] / t4[3]), (double)(t4[2] / t4[3])};
   if (!gn3_exact(S, v, pt, X)) return false;
   Xo[0] = (float)X[0]; Xo[1] = (float)X[1]; Xo[2] = (float)X[2];
@@ -744,6 +732,9 @@ EG3D_D void gn_accumulate_fast(const double* __restrict__ P, float px, float py,
 // called by all 32 lanes; groups without a problem pass active = false.  Returns the accept decision (last_mse < 9) of
 // the caller's group.  Loop-invariant scalars are re-read from the (constant-bank) scene instead of being kept in
 // registers: the observation loop has to stay spill-free at 64 registers.
+#ifdef EG3D_K3_PROFILE
+__device__ unsigned long long g_gnprof[8];   // [0] calls, [1] iterations, [2] observation-loop passes (max over lanes), [3] active lanes x iterations
+#endif
 static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o, bool active, int G, int lane, double X[3]) {
   const int* __restrict__ ov = o.v;
   const float* __restrict__ ox = o.x;
@@ -753,8 +744,20 @@ static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o,
   double X0 = X[0], X1 = X[1], X2 = X[2];
   double last_mse = 0;
   bool running = active, failed = false;
+#ifdef EG3D_K3_PROFILE
+  if (lane == 0) atomicAdd(&g_gnprof[0], 1ull);
+#endif
   for (int it = 0; it < S.prm.gn_max_iters; it++) {
     if (!__any_sync(0xffffffffu, running)) break;
+#ifdef EG3D_K3_PROFILE
+    {
+      const int passes = running ? (ntot - sub + G - 1) / G : 0;
+      int mp = passes;
+      for (int o2 = 16; o2 > 0; o2 >>= 1) mp = max(mp, __shfl_xor_sync(0xffffffffu, mp, o2));
+      const unsigned rm = __ballot_sync(0xffffffffu, running);
+      if (lane == 0) { atomicAdd(&g_gnprof[1], 1ull); atomicAdd(&g_gnprof[2], (unsigned long long)mp); atomicAdd(&g_gnprof[3], (unsigned long long)__popc(rm)); }
+    }
+#endif
     GnAcc a = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (running) {
       const double* __restrict__ P64 = S.P64;

@@ -136,7 +136,7 @@ EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
 struct Ctx {
   const DevScene* S; const K3Args* A; WS w;
 #ifdef EG3D_K3_PROFILE
-  long long pc[12];   // profiling accumulators (profile builds only: build.sh -DEG3D_K3_PROFILE)
+  long long pc[32];   // profiling accumulators (profile builds only: build.sh -DEG3D_K3_PROFILE)
 #endif
   int lane, seed, sv;
   long long hrow;  // phase B: first row of this seed in hit_off_b
@@ -440,20 +440,11 @@ static __device__ __noinline__ bool est_slot(Ctx& c, int slot, int n, float Xo[3
     if (ov2 < bestv || (ov2 == bestv && oi2 < besti)) { bestv = ov2; besti = oi2; }
   }
   int mi = besti, ma = n - 1;
-#if EG3D_DLT_OPENCV
   if (S.prm.dlt_wellposed == 1 && ov[ma] == ov[mi]) {
-#else
-  if (S.prm.dlt_wellposed && ov[ma] == ov[mi]) {
-#endif
     for (int j = n - 1; j >= 0; j--) if (ov[j] != ov[mi]) { ma = j; break; }
   }
   float t4[4];
-#if EG3D_DLT_OPENCV
-  if (S.prm.dlt_wellposed == 2)
-    dlt_null_opencv(S.P + 12 * ov[mi], S.P + 12 * ov[ma], make_float2(c.w.ox[b + mi], c.w.oy[b + mi]), make_float2(c.w.ox[b + ma], c.w.oy[b + ma]), t4);
-  else
-#endif
-  dlt_null(S.P + 12 * ov[mi], S.P + 12 * ov[ma], make_float2(c.w.ox[b + mi], c.w.oy[b + mi]), make_float2(c.w.ox[b + ma], c.w.oy[b + ma]), t4);
+  dlt_null_opencv(S.P + 12 * ov[mi], S.P + 12 * ov[ma], make_float2(c.w.ox[b + mi], c.w.oy[b + mi]), make_float2(c.w.ox[b + ma], c.w.oy[b + ma]), t4);
   double X[3] = {(double)(t4[0] / t4[3]), (double)(t4[1] / t4[3]), (double)(t4[2] / t4[3])};
   if (!gn_group(S, slot_obs(c, slot, n, false, 0, 0.f, 0.f), true, 32, c.lane, X)) return false;
   Xo[0] = (float)X[0]; Xo[1] = (float)X[1]; Xo[2] = (float)X[2];
@@ -601,8 +592,9 @@ static __device__ __noinline__ bool step_all_big(Ctx& c, const uint32_t* dirs, i
       __syncwarp();
       if (count < 3) continue;
       float X[3];
+      K3P_ADD(c, 22, 1);
       bool valid = est_slot(c, t, count, X);
-      if (!valid) valid = combos_slot(c, t, count, X);
+      if (!valid) { K3P_ADD(c, 23, 1); valid = combos_slot(c, t, count, X); }
       if (valid) {
         __syncwarp();
         if (c.lane == 0) { c.w.snobs[t] = count; c.w.sX[3 * t] = X[0]; c.w.sX[3 * t + 1] = X[1]; c.w.sX[3 * t + 2] = X[2]; }
@@ -617,6 +609,7 @@ static __device__ __noinline__ bool step_all_big(Ctx& c, const uint32_t* dirs, i
 // follow_direction_vector_start / _end, plg_matching.cpp:771-795.  Returns the number of points added.
 static __device__ __noinline__ int follow_big(Ctx& c, const uint32_t* dirs, bool at_start) {
   int added = 0;
+  K3P_ADD(c, 21, 1);
   while (true) {
     int cur_slot = slot_of(c, at_start ? 0 : c.len - 1);
     if (!step_all_big(c, dirs, cur_slot)) break;
@@ -646,6 +639,7 @@ static __device__ __noinline__ int walk_geo(Ctx& c, int v, const Plg& p, uint32_
   // the chain points in walking order; their epipolar lines (from each point's FIRST observation, :797-806) are
   // independent of the walk and are computed 32 at a time, the walk itself is sequential with a 32-segment-wide step
   const int nwalk = towards_start ? cur - lo : hi - cur - 1;
+  K3P_ADD(c, 27, 1); K3P_ADD(c, 28, nwalk);
   bool stop = false;
   for (int base = 0; base < nwalk && !stop; base += 32) {
     const int k = base + c.lane;
@@ -693,6 +687,7 @@ static __device__ __noinline__ void walk_solve(Ctx& c, int v, int cur, NTmp* tmp
       X[0] = c.w.sX[3 * slot]; X[1] = c.w.sX[3 * slot + 1]; X[2] = c.w.sX[3 * slot + 2];
       ex = tmp[k].cx; ey = tmp[k].cy;
     }
+    K3P_ADD(c, 16, 1); K3P_ADD(c, 17, P);
     const bool ok = gn_group(S, slot_obs(c, slot, n, true, v, ex, ey), active, G, c.lane, X);
     if (active) {
       if (ok) { if ((c.lane & (G - 1)) == 0) { tmp[k].X[0] = (float)X[0]; tmp[k].X[1] = (float)X[1]; tmp[k].X[2] = (float)X[2]; } }
@@ -855,6 +850,7 @@ static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) 
     if (active) { eg3d_hit h = epcs[e]; hx = h.x; hy = h.y; }
     double X[3] = {c.w.sX[3 * cslot], c.w.sX[3 * cslot + 1], c.w.sX[3 * cslot + 2]};
     K3P_BEGIN(te1);
+    K3P_ADD(c, 12, 1);
     bool ok = gn_group(S, slot_obs(c, cslot, n, true, v, hx, hy), active, G, c.lane, X);
     K3P_END(c, 4, te1);
     float Xe[3] = {(float)X[0], (float)X[1], (float)X[2]};
@@ -888,20 +884,25 @@ static __device__ __noinline__ void expand_view_main(Ctx& c, int v, const EvStat
   K3P_BEGIN(te3);
   for (int cur = 0; cur < c.len; cur++) {
     if (matched && cur == iv0) { cur = iv1; last = iv1; continue; }
+    K3P_ADD(c, 18, 1);
     const int slot = slot_of(c, cur);
     float2 q = project(S.P + 12 * v, c.w.sX[3 * slot], c.w.sX[3 * slot + 1], c.w.sX[3 * slot + 2]);
     uint32_t pl_id;
     if (!grid_unique_warp(S.g_expand, v, S.width, S.height, q, pl_id, c.lane)) continue;
+    K3P_ADD(c, 19, 1);
     Pl pl = get_pl(S, v, pl_id);
     Plg init; init.pl = pl_id;
     if (pl_distancesq_warp(pl, q, init.seg, init.c, c.lane) > S.prm.max_proj_distsq_expand) return;  // abandons the view
     const int hi = matched ? (cur <= iv0 ? iv0 : c.len) : c.len;
     const int n = c.w.snobs[slot];
     double X[3] = {c.w.sX[3 * slot], c.w.sX[3 * slot + 1], c.w.sX[3 * slot + 2]};
+    K3P_ADD(c, 13, 1);
     if (!gn_group(S, slot_obs(c, slot, n, true, v, init.c.x, init.c.y), true, 32, c.lane, X)) continue;
     float Xc[3] = {(float)X[0], (float)X[1], (float)X[2]};
     int ns = 0, ne = 0;
+    K3P_ADD(c, 14, 1);
     if (add_view_finish(c, v, init, Xc, last + 1, cur, hi, ns, ne)) {
+      K3P_ADD(c, 15, 1);
       if (ns > cur) { c.central = ns; cur = ns + ne; }
       else cur = cur + ne;
       last = cur;
@@ -1069,7 +1070,7 @@ __global__ void __launch_bounds__(K3_THREADS, EG3D_K3A_MIN_BLOCKS) k3a_hypothesi
     c.seed = seed; c.sv = A.seed_view[seed];
     c.len = 0; c.nslots = 0; c.central = 0; c.overflow = false;
 #ifdef EG3D_K3_PROFILE
-    for (int k = 0; k < 12; k++) c.pc[k] = 0;
+    for (int k = 0; k < 32; k++) c.pc[k] = 0;
 #endif
     K3P_BEGIN(tall);
     PaRec r;
@@ -1090,7 +1091,7 @@ __global__ void __launch_bounds__(K3_THREADS, EG3D_K3A_MIN_BLOCKS) k3a_hypothesi
       }
     }
 #ifdef EG3D_K3_PROFILE
-    if (A.prof && lane == 0) for (int k = 0; k < 12; k++) if (c.pc[k]) atomicAdd(&A.prof[k], (unsigned long long)c.pc[k]);
+    if (A.prof && lane == 0) for (int k = 0; k < 32; k++) if (c.pc[k]) atomicAdd(&A.prof[k], (unsigned long long)c.pc[k]);
 #endif
     __syncwarp();
   }
@@ -1219,7 +1220,7 @@ __global__ void __launch_bounds__(K3B_THREADS, 1) k3b_expand_kernel(const __grid
     __syncwarp();
   };
 #ifdef EG3D_K3_PROFILE
-  for (int k = 0; k < 12; k++) c.pc[k] = 0;
+  for (int k = 0; k < 32; k++) c.pc[k] = 0;
 #endif
   while (true) {
     bool any = false;
@@ -1310,7 +1311,7 @@ __global__ void __launch_bounds__(K3B_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_k
     c.len = 0; c.nslots = 0; c.central = 0; c.overflow = false;
     c.sel[0] = c.sel[1] = c.sel[2] = -1;
 #ifdef EG3D_K3_PROFILE
-    for (int k = 0; k < 12; k++) c.pc[k] = 0;
+    for (int k = 0; k < 32; k++) c.pc[k] = 0;
 #endif
     K3P_BEGIN(tall);
     bool live = false;
@@ -1338,7 +1339,7 @@ __global__ void __launch_bounds__(K3B_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_k
 #if EG3D_K3B_SYNC
       __syncthreads();
 #endif
-      if (run) expand_view_epc(c, v, st);
+      if (run) { K3P_ADD(c, 24, 1); expand_view_epc(c, v, st); if (st.matched) K3P_ADD(c, 25, 1); K3P_ADD(c, 26, c.len); }
 #if EG3D_K3B_SYNC
       __syncthreads();
 #endif
@@ -1348,10 +1349,10 @@ __global__ void __launch_bounds__(K3B_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_k
     if (!has) continue;
 #ifdef EG3D_K3_PROFILE
     if (A.prof && lane == 0) {
-      for (int k = 0; k < 12; k++) if (c.pc[k]) atomicAdd(&A.prof[k], (unsigned long long)c.pc[k]);
-      atomicMax(&A.prof[12], (unsigned long long)c.pc[7]);
-      if (c.pc[7] > 50000000ll) atomicAdd(&A.prof[13], 1ull);
-      if (c.pc[7] > 200000000ll) atomicAdd(&A.prof[14], 1ull);
+      for (int k = 0; k < 32; k++) if (c.pc[k]) atomicAdd(&A.prof[k], (unsigned long long)c.pc[k]);
+      atomicMax(&A.prof[40], (unsigned long long)c.pc[7]);
+      if (c.pc[7] > 50000000ll) atomicAdd(&A.prof[41], 1ull);
+      if (c.pc[7] > 200000000ll) atomicAdd(&A.prof[42], 1ull);
       if (A.prof_seed) { A.prof_seed[2 * (size_t)seed] = (unsigned long long)c.pc[7]; A.prof_seed[2 * (size_t)seed + 1] = (unsigned long long)len0 | ((unsigned long long)c.len << 32); }
     }
 #endif

@@ -89,11 +89,12 @@ typedef struct eg3d_params {
   float  filter_gn_max_mse;           /* 2.25  gauss_newton.hpp:18 */
   int32_t filter_3views_amount;       /* 3     outliers_filtering.hpp:16 */
   float  dedup_cell;                  /* 3     filtering_close_plgps.cpp:75 */
-  /* 1 (default): when get_min_max's "last index" quirk selects the same camera twice for the 2-view DLT
-   * initialiser (edge_graph_3d_utilities.hpp:86-88), use the last list entry whose view differs instead
-   * (SURVEY A.2.1).  0: keep the rank-deficient DLT with this library's own SVD (a point of the null-space ray that differs
-   * from OpenCV's).  2 (oracle only this round; the kernels treat it as 1): the quirk's pair with OpenCV 4.x's own Jacobi SVD
-   * restated — the setting that reproduces a reference linked against OpenCV.                            */
+  /* The 2-view DLT initialiser of em_estimate3Dpositions (triangulation.cpp:252-290) gets the camera pair chosen by
+   * get_min_max, whose "max" is always the LAST list entry (edge_graph_3d_utilities.hpp:86-88); when that is also the lowest
+   * view, cv::triangulatePoints sees the same camera twice and returns whichever point of the back-projected ray its SVD lands on.
+   * 2 (default; 0 is an alias): the reference's pair with OpenCV 4.x's own Jacobi SVD restated (bit-identical to
+   *    cv2.triangulatePoints incl. the degenerate case) — reproduces a reference linked against OpenCV.
+   * 1: use the last list entry whose view differs instead (well-posed; NOT what the reference computes).  Same SVD arithmetic. */
   int32_t dlt_wellposed;
   /* 0 (default): `abs(mse/(2n) - last_mse)` in gauss_newton.cpp:114 is the float overload (GCC >= 6).
    * 1: emulate the truncating `int abs(int)` binding of the author's GCC 5 toolchain.         */
@@ -176,9 +177,9 @@ int         eg3d_device_count(void);
 /* Host evaluation of compute_projection (geometric_utilities.cpp:973-977) as the kernels compute it (tests). */
 void        eg3d_project_host(const float* cam12, const float* x3, float* out2);
 const char* eg3d_build_info(void);   /* the compile-time switches of this build, "NAME=value ..." */
-/* Host evaluation of the 2-view DLT initialiser (cv::triangulatePoints at triangulation.cpp:216,290) as the kernels compute
- * it: opencv_svd = 0 -> the current one-sided Jacobi SVD, 1 -> OpenCV's own Jacobi SVD restated (bit-identical to
- * cv2.triangulatePoints, degenerate inputs included; the kernels adopt it as eg3d_params.dlt_wellposed = 2 next round). */
+/* Host evaluation of the 2-view DLT initialiser (cv::triangulatePoints at triangulation.cpp:216,290): opencv_svd = 1 -> what the
+ * kernels compute, OpenCV's own Jacobi SVD restated (bit-identical to cv2.triangulatePoints, degenerate inputs included);
+ * 0 -> a plain one-sided Jacobi SVD (round 1's initialiser, host only now; kept to show that another SVD returns another point). */
 void        eg3d_triangulate_dlt_host(const float* P1, const float* P2, const float* x1, const float* x2,
                                       int32_t opencv_svd, float* out4);
 

@@ -236,7 +236,7 @@ void eg3d_oracle_params_default(eg3d_params* p) {
   p->detection_starting_radius = 10.0f; p->detection_mult = 3.0f;
   p->gn_max_iters = 30; p->gn_stop = 0.0000005; p->gn_det_min = 0.00001; p->gn_accept_mse = 9;
   p->filter_gn_stop = 0.0000000005; p->filter_gn_det_min = 0.0000000001; p->filter_gn_max_mse = 2.25f;
-  p->filter_3views_amount = 3; p->dedup_cell = 3.0f; p->dlt_wellposed = 1; p->filter_abs_int = 0;
+  p->filter_3views_amount = 3; p->dedup_cell = 3.0f; p->dlt_wellposed = 2; p->filter_abs_int = 0;
   p->max_chain_points = 96; p->max_follow_points = 160;
 }
 

@@ -233,10 +233,9 @@ void em_estimate3Dpositions(const Scene& s, const std::vector<V2>& coords, const
     for (int j = (int)ids.size() - 1; j >= 0; j--) if (ids[j] != ids[min_index]) { max_index = j; break; }
   }
   float t4[4];
-  if (s.prm.dlt_wellposed == 2)   /* the reference linked against OpenCV 4.x, quirk and all */
-    triangulate_dlt_opencv(s.P[ids[min_index]].data(), s.P[ids[max_index]].data(), coords[min_index], coords[max_index], t4);
-  else
-    triangulate_dlt(s.P[ids[min_index]].data(), s.P[ids[max_index]].data(), coords[min_index], coords[max_index], t4);
+  /* always OpenCV's own SVD (cv::triangulatePoints restated): with dlt_wellposed != 1 this is the reference linked against
+   * OpenCV 4.x, quirk and all; with 1 the same arithmetic on a well-posed camera pair */
+  triangulate_dlt_opencv(s.P[ids[min_index]].data(), s.P[ids[max_index]].data(), coords[min_index], coords[max_index], t4);
   double init[3] = {(double)(t4[0] / t4[3]), (double)(t4[1] / t4[3]), (double)(t4[2] / t4[3])}; /* Vec4f / float */
   double out[3];
   if (em_GaussNewton(s, ids, coords, init, out, nullptr) != -1) {

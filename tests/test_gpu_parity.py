@@ -249,7 +249,7 @@ def test_k1_device_only_entry_point_counts_the_same_hits(small):
     assert tm_dev["n_segment_tests"] == tm["n_segment_tests"] and tm_dev["k1_algorithmic_bytes"] == tm["k1_algorithmic_bytes"]
 
 
-@pytest.mark.parametrize("overrides", [dict(dlt_wellposed=0), dict(filter_abs_int=1), dict(split_interval_distance=7.0, follow_first_image_distance=6.0),
+@pytest.mark.parametrize("overrides", [dict(dlt_wellposed=1), dict(filter_abs_int=1), dict(split_interval_distance=7.0, follow_first_image_distance=6.0),
                                         dict(max_proj_distsq_expand=4.0, quasiparallel_cos=0.9)])
 def test_parameter_variants_parity(overrides):
     """The policy switches and a few of the reference's compile-time constants (eg3d_params) away from their defaults:

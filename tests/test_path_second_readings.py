@@ -226,8 +226,9 @@ def test_view_expansion_appends_views_in_ascending_order():
         later = pos >= 4
         dec = v[later] < v[np.where(later)[0] - 1]                                        # a decrease after entry 3
         # points PREPENDED / APPENDED to the chain by later all-view following start with more than three views in following
-        # order (driving view first); they are rare (5 of 20 311 on the real sample) and the only exception
-        assert dec.sum() <= 0.001 * pts.n_points, int(dec.sum())
+        # order (driving view first); they are rare (22 of 20 143 on the real sample in the default, OpenCV-faithful DLT mode; 5 of
+        # 20 311 with dlt_wellposed = 1) and the only exception
+        assert dec.sum() <= 0.002 * pts.n_points, int(dec.sum())
         first3 = np.stack([v[pts.obs_off[:-1] + k] for k in range(3)], 1)                 # [n_points, 3]
         rest = pos >= 3
         owner = np.repeat(np.arange(pts.n_points), lens)[rest]

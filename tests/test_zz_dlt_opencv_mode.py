@@ -1,6 +1,6 @@
-"""eg3d_params.dlt_wellposed = 2 (the quirk's camera pair with OpenCV's own SVD restated) on the GPU against the
-oracle in the same mode.  Runs only with a library built with -DEG3D_DLT_OPENCV=1 (bash edgegraph3d_b200/csrc/build.sh
--DEG3D_DLT_OPENCV=1): the default build of round 1 does not call dlt_null_opencv from the kernels and is skipped here."""
+"""eg3d_params.dlt_wellposed = 2 — the DEFAULT since round 2: the get_min_max quirk's camera pair handed to OpenCV's own SVD
+restated, i.e. what a reference linked against OpenCV 4.x computes also after a degenerate 2-view DLT — on the
+GPU against the oracle, on a synthetic scene and on the packaged dtu006 example (all three pipelines)."""
 import os
 import numpy as np
 import pytest
@@ -17,8 +17,7 @@ def _same(g, r):
 def test_opencv_faithful_mode_matches_oracle_synthetic_and_real():
     from edgegraph3d_b200 import lib as E, synthetic as syn, pipeline as P, real_scene
     from tests import oracle_lib as O
-    if E.build_info().get("EG3D_DLT_OPENCV") != "1":
-        pytest.skip("library built without -DEG3D_DLT_OPENCV=1")
+    assert E.default_params().dlt_wellposed == 2 and O.default_params().dlt_wellposed == 2
     sc = syn.make_scene(n_views=9, n_curves=20, seed=7, closed_frac=0.2, drop_view_frac=0.1)
     cands = syn.curve_candidate_sets(sc, seed=7)
     prm = E.default_params(dlt_wellposed=2)
