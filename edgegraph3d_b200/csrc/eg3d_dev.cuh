@@ -798,6 +798,66 @@ static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o,
   return active && !failed && last_mse < S.prm.gn_accept_mse;
 }
 
+// em_GaussNewton (triangulation.cpp:105-176) over n observations in the reference's own operation order — true divisions, no
+// FMA, every sum accumulated observation by observation — so the iterates are bit-identical to the oracle's (as gn3_exact is
+// for three observations).  Used where Gauss-Newton starts from the 2-view DLT point instead of a converged estimate
+// (est_slot, combos_slot): from such a start, and above all from the arbitrary point of the ray a degenerate DLT returns, the
+// iteration can wander for tens of steps and amplifies rounding-level differences into different accept decisions, which the
+// lane-parallel gn_group (different summation order) would not reproduce.  Thread-sequential; the warp executes it uniformly.
+// Rare: ~1 call per 50 gn_group calls on BASELINE configs[1].
+static __device__ __noinline__ bool gn_seq_exact(const DevScene& S, const ObsSrc& o, double X[3]) {
+  const eg3d_params& prm = S.prm;
+  const int n = o.n, ntot = o.n + o.has_extra;
+  double last_mse = 0;
+  for (int it = 0; it < prm.gn_max_iters; it++) {
+    double mse = 0;
+    double H[9];
+#pragma unroll
+    for (int a = 0; a < 9; a++) H[a] = 0;
+#pragma unroll 1
+    for (int m = 0; m < ntot; m++) {
+      int v; float px, py;
+      if (m < n) { v = o.v[m]; px = o.x[m]; py = o.y[m]; } else { v = o.ev; px = o.ex; py = o.ey; }
+      const double* __restrict__ P = S.P64 + 12 * v;
+      const double h0 = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3] * 1.0;
+      const double h1 = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7] * 1.0;
+      const double h2 = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11] * 1.0;
+      const double rx = (double)px - h0 / h2;
+      mse += rx * rx;
+      const double ry = (double)py - h1 / h2;
+      mse += ry * ry;
+      const double zz = h2 * h2;
+      double j0 = (P[0] * h2 - P[8] * h0) / zz, j1 = (P[1] * h2 - P[9] * h0) / zz, j2 = (P[2] * h2 - P[10] * h0) / zz;
+      H[0] += j0 * j0; H[1] += j0 * j1; H[2] += j0 * j2; H[3] += j1 * j0; H[4] += j1 * j1; H[5] += j1 * j2; H[6] += j2 * j0; H[7] += j2 * j1; H[8] += j2 * j2;
+      j0 = (P[4] * h2 - P[8] * h1) / zz; j1 = (P[5] * h2 - P[9] * h1) / zz; j2 = (P[6] * h2 - P[10] * h1) / zz;
+      H[0] += j0 * j0; H[1] += j0 * j1; H[2] += j0 * j2; H[3] += j1 * j0; H[4] += j1 * j1; H[5] += j1 * j2; H[6] += j2 * j0; H[7] += j2 * j1; H[8] += j2 * j2;
+    }
+    if (fabs(mse / (ntot * 2) - last_mse) < prm.gn_stop) break;
+    last_mse = mse / (ntot * 2);
+    const double d = det3d(H);
+    if (d < prm.gn_det_min) return false;
+    double Hi[9]; inv3d(H, d, Hi);
+    double a0 = 0, a1 = 0, a2 = 0;      // curEstimate += (H^-1 J^T) r, row by row
+#pragma unroll 1
+    for (int m = 0; m < ntot; m++) {
+      int v; float px, py;
+      if (m < n) { v = o.v[m]; px = o.x[m]; py = o.y[m]; } else { v = o.ev; px = o.ex; py = o.ey; }
+      const double* __restrict__ P = S.P64 + 12 * v;
+      const double h0 = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3] * 1.0;
+      const double h1 = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7] * 1.0;
+      const double h2 = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11] * 1.0;
+      const double rx = (double)px - h0 / h2, ry = (double)py - h1 / h2;
+      const double zz = h2 * h2;
+      double j0 = (P[0] * h2 - P[8] * h0) / zz, j1 = (P[1] * h2 - P[9] * h0) / zz, j2 = (P[2] * h2 - P[10] * h0) / zz;
+      a0 += (Hi[0] * j0 + Hi[1] * j1 + Hi[2] * j2) * rx; a1 += (Hi[3] * j0 + Hi[4] * j1 + Hi[5] * j2) * rx; a2 += (Hi[6] * j0 + Hi[7] * j1 + Hi[8] * j2) * rx;
+      j0 = (P[4] * h2 - P[8] * h1) / zz; j1 = (P[5] * h2 - P[9] * h1) / zz; j2 = (P[6] * h2 - P[10] * h1) / zz;
+      a0 += (Hi[0] * j0 + Hi[1] * j1 + Hi[2] * j2) * ry; a1 += (Hi[3] * j0 + Hi[4] * j1 + Hi[5] * j2) * ry; a2 += (Hi[6] * j0 + Hi[7] * j1 + Hi[8] * j2) * ry;
+    }
+    X[0] += a0; X[1] += a1; X[2] += a2;
+  }
+  return last_mse < prm.gn_accept_mse;
+}
+
 // lanes per problem for `p` (1..32) simultaneous problems
 EG3D_D int gn_group_width(int p) { return p > 16 ? 1 : p > 8 ? 2 : p > 4 ? 4 : p > 2 ? 8 : p > 1 ? 16 : 32; }
 

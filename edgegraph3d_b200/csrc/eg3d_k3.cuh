@@ -446,7 +446,7 @@ static __device__ __noinline__ bool est_slot(Ctx& c, int slot, int n, float Xo[3
   float t4[4];
   dlt_null_opencv(S.P + 12 * ov[mi], S.P + 12 * ov[ma], make_float2(c.w.ox[b + mi], c.w.oy[b + mi]), make_float2(c.w.ox[b + ma], c.w.oy[b + ma]), t4);
   double X[3] = {(double)(t4[0] / t4[3]), (double)(t4[1] / t4[3]), (double)(t4[2] / t4[3])};
-  if (!gn_group(S, slot_obs(c, slot, n, false, 0, 0.f, 0.f), true, 32, c.lane, X)) return false;
+  if (!gn_seq_exact(S, slot_obs(c, slot, n, false, 0, 0.f, 0.f), X)) return false;
   Xo[0] = (float)X[0]; Xo[1] = (float)X[1]; Xo[2] = (float)X[2];
   return true;
 }
@@ -509,7 +509,7 @@ static __device__ __noinline__ bool combos_slot(Ctx& c, int slot, int& n, float 
     if (c.w.selmask[i]) continue;
     ObsSrc obs; obs.v = tv; obs.x = tx; obs.y = ty; obs.n = m; obs.has_extra = 1; obs.ev = ov[i]; obs.ex = ox[i]; obs.ey = oy[i];
     double Xd[3] = {X[0], X[1], X[2]};
-    if (gn_group(S, obs, true, 32, c.lane, Xd)) {
+    if (gn_seq_exact(S, obs, Xd)) {
       X[0] = (float)Xd[0]; X[1] = (float)Xd[1]; X[2] = (float)Xd[2];
       __syncwarp();
       if (c.lane == 0) { c.w.selmask[i] = 1; tv[m] = ov[i]; tx[m] = ox[i]; ty[m] = oy[i]; }

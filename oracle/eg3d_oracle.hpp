@@ -87,6 +87,7 @@ bool computeCorrespondEpilineSinglePoint(const V2& p, const double* F9, bool Fva
 V2 compute_projection(const float P12[12], const V3& X);
 
 /* --- triangulation (triangulation.cpp) --- */
+extern thread_local int g_trace;
 void triangulate_dlt(const float P1[12], const float P2[12], const V2& x1, const V2& x2, float out4[4]);
 void triangulate_dlt_opencv(const float P1[12], const float P2[12], const V2& x1, const V2& x2, float out4[4]);
 int em_GaussNewton(const Scene& s, const std::vector<int>& views, const std::vector<V2>& pts, const double init[3],

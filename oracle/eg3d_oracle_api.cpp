@@ -84,7 +84,9 @@ static Points* run_seeds(const Scene& s, const std::vector<SeedRec>& seeds, cons
     const SeedRec& sd = seeds[i];
     const std::vector<std::vector<ulong_t>>* cs = (c && sd.cand_set >= 0) ? &csets[sd.cand_set] : nullptr;
     auto epc = find_epipolar_correspondences(s, cs, sd.view, sd.p);
+    { const char* t = getenv("EG3D_ORACLE_TRACE_SEED"); g_trace = (t && atoll(t) == i) ? 1 : 0; }
     chains[i] = compute_3D_point_multiple_views_plg_following_expandallviews_vector(s, sd.view, epc);
+    g_trace = 0;
   }
   Points* out = new Points();
   for (size_t i = 0; i < seeds.size(); i++) out->append(chains[i], (int32_t)i);
@@ -376,8 +378,11 @@ void* eg3d_oracle_match_refpoints(void* sc, int64_t tb, int64_t te, int n_thread
   std::vector<std::vector<Match>> chains(seeds.size());
   if (n_threads < 1) n_threads = 1;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
-  for (int64_t i = 0; i < (int64_t)seeds.size(); i++)
+  for (int64_t i = 0; i < (int64_t)seeds.size(); i++) {
+    { const char* t = getenv("EG3D_ORACLE_TRACE_SEED"); g_trace = (t && atoll(t) == i) ? 1 : 0; }
     chains[i] = compute_3D_point_multiple_views_plg_following_expandallviews_vector(*s, seeds[i].view, epcs[i]);
+    g_trace = 0;
+  }
   Points* out = new Points();
   for (size_t i = 0; i < seeds.size(); i++) out->append(chains[i], (int32_t)i);
   return out;

@@ -5,6 +5,8 @@
  */
 #include "eg3d_oracle.hpp"
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <tuple>
 
@@ -162,9 +164,11 @@ static inline void inv3(const double m[9], double d, double t[9]) {
 }
 
 /* triangulation.cpp:105-176 (+ em_point2D3DJacobian :53-103).  Returns 1 / -1. */
+thread_local int g_trace = 0;   /* EG3D_ORACLE_TRACE_SEED=<ordinal>: print the margins of every GN call of that seed (debug aid) */
 int em_GaussNewton(const Scene& s, const std::vector<int>& views, const std::vector<V2>& pts, const double init[3],
                    double out[3], double* last_mse_out) {
   const int n = (int)pts.size();
+  double tr_min_stop = 1e300, tr_min_det = 1e300; int tr_it = 0;
   std::vector<double> r(2 * n), J(6 * n), cams(12 * n);
   for (int m = 0; m < n; m++) cam4(s, views[m], &cams[12 * m]);
   double X[3] = {init[0], init[1], init[2]};
@@ -181,6 +185,7 @@ int em_GaussNewton(const Scene& s, const std::vector<int>& views, const std::vec
       r[2 * m + 1] = (double)pts[m].y - h1 / h2;
       mse += r[2 * m + 1] * r[2 * m + 1];
     }
+    if (g_trace) { tr_it = it; tr_min_stop = std::min(tr_min_stop, std::abs(std::abs(mse / (n * 2) - last_mse) - s.prm.gn_stop)); }
     if (std::abs(mse / (n * 2) - last_mse) < s.prm.gn_stop) break;
     last_mse = mse / (n * 2);
     for (int m = 0; m < n; m++) {
@@ -201,7 +206,8 @@ int em_GaussNewton(const Scene& s, const std::vector<int>& views, const std::vec
         H[3 * a + b] = acc;
       }
     double d = det3(H);
-    if (d < s.prm.gn_det_min) { if (last_mse_out) *last_mse_out = last_mse; return -1; }
+    if (g_trace) tr_min_det = std::min(tr_min_det, d);
+    if (d < s.prm.gn_det_min) { if (g_trace) fprintf(stderr, "[gn] n=%d it=%d DET FAIL det=%.3e last_mse=%.6g views0=%d init=(%.4f %.4f %.4f)\n", n, it, d, last_mse, views[0], init[0], init[1], init[2]); if (last_mse_out) *last_mse_out = last_mse; return -1; }
     double Hi[9]; inv3(H, d, Hi);
     /* curEstimate += H.inv() * J.t() * r  evaluates (H^-1 J^T) first, then times r (MatExpr order) */
     for (int a = 0; a < 3; a++) {
@@ -212,6 +218,10 @@ int em_GaussNewton(const Scene& s, const std::vector<int>& views, const std::vec
       }
       X[a] += acc;
     }
+  }
+  if (g_trace) {
+    fprintf(stderr, "[gn] n=%d its=%d last_mse=%.9g min|stop margin|=%.3e min det=%.3e lastview=%d init=(%.4f %.4f %.4f) X=(%.5f %.5f %.5f) %s\n", n, tr_it, last_mse, tr_min_stop, tr_min_det, views[n - 1],
+            init[0], init[1], init[2], X[0], X[1], X[2], last_mse < s.prm.gn_accept_mse ? "ok" : "REJECT");
   }
   if (last_mse_out) *last_mse_out = last_mse;
   if (last_mse < s.prm.gn_accept_mse) { out[0] = X[0]; out[1] = X[1]; out[2] = X[2]; return 1; }
@@ -614,6 +624,7 @@ static void expand_allpoints_to_other_view_using_plmap(const Scene& s, int other
   bool matched = false;
   for (const auto& epc : epcs) {
     m = add_view_to_3dpoint_and_sides_plgp_matches_vector(s, pts, start_dirs, end_dirs, other, epc, 0, central_index, (int)pts.size(), matched);
+    if (g_trace) fprintf(stderr, "[epc] view=%d hit pl=%lu seg=%lu matched=%d ns=%d ne=%d central=%d len=%d\n", other, (unsigned long)epc.pl, (unsigned long)epc.plp.seg, (int)matched, m.first, m.second, central_index, (int)pts.size());
     if (matched) {
       if (m.first > central_index) {
         central_index = m.first;
@@ -630,11 +641,14 @@ static void expand_allpoints_to_other_view_using_plmap(const Scene& s, int other
     V2 q = compute_projection(s.P[other].data(), pts[cur].X);
     ulong_t pl_id; bool valid;
     plmap.find_unique_polyline_potentially_within_search_dist(q, pl_id, valid);
+    if (g_trace) fprintf(stderr, "[main] view=%d cur=%d/%d X=(%.9g %.9g %.9g) q=(%.6f %.6f) unique=%d pl=%lu\n", other, cur, (int)pts.size(), pts[cur].X.x, pts[cur].X.y, pts[cur].X.z, q.x, q.y, (int)valid, (unsigned long)pl_id);
     if (valid) {
       int central = cur;
       const Polyline& pl = s.plgs[other][pl_id];
       PlPoint ip{};
-      if (pl.compute_distancesq(q, ip.seg, ip.c) > s.prm.max_proj_distsq_expand) return; /* abandons the view */
+      const float dsq_ = pl.compute_distancesq(q, ip.seg, ip.c);
+      if (g_trace) fprintf(stderr, "[main]   distsq=%.9g %s\n", dsq_, dsq_ > s.prm.max_proj_distsq_expand ? "ABANDON VIEW" : "");
+      if (dsq_ > s.prm.max_proj_distsq_expand) return; /* abandons the view */
       PlgPoint init{pl_id, ip};
       int interval_end = matched ? (central <= mi.first ? mi.first : (int)pts.size()) : (int)pts.size();
       auto added = add_view_to_3dpoint_and_sides_plgp_matches_vector(s, pts, start_dirs, end_dirs, other, init, last_matched + 1, central, interval_end, success);
