@@ -88,6 +88,7 @@ V2 compute_projection(const float P12[12], const V3& X);
 
 /* --- triangulation (triangulation.cpp) --- */
 extern thread_local int g_trace;
+extern thread_local long long g_foreign_direction_calls;   /* calls of next_pl_point_by_distance with a direction that is neither extreme (UB in the reference) */
 void triangulate_dlt(const float P1[12], const float P2[12], const V2& x1, const V2& x2, float out4[4]);
 void triangulate_dlt_opencv(const float P1[12], const float P2[12], const V2& x1, const V2& x2, float out4[4]);
 int em_GaussNewton(const Scene& s, const std::vector<int>& views, const std::vector<V2>& pts, const double init[3],

@@ -50,6 +50,8 @@ Scene* scene_from_desc(const eg3d_scene_desc* d, const eg3d_params* p) {
 struct Points {
   std::vector<float> xyz; std::vector<int32_t> seed, chain_pos; std::vector<int64_t> obs_off{0};
   std::vector<int32_t> obs_view; std::vector<uint32_t> obs_poly, obs_seg; std::vector<float> obs_xy;
+  std::vector<int64_t> seed_track; std::vector<int32_t> seed_set;   /* per seed: SfM point (pipeline 3) / candidate set (pipelines 1-2) */
+  std::vector<uint8_t> seed_ub;   /* per seed: the reference's behaviour is undefined on it */
   void append(const std::vector<Match>& chain, int32_t seed_ord) {
     for (size_t k = 0; k < chain.size(); k++) {
       const Match& m = chain[k];
@@ -64,7 +66,7 @@ struct Points {
   }
 };
 
-struct SeedRec { int view; PlgPoint p; int cand_set; };
+struct SeedRec { int view; PlgPoint p; int cand_set; int64_t track = -1; };
 
 static std::vector<std::vector<ulong_t>> cand_of(const Scene& s, const eg3d_candidates* c, int set) {
   std::vector<std::vector<ulong_t>> r(s.V);
@@ -79,17 +81,22 @@ static Points* run_seeds(const Scene& s, const std::vector<SeedRec>& seeds, cons
   std::vector<std::vector<std::vector<ulong_t>>> csets;
   if (c) for (int k = 0; k < c->n_sets; k++) csets.push_back(cand_of(s, c, k));
   if (n_threads < 1) n_threads = 1;
+  std::vector<uint8_t> ub(seeds.size(), 0);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
   for (int64_t i = 0; i < (int64_t)seeds.size(); i++) {
     const SeedRec& sd = seeds[i];
     const std::vector<std::vector<ulong_t>>* cs = (c && sd.cand_set >= 0) ? &csets[sd.cand_set] : nullptr;
     auto epc = find_epipolar_correspondences(s, cs, sd.view, sd.p);
     { const char* t = getenv("EG3D_ORACLE_TRACE_SEED"); g_trace = (t && atoll(t) == i) ? 1 : 0; }
+    const long long ub0 = g_foreign_direction_calls;
     chains[i] = compute_3D_point_multiple_views_plg_following_expandallviews_vector(s, sd.view, epc);
+    ub[i] = g_foreign_direction_calls != ub0;
     g_trace = 0;
   }
   Points* out = new Points();
   for (size_t i = 0; i < seeds.size(); i++) out->append(chains[i], (int32_t)i);
+  out->seed_ub = ub;
+  for (size_t i = 0; i < seeds.size(); i++) { out->seed_set.push_back(seeds[i].cand_set); out->seed_track.push_back(-1); }
   return out;
 }
 
@@ -147,7 +154,7 @@ static void refpoint_seeds(const Scene& s, int64_t rp, std::vector<SeedRec>& see
         } else cur.push_back(seed);
         all[img] = cur; /* scatter to the V-vector, plgpcm_3views_plg_following.cpp:41-43 */
       }
-      seeds.push_back(SeedRec{simg, seed, -1});
+      seeds.push_back(SeedRec{simg, seed, -1, rp});
       epcs.push_back(all);
     }
   }
@@ -377,14 +384,19 @@ void* eg3d_oracle_match_refpoints(void* sc, int64_t tb, int64_t te, int n_thread
   for (int64_t rp = tb; rp < te; rp++) refpoint_seeds(*s, rp, seeds, epcs);
   std::vector<std::vector<Match>> chains(seeds.size());
   if (n_threads < 1) n_threads = 1;
+  std::vector<uint8_t> ub(seeds.size(), 0);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
   for (int64_t i = 0; i < (int64_t)seeds.size(); i++) {
     { const char* t = getenv("EG3D_ORACLE_TRACE_SEED"); g_trace = (t && atoll(t) == i) ? 1 : 0; }
+    const long long ub0 = g_foreign_direction_calls;
     chains[i] = compute_3D_point_multiple_views_plg_following_expandallviews_vector(*s, seeds[i].view, epcs[i]);
+    ub[i] = g_foreign_direction_calls != ub0;
     g_trace = 0;
   }
   Points* out = new Points();
   for (size_t i = 0; i < seeds.size(); i++) out->append(chains[i], (int32_t)i);
+  out->seed_ub = ub;
+  for (size_t i = 0; i < seeds.size(); i++) { out->seed_track.push_back(seeds[i].track); out->seed_set.push_back(-1); }
   return out;
 }
 /* the seeds + hit lists pipeline 3 feeds to the consensus manager (for K1-level parity of the refpoint variant) */
@@ -408,6 +420,13 @@ int eg3d_oracle_points_get(void* pp, eg3d_points_view* v) {
   v->xyz = p->xyz.data(); v->seed = p->seed.data(); v->chain_pos = p->chain_pos.data(); v->obs_off = p->obs_off.data();
   v->obs_view = p->obs_view.data(); v->obs_poly = p->obs_poly.data(); v->obs_seg = p->obs_seg.data(); v->obs_xy = p->obs_xy.data();
   return 0;
+}
+/* per seed of the call: ub = the reference's behaviour is undefined on it, the SfM point (pipeline 3) or the
+ * candidate set (pipelines 1-2) it belongs to */
+int64_t eg3d_oracle_points_seed_info(void* pp, const uint8_t** ub, const int64_t** track, const int32_t** cand_set) {
+  Points* p = (Points*)pp;
+  *ub = p->seed_ub.data(); *track = p->seed_track.data(); *cand_set = p->seed_set.data();
+  return (int64_t)p->seed_ub.size();
 }
 void eg3d_oracle_points_free(void* p) { delete (Points*)p; }
 

@@ -119,6 +119,7 @@ static V2 first_plus_ratio_of_segment(const V2& a, const V2& b, float ratio) {
   return V2{a.x + ratio * (b.x - a.x), a.y + ratio * (b.y - a.y)};
 }
 
+thread_local long long g_foreign_direction_calls = 0;
 /* ------------------------------------------------------------------ polyline ---- */
 PlPoint Polyline::get_start_plp() const { return PlPoint{0, pc[0]}; } /* polyline_graph_2d.cpp:134-136 */
 
@@ -159,6 +160,7 @@ PlPoint Polyline::next_pl_point_by_distance(const PlPoint& init, ulong_t directi
     ratio = (distance - prevdist) / (curdist - prevdist);
     return PlPoint{i, first_plus_ratio_of_segment(pc[i], pc[i + 1], ratio)};
   }
+  g_foreign_direction_calls++;   /* the reference's behaviour is undefined here: tests that execute the reference's own code skip such seeds */
   reached = true;
   return init;
 }

@@ -1,0 +1,2 @@
+/* stand-in */
+#include "../eg3d_cgal_stub.hpp"

@@ -43,6 +43,8 @@ def lib():
         L.eg3d_oracle_hits_free.argtypes = [C.c_void_p]
         L.eg3d_oracle_points_get.argtypes = [C.c_void_p, C.POINTER(A.PointsView)]
         L.eg3d_oracle_points_free.argtypes = [C.c_void_p]
+        L.eg3d_oracle_points_seed_info.restype = C.c_int64
+        L.eg3d_oracle_points_seed_info.argtypes = [C.c_void_p, C.POINTER(A.c_u8p), C.POINTER(A.c_i64p), C.POINTER(A.c_i32p)]
         L.eg3d_oracle_gn_triangulate.argtypes = [C.c_void_p, C.c_int64, A.c_i64p, A.c_i32p, A.c_f32p, A.c_f32p, C.c_int,
                                                  A.c_f32p, A.c_f32p, A.c_u8p, C.c_int]
         L.eg3d_oracle_dedup_close_points.argtypes = [C.c_void_p, C.POINTER(A.PointsView), A.c_u8p]
@@ -116,6 +118,12 @@ class OracleScene:
         v = A.PointsView()
         lib().eg3d_oracle_points_get(handle, C.byref(v))
         ps = PointSet.from_view(v)
+        ub, tr, cs = A.c_u8p(), A.c_i64p(), A.c_i32p()
+        n = lib().eg3d_oracle_points_seed_info(handle, C.byref(ub), C.byref(tr), C.byref(cs))
+        # per seed of the call: undefined behaviour in the reference, SfM point id, candidate set
+        ps.seed_ub = np.ctypeslib.as_array(ub, shape=(n,)).copy() if n else np.zeros(0, np.uint8)
+        ps.seed_track = np.ctypeslib.as_array(tr, shape=(n,)).copy() if n else np.zeros(0, np.int64)
+        ps.seed_set = np.ctypeslib.as_array(cs, shape=(n,)).copy() if n else np.zeros(0, np.int32)
         lib().eg3d_oracle_points_free(handle)
         return ps
 
