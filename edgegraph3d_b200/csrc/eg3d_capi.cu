@@ -1275,26 +1275,65 @@ eg3d_status eg3d_points_device_get(const eg3d_points* p, eg3d_points_view* v) {
 }
 void eg3d_points_free(eg3d_points* p) { if (p) { cudaSetDevice(p->device); delete p; } }
 
-static eg3d_status launch_gn(eg3d_scene* sc, const GnProblem& pr, int fp64, eg3d_timing* tm) {
-  const size_t smem = (size_t)sc->V * 12 * sizeof(float);
-  if (smem > 48 * 1024) {
-    CK(cudaFuncSetAttribute(gn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(gn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+}  // extern "C" (templates below)
+// lanes per hypothesis of the warp-cooperative fp64 kernel: EG3D_GN_LANES=1|2|4|8|16|32 overrides (A/B runs)
+static int gn64_lanes(int typical_obs) {
+  if (const char* e = getenv("EG3D_GN_LANES")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g; }
+  return typical_obs >= 64 ? 8 : 4;
+}
+template <int G>
+static cudaError_t launch_gn64(eg3d_scene* sc, const GnProblem& pr, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(gn64_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const unsigned blocks = (unsigned)(((size_t)pr.n * G + GN_THREADS - 1) / GN_THREADS);
+  gn64_kernel<G><<<blocks, GN_THREADS, smem, sc->stream>>>(sc->dev, pr);
+  return cudaGetLastError();
+}
+static eg3d_status launch_gn(eg3d_scene* sc, const GnProblem& pr, int fp64, int max_obs, eg3d_timing* tm) {
   Timer t(sc->stream);
-  const unsigned blocks = (unsigned)((pr.n + GN_THREADS - 1) / GN_THREADS);
   t.start();
   if (pr.n > 0) {
-    if (fp64) gn_kernel<true><<<blocks, GN_THREADS, smem, sc->stream>>>(sc->dev, pr);
-    else gn_kernel<false><<<blocks, GN_THREADS, smem, sc->stream>>>(sc->dev, pr);
+    if (fp64) {
+      const size_t smem = (size_t)sc->V * 12 * sizeof(double);
+      if (smem > 200 * 1024) return fail(EG3D_ERR_INVALID_ARG, "too many views for the stand-alone GN kernel's shared-memory camera table");
+      cudaError_t e;
+      switch (gn64_lanes(max_obs)) {
+        case 1: e = launch_gn64<1>(sc, pr, smem); break;
+        case 2: e = launch_gn64<2>(sc, pr, smem); break;
+        case 8: e = launch_gn64<8>(sc, pr, smem); break;
+        case 16: e = launch_gn64<16>(sc, pr, smem); break;
+        case 32: e = launch_gn64<32>(sc, pr, smem); break;
+        default: e = launch_gn64<4>(sc, pr, smem); break;
+      }
+      CK(e);
+    } else {
+      const size_t cam = (((size_t)sc->V * 12 + 3) & ~(size_t)3) * sizeof(float);
+      const size_t stage = (size_t)max_obs * 12 * GN_THREADS;                       // float2 + int per observation and thread
+      const bool use_stage = max_obs > 0 && cam + stage <= 56 * 1024 && !getenv("EG3D_GN_NO_STAGE");   // >= 4 CTAs per SM
+      const size_t smem = cam + (use_stage ? stage : 0);
+      if (smem > 200 * 1024) return fail(EG3D_ERR_INVALID_ARG, "too many views for the stand-alone GN kernel's shared-memory camera table");
+      auto kern = use_stage ? gn32_kernel<true> : gn32_kernel<false>;
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 1;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, GN_THREADS, smem));
+      // persistent grid: every resident thread walks the hypotheses with stride T (lane-level scheduling, see gn32_kernel)
+      const int64_t want = (pr.n + GN_THREADS - 1) / GN_THREADS;
+      unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sc->num_sms * std::max(per_sm, 1)));
+      if (const char* e = getenv("EG3D_GN32_BLOCKS_PER_SM")) blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sc->num_sms * atoi(e)));   // A/B runs
+      kern<<<blocks, GN_THREADS, smem, sc->stream>>>(sc->dev, pr, use_stage ? max_obs : 0);
+#ifdef EG3D_GN_DEBUG
+      { cudaStreamSynchronize(sc->stream); unsigned long long d[4]; cudaMemcpyFromSymbol(d, g_gn32_dbg, sizeof d); fprintf(stderr, "[gn32] blocks %u warp-trips %llu lane-steps %llu fresh %llu (cumulative)\n", blocks, d[0], d[1], d[2]); }
+#endif
+      CK(cudaGetLastError());
+    }
   }
   t.stop();
-  CK(cudaGetLastError());
   CK(cudaStreamSynchronize(sc->stream));
   if (tm) { tm->gn_ms += t.ms(); tm->total_ms += t.ms(); tm->kernel_launches += 1; }
   return EG3D_OK;
 }
 
+extern "C" {
 eg3d_status eg3d_gn_triangulate(eg3d_scene* sc, int64_t n, const int64_t* obs_off, const int32_t* obs_view, const float* obs_xy,
                                 const float* init_xyz, int fp64, float* out_xyz, float* out_mse, uint8_t* out_ok, eg3d_timing* tm) {
   eg3d_status st = require_device(); if (st != EG3D_OK) return st;
@@ -1310,7 +1349,8 @@ eg3d_status eg3d_gn_triangulate(eg3d_scene* sc, int64_t n, const int64_t* obs_of
   GnProblem pr; memset(&pr, 0, sizeof pr);
   pr.n = n; pr.obs_off = d_off.p; pr.obs_view = d_v.p; pr.obs_xy = d_xy.p; pr.init = d_init.p;
   pr.out_xyz = d_x.p; pr.out_mse = d_m.p; pr.out_ok = d_ok.p; pr.gn_max_mse = sc->prm.filter_gn_max_mse; pr.write_back_only_ok = 0;
-  st = launch_gn(sc, pr, fp64, tm); if (st != EG3D_OK) return st;
+  int max_obs = 0; for (int64_t i = 0; i < n; i++) max_obs = std::max<int>(max_obs, (int)(obs_off[i + 1] - obs_off[i]));
+  st = launch_gn(sc, pr, fp64, max_obs, tm); if (st != EG3D_OK) return st;
   CK(cudaMemcpy(out_xyz, d_x.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(out_mse, d_m.p, n * sizeof(float), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(out_ok, d_ok.p, n, cudaMemcpyDeviceToHost));
@@ -1327,7 +1367,7 @@ eg3d_status eg3d_gn_triangulate_device(eg3d_scene* sc, int64_t n, int32_t k, con
   GnProblem pr; memset(&pr, 0, sizeof pr);
   pr.n = n; pr.obs_off = nullptr; pr.k = k; pr.obs_view = d_obs_view; pr.obs_xy = (const float2*)d_obs_xy; pr.init = d_init;
   pr.out_xyz = d_out_xyz; pr.out_mse = d_out_mse; pr.out_ok = d_out_ok; pr.gn_max_mse = sc->prm.filter_gn_max_mse; pr.write_back_only_ok = 0;
-  return launch_gn(sc, pr, fp64, tm);
+  return launch_gn(sc, pr, fp64, k, tm);
 }
 
 // a13: order-dependent first-come-first-kept density limiter (filtering_close_plgps.cpp:75-124).  The dependency chain
@@ -1370,7 +1410,8 @@ eg3d_status eg3d_filter(eg3d_scene* sc, int64_t n, float* xyz, const int64_t* ob
   GnProblem pr; memset(&pr, 0, sizeof pr);
   pr.n = n; pr.obs_off = d_off.p; pr.obs_view = d_v.p; pr.obs_xy = d_xy.p; pr.init = d_x.p;
   pr.out_xyz = d_x.p; pr.out_mse = nullptr; pr.out_ok = d_ok.p; pr.gn_max_mse = gn_max_mse; pr.write_back_only_ok = 1;
-  st = launch_gn(sc, pr, 0, tm); if (st != EG3D_OK) return st;   // gaussNewtonFiltering, gauss_newton.cpp:136-178
+  int max_obs = 0; for (int64_t i = 0; i < n; i++) max_obs = std::max<int>(max_obs, (int)(obs_off[i + 1] - obs_off[i]));
+  st = launch_gn(sc, pr, 0, max_obs, tm); if (st != EG3D_OK) return st;   // gaussNewtonFiltering, gauss_newton.cpp:136-178
   CK(cudaMemcpy(xyz, d_x.p, 3 * n * sizeof(float), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(inliers, d_ok.p, n, cudaMemcpyDeviceToHost));
   // compute_ray_stats + view-count rule (outliers_filtering.cpp:14-64): O(n) bookkeeping on the returned bitmap
