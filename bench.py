@@ -1,21 +1,27 @@
 #!/usr/bin/env python
 """bench.py — triangulated 3D edge-points/sec on the BASELINE.json workload (see DESIGN.md "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|small|c1|c1real]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2strong|c3|c5|small|c1|c1real]
 
 A "step" is one pass of the hot path (K1 epipolar intersection -> K3 triple enumeration / PLG following / view expansion
--> ordered packing [-> NCCL all-gather of the accepted points when N > 1]) over the whole seed batch of the workload.
-K1 runs lazily inside the path (any-hit pass, the three selected views of every seed, every view of the accepted seeds:
-the lists nobody reads are not materialised); `roofline_k1` therefore times the FULL sweep of the same batch separately,
-through eg3d_epipolar_intersect_device, after the timed steps.
-N = 1 runs BASELINE configs[1]: the synthetic 200-view rig, 1920x1080, 8 000 polyline segments per view, 50 000 seeds.
-N > 1 is weak scaling on the same rig: every rank keeps 50 000 seeds (seed spacing 20/N px => 250*N seeds per view) and
-owns the starting views r, r+N, ... (the reference's outer loop over starting views, polyline_matching.cpp:162, dealt round-robin).
+-> ordered packing [-> the library's NCCL exchange of the accepted points + device merge when N > 1]) over the whole seed
+batch of the workload.  K1 runs lazily inside the path (any-hit pass, the three selected views of every seed, every view of
+the accepted seeds: the lists nobody reads are not materialised); `roofline_k1` therefore times the FULL sweep of the same
+batch separately, through eg3d_epipolar_intersect_device, after the timed steps.
+
+Workloads.  c2 (default) = BASELINE configs[1]: synthetic 200-view rig, 1920x1080, 8 000 polyline segments per view, 50 000
+seeds; N > 1 is WEAK scaling on the same rig (every rank keeps 50 000 seeds: spacing 20/N px => 250*N seeds per view, starting
+views r, r+N, ... per rank).  c2strong = the same 50 000 seeds split over the N ranks (STRONG scaling).  c3 = BASELINE
+configs[2]: the 1000-view rig, 250 000 seeds, starting views sharded over the N ranks (strong scaling; 8 GPUs is the
+configuration BASELINE names).  c5 = BASELINE configs[4], the Gauss-Newton microbenchmark (10 M hypotheses x 20 observations).
+small / c1 / c1real are documentation workloads.
 
 `value` = accepted (pre-dedup) 3D edge-points of all ranks / max-over-ranks device time of a step (CUDA events on the
 library's stream; inputs already resident).  `e2e` = the same count / wall time of the C-ABI call sequence a user makes
-with HOST buffers: eg3d_match_seeds (pinned seeds H2D + kernels) + eg3d_points_get (D2H of the result into pinned memory).
---impl reference times the CPU oracle (the reference cannot be compiled in this image: DESIGN.md) on a bounded seed sample.
+with HOST buffers: eg3d_match_seeds (pinned seeds H2D + kernels) [+ eg3d_points_allgather] + eg3d_points_get (D2H into
+pinned memory).  --impl reference times the reference's own code (oracle/_ref/libref_path.so: the reference's sources compiled
+against stand-in OpenCV headers, see oracle/ref_path_wrapper.cpp) when that library is present, else the oracle port, on a
+bounded seed sample with all host threads.
 """
 import argparse
 import json
@@ -37,8 +43,13 @@ UNIT = "points/s"
 
 
 def build_workload(name, n_gpus):
-    if name == "c2":
+    if name in ("c2", "c2strong"):
         cfg = dict(n_views=200, width=1920, height=1080, focal=1600.0, n_curves=400, segs_per_curve=20, curve_len=0.2,
+                   seed=1234, extent=0.9, closed_frac=0.05)
+        per_view = 250
+    elif name == "c3":
+        # BASELINE configs[2]: same generator and per-view density, 1000 views (20 rings of 50), 250 seeds per view
+        cfg = dict(n_views=1000, width=1920, height=1080, focal=1600.0, n_curves=400, segs_per_curve=20, curve_len=0.2,
                    seed=1234, extent=0.9, closed_frac=0.05)
         per_view = 250
     elif name == "c1":
@@ -56,12 +67,19 @@ def build_workload(name, n_gpus):
     return scene, cfg, per_view
 
 
-def make_seeds(scene, sampler, per_view, n_gpus, rank):
-    """250*N seeds per view at spacing 20/N px, first polylines first; rank r owns the starting views r, r+N, r+2N, ...
-    (multigpu.view_round_robin: better balanced than contiguous blocks; the merged result is put back into the
-    reference's loop order by global seed ordinal, multigpu.all_gather_points(order_keys=...))."""
-    from edgegraph3d_b200 import multigpu as mg
-    return syn.sample_seeds(sampler, scene, per_view=per_view * n_gpus, spacing=20.0 / n_gpus, views=mg.view_round_robin(scene.n_views, n_gpus, rank))
+STRONG = ("c2strong", "c3")
+
+
+def make_seeds(scene, sampler, per_view, n_gpus, rank, workload="c2"):
+    """The rank's seeds and their ordinals in the unsharded seed list (the canonical order of the merged result).
+    Weak (c2, small): 250*N seeds per view at spacing 20/N px.  Strong (c2strong, c3): 250 per view at 20 px.  Either way rank r
+    owns the starting views r, r+N, r+2N, ... (multigpu.view_round_robin: better balanced than contiguous blocks)."""
+    strong = workload in STRONG
+    allseeds = syn.sample_seeds(sampler, scene, per_view=per_view * (1 if strong else n_gpus), spacing=20.0 / (1 if strong else n_gpus))
+    if n_gpus == 1:
+        return allseeds, np.arange(len(allseeds), dtype=np.int64)
+    mine = np.where(allseeds.view % n_gpus == rank)[0]
+    return allseeds.take(mine), mine.astype(np.int64)
 
 
 class ClockSampler:
@@ -119,12 +137,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_traffic.json); None if absent."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if not os.path.exists(p):
-        return {}
-    return json.load(open(p))
+def ncu_capture():
+    """Per-launch counters of the committed ncu --set full capture of this round's kernels on the c2 batch
+    (profiles/r02_capture.json: DRAM bytes, executed warp instructions, instruction-cache requests); {} if absent.
+    These are NOT measured in the bench run — ncu replays kernels — and the keys that carry them say so."""
+    for name in ("r02_capture.json", "r01_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            d["_file"] = "profiles/" + name
+            return d
+    return {}
 
 
 def pinned_seeds(seeds):
@@ -146,57 +169,102 @@ def pinned_seeds(seeds):
     return sb
 
 
-def cpu_baseline(scene, seeds, target_seconds=15.0, threads=None):
-    """The CPU oracle (the port of the reference path) on a bounded stratified sample of the same seed batch."""
+def _ref_available():
+    try:
+        from tests import ref_lib as R
+        return R.available()
+    except Exception:
+        return False
+
+
+def cpu_arms(scene, seeds, budget_s, threads=None, want_port=True, want_1thread=True):
+    """The CPU implementations of the path on a bounded stratified sample of the seed batch:
+      reference  the reference's OWN code (oracle/_ref/libref_path.so), its per-seed entry called from an OpenMP loop over the
+                 seeds on all host threads (as shipped its loops are serial: orphaned `omp for`, SURVEY finding 4)
+      port       the oracle restatement (leaner: no per-hypothesis PLG deep copies, no cv::Mat churn) on all host threads
+      1thread    the reference's code on ONE thread = the reference as shipped
+    Seeds on which the reference's behaviour is undefined (~1-5 %) are left out of every sample: its code
+    crashes on them in this build; the oracle flags them (outside the timed region).  Returns (dict of arms, runner)."""
     from tests import oracle_lib as O
     threads = threads or os.cpu_count()
     osc = O.OracleScene(scene)
     n = len(seeds)
-    probe = seeds.take(np.linspace(0, n - 1, min(n, 64)).astype(np.int64))
+    probe = seeds.take(np.linspace(0, n - 1, min(n, 96)).astype(np.int64))
     t = time.perf_counter()
-    osc.match_seeds(probe, n_threads=threads)
-    per_seed = max((time.perf_counter() - t) / len(probe), 1e-6)
-    m = int(min(n, max(64, target_seconds / per_seed)))
+    flags = osc.match_seeds(probe, n_threads=threads).seed_ub
+    per_seed_port = max((time.perf_counter() - t) / len(probe), 1e-6)
+    have_ref = _ref_available()
+    arms = {}
+    rs = None
+    if have_ref:
+        from tests import ref_lib as R
+        rs = R.RefScene(scene)
+        pr = probe.take(np.where(flags == 0)[0])
+        t = time.perf_counter(); rs.match_seeds(pr, n_threads=threads); per_seed_ref = max((time.perf_counter() - t) / max(1, len(pr)), 1e-6)
+    per_seed = per_seed_ref if have_ref else per_seed_port
+    m = int(min(n, max(64, budget_s / per_seed)))
     sample = seeds.take(np.linspace(0, n - 1, m).astype(np.int64))
-    t = time.perf_counter()
-    pts = osc.match_seeds(sample, n_threads=threads)
-    dt = time.perf_counter() - t
-    return {"value": pts.n_points / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{m} of {n} seeds (stratified: every {n / m:.1f}th seed of the batch), full per-seed path (K1 sweep + "
-                      f"triples + PLG following + view expansion), {pts.n_points} points in {dt:.2f} s",
-            "seconds": dt, "seeds": m, "points": pts.n_points}, osc, sample
+    ub = osc.match_seeds(sample, n_threads=threads).seed_ub           # untimed: find the seeds the reference cannot run
+    sample = sample.take(np.where(ub == 0)[0])
+    note = f"{len(sample)} of {n} seeds (stratified: every {n / m:.1f}th seed of the batch, {int(ub.sum())} with undefined reference behaviour left out), full per-seed path (K1 sweep + triples + PLG following + view expansion)"
+
+    def run_main():
+        if have_ref:
+            return rs.match_seeds(sample, n_threads=threads).n_points
+        return osc.match_seeds(sample, n_threads=threads).n_points
+    t = time.perf_counter(); pts = run_main(); dt = time.perf_counter() - t
+    arms["main"] = {"value": pts / dt, "unit": UNIT, "cores": threads, "kind": "reference" if have_ref else "port",
+                    "sample": note + f", {pts} points in {dt:.2f} s" + ("; the reference's own sources compiled against stand-in OpenCV headers (oracle/ref_path_wrapper.cpp), per-seed entry in an OpenMP loop" if have_ref else "; oracle port (OpenMP over seeds)"),
+                    "seconds": dt, "seeds": len(sample), "points": pts}
+    if want_port and have_ref:
+        t = time.perf_counter(); p2 = osc.match_seeds(sample, n_threads=threads).n_points; d2 = time.perf_counter() - t
+        arms["port"] = {"value": p2 / d2, "unit": UNIT, "cores": threads, "kind": "port", "sample": f"the oracle restatement on the same {len(sample)} seeds, {d2:.2f} s", "points": p2}
+    if want_1thread:
+        k = max(16, len(sample) // max(2, threads))
+        s1 = sample.take(np.linspace(0, len(sample) - 1, min(k, len(sample))).astype(np.int64))
+        t = time.perf_counter()
+        p1 = (rs.match_seeds(s1, n_threads=1) if have_ref else osc.match_seeds(s1, n_threads=1)).n_points
+        d1 = time.perf_counter() - t
+        arms["1thread"] = {"value": p1 / d1, "unit": UNIT, "cores": 1, "kind": "reference" if have_ref else "port",
+                           "sample": f"{len(s1)} of those seeds on ONE thread (the reference as shipped runs its loops serially), {p1} points in {d1:.2f} s"}
+    return arms, run_main, sample
+
+
+def bench_config(args, cfg, per_view, n_gpus):
+    """The `config` object both arms print: only what names the workload (measured quantities live outside it)."""
+    return {"workload": workload_name(args.workload, cfg, per_view, n_gpus),
+            "l2": "GPU arm: flushed between iterations (256 MiB write), per-step hit lists (GBs) exceed L2 anyway; CPU arm: n/a",
+            "seeds_per_gpu": per_view * cfg["n_views"] // (n_gpus if args.workload in STRONG else 1),
+            "parallelism": (f"starting views dealt round-robin to {n_gpus} GPU(s); one NCCL exchange (counts all-gather + one grouped broadcast of the packed records) + device merge"
+                            if n_gpus > 1 else "1 GPU")}
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path = the oracle port (reference unbuildable here)."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores (see cpu_arms)."""
     if rank != 0:
         return
     from tests import oracle_lib as O
     scene, cfg, per_view = build_workload(args.workload, 1)
-    seeds = make_seeds(scene, O.sample_seeds, per_view, 1, 0)
+    seeds, _ = make_seeds(scene, O.sample_seeds, per_view, 1, 0, args.workload)
     threads = os.cpu_count()
-    osc = O.OracleScene(scene)
-    n = len(seeds)
-    probe = seeds.take(np.linspace(0, n - 1, 64).astype(np.int64))
-    t = time.perf_counter(); osc.match_seeds(probe, n_threads=threads); per_seed = (time.perf_counter() - t) / 64
-    budget = 150.0 / max(1, args.steps + args.warmup)             # whole run within a few minutes
-    m = int(min(n, max(64, budget / max(per_seed, 1e-6))))
-    sample = seeds.take(np.linspace(0, n - 1, m).astype(np.int64))
-    for _ in range(args.warmup):
-        osc.match_seeds(sample, n_threads=threads)
+    budget = 150.0 / max(1, args.steps + args.warmup + 1)            # whole run within a few minutes
+    arms, run_main, sample = cpu_arms(scene, seeds, budget, threads, want_port=False, want_1thread=False)
+    for _ in range(max(0, args.warmup - 1)):                          # cpu_arms already ran the sample once
+        run_main()
     t0 = time.perf_counter()
     npts = 0
     for _ in range(args.steps):
-        npts += osc.match_seeds(sample, n_threads=threads).n_points
+        npts += run_main()
     dt = time.perf_counter() - t0
     value = npts / dt
+    cb = dict(arms["main"]); cb["value"] = value
+    cb["sample"] = "each step = " + arms["main"]["sample"].split(", full per-seed path")[0] + f"; {threads} host threads"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.workload in STRONG else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, cfg, per_view, 1), "l2": "n/a (CPU)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"each step = {m} of {n} seeds (stratified), OpenMP over seeds on {threads} threads; "
-                                       "the reference itself is effectively single-threaded (orphaned omp for, SURVEY finding 4)"},
+            "config": bench_config(args, cfg, per_view, args.gpus),
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -247,11 +315,73 @@ def run_c1(args, scene, cfg, E):
 
 
 def workload_name(name, cfg, per_view, n):
+    segs = cfg["n_curves"] * cfg["segs_per_curve"]
     if name == "c2":
         return (f"BASELINE configs[1]: synthetic {cfg['n_views']}-view rig, {cfg['width']}x{cfg['height']}, "
-                f"{cfg['n_curves'] * cfg['segs_per_curve']} polyline segments/view, {per_view * cfg['n_views']} seeds per GPU "
+                f"{segs} polyline segments/view, {per_view * cfg['n_views']} seeds per GPU "
                 f"({per_view * n}/view at {20.0 / n:g} px), all-segment sweep, seed {cfg['seed']}")
+    if name == "c2strong":
+        return (f"BASELINE configs[1], strong scaling: synthetic {cfg['n_views']}-view rig, {cfg['width']}x{cfg['height']}, {segs} polyline segments/view, "
+                f"{per_view * cfg['n_views']} seeds in total ({per_view}/view at 20 px) split over {n} GPU(s) by starting view, all-segment sweep, seed {cfg['seed']}")
+    if name == "c3":
+        return (f"BASELINE configs[2]: synthetic {cfg['n_views']}-view rig, {cfg['width']}x{cfg['height']}, {segs} polyline segments/view, "
+                f"{per_view * cfg['n_views']} seeds in total ({per_view}/view at 20 px), starting views sharded across {n} GPU(s), NCCL exchange of the accepted points, seed {cfg['seed']}")
     return f"{name}: {cfg}"
+
+
+def run_c5(args, E):
+    """BASELINE configs[4]: the Gauss-Newton microbenchmark — 10 M random hypotheses x 20 observing views, device resident;
+    fp32 = the outlier filter's solver (a14 semantics, bit-exact), fp64 = the matching path's solver.  One JSON line."""
+    import torch
+    from tests import oracle_lib as O
+    sc = syn.make_scene(n_views=200, width=1920, height=1080, focal=1600.0, n_curves=8, segs_per_curve=20, curve_len=0.2, seed=1234,
+                        extent=0.9, closed_frac=0.05)
+    dev = E.DeviceScene(sc)
+    base_n, k = 1_000_000, 20
+    views, xy, init, _ = syn.gn_microbench_inputs(sc, base_n, k, seed=99)
+    reps = 10
+    n = base_n * reps      # the 1 M generated hypotheses repeated 10x on the device (host generation of 10 M x 200 view permutations does not fit)
+    dv = torch.from_numpy(views).cuda().repeat(reps, 1).contiguous(); dxy = torch.from_numpy(xy).cuda().repeat(reps, 1, 1).contiguous()
+    di = torch.from_numpy(init).cuda().repeat(reps, 1).contiguous()
+    ox = torch.empty((n, 3), dtype=torch.float32, device="cuda"); om = torch.empty(n, dtype=torch.float32, device="cuda")
+    ok = torch.empty(n, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    peak, peak_src = measured_peaks()
+    bytes_alg = n * (k * 12 + 12 + 17)                                # SURVEY 8(d): 269 B per hypothesis
+    sampler = ClockSampler(0); sampler.start()
+    out = {}
+    for fp64 in (0, 1):
+        ms = []
+        for i in range(args.warmup + args.steps):
+            flush.fill_(1); torch.cuda.synchronize()
+            tm = dev.gn_triangulate_device(n, k, dv.data_ptr(), dxy.data_ptr(), di.data_ptr(), fp64, ox.data_ptr(), om.data_ptr(), ok.data_ptr())
+            if i >= args.warmup:
+                ms.append(tm["gn_ms"])
+        torch.cuda.synchronize()
+        sel = np.arange(0, base_n, 1009)
+        off = np.arange(len(sel) + 1, dtype=np.int64) * k
+        x, m, o = O.OracleScene(sc).gn_triangulate(off, views[sel].reshape(-1), xy[sel].reshape(-1, 2), init[sel], fp64, n_threads=os.cpu_count())
+        gx, go = ox[:base_n].cpu().numpy()[sel], ok[:base_n].cpu().numpy()[sel]
+        good = o == 1
+        avg = float(np.mean(ms))
+        out["fp64" if fp64 else "fp32"] = {
+            "ms": avg, "hypotheses_per_s": n / (avg * 1e-3), "inlier_frac": float(ok.float().mean()),
+            "roofline": {"kernel": "gn64_kernel<G> (warp-cooperative, G lanes per hypothesis)" if fp64 else "gn32_kernel (lane-persistent, phase-synchronised)",
+                         "bound": "hbm", "achieved": bytes_alg / (avg * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_alg / (avg * 1e-3) / 1e9 / peak,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg, "avg_launch_ms": avg, "traffic": None},
+            "oracle_sample": {"hypotheses": len(sel), "flags_identical": bool(np.array_equal(go, o)),
+                              "x_bits_identical": bool(gx[good].tobytes() == x[good].astype(np.float32).tobytes()) if not fp64 else None,
+                              "x_max_abs_diff": float(np.abs(gx[good] - x[good]).max()) if good.any() else 0.0}}
+    clocks = sampler.stop()
+    print(json.dumps({"metric": "Gauss-Newton hypotheses/sec (device-timed)", "unit": "hypotheses/s", "value": out["fp32"]["hypotheses_per_s"], "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": out["fp32"]["ms"], "higher_is_better": True, "dtype": "f32 (primary, the filter's solver) / f64",
+                      "data": "synthetic", "vs_baseline": None,
+                      "config": {"workload": f"BASELINE configs[4]: Gauss-Newton filter microbench, {n} hypotheses x {k} observations (seed 99; 1 M generated, repeated 10x on the device), device resident",
+                                 "l2": "flushed between launches (256 MiB write); inputs (3.2 GB) exceed L2 anyway"},
+                      "fp32": out["fp32"], "fp64": out["fp64"], "roofline": out["fp32"]["roofline"], "clocks": clocks,
+                      "note": "the float loop of gauss_newton.cpp:97-116 stops only when the float MSE repeats exactly (5e-10): 10.3 iterations per hypothesis "
+                              "on average here even with the exact cycle shortcut, each two passes over the 20 observations with 8 IEEE divisions per "
+                              "observation and pass; the HBM fraction is therefore low by nature (the kernel is issue-bound), see DESIGN.md"}))
 
 
 def main():
@@ -294,23 +424,33 @@ def main():
     n_gpus = world
 
     if args.workload == "c1real":
-        # BASELINE configs[0] on the packaged files: real edge maps -> polyline graphs -> candidate sets -> pipelines 2+3 ->
+        # BASELINE configs[0] on the packaged files: real edge maps -> polyline graphs -> candidate sets -> pipelines 1-3 ->
         # density limiter -> filter, every stage checked against the oracle (documentation line, not the headline configuration)
         sys.path.insert(0, os.path.join(ROOT, "profiles"))
         import c1_real_dtu006
         print(json.dumps(c1_real_dtu006.run(os.path.join(ROOT, "tests", "golden"), os.cpu_count())))
         return
+    if args.workload == "c5":
+        return run_c5(args, E)
     scene, cfg, per_view = build_workload(args.workload, n_gpus)
     if args.workload == "c1":
         return run_c1(args, scene, cfg, E)
-    seeds = make_seeds(scene, E.sample_seeds, per_view, n_gpus, rank)
+    seeds, seed_global = make_seeds(scene, E.sample_seeds, per_view, n_gpus, rank, args.workload)
     if args.seeds_limit and args.seeds_limit < len(seeds):
-        seeds = seeds.take(np.linspace(0, len(seeds) - 1, args.seeds_limit).astype(np.int64))
+        keep = np.linspace(0, len(seeds) - 1, args.seeds_limit).astype(np.int64)
+        seeds, seed_global = seeds.take(keep), seed_global[keep]
     seeds = pinned_seeds(seeds)
     t = time.perf_counter()
     dev = E.DeviceScene(scene)
     torch.cuda.synchronize()
     scene_ms = 1e3 * (time.perf_counter() - t)
+    if world > 1:
+        # the scene handle owns the NCCL communicator of the exchange; rank 0's unique id travels over torch.distributed
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(E.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        dev.comm_create(uid.cpu().numpy().tobytes(), rank, world)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")    # > 126 MB L2
 
@@ -320,51 +460,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def allgather_points(dp):
-        """The path's one exchange step: accepted records of every rank to every rank over NCCL (NVLink)."""
-        v = dp.device_view()
-        n, m = int(v.n_points), int(v.n_obs)
-        cnt = torch.tensor([n, m], dtype=torch.int64, device="cuda")
-        cnts = torch.empty(world * 2, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(cnts, cnt)
-        cnts = cnts.view(world, 2).cpu()
-        maxn, maxm = int(cnts[:, 0].max()), int(cnts[:, 1].max())
-
-        def wrap(ptr, nbytes):
-            import ctypes
-            if nbytes == 0:
-                return torch.empty(0, dtype=torch.uint8, device="cuda")
-            addr = ctypes.cast(ptr, ctypes.c_void_p).value
-
-            class _W:
-                __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (addr, False), "version": 2}
-            return torch.as_tensor(_W(), device="cuda")
-        total = 0
-        for ptr, per, mx, k in ((v.xyz, 12, maxn, n), (v.seed, 4, maxn, n), (v.chain_pos, 4, maxn, n), (v.obs_off, 8, maxn + 1, n + 1),
-                                (v.obs_view, 4, maxm, m), (v.obs_poly, 4, maxm, m), (v.obs_seg, 4, maxm, m), (v.obs_xy, 8, maxm, m)):
-            send = torch.zeros(mx * per, dtype=torch.uint8, device="cuda")
-            send[:k * per] = wrap(ptr, k * per)
-            recv = torch.empty(world * mx * per, dtype=torch.uint8, device="cuda")
-            dist.all_gather_into_tensor(recv, send)
-            total += recv.numel()
-        return int(cnts[:, 0].sum()), total
-
     def step(timed):
         flush.fill_(1)                                   # evict L2 between iterations
         barrier()
         t0 = time.perf_counter()
         dp, tm = dev.match_seeds(seeds, fetch=False)     # pinned seeds H2D + K1 + K3 + pack (device-resident result)
-        ag_ms, total_pts = 0.0, tm["n_points"]
+        x_ms, bc_ms, total_pts, merged = 0.0, 0.0, tm["n_points"], None
         if world > 1:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            total_pts, _ = allgather_points(dp)
-            e1.record(); torch.cuda.synchronize()
-            ag_ms = e0.elapsed_time(e1)
+            # the path's one exchange step, inside the library: counts all-gather + ONE grouped broadcast of the packed records
+            # + device merge into (global seed ordinal, chain position) order; timed on the library's stream (exchange AND merge)
+            merged, tx = dev.points_allgather(dp, seed_global)
+            x_ms, bc_ms, total_pts = tx["total_ms"], tx["scan_ms"], tx["n_points"]
         d2h = dp.fetch_raw()                             # D2H of this rank's result into pinned host memory
         t1 = time.perf_counter()
         dp.free()
-        return tm, ag_ms, d2h, t1 - t0, total_pts
+        if merged is not None:
+            merged.free()
+        return tm, x_ms, bc_ms, d2h, t1 - t0, total_pts
 
     for _ in range(args.warmup):
         step(False)
@@ -372,32 +484,37 @@ def main():
     if rank == 0:
         sampler.start()
     dev_ms, e2e_s, launches = [], [], 0
-    k1_ms, k3_ms, pack_ms, ag_all, k3a_ms, k3b_ms, k1any_ms, scan_ms = [], [], [], [], [], [], [], []
+    k1_ms, k3_ms, pack_ms, ag_all, bc_all, k3a_ms, k3b_ms, k1any_ms, scan_ms = [], [], [], [], [], [], [], [], []
     last_tm = None
-    pts_total = 0
     for _ in range(args.steps):
-        tm, ag_ms, d2h, wall, total_pts = step(True)
-        dev_ms.append(tm["total_ms"] + ag_ms); e2e_s.append(wall); launches += tm["kernel_launches"] + (9 if world > 1 else 0)
-        k1_ms.append((tm["k1_count_ms"], tm["k1_fill_ms"])); k3_ms.append(tm["k3_ms"]); pack_ms.append(tm["pack_ms"]); ag_all.append(ag_ms); k3a_ms.append(tm["k3a_ms"]); k3b_ms.append(tm["k3b_ms"])
-        k1any_ms.append(tm["k1_any_ms"]); scan_ms.append(tm["scan_ms"])
-        last_tm = tm; pts_total = total_pts; d2h_bytes = d2h
+        tm, x_ms, bc_ms, d2h, wall, total_pts = step(True)
+        dev_ms.append(tm["total_ms"] + x_ms); e2e_s.append(wall); launches += tm["kernel_launches"] + (4 if world > 1 else 0)
+        k1_ms.append((tm["k1_count_ms"], tm["k1_fill_ms"])); k3_ms.append(tm["k3_ms"]); pack_ms.append(tm["pack_ms"]); ag_all.append(x_ms); bc_all.append(bc_ms)
+        k3a_ms.append(tm["k3a_ms"]); k3b_ms.append(tm["k3b_ms"]); k1any_ms.append(tm["k1_any_ms"]); scan_ms.append(tm["scan_ms"])
+        last_tm = tm; d2h_bytes = d2h
     clocks = sampler.stop() if rank == 0 else None
     # max over ranks of the summed device time / wall time
     tdev = torch.tensor([sum(dev_ms), sum(e2e_s)], dtype=torch.float64, device="cuda")
     npts_local = torch.tensor([last_tm["n_points"]], dtype=torch.float64, device="cuda")
+    per_rank = torch.tensor([np.mean(k1any_ms) + np.mean([a + b for a, b in k1_ms]), np.mean(k3a_ms), np.mean(k3b_ms), np.mean(ag_all), float(last_tm["n_points"])], dtype=torch.float64, device="cuda")
+    all_ranks = [torch.zeros_like(per_rank) for _ in range(world)]
     if world > 1:
         dist.all_reduce(tdev, op=dist.ReduceOp.MAX)
         dist.all_reduce(npts_local, op=dist.ReduceOp.SUM)
+        dist.all_gather(all_ranks, per_rank)
+    else:
+        all_ranks = [per_rank]
     dev_total_ms, e2e_total_s = float(tdev[0]), float(tdev[1])
     job_points = float(npts_local[0])                   # accepted points of all ranks per step
     if rank != 0:
         if world > 1:
+            dev.comm_destroy()
             dist.destroy_process_group()
         return
 
     # the full epipolar sweep of the same batch (BASELINE configs 2-4's kernel), timed on its own: 1 warm-up + 2 runs
     sweep = None
-    if args.workload == "c2" or args.workload == "small":
+    if args.workload in ("c2", "small", "c2strong"):
         dev.epipolar_intersect_device(seeds)
         runs = [dev.epipolar_intersect_device(seeds) for _ in range(2)]
         sweep = {k: float(np.mean([r[k] for r in runs])) for k in ("k1_count_ms", "k1_fill_ms", "scan_ms")}
@@ -406,74 +523,81 @@ def main():
     value = job_points * args.steps / (dev_total_ms / 1e3)
     e2e_value = job_points * args.steps / e2e_total_s
     peak, peak_src = measured_peaks()
-    tr = ncu_traffic()
-    t_k3b = tr.get("k3b_expand_kernel")
-    t_k1 = [tr.get("k1_sweep_kernel<count>"), tr.get("k1_sweep_kernel<fill>")]
-    traffic_k3b = (t_k3b["dram_read_bytes"] + t_k3b["dram_write_bytes"]) if (t_k3b and args.workload == "c2" and not args.seeds_limit) else None
-    traffic_k1 = (sum(x["dram_read_bytes"] + x["dram_write_bytes"] for x in t_k1) / 2) if (all(t_k1) and args.workload == "c2" and not args.seeds_limit) else None
-    icache = {}
-    ip = os.path.join(ROOT, "profiles", "r01_icache.json")
-    if os.path.exists(ip) and args.workload == "c2" and not args.seeds_limit:
-        icache = json.load(open(ip))
-    k1c = float(np.mean([a for a, _ in k1_ms])); k1f = float(np.mean([b for _, b in k1_ms])); k3 = float(np.mean(k3_ms)); k3a = float(np.mean(k3a_ms)); k3b = float(np.mean(k3b_ms))
+    cap = ncu_capture() if (args.workload == "c2" and n_gpus == 1 and not args.seeds_limit) else {}
+    cap_file = cap.get("_file")
+
+    def cap_bytes(name):
+        c = cap.get(name)
+        return (c["dram_read_bytes"] + c["dram_write_bytes"]) if c else None
+    traffic_k3b = cap_bytes("k3b_expand_kernel")
+    t_k1 = [cap_bytes("k1_sweep_kernel<count>"), cap_bytes("k1_sweep_kernel<fill>")]
+    traffic_k1 = (sum(t_k1) / 2) if all(x is not None for x in t_k1) else None
+    k1c = float(np.mean([a for a, _ in k1_ms])); k1f = float(np.mean([b for _, b in k1_ms])); k3a = float(np.mean(k3a_ms)); k3b = float(np.mean(k3b_ms))
     step_ms = dev_total_ms / args.steps
     k1_bytes = sweep["k1_algorithmic_bytes"] if sweep else last_tm["k1_algorithmic_bytes"]
     k1_avg_launch_ms = (sweep["k1_count_ms"] + sweep["k1_fill_ms"]) / 2 if sweep else (k1c + k1f) / 2
-    # K3 algorithmic bytes: the hit lists it reads (16 B/hit) + the observations it writes (20 B/obs) + point headers
     # K3b algorithmic bytes: the hit lists of the accepted seeds it reads (16 B/hit) + the observations (20 B) and point headers it writes
     acc_frac = last_tm["n_accepted_seeds"] / max(1, last_tm["n_seeds"])
     full_hits = sweep["n_hits"] if sweep else last_tm["n_hits"]
     k3b_bytes = 16 * full_hits * acc_frac + 20 * last_tm["n_obs"] + 24 * last_tm["n_points"]
+    sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = 4 * 148 * sm_hz * 1e6                                 # warp instructions per second the chip can issue (4 schedulers x 148 SMs x clock)
+    k1_inst = [cap.get(n, {}).get("inst_executed") for n in ("k1_sweep_kernel<count>", "k1_sweep_kernel<fill>")]
+    k3b_inst = cap.get("k3b_expand_kernel", {}).get("inst_executed")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong" if args.workload in STRONG else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, cfg, per_view, n_gpus),
-                   "l2": "flushed between iterations (256 MiB write); per-step hit lists (GBs) exceed L2 anyway",
-                   "seeds_per_gpu": len(seeds), "points_per_step": job_points, "scene_upload_ms": scene_ms,
-                   "parallelism": f"starting views dealt round-robin to {n_gpus} GPU(s); one NCCL all-gather of accepted records" if n_gpus > 1 else "1 GPU"},
+        "config": bench_config(args, cfg, per_view, n_gpus),
+        "measured": {"seeds_this_rank": len(seeds), "points_per_step": job_points, "scene_upload_ms": scene_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": seeds.nbytes(), "d2h_bytes_per_step": int(d2h_bytes),
                 "ms_per_step": 1e3 * e2e_total_s / args.steps,
-                "note": "eg3d_match_seeds (pinned seeds H2D + kernels) + eg3d_points_get (D2H into pinned memory); the scene handle "
-                        "is resident, as the reference's PLGs / plmaps are across its per-match calls"},
+                "note": "eg3d_match_seeds (pinned seeds H2D + kernels) [+ eg3d_points_allgather] + eg3d_points_get of the rank's own result (D2H into pinned "
+                        "memory); the scene handle is resident, as the reference's PLGs / plmaps are across its per-match calls"},
         "gpu_launches": launches,
         "roofline": {"kernel": "k3b_expand_kernel (view expansion of the accepted seeds: warm-started FP64 Gauss-Newton + polyline walks)",
                      "bound": "hbm", "achieved": k3b_bytes / (k3b * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": k3b_bytes / (k3b * 1e-3) / 1e9 / peak, "traffic": traffic_k3b, "peak_source": peak_src, "share_of_step": k3b / step_ms,
-                     "traffic_note": "bytes per launch from the committed ncu capture (profiles/r01_traffic.json); above the algorithmic "
-                                     "bytes because the per-lane stack frames and per-warp scratch arenas of the scalar walk spill past L1 "
-                                     "(16 warps/SM keep them inside the L2: 21 GB; at 28 warps/SM the same kernel moved 93 GB at the same speed)",
+                     "frac": k3b_bytes / (k3b * 1e-3) / 1e9 / peak, "traffic": traffic_k3b, "traffic_source": (f"committed ncu --set full capture ({cap_file}), per launch; NOT measured in this run" if traffic_k3b else None),
+                     "peak_source": peak_src, "share_of_step": k3b / step_ms,
                      "algorithmic_bytes_per_launch": k3b_bytes, "avg_launch_ms": k3b,
-                     "note": "dominant kernel of the step; bound by INSTRUCTION-CACHE refills, not by bandwidth or occupancy (ncu: GPC "
-                             "instruction-cache request rate at 78-80 % of peak, same kernel time with 8..32 resident warps/SM, "
-                             "profiles/r01_k3b_icache.md); the HBM fraction is reported because the contract asks for the dominant "
-                             "kernel; see roofline_k1 for north_star's epipolar-intersection kernel and DESIGN.md §5"},
+                     "issue_slots": ({"inst_executed_from_capture": k3b_inst, "achieved_inst_per_s": k3b_inst / (k3b * 1e-3), "peak_inst_per_s": issue_peak,
+                                      "frac": k3b_inst / (k3b * 1e-3) / issue_peak} if k3b_inst else None),
+                     "note": "dominant kernel of the step; one warp per accepted seed walks ~200 views sequentially: bound by instruction issue / "
+                             "instruction-cache refills, not by bandwidth (DESIGN.md §5); the HBM fraction is reported because the contract asks for the "
+                             "dominant kernel; see roofline_k1 for north_star's epipolar-intersection kernel"},
         "roofline_k1": {"kernel": "k1_sweep_kernel (epipolar intersection, north_star's roofline kernel)", "bound": "hbm",
                         "achieved": k1_bytes / (k1_avg_launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": k1_bytes / (k1_avg_launch_ms * 1e-3) / 1e9 / peak, "traffic": traffic_k1, "peak_source": peak_src,
+                        "frac": k1_bytes / (k1_avg_launch_ms * 1e-3) / 1e9 / peak, "traffic": traffic_k1,
+                        "traffic_source": (f"committed ncu --set full capture ({cap_file}), mean of the count and fill launches; NOT measured in this run" if traffic_k1 else None),
+                        "peak_source": peak_src,
                         "share_of_step": (float(np.mean(k1any_ms)) + k1c + k1f) / step_ms, "launches_per_sweep": 2, "avg_launch_ms": k1_avg_launch_ms,
                         "algorithmic_bytes_per_launch": k1_bytes, "segment_tests_per_launch": sweep["n_segment_tests"] if sweep else last_tm["n_segment_tests"],
                         "full_sweep_ms": sweep, "hits_full_sweep": full_hits, "hits_materialised_in_step": last_tm["n_hits"],
+                        "issue_slots": ({"inst_executed_from_capture": float(np.mean(k1_inst)), "achieved_inst_per_s": float(np.mean(k1_inst)) / (k1_avg_launch_ms * 1e-3),
+                                         "peak_inst_per_s": issue_peak, "frac": float(np.mean(k1_inst)) / (k1_avg_launch_ms * 1e-3) / issue_peak,
+                                         "note": "the roofline that actually bounds this kernel: warp instructions per launch (ncu smsp__inst_executed.sum of the committed capture) / "
+                                                 "launch time measured live / (4 schedulers x 148 SMs x SM clock)"} if all(k1_inst) and sweep else None),
                         "note": "FULL sweep (count + fill passes over every seed x view pair) timed on its own after the steps; inside "
                                 "the step K1 is lazy (kernel_ms.k1_*; share_of_step is that lazy K1).  Algorithmic (streaming) bytes per "
                                 "SURVEY 8(d); a view's segments are staged once per CTA in shared memory, so real DRAM traffic is far "
-                                "lower and the fraction exceeds 1"},
-        "roofline_icache": ({"kernel": "k3b_expand_kernel", "bound": "GPC instruction-cache request rate (what actually limits K3, profiles/r01_k3b_icache.md)",
-                             "achieved": icache["k3b_expand_kernel"]["instruction_requests"] / (k3b * 1e-3), "peak": icache["gcc_peak_requests_per_s"],
-                             "unit": "instruction-line requests/s", "frac": icache["k3b_expand_kernel"]["instruction_requests"] / (k3b * 1e-3) / icache["gcc_peak_requests_per_s"],
-                             "note": "request count per launch from the committed ncu counter capture (profiles/r01_icache.json), divided by the "
-                                     "kernel time measured live in this run; ncu itself reports 77 % (k3b) and 92 % (k3a) of peak"} if icache else None),
+                                "lower and the fraction exceeds 1: the kernel is issue-bound, see issue_slots"},
         "kernel_ms": {"k1_any": float(np.mean(k1any_ms)), "k1_count": k1c, "k1_fill": k1f, "scan_select": float(np.mean(scan_ms)), "k3a_hypothesis": k3a, "k3b_expand": k3b,
-                      "pack": float(np.mean(pack_ms)), "allgather": float(np.mean(ag_all))},
+                      "pack": float(np.mean(pack_ms)), "allgather": float(np.mean(ag_all)), "allgather_broadcast_only": float(np.mean(bc_all))},
+        "per_rank": [{"rank": r, "k1_ms": float(x[0]), "k3a_ms": float(x[1]), "k3b_ms": float(x[2]), "exchange_ms": float(x[3]), "points": float(x[4])} for r, x in enumerate(all_ranks)],
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and n_gpus == 1:
-        cb, _, _ = cpu_baseline(scene, seeds)
-        line["cpu_baseline"] = cb
+        arms, _, _ = cpu_arms(scene, seeds, 12.0)
+        line["cpu_baseline"] = arms["main"]
+        if "port" in arms:
+            line["cpu_baseline_port"] = arms["port"]
+        if "1thread" in arms:
+            line["cpu_baseline_1thread"] = arms["1thread"]
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line))
     if world > 1:
+        dev.comm_destroy()
         dist.destroy_process_group()
 
 

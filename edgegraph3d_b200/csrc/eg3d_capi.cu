@@ -12,6 +12,8 @@
 #include <limits>
 #include <sstream>
 #include <cub/cub.cuh>
+#include <dlfcn.h>
+#include <nccl.h>
 #include "eg3d_dev.cuh"
 #include "eg3d_k1.cuh"
 #include "eg3d_k3.cuh"
@@ -84,6 +86,8 @@ struct eg3d_scene {
   HostGrid hg30;
   std::vector<int64_t> h_track_off; std::vector<int32_t> h_track_view; std::vector<float2> h_track_xy;
   int max_view_segs = 0;
+  // multi-GPU exchange (eg3d_comm_create): an NCCL communicator owned by the scene handle
+  ncclComm_t comm = nullptr; int comm_rank = 0, comm_world = 1;
 };
 
 // Page-locked host staging for results: one block per result, recycled through a process-wide free list so that the
@@ -119,7 +123,7 @@ static PinnedPool g_pinned;
 struct eg3d_points {
   std::shared_ptr<StreamHolder> sh;
   int device = 0; cudaStream_t stream = nullptr;
-  int64_t n_points = 0, n_obs = 0;
+  int64_t n_points = 0, n_obs = 0, n_seeds = 0;
   // device-resident, ordered by (seed, chain position)
   DBuf<float> d_xyz; DBuf<int> d_seed, d_pos; DBuf<int64_t> d_obs_off; DBuf<int> d_ov; DBuf<uint32_t> d_opl, d_oseg; DBuf<float> d_oxy;
   // host copies (filled on first eg3d_points_get), carved out of one pinned block
@@ -399,7 +403,7 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
                                int64_t cap_scale, bool& out_overflow) {
   out_overflow = false;
   const int V = sc->V; const int n = ds.n;
-  out->sh = sc->sh; out->device = sc->device; out->stream = sc->stream;
+  out->sh = sc->sh; out->device = sc->device; out->stream = sc->stream; out->n_seeds = n;
   if (n == 0) { CK(out->d_obs_off.alloc(1)); CK(cudaMemsetAsync(out->d_obs_off.p, 0, sizeof(int64_t), sc->stream)); CK(cudaStreamSynchronize(sc->stream)); return EG3D_OK; }
   const int capf = sc->prm.max_follow_points, capc = sc->prm.max_chain_points, oc = V + 16;
   const size_t spw = k3_scratch_bytes(V, capf, capc, oc);
@@ -620,6 +624,106 @@ static void k1_accounting(const eg3d_scene* sc, const eg3d_seeds* seeds, const e
   tm->n_segment_tests += tests;
 }
 
+// ------------------------------------------------------------------------------------------- multi-GPU exchange ----
+// NCCL is resolved at run time (dlopen by soname): a host process that already carries an NCCL — torch's bundled one under
+// torch.distributed, for instance — shares it, a plain C++ host gets the system library, and libeg3d.so has no link-time
+// dependency on either.
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl_api() {
+  static NcclApi a;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (const char* name : {"libnccl.so.2", "libnccl.so"}) { a.h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (a.h) break; }
+    if (!a.h) return;
+    auto sym = [&](const char* n) { return dlsym(a.h, n); };
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId"); a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy"); a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+    a.Broadcast = (decltype(a.Broadcast))sym("ncclBroadcast"); a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd"); a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.Broadcast && a.GroupStart && a.GroupEnd && a.GetErrorString;
+  });
+  return a;
+}
+#define NCK(call)                                                                                              \
+  do {                                                                                                         \
+    ncclResult_t r_ = (call);                                                                                  \
+    if (r_ != ncclSuccess) {                                                                                   \
+      char b_[512]; snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(r_), __FILE__, __LINE__); \
+      return fail(EG3D_ERR_CUDA, b_);                                                                          \
+    }                                                                                                          \
+  } while (0)
+
+// One rank's records as ONE byte-packed buffer (no padding to a common size, no per-field collectives):
+//   [xyz f32 x3 | n][key i64 | n][obs_off i64 | n+1][obs_view i32 | m][obs_poly u32 | m][obs_seg u32 | m][obs_xy f32 x2 | m]
+// key = (global seed ordinal << 20) | chain position: the canonical order of the merged result.
+struct PackLayout { int64_t n, m; size_t o_xyz, o_key, o_off, o_ov, o_opl, o_oseg, o_oxy, bytes; };
+static PackLayout pack_layout(int64_t n, int64_t m) {
+  PackLayout L; L.n = n; L.m = m;
+  auto al = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  size_t o = 0;
+  L.o_xyz = o; o = al(o + 12 * (size_t)n); L.o_key = o; o = al(o + 8 * (size_t)n); L.o_off = o; o = al(o + 8 * (size_t)(n + 1));
+  L.o_ov = o; o = al(o + 4 * (size_t)m); L.o_opl = o; o = al(o + 4 * (size_t)m); L.o_oseg = o; o = al(o + 4 * (size_t)m); L.o_oxy = o; o = al(o + 8 * (size_t)m);
+  L.bytes = o;
+  return L;
+}
+__global__ void xchg_pack_points_kernel(int64_t n, const float* __restrict__ xyz, const int* __restrict__ seed, const int* __restrict__ pos,
+                                        const int64_t* __restrict__ obs_off, const int64_t* __restrict__ seed_global, int64_t seed_base,
+                                        float* __restrict__ o_xyz, int64_t* __restrict__ o_key, int64_t* __restrict__ o_off) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  o_off[i] = obs_off[i];
+  if (i == n) return;
+  o_xyz[3 * i] = xyz[3 * i]; o_xyz[3 * i + 1] = xyz[3 * i + 1]; o_xyz[3 * i + 2] = xyz[3 * i + 2];
+  const int64_t g = seed_global ? seed_global[seed[i]] : seed_base + seed[i];
+  o_key[i] = (g << 20) | (int64_t)pos[i];
+}
+struct XchgRanks {   // per-rank views of the received buffers (<= 64 ranks)
+  int world; int64_t pbase[65], obase[65];
+  const float* xyz[64]; const int64_t* key[64]; const int64_t* off[64]; const int* ov[64]; const uint32_t* opl[64]; const uint32_t* oseg[64]; const float* oxy[64];
+};
+__device__ __forceinline__ int xchg_rank_of(const XchgRanks& R, int64_t g) { int r = 0; while (r + 1 < R.world && g >= R.pbase[r + 1]) r++; return r; }
+__global__ void xchg_keys_kernel(const __grid_constant__ XchgRanks R, int64_t N, unsigned long long* __restrict__ keys, int64_t* __restrict__ idx) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  const int r = xchg_rank_of(R, g);
+  keys[g] = (unsigned long long)R.key[r][g - R.pbase[r]]; idx[g] = g;
+}
+__global__ void xchg_counts_kernel(const __grid_constant__ XchgRanks R, int64_t N, const int64_t* __restrict__ idx, int64_t* __restrict__ nobs) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > N) return;
+  if (j == N) { nobs[j] = 0; return; }
+  const int64_t g = idx[j]; const int r = xchg_rank_of(R, g); const int64_t l = g - R.pbase[r];
+  nobs[j] = R.off[r][l + 1] - R.off[r][l];
+}
+__global__ void xchg_copy_kernel(const __grid_constant__ XchgRanks R, int64_t N, const int64_t* __restrict__ idx, const unsigned long long* __restrict__ keys,
+                                 const int64_t* __restrict__ obs_off, float* __restrict__ xyz, int* __restrict__ seed, int* __restrict__ pos,
+                                 int* __restrict__ ov, uint32_t* __restrict__ opl, uint32_t* __restrict__ oseg, float* __restrict__ oxy) {
+  const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= N) return;
+  const int64_t g = idx[j]; const int r = xchg_rank_of(R, g); const int64_t l = g - R.pbase[r];
+  if (lane == 0) {
+    xyz[3 * j] = R.xyz[r][3 * l]; xyz[3 * j + 1] = R.xyz[r][3 * l + 1]; xyz[3 * j + 2] = R.xyz[r][3 * l + 2];
+    seed[j] = (int)(keys[j] >> 20); pos[j] = (int)(keys[j] & 0xfffffull);
+  }
+  const int64_t s0 = R.off[r][l], n = R.off[r][l + 1] - s0, d0 = obs_off[j];
+  for (int64_t k = lane; k < n; k += 32) {
+    ov[d0 + k] = R.ov[r][s0 + k]; opl[d0 + k] = R.opl[r][s0 + k]; oseg[d0 + k] = R.oseg[r][s0 + k];
+    oxy[2 * (d0 + k)] = R.oxy[r][2 * (s0 + k)]; oxy[2 * (d0 + k) + 1] = R.oxy[r][2 * (s0 + k) + 1];
+  }
+}
+
 // ================================================================================================ C ABI ============
 extern "C" {
 
@@ -775,6 +879,7 @@ void eg3d_scene_destroy(eg3d_scene* sc) {
   if (!sc) return;
   cudaSetDevice(sc->device);
   if (sc->stream) cudaStreamSynchronize(sc->stream);
+  if (sc->comm && nccl_api().ok) { nccl_api().CommDestroy(sc->comm); sc->comm = nullptr; }
   delete sc;   // buffers are returned to the pool on the stream, which lives until the last result of this scene is freed
 }
 
@@ -1496,6 +1601,127 @@ eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_po
   if (tm) *tm = local;
   if (st != EG3D_OK) return st;
   *out = pts.release();
+  return EG3D_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// the path's one exchange step.  Every rank contributes the accepted points of its shard (device resident);
+// every rank receives the records of all ranks, merged on the device into the reference's loop order = ascending
+// (global seed ordinal, chain position): one ncclAllGather of the counts, ONE grouped broadcast of the byte-packed
+// records (rank r's buffer to everybody, all ranks in one NCCL group: no padding, no staging copies), one radix sort.
+eg3d_status eg3d_comm_unique_id(uint8_t id[EG3D_COMM_ID_BYTES]) {
+  if (!id) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  if (!nccl_api().ok) return fail(EG3D_ERR_CUDA, "NCCL (libnccl.so.2) could not be loaded");
+  static_assert(sizeof(ncclUniqueId) == EG3D_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId u; NCK(nccl_api().GetUniqueId(&u));
+  memcpy(id, &u, sizeof u);
+  return EG3D_OK;
+}
+eg3d_status eg3d_comm_create(eg3d_scene* sc, const uint8_t id[EG3D_COMM_ID_BYTES], int32_t rank, int32_t world) {
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  if (!sc || !id || world < 1 || world > 64 || rank < 0 || rank >= world) return fail(EG3D_ERR_INVALID_ARG, "bad communicator arguments (1 <= world <= 64)");
+  if (!nccl_api().ok) return fail(EG3D_ERR_CUDA, "NCCL (libnccl.so.2) could not be loaded");
+  if (sc->comm) return fail(EG3D_ERR_INVALID_ARG, "the scene already has a communicator");
+  CK(cudaSetDevice(sc->device));
+  ncclUniqueId u; memcpy(&u, id, sizeof u);
+  NCK(nccl_api().CommInitRank(&sc->comm, world, u, rank));
+  sc->comm_rank = rank; sc->comm_world = world;
+  return EG3D_OK;
+}
+eg3d_status eg3d_comm_destroy(eg3d_scene* sc) {
+  if (!sc) return fail(EG3D_ERR_INVALID_ARG, "null scene");
+  if (sc->comm) { cudaSetDevice(sc->device); cudaStreamSynchronize(sc->stream); nccl_api().CommDestroy(sc->comm); sc->comm = nullptr; sc->comm_world = 1; sc->comm_rank = 0; }
+  return EG3D_OK;
+}
+
+eg3d_status eg3d_points_allgather(eg3d_scene* sc, const eg3d_points* mine, const int64_t* seed_global, eg3d_points** out, eg3d_timing* tm) {
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  if (!sc || !mine || !out) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  if (!sc->comm) return fail(EG3D_ERR_INVALID_ARG, "no communicator: call eg3d_comm_create first");
+  CK(cudaSetDevice(sc->device));
+  g_alloc_stream = sc->stream;
+  auto& N = nccl_api();
+  const int W = sc->comm_world, me = sc->comm_rank;
+  cudaStream_t s = sc->stream;
+  Timer tall(s); tall.start();
+  // 1) counts of every rank: (points, observations, seeds of the call)
+  DBuf<int64_t> d_cnt, d_cnts; CK(d_cnt.alloc(3)); CK(d_cnts.alloc(3 * (size_t)W));
+  const int64_t h_cnt[3] = {mine->n_points, mine->n_obs, mine->n_seeds};
+  CK(cudaMemcpyAsync(d_cnt.p, h_cnt, sizeof h_cnt, cudaMemcpyHostToDevice, s));
+  NCK(N.AllGather(d_cnt.p, d_cnts.p, 3, ncclInt64, sc->comm, s));
+  std::vector<int64_t> cnts(3 * (size_t)W);
+  CK(cudaMemcpyAsync(cnts.data(), d_cnts.p, cnts.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));                       // the one host sync of the exchange: buffer sizes
+  std::vector<PackLayout> L(W);
+  int64_t NP = 0, NO = 0, seed_base = 0;
+  XchgRanks R; memset(&R, 0, sizeof R); R.world = W;
+  for (int r = 0; r < W; r++) {
+    L[r] = pack_layout(cnts[3 * r], cnts[3 * r + 1]);
+    R.pbase[r] = NP; R.obase[r] = NO; NP += cnts[3 * r]; NO += cnts[3 * r + 1];
+    if (r < me) seed_base += cnts[3 * r + 2];
+  }
+  R.pbase[W] = NP; R.obase[W] = NO;
+  // 2) pack this rank's records straight into its slot of the receive area, then one grouped broadcast per rank
+  size_t total = 0; std::vector<size_t> slot(W);
+  for (int r = 0; r < W; r++) { slot[r] = total; total += L[r].bytes; }
+  DBuf<unsigned char> recv; CK(recv.alloc(total));
+  DBuf<int64_t> d_sg;
+  if (seed_global && mine->n_seeds > 0) CK(d_sg.upload(seed_global, (size_t)mine->n_seeds, s));
+  {
+    unsigned char* b = recv.p + slot[me]; const PackLayout& l = L[me];
+    const int64_t n = mine->n_points, m = mine->n_obs;
+    xchg_pack_points_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, s>>>(n, mine->d_xyz.p, mine->d_seed.p, mine->d_pos.p, mine->d_obs_off.p,
+        (seed_global && mine->n_seeds > 0) ? d_sg.p : nullptr, seed_base, (float*)(b + l.o_xyz), (int64_t*)(b + l.o_key), (int64_t*)(b + l.o_off));
+    CK(cudaGetLastError());
+    if (m > 0) {
+      CK(cudaMemcpyAsync(b + l.o_ov, mine->d_ov.p, 4 * (size_t)m, cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(b + l.o_opl, mine->d_opl.p, 4 * (size_t)m, cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(b + l.o_oseg, mine->d_oseg.p, 4 * (size_t)m, cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(b + l.o_oxy, mine->d_oxy.p, 8 * (size_t)m, cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  Timer tx(s); tx.start();
+  NCK(N.GroupStart());
+  for (int r = 0; r < W; r++) if (L[r].bytes) NCK(N.Broadcast(recv.p + slot[r], recv.p + slot[r], L[r].bytes, ncclUint8, r, sc->comm, s));
+  NCK(N.GroupEnd());
+  tx.stop();
+  for (int r = 0; r < W; r++) {
+    const unsigned char* b = recv.p + slot[r]; const PackLayout& l = L[r];
+    R.xyz[r] = (const float*)(b + l.o_xyz); R.key[r] = (const int64_t*)(b + l.o_key); R.off[r] = (const int64_t*)(b + l.o_off);
+    R.ov[r] = (const int*)(b + l.o_ov); R.opl[r] = (const uint32_t*)(b + l.o_opl); R.oseg[r] = (const uint32_t*)(b + l.o_oseg); R.oxy[r] = (const float*)(b + l.o_oxy);
+  }
+  // 3) merge on the device: radix sort of the keys, observation offsets by scan, one gather pass
+  std::unique_ptr<eg3d_points> p(new eg3d_points());
+  p->sh = sc->sh; p->device = sc->device; p->stream = s; p->n_points = NP; p->n_obs = NO;
+  for (int r = 0; r < W; r++) p->n_seeds += cnts[3 * r + 2];
+  CK(p->d_xyz.alloc(3 * NP)); CK(p->d_seed.alloc(NP)); CK(p->d_pos.alloc(NP)); CK(p->d_obs_off.alloc(NP + 1));
+  CK(p->d_ov.alloc(NO)); CK(p->d_opl.alloc(NO)); CK(p->d_oseg.alloc(NO)); CK(p->d_oxy.alloc(2 * NO));
+  DBuf<unsigned long long> k0, k1; DBuf<int64_t> i0, i1; DBuf<unsigned char> tmp;
+  CK(k0.alloc(NP)); CK(k1.alloc(NP)); CK(i0.alloc(NP)); CK(i1.alloc(NP));
+  if (NP > 0) {
+    xchg_keys_kernel<<<(unsigned)((NP + 255) / 256), 256, 0, s>>>(R, NP, k0.p, i0.p);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, i0.p, i1.p, (int)NP, 0, 64, s);
+    CK(tmp.alloc(tb));
+    cub::DeviceRadixSort::SortPairs(tmp.p, tb, k0.p, k1.p, i0.p, i1.p, (int)NP, 0, 64, s);
+  }
+  xchg_counts_kernel<<<(unsigned)((NP + 1 + 255) / 256), 256, 0, s>>>(R, NP, i1.p, p->d_obs_off.p);
+  {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, p->d_obs_off.p, p->d_obs_off.p, NP + 1, s);
+    DBuf<unsigned char> t2; CK(t2.alloc(tb));
+    cub::DeviceScan::ExclusiveSum(t2.p, tb, p->d_obs_off.p, p->d_obs_off.p, NP + 1, s);
+    CK(cudaStreamSynchronize(s));
+  }
+  if (NP > 0) xchg_copy_kernel<<<(unsigned)((NP * 32 + 255) / 256), 256, 0, s>>>(R, NP, i1.p, k1.p, p->d_obs_off.p, p->d_xyz.p, p->d_seed.p, p->d_pos.p,
+                                                                              p->d_ov.p, p->d_opl.p, p->d_oseg.p, p->d_oxy.p);
+  CK(cudaGetLastError());
+  tall.stop();
+  CK(cudaStreamSynchronize(s));
+  if (tm) { memset(tm, 0, sizeof *tm); tm->total_ms = tall.ms(); tm->scan_ms = tx.ms() /* the grouped broadcast alone */; tm->pack_ms = tall.ms() - tx.ms();
+            tm->n_points = NP; tm->n_obs = NO; tm->n_seeds = p->n_seeds; tm->kernel_launches = 4; }
+  *out = p.release();
   return EG3D_OK;
 }
 

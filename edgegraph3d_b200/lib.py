@@ -22,6 +22,7 @@ EXPORTS = [
     "eg3d_polyline_sets_from_refpoints", "eg3d_polyline_sets_get", "eg3d_polyline_sets_free",
     "eg3d_polyline_similarity_graph", "eg3d_similarity_graph_get", "eg3d_similarity_graph_communities", "eg3d_polyline_sets_from_communities",
     "eg3d_similarity_graph_free", "eg3d_triangulate_dlt_host", "eg3d_build_info", "eg3d_project_host",
+    "eg3d_comm_unique_id", "eg3d_comm_create", "eg3d_comm_destroy", "eg3d_points_allgather",
 ]
 
 
@@ -78,6 +79,10 @@ def load():
     L.eg3d_build_info.restype = C.c_char_p
     L.eg3d_project_host.argtypes = [A.c_f32p, A.c_f32p, A.c_f32p]
     L.eg3d_triangulate_dlt_host.argtypes = [A.c_f32p, A.c_f32p, A.c_f32p, A.c_f32p, C.c_int32, A.c_f32p]
+    L.eg3d_comm_unique_id.argtypes = [A.c_u8p]
+    L.eg3d_comm_create.argtypes = [C.c_void_p, A.c_u8p, C.c_int32, C.c_int32]
+    L.eg3d_comm_destroy.argtypes = [C.c_void_p]
+    L.eg3d_points_allgather.argtypes = [C.c_void_p, C.c_void_p, A.c_i64p, C.POINTER(C.c_void_p), C.POINTER(A.Timing)]
     _lib = L
     return L
 
@@ -189,6 +194,13 @@ class SimilarityGraph:
             pass
 
 
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 calls this and ships it to the other ranks)."""
+    uid = np.zeros(128, np.uint8)
+    _check(load().eg3d_comm_unique_id(A.ptr(uid, A.c_u8p)))
+    return uid.tobytes()
+
+
 def sample_seeds(scene, views, polylines, spacing):
     """a3 seed sampler (host C++): polyline_matching.cpp:168-190."""
     L = load()
@@ -200,9 +212,11 @@ def sample_seeds(scene, views, polylines, spacing):
         ov = np.zeros(cap, np.int32); op = np.zeros(cap, np.uint32); os_ = np.zeros(cap, np.uint32)
         oxy = np.zeros((cap, 2), np.float32); osrc = np.zeros(cap, np.int32)
         n = C.c_int64()
-        L.eg3d_sample_seeds(C.byref(d), A.ptr(views, A.c_i32p), A.ptr(polylines, A.c_u32p), len(views), spacing, cap,
-                            A.ptr(ov, A.c_i32p), A.ptr(op, A.c_u32p), A.ptr(os_, A.c_u32p), A.ptr(oxy, A.c_f32p),
-                            A.ptr(osrc, A.c_i32p), C.byref(n))
+        st = L.eg3d_sample_seeds(C.byref(d), A.ptr(views, A.c_i32p), A.ptr(polylines, A.c_u32p), len(views), spacing, cap,
+                                 A.ptr(ov, A.c_i32p), A.ptr(op, A.c_u32p), A.ptr(os_, A.c_u32p), A.ptr(oxy, A.c_f32p),
+                                 A.ptr(osrc, A.c_i32p), C.byref(n))
+        if st not in (A.EG3D_OK, A.EG3D_ERR_CAPACITY):      # capacity = "call again with a larger buffer" (n holds the count)
+            _check(st)
         if n.value <= cap:
             k = int(n.value)
             return ov[:k].copy(), op[:k].copy(), os_[:k].copy(), oxy[:k].copy(), osrc[:k].copy()
@@ -328,7 +342,7 @@ class DeviceScene:
         _check(st)
         return self._points(h, fetch), tm.as_dict()
 
-    def match_polyline_sets(self, cands, view_begin=0, view_end=None):
+    def match_polyline_sets(self, cands, view_begin=0, view_end=None, fetch=True):
         L = load()
         cd = cands.desc()
         ve = self.scene.n_views if view_end is None else view_end
@@ -337,15 +351,36 @@ class DeviceScene:
         st = L.eg3d_match_polyline_sets(self.h, C.byref(cd), view_begin, ve, C.byref(h), C.byref(tm))
         self.last_timing = tm.as_dict()
         _check(st)
-        return self._points(h), tm.as_dict()
+        return self._points(h, fetch), tm.as_dict()
 
-    def match_refpoints(self, tb=0, te=None):
+    def match_refpoints(self, tb=0, te=None, fetch=True):
         L = load()
         te = self.scene.n_tracks if te is None else te
         h = C.c_void_p()
         tm = A.Timing()
         _check(L.eg3d_match_refpoints(self.h, tb, te, C.byref(h), C.byref(tm)))
-        return self._points(h), tm.as_dict()
+        return self._points(h, fetch), tm.as_dict()
+
+    # --- multi-GPU exchange: the scene handle owns an NCCL communicator
+    def comm_create(self, unique_id, rank, world):
+        """Collective.  `unique_id`: the 128 bytes rank 0 got from lib.comm_unique_id() (shipped by the host's own channel)."""
+        uid = np.frombuffer(bytes(unique_id), np.uint8).copy()
+        assert uid.size == 128
+        _check(load().eg3d_comm_create(self.h, A.ptr(uid, A.c_u8p), rank, world))
+        self.has_comm = True
+
+    def comm_destroy(self):
+        _check(load().eg3d_comm_destroy(self.h))
+        self.has_comm = False
+
+    def points_allgather(self, mine, seed_global=None, fetch=False):
+        """Collective: `mine` (DevicePoints) of every rank -> the merged records of all ranks in (global seed ordinal, chain
+        position) order, on every rank.  seed_global: int64 per seed of the call that produced `mine` (None = rank-major)."""
+        sg = None if seed_global is None else np.ascontiguousarray(seed_global, np.int64)
+        h = C.c_void_p()
+        tm = A.Timing()
+        _check(load().eg3d_points_allgather(self.h, mine.h, A.ptr(sg, A.c_i64p) if sg is not None else None, C.byref(h), C.byref(tm)))
+        return self._points(h, fetch), tm.as_dict()
 
     def gn_triangulate(self, obs_off, obs_view, obs_xy, init_xyz, fp64):
         L = load()

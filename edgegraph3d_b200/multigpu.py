@@ -59,8 +59,12 @@ _FIELDS = (("xyz", np.float32, 3), ("seed", np.int32, 1), ("chain_pos", np.int32
            ("obs_poly", np.uint32, 1), ("obs_seg", np.uint32, 1), ("obs_xy", np.float32, 2))
 
 
-def all_gather_points(local, dist, device=None, seed_offset_by_rank=True, order_keys=None):
-    """All-gather a PointSet over the default process group; returns the concatenation in rank order on every rank.
+def all_gather_points(local, dist, device=None, order_keys=None):
+    """HOST-STAGED all-gather of a PointSet over torch.distributed (any backend): the CPU / gloo form of the exchange, used by
+    the tests and by callers without a device communicator.  On GPUs the exchange lives in the library
+    (eg3d_points_allgather through lib.DeviceScene.points_allgather: NCCL, device-side merge); pipeline.run_pipelines picks it
+    whenever the scene handle has a communicator.  Returns the concatenation in rank order on every rank; without
+    `order_keys` the `seed` field keeps the rank-LOCAL ordinals.
 
     `local` holds this rank's accepted points (host numpy arrays); tensors are staged on `device` (cuda for NCCL, cpu for
     gloo).  One count all-gather + one padded all-gather per field.  `order_keys` (int64 per local SEED: its ordinal in
@@ -106,5 +110,5 @@ def all_gather_points(local, dist, device=None, seed_offset_by_rank=True, order_
         keys = np.concatenate([got_key[r][:int(cnts[r, 0]), 0] for r in range(world)])
         order = np.lexsort((merged.chain_pos, keys))
         merged = merged.take(order)
-        merged.seed = keys[order].astype(np.int64)
+        merged.seed = keys[order].astype(np.int32 if keys.max(initial=0) < 2 ** 31 else np.int64)
     return merged, cnts

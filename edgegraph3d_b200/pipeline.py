@@ -63,17 +63,28 @@ def run_pipelines(matcher, scene, cands1, cands2, dist=None, device=None, spacin
     from . import multigpu as mg
     rank = dist.get_rank()
     lo, hi = mg.view_block(scene.n_views, world, rank)
+    in_library = getattr(matcher, "has_comm", False)      # a lib.DeviceScene after comm_create: the exchange runs inside libeg3d.so (NCCL + device merge)
     for cands in (cands1, cands2):
         views = mg.polyline_set_seed_views(scene, cands, spacing, E.sample_seeds)
         keys = np.where((views >= lo) & (views < hi))[0]
-        r = matcher.match_polyline_sets(cands, lo, hi)
-        pts, tm = r if isinstance(r, tuple) else (r, None)
-        merged, _ = mg.all_gather_points(pts, dist, device=device, order_keys=keys)
+        if in_library:
+            dp, tm = matcher.match_polyline_sets(cands, lo, hi, fetch=False)
+            merged, _ = matcher.points_allgather(dp, keys, fetch=True)
+            dp.free()
+        else:
+            r = matcher.match_polyline_sets(cands, lo, hi)
+            pts, tm = r if isinstance(r, tuple) else (r, None)
+            merged, _ = mg.all_gather_points(pts, dist, device=device, order_keys=keys)
         out.append(merged); tms.append(tm)
     tb, te = mg.track_block(scene.n_tracks, world, rank)
-    r = matcher.match_refpoints(tb, te)
-    pts, tm = r if isinstance(r, tuple) else (r, None)
-    merged, _ = mg.all_gather_points(pts, dist, device=device)
+    if in_library:
+        dp, tm = matcher.match_refpoints(tb, te, fetch=False)
+        merged, _ = matcher.points_allgather(dp, None, fetch=True)      # track blocks in rank order ARE the reference's loop order
+        dp.free()
+    else:
+        r = matcher.match_refpoints(tb, te)
+        pts, tm = r if isinstance(r, tuple) else (r, None)
+        merged, _ = mg.all_gather_points(pts, dist, device=device)
     out.append(merged); tms.append(tm)
     return out, tms
 

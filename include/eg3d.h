@@ -236,6 +236,31 @@ eg3d_status eg3d_points_get(const eg3d_points*, eg3d_points_view* view);
 eg3d_status eg3d_points_device_get(const eg3d_points*, eg3d_points_view* device_view);
 void        eg3d_points_free(eg3d_points*);
 
+/* ------------------------------------------------------------------------- */
+/* Multi-GPU exchange: the path's ONE collective step              */
+/* ------------------------------------------------------------------------- */
+/*
+ * The reference is one process; its loops over starting views (polyline_matching.cpp:162) and over SfM points
+ * (plg_matching_from_refpoints.cpp:90) are what the ranks of a multi-GPU run split between them, each on a full replica of
+ * the read-only scene.  Before the order-dependent density limiter (filtering_close_plgps.cpp:75-124) every rank needs
+ * every accepted record, in the reference's loop order.  One process per GPU; the scene handle owns the NCCL communicator
+ * (NCCL is loaded at run time by soname, so a host that already runs one — torch.distributed — shares it).
+ *   eg3d_comm_unique_id   rank 0 makes the id and hands it to the other ranks by whatever channel the host has
+ *   eg3d_comm_create      collective: attaches a communicator of `world` ranks to the scene
+ *   eg3d_points_allgather collective: one ncclAllGather of the counts + ONE grouped broadcast of the byte-packed records + a
+ *                         device-side merge (radix sort) into ascending (global seed ordinal, chain position).
+ *                         seed_global[i] (host, one per seed of the call that produced `mine`) is the ordinal of local seed i
+ *                         in the unsharded seed list; NULL = rank-major (shards are contiguous blocks of the loop).  The
+ *                         merged result is device resident like any other eg3d_points; its `seed` field holds global ordinals.
+ *                         timing: total_ms = exchange + merge, scan_ms = the grouped broadcast alone.
+ */
+#define EG3D_COMM_ID_BYTES 128
+eg3d_status eg3d_comm_unique_id(uint8_t id[EG3D_COMM_ID_BYTES]);
+eg3d_status eg3d_comm_create(eg3d_scene*, const uint8_t id[EG3D_COMM_ID_BYTES], int32_t rank, int32_t world);
+eg3d_status eg3d_comm_destroy(eg3d_scene*);
+eg3d_status eg3d_points_allgather(eg3d_scene*, const eg3d_points* mine, const int64_t* seed_global /* may be NULL */,
+                                  eg3d_points** merged, eg3d_timing* timing /* may be NULL */);
+
 /* K2 alone (B5/B6 primitives).  Hypotheses: CSR of (view, xy) observations + initial X.
  * fp64 = 1: em_GaussNewton semantics (triangulation.cpp:105-176), inputs f32, arithmetic f64.
  * fp64 = 0: GaussNewton of the outlier filter (filtering/gauss_newton.cpp:83-134), arithmetic f32.

@@ -249,6 +249,28 @@ void* eg3d_ref_match_seeds(void* sc, const eg3d_seeds* seeds, const eg3d_candida
   return out;
 }
 
+/* The same per-seed calls issued from a real `omp parallel for` over the seeds (the reference's own `#pragma omp for` is orphaned
+ * and runs on one thread, SURVEY finding 4; its per-seed function only reads shared state): bench.py's reference arm. */
+void* eg3d_ref_match_seeds_mt(void* sc, const eg3d_seeds* seeds, const eg3d_candidates* c, int n_threads) {
+  Quiet q;
+  RefScene* s = (RefScene*)sc;
+  vector<vector<set<ulong>>> csets;
+  if (c) for (int k = 0; k < c->n_sets; k++) csets.push_back(cand_of(*s, c, k));
+  vector<set<ulong>> all(s->V);
+  if (!c) for (int v = 0; v < s->V; v++) for (ulong p = 0; p < s->plgs[v].polylines.size(); p++) if (s->plgs[v].is_valid_polyline(p)) all[v].insert(p);
+  vector<vector<p3d_t>> res((size_t)seeds->n);
+  if (n_threads < 1) n_threads = 1;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
+  for (int64_t i = 0; i < seeds->n; i++) {
+    const vector<set<ulong>>& cs = (c && seeds->cand_set && seeds->cand_set[i] >= 0) ? csets[seeds->cand_set[i]] : all;
+    PolyLineGraph2D::plg_point p((ulong)seeds->polyline[i], (ulong)seeds->segment[i], glm::vec2(seeds->xy[2 * i], seeds->xy[2 * i + 1]));
+    res[i] = find_new_3d_points_from_compatible_polylines_starting_plgp_expandallviews(s->sfmd, s->plgs, (const cv::Mat**)s->F, cs, seeds->view[i], p, *s->plgmm, s->plmaps);
+  }
+  RefPoints* out = new RefPoints();
+  for (int64_t i = 0; i < seeds->n; i++) out->append(res[i], (int32_t)i);
+  return out;
+}
+
 /* K1 alone: find_epipolar_correspondences (polyline_matching.cpp:45-73): CSR over (seed, view) */
 void* eg3d_ref_epipolar_intersect(void* sc, const eg3d_seeds* seeds, const eg3d_candidates* c, int64_t* n_hits) {
   Quiet q;

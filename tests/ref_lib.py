@@ -29,6 +29,8 @@ def lib():
             getattr(L, name).restype = C.c_void_p
         L.eg3d_ref_match_polyline_sets.argtypes = [C.c_void_p, C.POINTER(A.Candidates)]
         L.eg3d_ref_match_seeds.argtypes = [C.c_void_p, C.POINTER(A.Seeds), C.POINTER(A.Candidates)]
+        L.eg3d_ref_match_seeds_mt.restype = C.c_void_p
+        L.eg3d_ref_match_seeds_mt.argtypes = [C.c_void_p, C.POINTER(A.Seeds), C.POINTER(A.Candidates), C.c_int]
         L.eg3d_ref_match_refpoints.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
         L.eg3d_ref_epipolar_intersect.argtypes = [C.c_void_p, C.POINTER(A.Seeds), C.POINTER(A.Candidates), A.c_i64p]
         L.eg3d_ref_hits_get.argtypes = [C.c_void_p, C.POINTER(A.c_i64p), C.POINTER(C.POINTER(A.Hit))]
@@ -64,9 +66,12 @@ class RefScene:
         cd = cands.desc()
         return self._points(lib().eg3d_ref_match_polyline_sets(self.h, C.byref(cd)))
 
-    def match_seeds(self, seeds, cands=None):
+    def match_seeds(self, seeds, cands=None, n_threads=1):
+        """n_threads > 1: the same per-seed calls from an OpenMP loop over the seeds (the reference's own loop is serial)."""
         sd = seeds.desc()
         cd = cands.desc() if cands is not None else None
+        if n_threads > 1:
+            return self._points(lib().eg3d_ref_match_seeds_mt(self.h, C.byref(sd), C.byref(cd) if cd is not None else None, n_threads))
         return self._points(lib().eg3d_ref_match_seeds(self.h, C.byref(sd), C.byref(cd) if cd is not None else None))
 
     def match_refpoints(self, tb=0, te=None):

@@ -20,7 +20,10 @@ def test_reference_arm_prints_one_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "points/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1 and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    from tests import ref_lib as R
+    # the reference's own code (oracle/_ref/libref_path.so) when it was built, else the oracle port
+    assert d["cpu_baseline"]["kind"] == ("reference" if R.available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
