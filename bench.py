@@ -183,15 +183,15 @@ def cpu_arms(scene, seeds, budget_s, threads=None, want_port=True, want_1thread=
                  seeds on all host threads (as shipped its loops are serial: orphaned `omp for`, SURVEY finding 4)
       port       the oracle restatement (leaner: no per-hypothesis PLG deep copies, no cv::Mat churn) on all host threads
       1thread    the reference's code on ONE thread = the reference as shipped
-    Seeds on which the reference's behaviour is undefined (~1-5 %) are left out of every sample: its code
-    crashes on them in this build; the oracle flags them (outside the timed region).  Returns (dict of arms, runner)."""
+    (The one call of the reference with undefined behaviour, SURVEY A.2.16, is guarded in that build: ref_path_wrapper.cpp.)
+    Returns (dict of arms, runner, sample)."""
     from tests import oracle_lib as O
     threads = threads or os.cpu_count()
     osc = O.OracleScene(scene)
     n = len(seeds)
     probe = seeds.take(np.linspace(0, n - 1, min(n, 96)).astype(np.int64))
     t = time.perf_counter()
-    flags = osc.match_seeds(probe, n_threads=threads).seed_ub
+    osc.match_seeds(probe, n_threads=threads)
     per_seed_port = max((time.perf_counter() - t) / len(probe), 1e-6)
     have_ref = _ref_available()
     arms = {}
@@ -199,14 +199,11 @@ def cpu_arms(scene, seeds, budget_s, threads=None, want_port=True, want_1thread=
     if have_ref:
         from tests import ref_lib as R
         rs = R.RefScene(scene)
-        pr = probe.take(np.where(flags == 0)[0])
-        t = time.perf_counter(); rs.match_seeds(pr, n_threads=threads); per_seed_ref = max((time.perf_counter() - t) / max(1, len(pr)), 1e-6)
+        t = time.perf_counter(); rs.match_seeds(probe, n_threads=threads); per_seed_ref = max((time.perf_counter() - t) / len(probe), 1e-6)
     per_seed = per_seed_ref if have_ref else per_seed_port
     m = int(min(n, max(64, budget_s / per_seed)))
     sample = seeds.take(np.linspace(0, n - 1, m).astype(np.int64))
-    ub = osc.match_seeds(sample, n_threads=threads).seed_ub           # untimed: find the seeds the reference cannot run
-    sample = sample.take(np.where(ub == 0)[0])
-    note = f"{len(sample)} of {n} seeds (stratified: every {n / m:.1f}th seed of the batch, {int(ub.sum())} with undefined reference behaviour left out), full per-seed path (K1 sweep + triples + PLG following + view expansion)"
+    note = f"{len(sample)} of {n} seeds (stratified: every {n / m:.1f}th seed of the batch), full per-seed path (K1 sweep + triples + PLG following + view expansion)"
 
     def run_main():
         if have_ref:

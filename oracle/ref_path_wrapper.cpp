@@ -70,6 +70,29 @@ void computeCorrespondEpilines(const Mat& points, int whichImage, const Mat& F, 
 }
 }  // namespace cv
 
+/* ONE GUARD around the reference's code.  PolyLineGraph2D::polyline::next_pl_point_by_distance (polyline_graph_2d.cpp:391-447) falls
+ * off its end without a return statement when `direction` is neither extreme of the polyline, and the path does call it that way
+ * (zero-filled per-view direction arrays; ~5-10 % of the productive seeds): undefined behaviour — garbage in the
+ * author's build, a crash in this one.  oracle/Makefile compiles polyline_graph_2d.cpp with
+ * -Dnext_pl_point_by_distance=next_pl_point_by_distance_refimpl, so the reference's own two overloads keep their bodies under
+ * that name, and the symbols every OTHER translation unit calls are defined here: the undefined case gets the rule the oracle
+ * and the product use ("cannot drive": reached_polyline_extreme = true), every defined case is forwarded to the reference's
+ * code untouched. */
+PolyLineGraph2D::polyline::pl_point eg3d_refimpl_next_a(PolyLineGraph2D::polyline* self, const PolyLineGraph2D::polyline::pl_point init_plp, const ulong direction,
+                                                        const float distance, bool& reached)
+    asm("_ZN15PolyLineGraph2D8polyline33next_pl_point_by_distance_refimplENS0_8pl_pointEmfRb");
+PolyLineGraph2D::polyline::pl_point eg3d_refimpl_next_b(PolyLineGraph2D::polyline* self, const ulong starting_extreme, const glm::vec2 coords, const float distance, bool& reached)
+    asm("_ZN15PolyLineGraph2D8polyline33next_pl_point_by_distance_refimplEmN3glm5tvec2IfLNS1_9precisionE0EEEfRb");
+PolyLineGraph2D::polyline::pl_point PolyLineGraph2D::polyline::next_pl_point_by_distance(const PolyLineGraph2D::polyline::pl_point init_plp, const ulong direction,
+                                                                                        const float distance, bool& reached_polyline_extreme) {
+  if (direction != start && direction != end) { reached_polyline_extreme = true; return init_plp; }
+  return eg3d_refimpl_next_a(this, init_plp, direction, distance, reached_polyline_extreme);
+}
+PolyLineGraph2D::polyline::pl_point PolyLineGraph2D::polyline::next_pl_point_by_distance(const ulong starting_extreme, const glm::vec2 coords, const float distance,
+                                                                                        bool& reached_polyline_extreme) {
+  return eg3d_refimpl_next_b(this, starting_extreme, coords, distance, reached_polyline_extreme);
+}
+
 /* debug drawing (src/edgegraph3d/utils/drawing_utilities.cpp, OpenCV imgproc) is behind the reference's -i switch and never
  * reached here: the symbols its callers name are defined as traps */
 #define EG3D_TRAP(name) { fprintf(stderr, "ref_path_wrapper: " name " (debug drawing) is not part of this build\n"); abort(); }

@@ -9,10 +9,13 @@ expansion, pipeline-3 seeding, the density limiter and the outlier filter that t
 oracle (the restatement every GPU parity test is checked against) must reproduce it bit for bit: chains, observation lists,
 2D coordinates and the float bits of every 3D point.
 
-One class of inputs is excluded, and counted: seeds on which the reference calls next_pl_point_by_distance with a direction
-that is neither extreme of the polyline (zero-filled direction arrays).  The reference function then falls off its
-end without a return statement (polyline_graph_2d.cpp:391-447): undefined behaviour, whatever the compiler makes of it (this
-build crashes on it).  The oracle's rule there is "cannot drive"; it flags such seeds (PointSet.seed_ub) and they are skipped."""
+One function of the reference has undefined behaviour on inputs the path does reach: next_pl_point_by_distance falls off its
+end without a return statement when the direction is neither extreme of the polyline (zero-filled direction arrays, SURVEY
+A.2.16; polyline_graph_2d.cpp:391-447).  The build interposes ONE guard there (oracle/ref_path_wrapper.cpp): that case gets the
+rule of the oracle and of the product ("cannot drive"), every defined call is forwarded to the reference's own body.  The
+oracle reports which seeds reach it (PointSet.seed_ub: ~3 % of the synthetic seeds, ~5 % of the real ones, and most of the
+productive ones); with the guard they run through the reference's code like all the others, so every comparison below is over
+ALL seeds."""
 import os
 import numpy as np
 import pytest
@@ -57,37 +60,24 @@ def test_oracle_equals_the_reference_code_on_synthetic_scenes(kw):
     assert np.array_equal(off_r, off_o) and hits_r.tobytes() == hits_o.tobytes() and len(hits_r) > 5000
     # --- a8-a11, sweep form: one call of find_new_3d_points_from_compatible_polylines_starting_plgp_expandallviews per seed
     o = osc.match_seeds(seeds, n_threads=8)
-    ok = np.where(o.seed_ub == 0)[0]
-    assert len(ok) >= 0.9 * len(seeds)
-    r = rs.match_seeds(seeds.take(ok))
-    o_ok = osc.match_seeds(seeds.take(ok), n_threads=8)
-    assert identical(r, o_ok) and r.n_points > 500
-    assert np.array_equal(r.seed, o_ok.seed) and np.array_equal(r.chain_pos, o_ok.chain_pos)
-    # --- candidate-set form (pipelines 1-2), per seed, and the reference's own set loop
-    #     (find_new_3d_points_from_compatible_polylines_expandallviews_parallel: seed sampler included) for sets without a UB seed
+    assert 0 < o.seed_ub.sum() < 0.1 * len(seeds)                       # the guarded case does occur
+    r = rs.match_seeds(seeds)
+    assert identical(r, o) and r.n_points > 500
+    assert np.array_equal(r.seed, o.seed) and np.array_equal(r.chain_pos, o.chain_pos)
+    assert identical(rs.match_seeds(seeds, n_threads=4), o)             # the per-seed entry from an OpenMP loop (bench.py's reference arm)
+    # --- candidate-set form (pipelines 1-2): per seed, and the reference's own loop over sets / starting views / polylines
+    #     (find_new_3d_points_from_compatible_polylines_expandallviews_parallel, its seed sampler included)
     cands = syn.curve_candidate_sets(sc, seed=kw["seed"])
     cs = set_seeds(sc, cands)
-    oc = osc.match_seeds(cs, cands, n_threads=8)
-    okc = np.where(oc.seed_ub == 0)[0]
-    assert identical(rs.match_seeds(cs.take(okc), cands), osc.match_seeds(cs.take(okc), cands, n_threads=8))
-    clean_sets = [s for s in range(cands.n_sets) if not oc.seed_ub[cs.cand_set == s].any()]
-    assert len(clean_sets) >= 1
-    V = sc.n_views
-    from edgegraph3d_b200.scene import CandidateSets
-    sub = CandidateSets.from_lists([[cands.polyline[int(cands.off[s * V + v]):int(cands.off[s * V + v + 1])] for v in range(V)] for s in clean_sets], V)
-    r_sets, o_sets = rs.match_polyline_sets(sub), osc.match_polyline_sets(sub, n_threads=8)
-    assert identical(r_sets, o_sets) and r_sets.n_points > 50
+    assert identical(rs.match_seeds(cs, cands), osc.match_seeds(cs, cands, n_threads=8))
+    r_sets, o_sets = rs.match_polyline_sets(cands), osc.match_polyline_sets(cands, n_threads=8)
+    assert identical(r_sets, o_sets) and r_sets.n_points > 500
     # --- a6 + a12: plg_matching_from_refpoint (PLGEdgeManager seeding -> PLGPCM3ViewsPLGFollowing -> a8-a11), per SfM point
+    #     the whole range goes through plg_matching_from_refpoints_parallel itself
     o3 = osc.match_refpoints(0, sc.n_tracks, n_threads=8)
-    bad = set(o3.seed_track[o3.seed_ub == 1].tolist())
-    good = [t for t in range(sc.n_tracks) if t not in bad]
-    assert len(good) >= 0.6 * sc.n_tracks
-    n_pts = 0
-    for t in good:
-        r3, oo = rs.match_refpoints(t, t + 1), osc.match_refpoints(t, t + 1, n_threads=1)
-        assert identical(r3, oo), t
-        n_pts += r3.n_points
-    assert n_pts > 1000
+    assert identical(rs.match_refpoints(0, sc.n_tracks), o3) and o3.n_points > 1000
+    for t in range(0, sc.n_tracks, 7):
+        assert identical(rs.match_refpoints(t, t + 1), osc.match_refpoints(t, t + 1, n_threads=1)), t
     # --- a13 + a14 on what the matching produced: filter_3d_points_close_2d_array, compute_inliers (gaussNewtonFiltering + view-count rule)
     keep_r, keep_o = rs.dedup_close_points(o), osc.dedup_close_points(o)
     assert np.array_equal(keep_r, keep_o) and 0 < keep_o.sum() < o.n_points
@@ -112,9 +102,7 @@ def test_oracle_equals_the_reference_code_on_the_packaged_dtu006_example():
     _, c2, _ = P.candidate_sets(real)
     cs = set_seeds(real, c2)
     cs = cs.take(np.arange(min(len(cs), 600)))
-    oc = osc.match_seeds(cs, c2, n_threads=8)
-    okc = np.where(oc.seed_ub == 0)[0]
-    r2, o2 = rs.match_seeds(cs.take(okc), c2), osc.match_seeds(cs.take(okc), c2, n_threads=8)
+    r2, o2 = rs.match_seeds(cs, c2, n_threads=4), osc.match_seeds(cs, c2, n_threads=8)
     assert identical(r2, o2) and r2.n_points > 1000
     assert np.array_equal(rs.dedup_close_points(o2), osc.dedup_close_points(o2))
     xr, ir = rs.filter(o2.xyz, o2.obs_off, o2.obs_view, o2.obs_xy, 0)
@@ -122,18 +110,11 @@ def test_oracle_equals_the_reference_code_on_the_packaged_dtu006_example():
     assert np.array_equal(ir, io) and xr.tobytes() == np.ascontiguousarray(xo, np.float32).tobytes() and 0 < io.sum() < len(io)
 
     # pipeline 3
-    o3 = osc.match_refpoints(0, 300, n_threads=8)
+    o3 = osc.match_refpoints(0, 400, n_threads=8)
     n_ub = int(o3.seed_ub.sum())
-    assert 0 < n_ub < 0.1 * len(o3.seed_ub)               # ~5 % of the real seeds reach the reference's undefined behaviour
-    bad = set(o3.seed_track[o3.seed_ub == 1].tolist())
-    good = [t for t in range(300) if t not in bad]
-    assert len(good) > 200
-    n_pts = 0
-    for t in good:
-        r3, oo = rs.match_refpoints(t, t + 1), osc.match_refpoints(t, t + 1, n_threads=1)
-        assert identical(r3, oo), t
-        n_pts += r3.n_points
-    assert n_pts > 2000
+    assert 0 < n_ub < 0.1 * len(o3.seed_ub)               # ~5 % of the real seeds reach the guarded case
+    r3 = rs.match_refpoints(0, 400)
+    assert identical(r3, o3) and r3.n_points > 5000
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/example/dtu006/input.json"), reason="needs the reference tree (build container only)")
