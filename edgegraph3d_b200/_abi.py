@@ -63,7 +63,8 @@ class Timing(C.Structure):
                 ("n_seeds", C.c_int64), ("n_hits", C.c_int64), ("n_segment_tests", C.c_int64),
                 ("n_points", C.c_int64), ("n_obs", C.c_int64), ("k1_algorithmic_bytes", C.c_int64),
                 ("kernel_launches", C.c_int32), ("n_capacity_overflows", C.c_int32),
-                ("k3a_ms", C.c_float), ("k3b_ms", C.c_float), ("n_accepted_seeds", C.c_int64), ("k1_any_ms", C.c_float)]
+                ("k3a_ms", C.c_float), ("k3b_ms", C.c_float), ("n_accepted_seeds", C.c_int64), ("k1_any_ms", C.c_float),
+                ("host_wall_ms", C.c_float), ("n_capacity_retries", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -13,6 +13,7 @@
 #include <sstream>
 #include <cub/cub.cuh>
 #include <dlfcn.h>
+#include <chrono>
 #include <nccl.h>
 #include "eg3d_dev.cuh"
 #include "eg3d_k1.cuh"
@@ -211,6 +212,11 @@ static eg3d_status require_device() {
   return EG3D_OK;
 }
 
+struct WallClock {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  float ms() const { return std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 struct Timer {
   cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s;
   explicit Timer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
@@ -400,12 +406,12 @@ static eg3d_status prepare_hits_b(eg3d_scene* sc, const DevSeeds& ds, HitLists& 
 
 // K3 + ordered packing + D2H into an eg3d_points
 static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, eg3d_points* out, eg3d_timing* tm,
-                               int64_t cap_scale, bool& out_overflow) {
-  out_overflow = false;
+                               int64_t cap_scale, int seed_cap_mult, bool& out_overflow, bool& seed_cap_overflow) {
+  out_overflow = false; seed_cap_overflow = false;
   const int V = sc->V; const int n = ds.n;
   out->sh = sc->sh; out->device = sc->device; out->stream = sc->stream; out->n_seeds = n;
   if (n == 0) { CK(out->d_obs_off.alloc(1)); CK(cudaMemsetAsync(out->d_obs_off.p, 0, sizeof(int64_t), sc->stream)); CK(cudaStreamSynchronize(sc->stream)); return EG3D_OK; }
-  const int capf = sc->prm.max_follow_points, capc = sc->prm.max_chain_points, oc = V + 16;
+  const int capf = sc->prm.max_follow_points * seed_cap_mult, capc = sc->prm.max_chain_points * seed_cap_mult, oc = V + 16;
   const size_t spw = k3_scratch_bytes(V, capf, capc, oc);
   int blocks_per_sm = 16;  // upper bound; residency is set by the kernel's register budget
   int nblocks = sc->num_sms * blocks_per_sm;
@@ -512,7 +518,7 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
     }
   }
   if (cnt[3]) { out_overflow = true; return EG3D_OK; }   // internal output bound exceeded: the caller retries with larger buffers
-  if (cnt[2]) return fail(EG3D_ERR_CAPACITY, "a per-seed capacity (max_chain_points / max_follow_points / observations per point) was exceeded; raise eg3d_params capacities");
+  if (cnt[2]) { seed_cap_overflow = true; return EG3D_OK; }   // a per-seed capacity was too small for some seed: the caller re-runs with doubled capacities
   // ordered packing
   tp.start();
   DBuf<int64_t> pt_off; CK(pt_off.alloc(n + 1));
@@ -554,16 +560,19 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
 // Output buffers are sized for the typical case; if a batch produces more, K3 is simply run again with larger buffers
 // (nothing is truncated and no result of the short run is used).
 static eg3d_status run_k3(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, eg3d_points* out, eg3d_timing* tm) {
-  int64_t scale = 1;
-  for (int attempt = 0; attempt < 7; attempt++, scale *= 4) {
+  int64_t scale = 1; int mult = 1;
+  for (int attempt = 0; attempt < 12; attempt++) {
     eg3d_timing t0; if (tm) t0 = *tm;
-    bool ovf = false;
-    eg3d_status st = run_k3_once(sc, ds, H, out, tm, scale, ovf);
-    if (st != EG3D_OK || !ovf) return st;
+    bool ovf = false, seed_ovf = false;
+    eg3d_status st = run_k3_once(sc, ds, H, out, tm, scale, mult, ovf, seed_ovf);
+    if (st != EG3D_OK || (!ovf && !seed_ovf)) return st;
+    // nothing of the short run is used; the time it took stays in the timing (it was spent)
     if (tm) { const eg3d_timing t1 = *tm; *tm = t0; tm->k3_ms = t1.k3_ms; tm->k3a_ms = t1.k3a_ms; tm->k3b_ms = t1.k3b_ms; tm->kernel_launches = t1.kernel_launches;
-              tm->k1_count_ms = t1.k1_count_ms; tm->k1_fill_ms = t1.k1_fill_ms; tm->scan_ms = t1.scan_ms; }
+              tm->k1_count_ms = t1.k1_count_ms; tm->k1_fill_ms = t1.k1_fill_ms; tm->scan_ms = t1.scan_ms; tm->n_capacity_retries = t1.n_capacity_retries + (seed_ovf ? 1 : 0); }
+    if (seed_ovf) { if (mult >= 64) break; mult *= 2; }     // per-seed chain / follow capacities: real polyline graphs give chains well above the synthetic rigs' (dtu006: 140 points)
+    else { if (scale >= 4096) break; scale *= 4; }          // unordered output buffers
   }
-  return fail(EG3D_ERR_CAPACITY, "accepted-point output exceeds 4096x the typical bound; split the seed batch");
+  return fail(EG3D_ERR_CAPACITY, "accepted-point output exceeds 4096x the typical bound, or a seed needs more than 64x the per-seed capacities; split the seed batch");
 }
 
 // lazily bring a result to (pinned) host memory
@@ -607,17 +616,22 @@ static void k1_accounting(const eg3d_scene* sc, const eg3d_seeds* seeds, const e
     for (int64_t i = 0; i < seeds->n; i++) tests += total - (sc->h_view_seg_off[seeds->view[i] + 1] - sc->h_view_seg_off[seeds->view[i]]);
     tm->k1_algorithmic_bytes += 16 * tests + (72 + 8) * seeds->n * (int64_t)(V - 1) + 16 * n_hits;
   } else {
+    // per (set, view): candidate polylines and their segments, once; then per seed the sum over the other views
+    const size_t nsv = (size_t)cands->n_sets * V;
+    std::vector<int64_t> segs(nsv, 0), ncs(nsv, 0), set_segs((size_t)cands->n_sets, 0), set_nc((size_t)cands->n_sets, 0);
+    for (size_t r = 0; r < nsv; r++) {
+      const int v = (int)(r % V);
+      for (int64_t k = cands->off[r]; k < cands->off[r + 1]; k++) {
+        const int g = sc->h_view_poly_off[v] + (int)cands->polyline[k];
+        const int nv = sc->h_poly_vert_off[g + 1] - sc->h_poly_vert_off[g];
+        segs[r] += nv > 1 ? nv - 1 : 0; ncs[r]++;
+      }
+      set_segs[r / V] += segs[r]; set_nc[r / V] += ncs[r];
+    }
     int64_t ncand = 0;
     for (int64_t i = 0; i < seeds->n; i++) {
-      int set = seeds->cand_set[i];
-      for (int v = 0; v < V; v++) {
-        if (v == seeds->view[i]) continue;
-        for (int64_t k = cands->off[(size_t)set * V + v]; k < cands->off[(size_t)set * V + v + 1]; k++) {
-          int g = sc->h_view_poly_off[v] + (int)cands->polyline[k];
-          int nv = sc->h_poly_vert_off[g + 1] - sc->h_poly_vert_off[g];
-          tests += nv > 1 ? nv - 1 : 0; ncand++;
-        }
-      }
+      const size_t set = (size_t)seeds->cand_set[i], own = set * V + seeds->view[i];
+      tests += set_segs[set] - segs[own]; ncand += set_nc[set] - ncs[own];
     }
     tm->k1_algorithmic_bytes += 16 * tests + 4 * ncand + (72 + 8) * seeds->n * (int64_t)(V - 1) + 16 * n_hits;
   }
@@ -1257,7 +1271,12 @@ void eg3d_triangulate_dlt_host(const float* P1, const float* P2, const float* x1
 
 static eg3d_status check_seeds(const eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d_candidates* cands) {
   if (!sc || !seeds) return fail(EG3D_ERR_INVALID_ARG, "null argument");
-  if (seeds->n > 0x7fffffff / std::max(1, sc->V)) {}
+  if (seeds->n < 0 || seeds->n > 0x7fffffff / std::max(1, sc->V)) return fail(EG3D_ERR_INVALID_ARG, "too many seeds in one call (n_seeds * n_views must fit 31 bits); split the batch");
+  for (int64_t i = 0; i < seeds->n; i++) {
+    const int v = seeds->view[i];
+    if (v < 0 || v >= sc->V) return fail(EG3D_ERR_INVALID_ARG, "seed view out of range");
+    if ((int64_t)seeds->polyline[i] >= (int64_t)(sc->h_view_poly_off[v + 1] - sc->h_view_poly_off[v])) return fail(EG3D_ERR_INVALID_ARG, "seed polyline id out of range");
+  }
   if (cands) {
     if (!seeds->cand_set) return fail(EG3D_ERR_INVALID_ARG, "candidates given but seeds->cand_set is null");
     for (int64_t i = 0; i < seeds->n; i++)
@@ -1315,6 +1334,7 @@ eg3d_status eg3d_hits_get(const eg3d_hits* h, int64_t* n_seeds, int32_t* n_views
 void eg3d_hits_free(eg3d_hits* h) { delete h; }
 
 eg3d_status eg3d_match_seeds(eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d_candidates* cands, eg3d_points** out, eg3d_timing* tm) {
+  WallClock wall;
   eg3d_status st = require_device(); if (st != EG3D_OK) return st;
   st = check_seeds(sc, seeds, cands); if (st != EG3D_OK) return st;
   CK(cudaSetDevice(sc->device));
@@ -1332,6 +1352,7 @@ eg3d_status eg3d_match_seeds(eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d
   local.n_seeds = seeds->n;
   local.total_ms = tall.ms();   // first kernel launch .. last kernel end, everything in between included
   k1_accounting(sc, seeds, cands, local.n_hits, &local);
+  local.host_wall_ms = wall.ms();
   if (tm) *tm = local;
   if (st != EG3D_OK) return st;
   *out = pts.release();
@@ -1339,7 +1360,15 @@ eg3d_status eg3d_match_seeds(eg3d_scene* sc, const eg3d_seeds* seeds, const eg3d
 }
 
 eg3d_status eg3d_match_polyline_sets(eg3d_scene* sc, const eg3d_candidates* c, int32_t view_begin, int32_t view_end, eg3d_points** out, eg3d_timing* tm) {
+  WallClock wall;
   if (!sc || !c) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  if (view_begin < 0 || view_end > sc->V || view_begin > view_end) return fail(EG3D_ERR_INVALID_ARG, "starting-view range out of bounds");
+  if (c->n_sets < 0 || (c->n_sets > 0 && (!c->off || c->off[0] != 0))) return fail(EG3D_ERR_INVALID_ARG, "bad candidate sets");
+  for (size_t r = 0; r < (size_t)c->n_sets * sc->V; r++) {
+    if (c->off[r + 1] < c->off[r]) return fail(EG3D_ERR_INVALID_ARG, "candidate offsets must be non-decreasing");
+    const int v = (int)(r % sc->V), npl = sc->h_view_poly_off[v + 1] - sc->h_view_poly_off[v];
+    for (int64_t k = c->off[r]; k < c->off[r + 1]; k++) if ((int64_t)c->polyline[k] >= npl) return fail(EG3D_ERR_INVALID_ARG, "candidate polyline id out of range");
+  }
   // seed sampler (polyline_matching.cpp:162-190): sets in order, starting views ascending, candidate polylines ascending
   std::vector<int32_t> sv, scs; std::vector<uint32_t> spl, sseg; std::vector<float> sxy;
   DevScene hs; memset(&hs, 0, sizeof hs);
@@ -1359,7 +1388,10 @@ eg3d_status eg3d_match_polyline_sets(eg3d_scene* sc, const eg3d_candidates* c, i
         }
       }
   eg3d_seeds s; s.n = (int64_t)sv.size(); s.view = sv.data(); s.polyline = spl.data(); s.segment = sseg.data(); s.xy = sxy.data(); s.cand_set = scs.data();
-  return eg3d_match_seeds(sc, &s, c, out, tm);
+  const float sample_ms = wall.ms();
+  const eg3d_status st = eg3d_match_seeds(sc, &s, c, out, tm);
+  if (tm) tm->host_wall_ms += sample_ms;
+  return st;
 }
 
 eg3d_status eg3d_points_get(const eg3d_points* pc, eg3d_points_view* v) {
@@ -1483,6 +1515,13 @@ eg3d_status eg3d_dedup_close_points(eg3d_scene* sc, const eg3d_points_view* pts,
   const int w = (int)ceilf((float)sc->width / cs), h = (int)ceilf((float)sc->height / cs);
   std::vector<std::vector<uint8_t>> bm(sc->V);
   auto cell = [&](int64_t o) -> size_t { return (size_t)(int)(pts->obs_xy[2 * o + 1] / cs) * w + (size_t)(int)(pts->obs_xy[2 * o] / cs); };
+  // the reference indexes its bitmaps unchecked (filtering_close_plgps.cpp:77-85: undefined behaviour for an observation outside
+  // the image); a public C ABI refuses such input instead
+  for (int64_t o = 0; o < pts->n_obs; o++) {
+    const float x = pts->obs_xy[2 * o], y = pts->obs_xy[2 * o + 1];
+    if (pts->obs_view[o] < 0 || pts->obs_view[o] >= sc->V || !(x >= 0) || !(y >= 0) || (int)(x / cs) >= w || (int)(y / cs) >= h)
+      return fail(EG3D_ERR_INVALID_ARG, "an observation lies outside its image (or names a view that does not exist)");
+  }
   for (int64_t i = 0; i < pts->n_points; i++) {
     bool is_new = false;
     for (int64_t o = pts->obs_off[i]; o < pts->obs_off[i + 1]; o++) {
@@ -1536,15 +1575,11 @@ eg3d_status eg3d_filter(eg3d_scene* sc, int64_t n, float* xyz, const int64_t* ob
 // (plg_edge_manager.cpp:261-288) — runs on the device, one warp per observation (eg3d_a6.cuh); the epipolar
 // intersections with the radius filter (:191-259) run in k1_cand_kernel, then K3 exactly as for pipelines 1-2
 // (plgpcm_3views_plg_following.cpp:40-50 scatters the per-observing-view lists into a V-vector = the CSR rows).
-eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_points** out, eg3d_timing* tm) {
-  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
-  if (!sc || !out) return fail(EG3D_ERR_INVALID_ARG, "null argument");
-  if (sc->dev.n_tracks <= 0) return fail(EG3D_ERR_INVALID_ARG, "the scene was created without SfM tracks");
-  if (tb < 0 || te > sc->dev.n_tracks || tb > te) return fail(EG3D_ERR_INVALID_ARG, "track range out of bounds");
-  CK(cudaSetDevice(sc->device));
-  g_alloc_stream = sc->stream;
+}  // extern "C"
+// a6 seeding on the device for the tracks [tb, te): seeds (view, polyline, segment, xy, row = track * V), per-seed radius and the
+// candidate rows, ready for k1_cand_kernel.  Shared by eg3d_match_refpoints and eg3d_refpoint_correspondences.
+static eg3d_status refpoint_seeding(eg3d_scene* sc, int64_t tb, int64_t te, DevSeeds& ds, DevCand& dc, int64_t& n_seeds, eg3d_timing& local) {
   const int V = sc->V;
-  eg3d_timing local; memset(&local, 0, sizeof local);
   const int64_t nt = te - tb, o_begin = sc->h_track_off[tb], o_end = sc->h_track_off[te], n_o = o_end - o_begin;
   const size_t n_rows = (size_t)nt * V;
   DBuf<A6Rec> recs; DBuf<int> n_ids, n_cand, n_seed, ovf; DBuf<unsigned char> is_last; DBuf<int64_t> seed_off, coff;
@@ -1556,8 +1591,7 @@ eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_po
   A6Args a; memset(&a, 0, sizeof a);
   a.o_begin = o_begin; a.o_end = o_end; a.tb = tb; a.obs_track = sc->obs_track.p;
   a.recs = recs.p; a.n_ids = n_ids.p; a.n_cand = n_cand.p; a.n_seed = n_seed.p; a.is_last = is_last.p; a.overflow = ovf.p; a.row_cnt = coff.p;
-  Timer ts(sc->stream), tall(sc->stream);
-  tall.start();
+  Timer ts(sc->stream);
   ts.start();
   const unsigned blocks = (unsigned)(((size_t)n_o * 32 + A6_THREADS - 1) / A6_THREADS);
   if (n_o > 0) a6_classify_kernel<<<blocks, A6_THREADS, 0, sc->stream>>>(sc->dev, a);
@@ -1568,17 +1602,18 @@ eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_po
     DBuf<unsigned char> tmp; CK(tmp.alloc(tb1));
     cub::DeviceScan::ExclusiveSum(tmp.p, tb1, n_seed.p, seed_off.p, n_o + 1, sc->stream);
   }
-  st = exclusive_scan_i64(sc, coff.p, n_rows + 1); if (st != EG3D_OK) return st;
-  int64_t n_seeds = 0, n_cands = 0; int h_ovf = 0;
+  eg3d_status st = exclusive_scan_i64(sc, coff.p, n_rows + 1); if (st != EG3D_OK) return st;
+  int64_t n_cands = 0; int h_ovf = 0;
+  n_seeds = 0;
   CK(cudaMemcpyAsync(&n_seeds, seed_off.p + n_o, sizeof(int64_t), cudaMemcpyDeviceToHost, sc->stream));
   CK(cudaMemcpyAsync(&n_cands, coff.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, sc->stream));
   CK(cudaMemcpyAsync(&h_ovf, ovf.p, sizeof(int), cudaMemcpyDeviceToHost, sc->stream));
   CK(cudaStreamSynchronize(sc->stream));
   if (h_ovf) return fail(EG3D_ERR_CAPACITY, "an observation has more polylines in its 30 px neighbourhood than the device seeding holds (A6_RAW / A6_IDS)");
   if (n_seeds > 0x7fffffff) return fail(EG3D_ERR_CAPACITY, "too many seeds in one call; split the track range");
-  DevSeeds ds; ds.n = (int)n_seeds;
+  ds.n = (int)n_seeds;
   CK(ds.view.alloc(n_seeds)); CK(ds.pl.alloc(n_seeds)); CK(ds.seg.alloc(n_seeds)); CK(ds.xy.alloc(n_seeds)); CK(ds.cand_set.alloc(n_seeds));
-  DevCand dc; dc.filtered = true;
+  dc.filtered = true;
   CK(dc.pl.alloc(n_cands)); CK(dc.center.alloc(n_rows)); CK(dc.seed_r2.alloc(n_seeds));
   CK(cudaMemsetAsync(dc.center.p, 0, std::max<size_t>(n_rows, 1) * sizeof(float2), sc->stream));
   a.seed_off = seed_off.p; a.coff = coff.p;
@@ -1591,6 +1626,27 @@ eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_po
   local.scan_ms += ts.ms(); local.kernel_launches += 5;
   // hand the CSR offsets to the candidate descriptor (the buffer changes owner)
   dc.off.p = coff.p; dc.off.n = coff.n; dc.off.s = coff.s; coff.p = nullptr;
+  return EG3D_OK;
+}
+struct eg3d_corr {
+  int V = 0; int64_t n_seeds = 0;
+  std::vector<int32_t> view; std::vector<uint32_t> pl, seg; std::vector<float> xy; std::vector<int64_t> track; std::vector<int64_t> off; std::vector<eg3d_hit> hits;
+};
+extern "C" {
+
+eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_points** out, eg3d_timing* tm) {
+  WallClock wall;
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  if (!sc || !out) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  if (sc->dev.n_tracks <= 0) return fail(EG3D_ERR_INVALID_ARG, "the scene was created without SfM tracks");
+  if (tb < 0 || te > sc->dev.n_tracks || tb > te) return fail(EG3D_ERR_INVALID_ARG, "track range out of bounds");
+  CK(cudaSetDevice(sc->device));
+  g_alloc_stream = sc->stream;
+  eg3d_timing local; memset(&local, 0, sizeof local);
+  Timer tall(sc->stream);
+  tall.start();
+  DevSeeds ds; DevCand dc; int64_t n_seeds = 0;
+  st = refpoint_seeding(sc, tb, te, ds, dc, n_seeds, local); if (st != EG3D_OK) return st;
   HitLists H;
   st = prepare_hits_a(sc, ds, &dc, H, &local); if (st != EG3D_OK) return st;
   std::unique_ptr<eg3d_points> pts(new eg3d_points());
@@ -1598,12 +1654,93 @@ eg3d_status eg3d_match_refpoints(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_po
   tall.stop();
   local.n_seeds = n_seeds;
   local.total_ms = tall.ms();
+  local.host_wall_ms = wall.ms();
   if (tm) *tm = local;
   if (st != EG3D_OK) return st;
   *out = pts.release();
   return EG3D_OK;
 }
 
+// B3 (EdgeManager side): PLGEdgeManager::detect_nearby_intersections_and_correspondences_plgp(refpoint) for the tracks [tb, te)
+// (plg_edge_manager.cpp:261-300): the seeds (projections onto the polylines within 10 px of an observation) and, per seed, the
+// epipolar hits on the other observing views within the 30 px grid neighbourhood and the radius 3 x |observation - seed|.
+// Exactly what eg3d_match_refpoints feeds its own consensus step; here it is handed back so that a caller can run its own.
+eg3d_status eg3d_refpoint_correspondences(eg3d_scene* sc, int64_t tb, int64_t te, eg3d_corr** out) {
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  if (!sc || !out) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  if (sc->dev.n_tracks <= 0) return fail(EG3D_ERR_INVALID_ARG, "the scene was created without SfM tracks");
+  if (tb < 0 || te > sc->dev.n_tracks || tb > te) return fail(EG3D_ERR_INVALID_ARG, "track range out of bounds");
+  CK(cudaSetDevice(sc->device));
+  g_alloc_stream = sc->stream;
+  eg3d_timing local; memset(&local, 0, sizeof local);
+  DevSeeds ds; DevCand dc; int64_t n_seeds = 0;
+  st = refpoint_seeding(sc, tb, te, ds, dc, n_seeds, local); if (st != EG3D_OK) return st;
+  DBuf<int64_t> off; DBuf<eg3d_hit> hits; int64_t nh = 0;
+  st = run_k1(sc, ds, &dc, off, hits, nh, &local); if (st != EG3D_OK) return st;
+  std::unique_ptr<eg3d_corr> c(new eg3d_corr());
+  c->V = sc->V; c->n_seeds = n_seeds;
+  c->view.resize(n_seeds); c->pl.resize(n_seeds); c->seg.resize(n_seeds); c->xy.resize(2 * n_seeds); c->track.resize(n_seeds);
+  c->off.resize((size_t)n_seeds * sc->V + 1); c->hits.resize((size_t)nh);
+  std::vector<int> set((size_t)n_seeds);
+  if (n_seeds > 0) {
+    CK(cudaMemcpy(c->view.data(), ds.view.p, n_seeds * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c->pl.data(), ds.pl.p, n_seeds * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c->seg.data(), ds.seg.p, n_seeds * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(c->xy.data(), ds.xy.p, n_seeds * sizeof(float2), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(set.data(), ds.cand_set.p, n_seeds * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  for (int64_t i = 0; i < n_seeds; i++) c->track[i] = tb + set[i];                    // candidate row = track - tb
+  CK(cudaMemcpy(c->off.data(), off.p, c->off.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  if (nh) CK(cudaMemcpy(c->hits.data(), hits.p, (size_t)nh * sizeof(eg3d_hit), cudaMemcpyDeviceToHost));
+  *out = c.release();
+  return EG3D_OK;
+}
+eg3d_status eg3d_corr_get(const eg3d_corr* c, int64_t* n_seeds, int32_t* n_views, const int32_t** view, const uint32_t** polyline, const uint32_t** segment,
+                          const float** xy, const int64_t** track, const int64_t** hit_off, const eg3d_hit** hits) {
+  if (!c) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  if (n_seeds) *n_seeds = c->n_seeds; if (n_views) *n_views = c->V;
+  if (view) *view = c->view.data(); if (polyline) *polyline = c->pl.data(); if (segment) *segment = c->seg.data(); if (xy) *xy = c->xy.data();
+  if (track) *track = c->track.data(); if (hit_off) *hit_off = c->off.data(); if (hits) *hits = c->hits.data();
+  return EG3D_OK;
+}
+void eg3d_corr_free(eg3d_corr* c) { delete c; }
+
+// B4: compute_3D_point_multiple_views_plg_following_expandallviews_vector (triangulation.hpp:98, triangulation.cpp:1027-1088) for a
+// batch of seeds whose V hit lists the CALLER supplies (any EdgeManager / correspondence search): view-triple selection,
+// triple enumeration with the uniqueness test, PLG following, view expansion — K3 alone, no K1.
+eg3d_status eg3d_match_correspondences(eg3d_scene* sc, int64_t n_seeds, const int32_t* start_view, const int64_t* hit_off, const eg3d_hit* hits,
+                                       eg3d_points** out, eg3d_timing* tm) {
+  eg3d_status st = require_device(); if (st != EG3D_OK) return st;
+  if (!sc || !out || n_seeds < 0 || (n_seeds > 0 && (!start_view || !hit_off))) return fail(EG3D_ERR_INVALID_ARG, "null argument");
+  if (n_seeds > 0x7fffffff / std::max(1, sc->V)) return fail(EG3D_ERR_INVALID_ARG, "too many seeds in one call");
+  const int V = sc->V;
+  const size_t n_rows = (size_t)n_seeds * V;
+  for (int64_t i = 0; i < n_seeds; i++) if (start_view[i] < 0 || start_view[i] >= V) return fail(EG3D_ERR_INVALID_ARG, "start_view out of range");
+  for (size_t r = 0; r < n_rows; r++) if (hit_off[r + 1] < hit_off[r]) return fail(EG3D_ERR_INVALID_ARG, "hit_off must be non-decreasing");
+  const int64_t nh = n_seeds > 0 ? hit_off[n_rows] : 0;
+  if (nh > 0 && !hits) return fail(EG3D_ERR_INVALID_ARG, "null hits");
+  CK(cudaSetDevice(sc->device));
+  g_alloc_stream = sc->stream;
+  eg3d_timing local; memset(&local, 0, sizeof local);
+  DevSeeds ds; ds.n = (int)n_seeds;
+  CK(ds.view.upload(start_view, (size_t)n_seeds, sc->stream));
+  CK(ds.pl.alloc((size_t)n_seeds)); CK(ds.seg.alloc((size_t)n_seeds)); CK(ds.xy.alloc((size_t)n_seeds));
+  Timer tall(sc->stream);
+  tall.start();
+  HitLists H; H.lazy = false;
+  if (n_seeds > 0) { CK(H.off_a.upload(hit_off, n_rows + 1, sc->stream)); CK(H.hits_a.upload(hits, (size_t)nh, sc->stream)); }
+  else { CK(H.off_a.alloc(1)); CK(H.hits_a.alloc(0)); }
+  st = select_views(sc, ds, H, &local); if (st != EG3D_OK) return st;
+  std::unique_ptr<eg3d_points> pts(new eg3d_points());
+  st = run_k3(sc, ds, H, pts.get(), &local);
+  tall.stop();
+  local.n_seeds = n_seeds; local.n_hits = nh;
+  local.total_ms = tall.ms();
+  if (tm) *tm = local;
+  if (st != EG3D_OK) return st;
+  *out = pts.release();
+  return EG3D_OK;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // the path's one exchange step.  Every rank contributes the accepted points of its shard (device resident);

@@ -23,6 +23,7 @@ EXPORTS = [
     "eg3d_polyline_similarity_graph", "eg3d_similarity_graph_get", "eg3d_similarity_graph_communities", "eg3d_polyline_sets_from_communities",
     "eg3d_similarity_graph_free", "eg3d_triangulate_dlt_host", "eg3d_build_info", "eg3d_project_host",
     "eg3d_comm_unique_id", "eg3d_comm_create", "eg3d_comm_destroy", "eg3d_points_allgather",
+    "eg3d_match_correspondences", "eg3d_refpoint_correspondences", "eg3d_corr_get", "eg3d_corr_free",
 ]
 
 
@@ -79,6 +80,11 @@ def load():
     L.eg3d_build_info.restype = C.c_char_p
     L.eg3d_project_host.argtypes = [A.c_f32p, A.c_f32p, A.c_f32p]
     L.eg3d_triangulate_dlt_host.argtypes = [A.c_f32p, A.c_f32p, A.c_f32p, A.c_f32p, C.c_int32, A.c_f32p]
+    L.eg3d_match_correspondences.argtypes = [C.c_void_p, C.c_int64, A.c_i32p, A.c_i64p, C.POINTER(A.Hit), C.POINTER(C.c_void_p), C.POINTER(A.Timing)]
+    L.eg3d_refpoint_correspondences.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_void_p)]
+    L.eg3d_corr_get.argtypes = [C.c_void_p, A.c_i64p, A.c_i32p, C.POINTER(A.c_i32p), C.POINTER(A.c_u32p), C.POINTER(A.c_u32p), C.POINTER(A.c_f32p), C.POINTER(A.c_i64p),
+                                C.POINTER(A.c_i64p), C.POINTER(C.POINTER(A.Hit))]
+    L.eg3d_corr_free.argtypes = [C.c_void_p]
     L.eg3d_comm_unique_id.argtypes = [A.c_u8p]
     L.eg3d_comm_create.argtypes = [C.c_void_p, A.c_u8p, C.c_int32, C.c_int32]
     L.eg3d_comm_destroy.argtypes = [C.c_void_p]
@@ -360,6 +366,40 @@ class DeviceScene:
         tm = A.Timing()
         _check(L.eg3d_match_refpoints(self.h, tb, te, C.byref(h), C.byref(tm)))
         return self._points(h, fetch), tm.as_dict()
+
+    def match_correspondences(self, start_view, hit_off, hits, fetch=True):
+        """B4: K3 alone on caller-supplied hit lists (CSR over (seed, view); `hits` is the structured array epipolar_intersect returns)."""
+        sv = np.ascontiguousarray(start_view, np.int32)
+        off = np.ascontiguousarray(hit_off, np.int64)
+        hh = np.ascontiguousarray(hits)
+        h = C.c_void_p()
+        tm = A.Timing()
+        st = load().eg3d_match_correspondences(self.h, len(sv), A.ptr(sv, A.c_i32p), A.ptr(off, A.c_i64p),
+                                               C.cast(hh.ctypes.data, C.POINTER(A.Hit)), C.byref(h), C.byref(tm))
+        self.last_timing = tm.as_dict()
+        _check(st)
+        return self._points(h, fetch), tm.as_dict()
+
+    def refpoint_correspondences(self, tb=0, te=None):
+        """B3 (EdgeManager side): the seeds of pipeline 3 and their per-view hit lists -> (SeedBatch, track per seed, hit_off, hits)."""
+        from .scene import SeedBatch
+        L = load()
+        te = self.scene.n_tracks if te is None else te
+        h = C.c_void_p()
+        _check(L.eg3d_refpoint_correspondences(self.h, tb, te, C.byref(h)))
+        try:
+            n = C.c_int64(); V = C.c_int32(); view = A.c_i32p(); pl = A.c_u32p(); seg = A.c_u32p(); xy = A.c_f32p(); tr = A.c_i64p(); off = A.c_i64p(); hits = C.POINTER(A.Hit)()
+            _check(L.eg3d_corr_get(h, C.byref(n), C.byref(V), C.byref(view), C.byref(pl), C.byref(seg), C.byref(xy), C.byref(tr), C.byref(off), C.byref(hits)))
+            k = int(n.value)
+            arr = lambda p, shape, dt: (np.ctypeslib.as_array(p, shape=shape).copy() if k else np.zeros(shape, dt))
+            off_np = np.ctypeslib.as_array(off, shape=(k * int(V.value) + 1,)).copy()
+            nh = int(off_np[-1])
+            dt = np.dtype([("polyline", np.uint32), ("segment", np.uint32), ("x", np.float32), ("y", np.float32)])
+            hn = np.frombuffer((C.c_char * (nh * 16)).from_address(C.addressof(hits.contents)), dtype=dt).copy() if nh else np.zeros(0, dt)
+            seeds = SeedBatch(arr(view, (k,), np.int32), arr(pl, (k,), np.uint32), arr(seg, (k,), np.uint32), arr(xy, (k, 2), np.float32), None)
+            return seeds, arr(tr, (k,), np.int64), off_np, hn
+        finally:
+            L.eg3d_corr_free(h)
 
     # --- multi-GPU exchange (SURVEY 8e): the scene handle owns an NCCL communicator
     def comm_create(self, unique_id, rank, world):

@@ -22,7 +22,8 @@ from . import openmvg_io as io
 from . import real_scene
 from .scene import PointSet, ranges
 
-# chains on real polyline graphs are longer than on the synthetic rigs the defaults are sized for
+# chains on real polyline graphs are longer than on the synthetic rigs the defaults are sized for: starting the
+# per-seed capacities here saves the library its own retry (eg3d_timing.n_capacity_retries); the defaults work too
 REAL_DATA_CAPACITIES = dict(max_chain_points=256, max_follow_points=320)
 
 

@@ -34,7 +34,7 @@ typedef enum eg3d_status {
   EG3D_ERR_INVALID_ARG = 1,
   EG3D_ERR_NO_DEVICE = 2,   /* no usable CUDA device: the product path never falls back to the CPU */
   EG3D_ERR_CUDA = 3,        /* a CUDA runtime call failed; see eg3d_last_error() */
-  EG3D_ERR_CAPACITY = 4,    /* a fixed per-seed capacity (chain length, hits) was exceeded; see eg3d_params */
+  EG3D_ERR_CAPACITY = 4,    /* an output or index capacity was exceeded even after the library's own retries (or a caller buffer is too small) */
   EG3D_ERR_OOM = 5
 } eg3d_status;
 
@@ -100,8 +100,8 @@ typedef struct eg3d_params {
    * 1: emulate the truncating `int abs(int)` binding of the author's GCC 5 toolchain.         */
   int32_t filter_abs_int;
   /* capacities of the device path (not reference constants) */
-  int32_t max_chain_points;           /* per seed; default 96 */
-  int32_t max_follow_points;          /* per direction during 3-view following; default 160 */
+  int32_t max_chain_points;           /* per seed; default 96.  Starting sizes: a batch that needs more is re-run inside the call with doubled  */
+  int32_t max_follow_points;          /* per direction during 3-view following; default 160.             capacities (eg3d_timing.n_capacity_retries) */
 } eg3d_params;
 
 void eg3d_params_default(eg3d_params* p);
@@ -162,6 +162,8 @@ typedef struct eg3d_timing {
   float k3b_ms;               /* K3 phase B: expansion to the remaining views (accepted seeds) */
   int64_t n_accepted_seeds;
   float k1_any_ms;            /* epipolar intersection, any-hit pass of the lazy sweep (eg3d_match_seeds without candidates) */
+  float host_wall_ms;         /* wall-clock time of the whole C call on the host (uploads, kernels, syncs; what e2e pays) */
+  int32_t n_capacity_retries; /* K3 was re-run with larger per-seed capacities this many times (never truncates, never fails on them) */
 } eg3d_timing;
 
 typedef struct eg3d_scene  eg3d_scene;   /* opaque, device resident */
@@ -228,6 +230,28 @@ eg3d_status eg3d_match_polyline_sets(eg3d_scene*, const eg3d_candidates*, int32_
  * [track_begin, track_end) of the scene (multi-GPU shard axis, plg_matching_from_refpoints.cpp:90). */
 eg3d_status eg3d_match_refpoints(eg3d_scene*, int64_t track_begin, int64_t track_end,
                                  eg3d_points** out, eg3d_timing* timing);
+
+/* B4: compute_3D_point_multiple_views_plg_following_expandallviews_vector(sfmd, plgs, F, starting_plg_id,
+ * epipolar_correspondences, plmaps) (include/edgegraph3d/utils/geometry/triangulation.hpp:98; triangulation.cpp:1027-1088) for a
+ * batch of seeds whose hit lists the CALLER supplies — what PLGPCM3ViewsPLGFollowing::consensus_strategy_single_point_single_
+ * intersection hands it (plgpcm_3views_plg_following.cpp:40-50) and what polyline_matching.cpp:140 hands it.  hit_off has
+ * n_seeds*V+1 entries (CSR over (seed, view), lists in the caller's order); the starting view's list normally holds the seed
+ * itself (polyline_matching.cpp:54-55).  View-triple selection, triple enumeration with the uniqueness test, PLG following and
+ * view expansion run on the device; no epipolar search is done here, so a host that keeps its own EdgeManager swaps only the
+ * consensus step. */
+eg3d_status eg3d_match_correspondences(eg3d_scene*, int64_t n_seeds, const int32_t* start_view, const int64_t* hit_off,
+                                       const eg3d_hit* hits, eg3d_points** out, eg3d_timing* timing);
+
+/* B3, EdgeManager side: PLGEdgeManager::detect_nearby_intersections_and_correspondences_plgp(refpoint)
+ * (include/edgegraph3d/edge_managers/plg_edge_manager.hpp:74; plg_edge_manager.cpp:261-300) for the SfM points [tb, te): the seeds
+ * (view, plg_point, producing track) in the reference's order and their per-view hit lists (CSR over (seed, view), radius
+ * filter applied), computed on the device and copied to host memory owned by the handle. */
+typedef struct eg3d_corr eg3d_corr;
+eg3d_status eg3d_refpoint_correspondences(eg3d_scene*, int64_t track_begin, int64_t track_end, eg3d_corr** out);
+eg3d_status eg3d_corr_get(const eg3d_corr*, int64_t* n_seeds, int32_t* n_views, const int32_t** view, const uint32_t** polyline,
+                          const uint32_t** segment, const float** xy, const int64_t** track, const int64_t** hit_off,
+                          const eg3d_hit** hits);   /* any out pointer may be NULL */
+void        eg3d_corr_free(eg3d_corr*);
 
 /* Results stay on the device until asked for: eg3d_points_get copies them (once) into page-locked host memory owned by
  * the handle; eg3d_points_device_get exposes the device-resident arrays (same layout, device pointers on the scene's

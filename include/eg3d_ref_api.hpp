@@ -169,6 +169,132 @@ inline std::vector<new_3dpoint_plgp_matches> plg_matching_from_refpoints_paralle
   return points_to_reference(pts);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// B4 + B3: the triangulation entry and the two abstract classes the reference carries in its data_bundle
+// (utils/data_bundle.hpp:45-54).  A maintainer may keep an EdgeManager of their own and swap only the consensus step, or the
+// other way round: both sides of the seam are here with the reference's signatures.
+// ---------------------------------------------------------------------------------------------------------------------
+typedef std::pair<std::vector<PolyLineGraph2D::plg_point>, std::vector<std::vector<std::vector<PolyLineGraph2D::plg_point>>>> intersections_and_correspondences_t;
+
+// B4, batched: compute_3D_point_multiple_views_plg_following_expandallviews_vector (triangulation.hpp:98) for several seeds at
+// once; epipolar_correspondences[i] is the V-vector of hit lists of seed i.  One result vector per seed.
+inline std::vector<std::vector<new_3dpoint_plgp_matches>> compute_3D_point_multiple_views_plg_following_expandallviews_vector_batch(
+    Eg3dScene& scene, const std::vector<int>& starting_plg_ids, const std::vector<std::vector<std::vector<PolyLineGraph2D::plg_point>>>& epipolar_correspondences) {
+  const int V = scene.n_views();
+  const int64_t n = (int64_t)starting_plg_ids.size();
+  std::vector<int32_t> sv(starting_plg_ids.begin(), starting_plg_ids.end());
+  std::vector<int64_t> off(1, 0); std::vector<eg3d_hit> hits;
+  for (int64_t i = 0; i < n; i++)
+    for (int v = 0; v < V; v++) {
+      if (v < (int)epipolar_correspondences[(size_t)i].size())
+        for (const auto& q : epipolar_correspondences[(size_t)i][(size_t)v]) { eg3d_hit h; h.polyline = (uint32_t)q.polyline_id; h.segment = (uint32_t)q.plp.segment_index; h.x = q.plp.coords[0]; h.y = q.plp.coords[1]; hits.push_back(h); }
+      off.push_back((int64_t)hits.size());
+    }
+  eg3d_points* pts = nullptr;
+  check(eg3d_match_correspondences(scene.handle(), n, sv.data(), off.data(), hits.data(), &pts, nullptr));
+  eg3d_points_view v; check(eg3d_points_get(pts, &v));
+  std::vector<std::vector<new_3dpoint_plgp_matches>> res((size_t)n);
+  for (int64_t i = 0; i < v.n_points; i++) {
+    new_3dpoint_plgp_matches p;
+    std::get<0>(p) = vec3(v.xyz[3 * i], v.xyz[3 * i + 1], v.xyz[3 * i + 2]);
+    for (int64_t o = v.obs_off[i]; o < v.obs_off[i + 1]; o++) {
+      std::get<1>(p).push_back(PolyLineGraph2D::plg_point(v.obs_poly[o], v.obs_seg[o], vec2(v.obs_xy[2 * o], v.obs_xy[2 * o + 1])));
+      std::get<2>(p).push_back(v.obs_view[o]);
+    }
+    res[(size_t)v.seed[i]].push_back(p);
+  }
+  eg3d_points_free(pts);
+  return res;
+}
+// B4 with the reference's own shape: one seed (the sfmd / plgs / F / plmaps arguments live in the scene handle)
+inline std::vector<new_3dpoint_plgp_matches> compute_3D_point_multiple_views_plg_following_expandallviews_vector(
+    Eg3dScene& scene, const int starting_plg_id, const std::vector<std::vector<PolyLineGraph2D::plg_point>>& epipolar_correspondences) {
+  return compute_3D_point_multiple_views_plg_following_expandallviews_vector_batch(scene, std::vector<int>(1, starting_plg_id),
+                                                                                  std::vector<std::vector<std::vector<PolyLineGraph2D::plg_point>>>(1, epipolar_correspondences))[0];
+}
+
+// plgp_consensus_manager.hpp:56-72
+class PLGPConsensusManager {
+ public:
+  virtual std::vector<new_3dpoint_plgp_matches> consensus_strategy_single_point(const int starting_img_id, const int refpoint, const intersections_and_correspondences_t& intersections_and_correspondences_pair) = 0;
+  virtual std::vector<std::vector<new_3dpoint_plgp_matches>> consensus_strategy_single_point_vector(const int starting_img_id, const int refpoint, const intersections_and_correspondences_t& intersections_and_correspondences_pair) = 0;
+  virtual ~PLGPConsensusManager() {}
+ protected:
+  const SfMData& sfmd;
+  Eg3dScene& scene;          // stands for the reference's (imgs, img_size, all_fundamental_matrices, plgs) members
+  PLGPConsensusManager(const SfMData& input_sfmd, Eg3dScene& input_scene) : sfmd(input_sfmd), scene(input_scene) {}
+};
+
+// plgpcm_3views_plg_following.hpp:50-58, plgpcm_3views_plg_following.cpp:40-69: scatter the per-observing-view hit lists of
+// every intersection into a V-vector and run the triangulation entry — all intersections of the pair in ONE device call.
+class PLGPCM3ViewsPLGFollowing : public PLGPConsensusManager {
+ public:
+  PLGPCM3ViewsPLGFollowing(const SfMData& input_sfmd, Eg3dScene& input_scene) : PLGPConsensusManager(input_sfmd, input_scene) {}
+  std::vector<std::vector<new_3dpoint_plgp_matches>> consensus_strategy_single_point_vector(const int starting_img_id, const int refpoint, const intersections_and_correspondences_t& iac) override {
+    const size_t n = iac.first.size();
+    std::vector<std::vector<std::vector<PolyLineGraph2D::plg_point>>> all(n, std::vector<std::vector<PolyLineGraph2D::plg_point>>((size_t)scene.n_views()));
+    for (size_t k = 0; k < n; k++)      // consensus_strategy_single_point_single_intersection, :40-44
+      for (size_t i = 0; i < sfmd.camViewingPointN_[(size_t)refpoint].size(); i++) all[k][(size_t)sfmd.camViewingPointN_[(size_t)refpoint][i]] = iac.second[k][i];
+    return compute_3D_point_multiple_views_plg_following_expandallviews_vector_batch(scene, std::vector<int>(n, starting_img_id), all);
+  }
+  std::vector<new_3dpoint_plgp_matches> consensus_strategy_single_point(const int starting_img_id, const int refpoint, const intersections_and_correspondences_t& iac) override {
+    std::vector<new_3dpoint_plgp_matches> res;
+    for (auto& cur : consensus_strategy_single_point_vector(starting_img_id, refpoint, iac)) res.insert(res.end(), cur.begin(), cur.end());
+    return res;
+  }
+};
+
+// edge_manager.hpp:54-73 narrowed to what pipeline 3 calls through its `(PLGEdgeManager*) em` downcast
+// (plg_matching_from_refpoints.cpp:67): one (intersections, correspondences) pair per observing view of the SfM point.
+class EdgeManager {
+ public:
+  virtual std::vector<intersections_and_correspondences_t> detect_nearby_intersections_and_correspondences_plgp(const int starting_point_id) = 0;
+  virtual ~EdgeManager() {}
+};
+
+// plg_edge_manager.hpp:58-105 (seeding part, plg_edge_manager.cpp:191-300) on the device: 10 px seeds, 30 px candidate
+// neighbourhoods, epipolar intersections within 3 x |observation - seed|.
+class PLGEdgeManager : public EdgeManager {
+ public:
+  PLGEdgeManager(const SfMData& input_sfmd, Eg3dScene& input_scene) : sfmd(input_sfmd), scene(input_scene) {}
+  std::vector<intersections_and_correspondences_t> detect_nearby_intersections_and_correspondences_plgp(const int starting_point_id) override {
+    eg3d_corr* c = nullptr;
+    check(eg3d_refpoint_correspondences(scene.handle(), starting_point_id, starting_point_id + 1, &c));
+    int64_t n = 0; int32_t V = 0; const int32_t* view; const uint32_t *pl, *seg; const float* xy; const int64_t* off; const eg3d_hit* hits;
+    check(eg3d_corr_get(c, &n, &V, &view, &pl, &seg, &xy, nullptr, &off, &hits));
+    const std::vector<int>& cams = sfmd.camViewingPointN_[(size_t)starting_point_id];
+    std::vector<intersections_and_correspondences_t> res(cams.size());
+    int64_t s = 0;
+    for (size_t i = 0; i < cams.size(); i++)            // seeds come in the reference's order: observing view by observing view
+      for (; s < n && view[s] == cams[i]; s++) {
+        res[i].first.push_back(PolyLineGraph2D::plg_point(pl[s], seg[s], vec2(xy[2 * s], xy[2 * s + 1])));
+        std::vector<std::vector<PolyLineGraph2D::plg_point>> per_cam(cams.size());
+        for (size_t j = 0; j < cams.size(); j++)
+          for (int64_t k = off[s * V + cams[j]]; k < off[s * V + cams[j] + 1]; k++)
+            per_cam[j].push_back(PolyLineGraph2D::plg_point(hits[k].polyline, hits[k].segment, vec2(hits[k].x, hits[k].y)));
+        res[i].second.push_back(per_cam);
+      }
+    eg3d_corr_free(c);
+    return res;
+  }
+ private:
+  const SfMData& sfmd;
+  Eg3dScene& scene;
+};
+
+// B2 with the reference's own shape (plg_matching_from_refpoints.hpp:53-55; plg_matching_from_refpoints.cpp:64-104): ANY EdgeManager
+// with ANY PLGPConsensusManager — the fused eg3d_match_refpoints (plg_matching_from_refpoints_parallel above) is the fast path
+// when both are the library's own.
+inline std::vector<new_3dpoint_plgp_matches> plg_matching_from_refpoints(const SfMData& sfm_data, EdgeManager* em, PLGPConsensusManager* cm) {
+  std::vector<new_3dpoint_plgp_matches> res;
+  for (size_t refpoint_id = 0; refpoint_id < sfm_data.points_.size(); refpoint_id++) {
+    const std::vector<intersections_and_correspondences_t> all = em->detect_nearby_intersections_and_correspondences_plgp((int)refpoint_id);
+    for (size_t i = 0; i < sfm_data.camViewingPointN_[refpoint_id].size(); i++)
+      for (const auto& cur : cm->consensus_strategy_single_point_vector(sfm_data.camViewingPointN_[refpoint_id][i], (int)refpoint_id, all[i])) res.insert(res.end(), cur.begin(), cur.end());
+  }
+  return res;
+}
+
 // a13 (filtering_close_plgps.hpp): first-come-first-kept density limiter over the gathered points
 inline std::vector<new_3dpoint_plgp_matches> filter_3d_points_close_2d_array(Eg3dScene& scene, const std::vector<new_3dpoint_plgp_matches>& p3ds) {
   std::vector<float> xyz, xy; std::vector<int32_t> seed(p3ds.size(), 0), pos(p3ds.size(), 0), view; std::vector<uint32_t> pl, seg; std::vector<int64_t> off(1, 0);

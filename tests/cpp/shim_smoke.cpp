@@ -56,7 +56,19 @@ int main() {
     (void)sets1;
     auto whole = edge_reconstruction_pipeline;          // pipelines.cpp:201-246 under its own name (needs tracks: compile check only)
     (void)whole;
-    std::printf("shim ok: %zu points, %zu after the density limiter\n", pts.size(), kept.size());
+    // B3 / B4: the plug-in seam.  The consensus manager on hit lists this test builds itself (every vertex of the other views'
+    // polylines that is close to the epipolar line would do; here: the seed's own chain neighbours are enough to exercise the call)
+    PLGPCM3ViewsPLGFollowing cm(sfmd, scene);
+    PLGPConsensusManager* cmp = &cm;
+    PLGEdgeManager em(sfmd, scene);
+    EdgeManager* emp = &em;
+    (void)emp; (void)cmp;
+    auto generic = plg_matching_from_refpoints;          // B2 over ANY EdgeManager / PLGPConsensusManager (needs tracks: compile check only)
+    (void)generic;
+    std::vector<std::vector<PolyLineGraph2D::plg_point>> epc((size_t)V);
+    for (int v = 0; v < V; v++) epc[(size_t)v].push_back(PolyLineGraph2D::plg_point(0, 14, plgs[(size_t)v].polylines[0].polyline_coords[14]));
+    auto one = compute_3D_point_multiple_views_plg_following_expandallviews_vector(scene, 1, epc);
+    std::printf("shim ok: %zu points, %zu after the density limiter, %zu from caller-supplied correspondences\n", pts.size(), kept.size(), one.size());
     return pts.empty() ? 2 : 0;
   } catch (const std::exception& e) {
     std::printf("shim: %s\n", e.what());

@@ -207,15 +207,55 @@ def test_output_capacity_retry(small, monkeypatch):
     assert tm["kernel_launches"] > 10          # more than one K3 attempt
 
 
-def test_per_seed_capacity_is_reported_not_truncated(small):
-    # max_chain_points too small for the chains of this scene: the call fails loudly with EG3D_ERR_CAPACITY
-    from edgegraph3d_b200 import _abi as A
-    sc, _, _ = small
+def test_per_seed_capacities_grow_inside_the_call(small):
+    """max_chain_points / max_follow_points are STARTING sizes: a batch with longer chains is re-run inside the call with doubled
+    capacities (real polyline graphs give chains of 140+ points against the default 96) — same result as with roomy capacities,
+    never a truncated chain, never an error the caller has to handle."""
+    sc, dev, orc = small
     cands = syn.curve_candidate_sets(sc)
-    with E.DeviceScene(sc, E.default_params(max_chain_points=3)) as tiny:
+    ref, tm0 = dev.match_polyline_sets(cands)
+    assert tm0["n_capacity_retries"] == 0
+    with E.DeviceScene(sc, E.default_params(max_chain_points=3, max_follow_points=4)) as tiny:
+        got, tm = tiny.match_polyline_sets(cands)
+        assert tm["n_capacity_retries"] >= 2
+        for f in ("xyz", "seed", "chain_pos", "obs_off", "obs_view", "obs_poly", "obs_seg", "obs_xy"):
+            assert np.array_equal(getattr(got, f), getattr(ref, f)), f
+        g3, tm3 = tiny.match_refpoints(0, sc.n_tracks)
+        w3, _ = dev.match_refpoints(0, sc.n_tracks)
+        assert tm3["n_capacity_retries"] >= 1 and np.array_equal(g3.obs_off, w3.obs_off) and np.array_equal(g3.xyz, w3.xyz)
+
+
+def test_bad_arguments_are_refused(small):
+    """Out-of-range views / polyline ids / ranges come back as EG3D_ERR_INVALID_ARG instead of reading past the caller's arrays."""
+    from edgegraph3d_b200 import _abi as A
+    from edgegraph3d_b200.scene import SeedBatch, CandidateSets, PointSet
+    sc, dev, _ = small
+    seeds = syn.sample_seeds(E.sample_seeds, sc, per_view=5)
+    bad = SeedBatch(seeds.view.copy(), seeds.polyline.copy(), seeds.segment, seeds.xy, None)
+    bad.view[0] = sc.n_views
+    with pytest.raises(E.Eg3dError) as ei:
+        dev.match_seeds(bad)
+    assert ei.value.status == A.EG3D_ERR_INVALID_ARG
+    bad.view[0] = 0; bad.polyline[0] = 10 ** 6
+    with pytest.raises(E.Eg3dError) as ei:
+        dev.match_seeds(bad)
+    assert ei.value.status == A.EG3D_ERR_INVALID_ARG
+    cands = syn.curve_candidate_sets(sc)
+    with pytest.raises(E.Eg3dError) as ei:
+        dev.match_polyline_sets(cands, 0, sc.n_views + 1)
+    assert ei.value.status == A.EG3D_ERR_INVALID_ARG
+    c2 = CandidateSets(cands.n_sets, cands.off.copy(), cands.polyline.copy())
+    c2.polyline[0] = 10 ** 6
+    with pytest.raises(E.Eg3dError) as ei:
+        dev.match_polyline_sets(c2)
+    assert ei.value.status == A.EG3D_ERR_INVALID_ARG
+    pts, _ = dev.match_seeds(seeds)
+    if pts.n_obs:
+        xy = pts.obs_xy.copy(); xy[0] = (-5.0, 10.0)
+        outside = PointSet(pts.xyz, pts.seed, pts.chain_pos, pts.obs_off, pts.obs_view, pts.obs_poly, pts.obs_seg, xy)
         with pytest.raises(E.Eg3dError) as ei:
-            tiny.match_polyline_sets(cands)
-    assert ei.value.status == A.EG3D_ERR_CAPACITY
+            dev.dedup_close_points(outside)
+        assert ei.value.status == A.EG3D_ERR_INVALID_ARG
 
 
 def test_lazy_sweep_equals_full_sweep(small):
@@ -298,3 +338,31 @@ def test_degenerate_scenes():
     assert not (seeds3.view == 2).any()
     with E.DeviceScene(sc3) as dev:
         assert_points_parity(sc3, dev.match_seeds(seeds3)[0], O.OracleScene(sc3).match_seeds(seeds3))
+
+
+def test_match_correspondences_is_the_consensus_step_alone(small):
+    """B4 (eg3d_match_correspondences): K3 on CALLER-supplied hit lists — here the lists K1 itself produces, so the result must be
+    what eg3d_match_seeds gives for the same seeds, and the oracle's; then with the lists of pipeline 3's EdgeManager side
+    (eg3d_refpoint_correspondences, B3), where it must equal eg3d_match_refpoints."""
+    sc, dev, orc = small
+    seeds = syn.sample_seeds(E.sample_seeds, sc, per_view=40)
+    off, hits, V, _ = dev.epipolar_intersect(seeds)
+    g, tm = dev.match_correspondences(seeds.view, off, hits)
+    assert tm["n_seeds"] == len(seeds) and g.n_points > 100
+    assert_points_parity(sc, g, orc.match_seeds(seeds))
+    whole, _ = dev.match_seeds(seeds)
+    for f in ("xyz", "seed", "chain_pos", "obs_off", "obs_view", "obs_poly", "obs_seg", "obs_xy"):
+        assert np.array_equal(getattr(g, f), getattr(whole, f)), f
+    # pipeline 3: seeds + per-view hit lists of the EdgeManager side, bit-exact vs the oracle's, then the consensus step on them
+    s3, track, off3, hits3 = dev.refpoint_correspondences(0, sc.n_tracks)
+    o_off, o_hits, _ = orc.refpoint_hits(0, sc.n_tracks)
+    assert np.array_equal(off3, o_off) and hits3.tobytes() == o_hits.tobytes() and len(s3) > 50
+    assert np.all(np.diff(track) >= 0)
+    g3, _ = dev.match_correspondences(s3.view, off3, hits3)
+    w3, _ = dev.match_refpoints(0, sc.n_tracks)
+    for f in ("xyz", "seed", "chain_pos", "obs_off", "obs_view", "obs_poly", "obs_seg", "obs_xy"):
+        assert np.array_equal(getattr(g3, f), getattr(w3, f)), f
+    assert_points_parity(sc, g3, orc.match_refpoints(0, sc.n_tracks))
+    # empty batch
+    e, _ = dev.match_correspondences(np.zeros(0, np.int32), np.zeros(1, np.int64), hits[:0])
+    assert e.n_points == 0
