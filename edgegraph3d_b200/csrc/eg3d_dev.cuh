@@ -803,55 +803,70 @@ static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o,
 // for three observations).  Used where Gauss-Newton starts from the 2-view DLT point instead of a converged estimate
 // (est_slot, combos_slot): from such a start, and above all from the arbitrary point of the ray a degenerate DLT returns, the
 // iteration can wander for tens of steps and amplifies rounding-level differences into different accept decisions, which the
-// lane-parallel gn_group (different summation order) would not reproduce.  Thread-sequential; the warp executes it uniformly.
-// Rare: ~1 call per 50 gn_group calls on BASELINE configs[1].
-static __device__ __noinline__ bool gn_seq_exact(const DevScene& S, const ObsSrc& o, double X[3]) {
+// lane-parallel gn_group (different summation order) would not reproduce.
+// Warp-uniform arguments.  The residual / Jacobian rows of 32 observations are computed one per lane (the expensive part: eight
+// IEEE divisions each); the sums are then accumulated in observation order by every lane from the broadcast rows, which keeps
+// the reference's summation order exactly.  Rare: ~1 call per 50 gn_group calls on BASELINE configs[1].
+struct GnRows { double rx, ry, jx0, jx1, jx2, jy0, jy1, jy2; };
+EG3D_D GnRows gn_rows_exact(const DevScene& S, const ObsSrc& o, int m, const double X[3]) {
+  int v; float px, py;
+  if (m < o.n) { v = o.v[m]; px = o.x[m]; py = o.y[m]; } else { v = o.ev; px = o.ex; py = o.ey; }
+  const double* __restrict__ P = S.P64 + 12 * v;
+  const double h0 = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3] * 1.0;
+  const double h1 = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7] * 1.0;
+  const double h2 = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11] * 1.0;
+  GnRows r;
+  r.rx = (double)px - h0 / h2; r.ry = (double)py - h1 / h2;
+  const double zz = h2 * h2;
+  r.jx0 = (P[0] * h2 - P[8] * h0) / zz; r.jx1 = (P[1] * h2 - P[9] * h0) / zz; r.jx2 = (P[2] * h2 - P[10] * h0) / zz;
+  r.jy0 = (P[4] * h2 - P[8] * h1) / zz; r.jy1 = (P[5] * h2 - P[9] * h1) / zz; r.jy2 = (P[6] * h2 - P[10] * h1) / zz;
+  return r;
+}
+EG3D_D GnRows gn_rows_bcast(const GnRows& r, int k) {
+  GnRows b;
+  b.rx = __shfl_sync(0xffffffffu, r.rx, k); b.ry = __shfl_sync(0xffffffffu, r.ry, k);
+  b.jx0 = __shfl_sync(0xffffffffu, r.jx0, k); b.jx1 = __shfl_sync(0xffffffffu, r.jx1, k); b.jx2 = __shfl_sync(0xffffffffu, r.jx2, k);
+  b.jy0 = __shfl_sync(0xffffffffu, r.jy0, k); b.jy1 = __shfl_sync(0xffffffffu, r.jy1, k); b.jy2 = __shfl_sync(0xffffffffu, r.jy2, k);
+  return b;
+}
+static __device__ __noinline__ bool gn_seq_exact(const DevScene& S, const ObsSrc& o, int lane, double X[3]) {
   const eg3d_params& prm = S.prm;
-  const int n = o.n, ntot = o.n + o.has_extra;
+  const int ntot = o.n + o.has_extra;
   double last_mse = 0;
   for (int it = 0; it < prm.gn_max_iters; it++) {
     double mse = 0;
-    double H[9];
-#pragma unroll
-    for (int a = 0; a < 9; a++) H[a] = 0;
+    double h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0;      // H is symmetric term by term (j_a * j_b == j_b * j_a): six sums
 #pragma unroll 1
-    for (int m = 0; m < ntot; m++) {
-      int v; float px, py;
-      if (m < n) { v = o.v[m]; px = o.x[m]; py = o.y[m]; } else { v = o.ev; px = o.ex; py = o.ey; }
-      const double* __restrict__ P = S.P64 + 12 * v;
-      const double h0 = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3] * 1.0;
-      const double h1 = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7] * 1.0;
-      const double h2 = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11] * 1.0;
-      const double rx = (double)px - h0 / h2;
-      mse += rx * rx;
-      const double ry = (double)py - h1 / h2;
-      mse += ry * ry;
-      const double zz = h2 * h2;
-      double j0 = (P[0] * h2 - P[8] * h0) / zz, j1 = (P[1] * h2 - P[9] * h0) / zz, j2 = (P[2] * h2 - P[10] * h0) / zz;
-      H[0] += j0 * j0; H[1] += j0 * j1; H[2] += j0 * j2; H[3] += j1 * j0; H[4] += j1 * j1; H[5] += j1 * j2; H[6] += j2 * j0; H[7] += j2 * j1; H[8] += j2 * j2;
-      j0 = (P[4] * h2 - P[8] * h1) / zz; j1 = (P[5] * h2 - P[9] * h1) / zz; j2 = (P[6] * h2 - P[10] * h1) / zz;
-      H[0] += j0 * j0; H[1] += j0 * j1; H[2] += j0 * j2; H[3] += j1 * j0; H[4] += j1 * j1; H[5] += j1 * j2; H[6] += j2 * j0; H[7] += j2 * j1; H[8] += j2 * j2;
+    for (int base = 0; base < ntot; base += 32) {
+      GnRows r = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (base + lane < ntot) r = gn_rows_exact(S, o, base + lane, X);
+      const int cnt = min(32, ntot - base);
+#pragma unroll 1
+      for (int k = 0; k < cnt; k++) {
+        const GnRows b = gn_rows_bcast(r, k);
+        mse += b.rx * b.rx; mse += b.ry * b.ry;
+        h00 += b.jx0 * b.jx0; h01 += b.jx0 * b.jx1; h02 += b.jx0 * b.jx2; h11 += b.jx1 * b.jx1; h12 += b.jx1 * b.jx2; h22 += b.jx2 * b.jx2;
+        h00 += b.jy0 * b.jy0; h01 += b.jy0 * b.jy1; h02 += b.jy0 * b.jy2; h11 += b.jy1 * b.jy1; h12 += b.jy1 * b.jy2; h22 += b.jy2 * b.jy2;
+      }
     }
     if (fabs(mse / (ntot * 2) - last_mse) < prm.gn_stop) break;
     last_mse = mse / (ntot * 2);
+    const double H[9] = {h00, h01, h02, h01, h11, h12, h02, h12, h22};
     const double d = det3d(H);
     if (d < prm.gn_det_min) return false;
     double Hi[9]; inv3d(H, d, Hi);
     double a0 = 0, a1 = 0, a2 = 0;      // curEstimate += (H^-1 J^T) r, row by row
 #pragma unroll 1
-    for (int m = 0; m < ntot; m++) {
-      int v; float px, py;
-      if (m < n) { v = o.v[m]; px = o.x[m]; py = o.y[m]; } else { v = o.ev; px = o.ex; py = o.ey; }
-      const double* __restrict__ P = S.P64 + 12 * v;
-      const double h0 = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[3] * 1.0;
-      const double h1 = P[4] * X[0] + P[5] * X[1] + P[6] * X[2] + P[7] * 1.0;
-      const double h2 = P[8] * X[0] + P[9] * X[1] + P[10] * X[2] + P[11] * 1.0;
-      const double rx = (double)px - h0 / h2, ry = (double)py - h1 / h2;
-      const double zz = h2 * h2;
-      double j0 = (P[0] * h2 - P[8] * h0) / zz, j1 = (P[1] * h2 - P[9] * h0) / zz, j2 = (P[2] * h2 - P[10] * h0) / zz;
-      a0 += (Hi[0] * j0 + Hi[1] * j1 + Hi[2] * j2) * rx; a1 += (Hi[3] * j0 + Hi[4] * j1 + Hi[5] * j2) * rx; a2 += (Hi[6] * j0 + Hi[7] * j1 + Hi[8] * j2) * rx;
-      j0 = (P[4] * h2 - P[8] * h1) / zz; j1 = (P[5] * h2 - P[9] * h1) / zz; j2 = (P[6] * h2 - P[10] * h1) / zz;
-      a0 += (Hi[0] * j0 + Hi[1] * j1 + Hi[2] * j2) * ry; a1 += (Hi[3] * j0 + Hi[4] * j1 + Hi[5] * j2) * ry; a2 += (Hi[6] * j0 + Hi[7] * j1 + Hi[8] * j2) * ry;
+    for (int base = 0; base < ntot; base += 32) {
+      GnRows r = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (base + lane < ntot) r = gn_rows_exact(S, o, base + lane, X);
+      const int cnt = min(32, ntot - base);
+#pragma unroll 1
+      for (int k = 0; k < cnt; k++) {
+        const GnRows b = gn_rows_bcast(r, k);
+        a0 += (Hi[0] * b.jx0 + Hi[1] * b.jx1 + Hi[2] * b.jx2) * b.rx; a1 += (Hi[3] * b.jx0 + Hi[4] * b.jx1 + Hi[5] * b.jx2) * b.rx; a2 += (Hi[6] * b.jx0 + Hi[7] * b.jx1 + Hi[8] * b.jx2) * b.rx;
+        a0 += (Hi[0] * b.jy0 + Hi[1] * b.jy1 + Hi[2] * b.jy2) * b.ry; a1 += (Hi[3] * b.jy0 + Hi[4] * b.jy1 + Hi[5] * b.jy2) * b.ry; a2 += (Hi[6] * b.jy0 + Hi[7] * b.jy1 + Hi[8] * b.jy2) * b.ry;
+      }
     }
     X[0] += a0; X[1] += a1; X[2] += a2;
   }

@@ -200,6 +200,16 @@ EG3D_D void store_pt3(Pt3* dst, const Cur3& c, const float X[3]) {
 EG3D_D bool est_pt3(const DevScene& S, const int sel[3], Pt3* p) {
   int v[3] = {sel[p->perm[0]], sel[p->perm[1]], sel[p->perm[2]]};
   float2 pt[3] = {make_float2(p->cx[0], p->cy[0]), make_float2(p->cx[1], p->cy[1]), make_float2(p->cx[2], p->cy[2])};
+  // Exact-safe pruning, as for the triples of phase A (pair_cannot_fit): a followed candidate lies on view a's epipolar lines by
+  // construction, but nothing ties its b and c observations to each other; when any view pair already costs more than the
+  // acceptance budget the solve cannot be accepted — and a rejected solve tends to be the expensive one (no convergence: all 30
+  // Gauss-Newton iterations after the DLT).  A rejected solve has no side effects, so skipping it changes nothing.
+  {
+    const double Tp = prune_radius(S.prm, 3);
+    const size_t i01 = (size_t)v[0] * S.V + v[1], i02 = (size_t)v[0] * S.V + v[2], i12 = (size_t)v[1] * S.V + v[2];
+    if (pair_cannot_fit(S.Fp + i12 * 9, S.Fph[i12], pt[1], pt[2], Tp) || pair_cannot_fit(S.Fp + i01 * 9, S.Fph[i01], pt[0], pt[1], Tp) ||
+        pair_cannot_fit(S.Fp + i02 * 9, S.Fph[i02], pt[0], pt[2], Tp)) return false;
+  }
   float X[3];
   if (!est3(S, v, pt, X)) return false;
   p->X[0] = X[0]; p->X[1] = X[1]; p->X[2] = X[2];
@@ -446,7 +456,7 @@ static __device__ __noinline__ bool est_slot(Ctx& c, int slot, int n, float Xo[3
   float t4[4];
   dlt_null_opencv(S.P + 12 * ov[mi], S.P + 12 * ov[ma], make_float2(c.w.ox[b + mi], c.w.oy[b + mi]), make_float2(c.w.ox[b + ma], c.w.oy[b + ma]), t4);
   double X[3] = {(double)(t4[0] / t4[3]), (double)(t4[1] / t4[3]), (double)(t4[2] / t4[3])};
-  if (!gn_seq_exact(S, slot_obs(c, slot, n, false, 0, 0.f, 0.f), X)) return false;
+  if (!gn_seq_exact(S, slot_obs(c, slot, n, false, 0, 0.f, 0.f), c.lane, X)) return false;
   Xo[0] = (float)X[0]; Xo[1] = (float)X[1]; Xo[2] = (float)X[2];
   return true;
 }
@@ -509,7 +519,7 @@ static __device__ __noinline__ bool combos_slot(Ctx& c, int slot, int& n, float 
     if (c.w.selmask[i]) continue;
     ObsSrc obs; obs.v = tv; obs.x = tx; obs.y = ty; obs.n = m; obs.has_extra = 1; obs.ev = ov[i]; obs.ex = ox[i]; obs.ey = oy[i];
     double Xd[3] = {X[0], X[1], X[2]};
-    if (gn_seq_exact(S, obs, Xd)) {
+    if (gn_seq_exact(S, obs, c.lane, Xd)) {
       X[0] = (float)Xd[0]; X[1] = (float)Xd[1]; X[2] = (float)Xd[2];
       __syncwarp();
       if (c.lane == 0) { c.w.selmask[i] = 1; tv[m] = ov[i]; tx[m] = ox[i]; ty[m] = oy[i]; }
