@@ -453,7 +453,7 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
   DBuf<unsigned long long> prof_seed;
   if (do_prof) {
     CK(prof.alloc(48)); CK(cudaMemsetAsync(prof.p, 0, 48 * sizeof(unsigned long long), sc->stream)); a.prof = prof.p;
-    CK(prof_seed.alloc(2 * (size_t)n)); CK(cudaMemsetAsync(prof_seed.p, 0, 2 * (size_t)n * sizeof(unsigned long long), sc->stream)); a.prof_seed = prof_seed.p;
+    CK(prof_seed.alloc(3 * (size_t)n)); CK(cudaMemsetAsync(prof_seed.p, 0, 3 * (size_t)n * sizeof(unsigned long long), sc->stream)); a.prof_seed = prof_seed.p;
   }
   // phase A -> phase B hand-over buffers
   DBuf<PaRec> pa_recs; DBuf<Pt3> pa_pool; DBuf<unsigned long long> pa_cnt; DBuf<int> counter_b;
@@ -510,9 +510,9 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
 #endif
     const char* dump = getenv("EG3D_K3_PROF");
     if (dump && (dump[0] == '/' || strchr(dump, '.'))) {   // EG3D_K3_PROF=<file>: per-seed (cycles, initial length, final length)
-      std::vector<unsigned long long> ps(2 * (size_t)n); CK(cudaMemcpy(ps.data(), prof_seed.p, ps.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      std::vector<unsigned long long> ps(3 * (size_t)n); CK(cudaMemcpy(ps.data(), prof_seed.p, ps.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
       if (FILE* f = fopen(dump, "w")) {
-        for (int i = 0; i < n; i++) if (ps[2 * i]) fprintf(f, "%d %llu %llu %llu\n", i, ps[2 * i], ps[2 * i + 1] & 0xffffffffull, ps[2 * i + 1] >> 32);
+        for (int i = 0; i < n; i++) if (ps[3 * i]) fprintf(f, "%d %llu %llu %llu %llu\n", i, ps[3 * i], ps[3 * i + 1] & 0xffffffffull, ps[3 * i + 1] >> 32, ps[3 * i + 2]);
         fclose(f);
       }
     }

@@ -70,7 +70,7 @@ struct K3Args {
   int* ob_view; uint32_t* ob_pl; uint32_t* ob_seg; float* ob_x; float* ob_y;
   int* seed_npts; int64_t* seed_pbase; int64_t* seed_nobs;
   unsigned long long* prof;   // optional [16] per-phase warp-cycle / event counters (null = off; profile builds only)
-  unsigned long long* prof_seed;  // optional [n_seeds][2]: phase-B warp cycles, initial | final chain length (profile builds only)
+  unsigned long long* prof_seed;  // optional [n_seeds][3]: phase-B warp cycles, initial | final chain length (profile builds only)
   // phase A -> phase B hand-over: one record per accepted seed + its two 3-view point lists in a pool
   struct PaRec* pa_recs; Pt3* pa_pool; long long pa_pool_cap;
   unsigned long long* pa_counters;    // [0] accepted seeds, [1] pool entries used
@@ -1363,7 +1363,8 @@ __global__ void __launch_bounds__(K3B_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_k
       atomicMax(&A.prof[40], (unsigned long long)c.pc[7]);
       if (c.pc[7] > 50000000ll) atomicAdd(&A.prof[41], 1ull);
       if (c.pc[7] > 200000000ll) atomicAdd(&A.prof[42], 1ull);
-      if (A.prof_seed) { A.prof_seed[2 * (size_t)seed] = (unsigned long long)c.pc[7]; A.prof_seed[2 * (size_t)seed + 1] = (unsigned long long)len0 | ((unsigned long long)c.len << 32); }
+      if (A.prof_seed) { A.prof_seed[3 * (size_t)seed] = (unsigned long long)c.pc[7]; A.prof_seed[3 * (size_t)seed + 1] = (unsigned long long)len0 | ((unsigned long long)c.len << 32);
+                         A.prof_seed[3 * (size_t)seed + 2] = (unsigned long long)(A.hit_off_b[c.hrow + V] - A.hit_off_b[c.hrow]); }
     }
 #endif
     emit_chain(c, seed);

@@ -31,11 +31,14 @@ def run(golden_dir, threads):
     odev = O.OracleDevice(sc, prm, n_threads=threads)
     osc = odev.osc
     with E.DeviceScene(sc, prm) as dev:
-        P.run_pipelines(dev, sc, cands1, cands2)       # warm-up pass
+        P.run_pipelines(dev, sc, cands1, cands2)       # warm-up passes (the second one runs with the memory pool at its final size)
+        P.run_pipelines(dev, sc, cands1, cands2)
         t = time.time(); r = P.edge_reconstruction(dev, sc, cands1, cands2); wall = time.time() - t
         t = time.time(); oparts, _ = P.run_pipelines(odev, sc, cands1, cands2); t_or = time.time() - t
         for k, (g, tm, o) in enumerate(zip(r["parts"], r["timings"], oparts)):
-            res["pipeline%d" % (k + 1)] = {"points": g.n_points, "obs": g.n_obs, "device_ms": tm["total_ms"], "seeds": tm["n_seeds"], "identical": same(g, o),
+            res["pipeline%d" % (k + 1)] = {"points": g.n_points, "obs": g.n_obs, "device_ms": tm["total_ms"], "host_wall_ms": tm["host_wall_ms"], "seeds": tm["n_seeds"],
+                                           "kernel_ms": {q: tm[q] for q in ("k1_count_ms", "k1_fill_ms", "scan_ms", "k3a_ms", "k3b_ms", "pack_ms")},
+                                           "capacity_retries": tm["n_capacity_retries"], "identical": same(g, o),
                                            "max_abs_xyz_diff": float(np.abs(g.xyz - o.xyz).max()) if same(g, o) and g.n_points else None}
         res["device_ms_pipelines_1_2_3"] = sum(tm["total_ms"] for tm in r["timings"])
         res["e2e_wall_ms_incl_density_limiter_and_filter"] = wall * 1e3

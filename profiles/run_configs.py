@@ -64,7 +64,7 @@ def run_c4(args):
     cands = syn.curve_candidate_sets(sc, seed=cfg["seed"])
     prm = E.default_params(split_interval_distance=2.0)          # SPLIT_INTERVAL_DISTANCE 20 -> 2
     dev = E.DeviceScene(sc, prm)
-    dev.match_polyline_sets(cands, 0, 2)
+    dev.match_polyline_sets(cands)                              # warm-up: the stream-ordered memory pool grows to its working size once
     t = time.perf_counter()
     pts, tm = dev.match_polyline_sets(cands)
     wall = time.perf_counter() - t
