@@ -48,6 +48,8 @@ struct Pt3 {  // a 3-view point of the following phase (64 B)
   float cx[3], cy[3];
 };
 struct NTmp { float X[3]; uint32_t seg; float cx, cy; };  // a neighbour candidate (polyline id is implied)
+struct GnQ { int slot; float ex, ey; int pad; };   // wavefront phase B (eg3d_k3w.cuh): a queued warm-started solve = the observations of `slot` + (current view, ex, ey)
+struct GnR { float X[3]; int ok; };                // ... and its result
 
 struct PaRec;
 struct K3Args {
@@ -92,6 +94,8 @@ struct WS {  // per-warp scratch view
   int* idx;                                        // [oc] scratch index list (combination fallback)
   unsigned char* selmask;                          // [oc]
   int* tq;                                         // [3*64] queue of triples that survived pruning
+  int *fbs, *fbe, *fbm, *fbfs, *fbfe;                            // [oc], [oc], [4]: per-observation candidate counts of step_all_big at the chain's start / end slot + (slot, #observations evaluated) per side
+  GnQ* gq; GnR* gr; GnR* er; int* pe;              // [capc], [capc], [32], [32]: wavefront phase B problem queue, results, results of the epipolar-hit batch, hit index per problem
   int capf, capc, oc;
 };
 
@@ -105,6 +109,8 @@ inline __host__ __device__ size_t k3_scratch_bytes(int V, int capf, int capc, in
   b += k3_align(sizeof(NTmp) * capc) * 2;
   b += k3_align(sizeof(int) * oc) + k3_align(oc);
   b += k3_align(sizeof(int) * 3 * 64);
+  b += k3_align(sizeof(int) * oc) * 4 + k3_align(sizeof(int) * 4);
+  b += k3_align(sizeof(GnQ) * (size_t)(capc + 32)) + k3_align(sizeof(GnR) * (size_t)(capc + 32)) + k3_align(sizeof(GnR) * 32) + k3_align(sizeof(int) * 32);
   return b;
 }
 EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
@@ -127,6 +133,12 @@ EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
   w.idx = (int*)take(sizeof(int) * oc);
   w.selmask = (unsigned char*)take(oc);
   w.tq = (int*)take(sizeof(int) * 3 * 64);
+  w.fbs = (int*)take(sizeof(int) * oc); w.fbe = (int*)take(sizeof(int) * oc); w.fbm = (int*)take(sizeof(int) * 4);
+  w.fbfs = (int*)take(sizeof(int) * oc); w.fbfe = (int*)take(sizeof(int) * oc);
+  w.gq = (GnQ*)take(sizeof(GnQ) * (size_t)(capc + 32));
+  w.gr = (GnR*)take(sizeof(GnR) * (size_t)(capc + 32));
+  w.er = (GnR*)take(sizeof(GnR) * 32);
+  w.pe = (int*)take(sizeof(int) * 32);
   w.capf = capf; w.capc = capc; w.oc = oc;
   return w;
 }
@@ -544,29 +556,64 @@ static __device__ __noinline__ bool combos_slot(Ctx& c, int slot, int& n, float 
 
 // all-view compatible (plg_matching.cpp:633-759) on a chain point with many views.  Builds the candidate in slot
 // c.nslots (not yet claimed); returns true and leaves the new point there when a step is found.
-static __device__ __noinline__ bool step_all_big(Ctx& c, const uint32_t* dirs, int cur_slot) {
+//
+// The reference re-evaluates every driving view of the extreme point each time a view has been added to it, although a
+// driving view's candidate only ever GAINS observations: candidate(si) = the 10 px step on view si + one bounded epipolar
+// walk per other observation i, and whether observation i contributes depends on (si, i) alone (the slot's observations are
+// append-only and a view's direction entry is written once, before its observation can be driven).  So per side the
+// number of observations each driving view collected is remembered (cnt[si]: -1 = cannot advance, >= 1 = count at the last
+// call), a call only walks the NEW observations for the old driving views — all of them at once, one per lane — and the
+// full candidate (with its DLT + Gauss-Newton) is rebuilt, in the reference's order, only for driving views that reach
+// three observations.  A candidate with fewer than three observations is skipped by the reference too (:708-709), so
+// the sequence of attempted solves, and with it every result, is unchanged.
+static __device__ __noinline__ bool step_all_big(Ctx& c, const uint32_t* dirs, int cur_slot, int side) {
   const DevScene& S = *c.S;
   if (c.nslots >= c.w.capc) { c.overflow = true; return false; }
   const int t = c.nslots;
   const int n = c.w.snobs[cur_slot];
   const size_t cb = (size_t)cur_slot * c.w.oc, tb = (size_t)t * c.w.oc;
-  // The driving-view loop (`for starting_plg_index`, plg_matching.cpp:635) mostly meets views whose polyline is already
-  // at its extreme: the 10 px step of 32 candidate driving views is evaluated at once, and only the views that can
-  // still advance are processed, in order.
+  int* cnt = side ? c.w.fbe : c.w.fbs;
+  int* failc = side ? c.w.fbfe : c.w.fbfs;     // count at which the candidate's solves last failed (0 = never tried)
+  int* meta = c.w.fbm + 2 * side;
+  const int n_old = meta[0] == cur_slot ? min(meta[1], n) : 0;
+  __syncwarp();
+  // phase 1, one observation per lane: old driving views take the new observations into account, new ones are classified
   for (int sbase = 0; sbase < n; sbase += 32) {
-    bool can = false;
-    {
-      const int si = sbase + c.lane;
-      if (si < n) {
+    const int si = sbase + c.lane;
+    if (si < n) {
+      int k = si < n_old ? cnt[si] : 0;
+      if (k != -1) {
         const int sv = c.w.ov[cb + si];
         Pl pls = get_pl(S, sv, c.w.opl[cb + si]);
         PlP ip; ip.seg = c.w.oseg[cb + si]; ip.c = make_float2(c.w.ox[cb + si], c.w.oy[cb + si]);
         bool reached;
-        (void)step_by_distance(pls, ip, dirs[sv], S.prm.follow_first_image_distance, reached);
-        can = !reached;
-      }
+        PlP ns = step_by_distance(pls, ip, dirs[sv], S.prm.follow_first_image_distance, reached);
+        if (si >= n_old) { k = reached ? -1 : 0; failc[si] = 0; }   // 0: can advance, candidate not built yet
+        else if (!reached) {
+          for (int j = n_old; j < n; j++) {
+            const int vv = c.w.ov[cb + j];
+            float3 l;
+            if (!epiline(S, sv, vv, ns.c, l)) continue;
+            Pl pl = get_pl(S, vv, c.w.opl[cb + j]);
+            PlP iq; iq.seg = c.w.oseg[cb + j]; iq.c = make_float2(c.w.ox[cb + j], c.w.oy[cb + j]);
+            PlP np;
+            if (walk_line(pl, iq, dirs[vv], l, S.prm, true, np)) k++;
+          }
+        }
+        cnt[si] = k;
+      } else cnt[si] = -1;
     }
-    unsigned cm = __ballot_sync(0xffffffffu, can);
+  }
+  __syncwarp();
+  if (c.lane == 0) { meta[0] = cur_slot; meta[1] = n; }
+  __syncwarp();
+  // phase 2, in the reference's order: driving views whose candidate is new or has (at least) three observations
+  for (int sbase = 0; sbase < n; sbase += 32) {
+    const int si0 = sbase + c.lane;
+    const int k0 = si0 < n ? cnt[si0] : -1;
+    // a candidate whose DLT + Gauss-Newton (and combination fall-back) failed is a deterministic function of its observations:
+    // it is tried again only once it has gained one
+    unsigned cm = __ballot_sync(0xffffffffu, k0 == 0 || (k0 >= 3 && failc[si0 < n ? si0 : 0] != k0));
     while (cm) {
       const int si = sbase + __ffs(cm) - 1;
       cm &= cm - 1;
@@ -600,6 +647,7 @@ static __device__ __noinline__ bool step_all_big(Ctx& c, const uint32_t* dirs, i
         count += __popc(m);
       }
       __syncwarp();
+      if (c.lane == 0) cnt[si] = count;
       if (count < 3) continue;
       float X[3];
       K3P_ADD(c, 22, 1);
@@ -611,6 +659,7 @@ static __device__ __noinline__ bool step_all_big(Ctx& c, const uint32_t* dirs, i
         __syncwarp();
         return true;
       }
+      if (c.lane == 0) failc[si] = count;
     }
   }
   return false;
@@ -622,7 +671,7 @@ static __device__ __noinline__ int follow_big(Ctx& c, const uint32_t* dirs, bool
   K3P_ADD(c, 21, 1);
   while (true) {
     int cur_slot = slot_of(c, at_start ? 0 : c.len - 1);
-    if (!step_all_big(c, dirs, cur_slot)) break;
+    if (!step_all_big(c, dirs, cur_slot, at_start ? 0 : 1)) break;
     if (c.len >= c.w.capc) { c.overflow = true; break; }
     const int t = c.nslots++;
     __syncwarp();
@@ -1061,6 +1110,8 @@ static __device__ __noinline__ void seed_phase_b(Ctx& c, const PaRec& r, const P
   for (int v = lane; v < V; v += 32) { c.w.sdirs[v] = 0; c.w.edirs[v] = 0; }
   __syncwarp();
   if (lane == 0) for (int k = 0; k < 3; k++) { c.w.sdirs[c.sel[k]] = r.fd1[k]; c.w.edirs[c.sel[k]] = r.fd2[k]; }
+  __syncwarp();
+  if (lane < 4) c.w.fbm[lane] = -1;
   __syncwarp();
   c.nslots = c.len;
   c.central = fn1;
