@@ -425,9 +425,9 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
   nblocks_b = std::max(1, std::min(nblocks_b, (n + warps_per_block_b - 1) / warps_per_block_b));
   const int batch_b = EG3D_K3B_BATCH > 0 ? EG3D_K3B_BATCH : 1;     // arenas per phase-B warp
   if (EG3D_K3B_BATCH > 0) nblocks_b = std::max(1, std::min(sc->num_sms, (n + warps_per_block_b * batch_b - 1) / (warps_per_block_b * batch_b)));
-  // Phase B runs as the CTA-resident wavefront (eg3d_k3w.cuh) unless EG3D_K3B_LEGACY is set (A/B runs against the
-  // one-warp-per-seed kernel).  The wavefront's arenas are allocated after phase A, when the number of accepted seeds is known.
-  const bool legacy_b = getenv("EG3D_K3B_LEGACY") != nullptr;
+  // Phase B runs as the CTA-resident wavefront (eg3d_k3w.cuh) only when EG3D_K3B_WAVE is set (experimental; the
+  // one-warp-per-seed kernel is faster, profiles/r02_k3b_wavefront.md).  The wavefront's arenas are allocated after phase A, when the number of accepted seeds is known.
+  const bool legacy_b = getenv("EG3D_K3B_WAVE") == nullptr;
   const size_t nwarps = legacy_b ? std::max((size_t)nblocks * warps_per_block, (size_t)nblocks_b * warps_per_block_b * batch_b) : (size_t)nblocks * warps_per_block;
   DBuf<unsigned char> scratch; CK(scratch.alloc(nwarps * spw));
   DBuf<int> counter; CK(counter.alloc(1)); CK(cudaMemsetAsync(counter.p, 0, sizeof(int), sc->stream));
