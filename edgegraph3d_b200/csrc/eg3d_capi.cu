@@ -506,7 +506,7 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
     CK(scratch_b.alloc((size_t)grid_w * nS * spw));
     b.scratch = scratch_b.p;
     const size_t p64_bytes = (size_t)V * 12 * sizeof(double);
-    const int p64_in_smem = p64_bytes <= 160 * 1024 ? 1 : 0;
+    const int p64_in_smem = (p64_bytes * KW_CTAS_PER_SM <= 160 * 1024 && !getenv("EG3D_K3W_NO_SMEM")) ? 1 : 0;
     const size_t dyn = p64_in_smem ? p64_bytes : 0;
     static thread_local size_t dyn_set = 0;
     if (dyn > 48 * 1024 && dyn > dyn_set) { CK(cudaFuncSetAttribute(k3w_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); dyn_set = dyn; }

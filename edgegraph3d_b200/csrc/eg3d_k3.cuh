@@ -26,6 +26,9 @@ namespace eg3d {
 // EG3D_K3B_SYNC=1 with EG3D_K3B_THREADS=640..1024, EG3D_K3B_MIN_BLOCKS=1 builds the lock-step form (one CTA per SM, a
 // CTA barrier in front of each half of a view's expansion so that the warps share the lines they pull in): 35 % fewer
 // instruction-cache requests but slower overall (barrier idling), kept for experiments.
+#ifndef EG3D_K3A_FIRST_LOOKAHEAD
+#define EG3D_K3A_FIRST_LOOKAHEAD 2
+#endif
 #ifndef EG3D_K3B_THREADS
 #define EG3D_K3B_THREADS 128
 #endif
@@ -238,7 +241,11 @@ EG3D_D bool est_pt3(const DevScene& S, const int sel[3], Pt3* p) {
 static __device__ __noinline__ int first_extreme(Ctx& c, const Cur3& start, uint32_t first_dir, uint32_t dir_out[3], Pt3* dst) {
   const DevScene& S = *c.S;
   const int lane = c.lane;
-  constexpr int R = 8;
+  // Look-ahead per batch: 2 steps in the first batch, 8 afterwards.  Almost every hypothesis handed to plg_compatible is a
+  // wrong one whose four combos all die within the first step or two (1-2 % of the calls end in an accepted seed), so a
+  // deep first batch mostly walks and solves points nobody asks for; the lifetimes, and with them the result, do not
+  // depend on the batch size.
+  int R = EG3D_K3A_FIRST_LOOKAHEAD;
   Pl plb = get_pl(S, c.sel[1], start.pl[1]), plc = get_pl(S, c.sel[2], start.pl[2]);
   uint32_t dir[3] = {first_dir, (lane & 2) ? plb.end : plb.start, (lane & 1) ? plc.end : plc.start};
   bool alive = lane < 4;
@@ -261,22 +268,23 @@ static __device__ __noinline__ int first_extreme(Ctx& c, const Cur3& start, uint
     }
     if (__any_sync(0xffffffffu, c.overflow)) { c.overflow = true; return 0; }
     __syncwarp();
-    // verification: lane (k*8 + r) solves candidate r of combo k
-    const int kk = lane >> 3, rr = lane & 7;
+    // verification: lane (k*R + r) solves candidate r of combo k
+    const int kk = (lane / R) & 3, rr = lane % R;
     const int gk = __shfl_sync(0xffffffffu, g, kk), Lk = __shfl_sync(0xffffffffu, L, kk);
     bool ok = false;
-    if (rr < gk) ok = est_pt3(S, c.sel, c.w.tri + (size_t)kk * c.w.capf + Lk + rr);
+    if (lane < 4 * R && rr < gk) ok = est_pt3(S, c.sel, c.w.tri + (size_t)kk * c.w.capf + Lk + rr);
     unsigned okm = __ballot_sync(0xffffffffu, ok);
     __syncwarp();
     if (alive) {
-      unsigned mine_ok = (okm >> (lane * 8)) & 0xffu;
-      int lead = __ffs(~mine_ok) - 1;         // leading successes (8 when all ok)
+      unsigned mine_ok = (okm >> (lane * R)) & ((1u << R) - 1u);
+      int lead = __ffs(~mine_ok) - 1;         // leading successes (R when all ok)
       if (lead > g) lead = g;
       L += lead;
       if (lead < R) alive = false;            // geometry ended or a solve failed: lifetime is final
     }
     unsigned am = __ballot_sync(0xffffffffu, alive);
     if (__popc(am) <= 1) break;
+    R = 8;
   }
   // lifetimes of the four combos
   int L0 = __shfl_sync(0xffffffffu, L, 0), L1 = __shfl_sync(0xffffffffu, L, 1), L2 = __shfl_sync(0xffffffffu, L, 2), L3 = __shfl_sync(0xffffffffu, L, 3);

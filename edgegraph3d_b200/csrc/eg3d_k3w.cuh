@@ -28,7 +28,10 @@ namespace eg3d {
 #endif
 constexpr int KW_THREADS = EG3D_K3W_THREADS;       // 16 warps, one CTA per SM
 constexpr int KW_CTAS_PER_SM = 512 / EG3D_K3W_THREADS;
-constexpr int KW_MAX_SEEDS = 64;      // resident seeds per CTA
+#ifndef EG3D_K3W_MAX_SEEDS
+#define EG3D_K3W_MAX_SEEDS 64
+#endif
+constexpr int KW_MAX_SEEDS = EG3D_K3W_MAX_SEEDS;      // resident seeds per CTA (<= 64)
 constexpr int KW_G = 8;               // lanes per Gauss-Newton problem in RG (fixed: results do not depend on scheduling)
 
 enum : int {
