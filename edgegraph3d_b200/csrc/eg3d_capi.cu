@@ -18,7 +18,6 @@
 #include "eg3d_dev.cuh"
 #include "eg3d_k1.cuh"
 #include "eg3d_k3.cuh"
-#include "eg3d_k3w.cuh"
 #include "eg3d_gn.cuh"
 #include "eg3d_a6.cuh"
 
@@ -425,10 +424,7 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
   nblocks_b = std::max(1, std::min(nblocks_b, (n + warps_per_block_b - 1) / warps_per_block_b));
   const int batch_b = EG3D_K3B_BATCH > 0 ? EG3D_K3B_BATCH : 1;     // arenas per phase-B warp
   if (EG3D_K3B_BATCH > 0) nblocks_b = std::max(1, std::min(sc->num_sms, (n + warps_per_block_b * batch_b - 1) / (warps_per_block_b * batch_b)));
-  // Phase B runs as the CTA-resident wavefront (eg3d_k3w.cuh) only when EG3D_K3B_WAVE is set (experimental; the
-  // one-warp-per-seed kernel is faster, profiles/r02_k3b_wavefront.md).  The wavefront's arenas are allocated after phase A, when the number of accepted seeds is known.
-  const bool legacy_b = getenv("EG3D_K3B_WAVE") == nullptr;
-  const size_t nwarps = legacy_b ? std::max((size_t)nblocks * warps_per_block, (size_t)nblocks_b * warps_per_block_b * batch_b) : (size_t)nblocks * warps_per_block;
+  const size_t nwarps = std::max((size_t)nblocks * warps_per_block, (size_t)nblocks_b * warps_per_block_b * batch_b);
   DBuf<unsigned char> scratch; CK(scratch.alloc(nwarps * spw));
   DBuf<int> counter; CK(counter.alloc(1)); CK(cudaMemsetAsync(counter.p, 0, sizeof(int), sc->stream));
   DBuf<unsigned long long> oc4; CK(oc4.alloc(4)); CK(cudaMemsetAsync(oc4.p, 0, 4 * sizeof(unsigned long long), sc->stream));
@@ -492,32 +488,9 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
     b.pa_order = oorder.p;
     if (tm) tm->kernel_launches += 1;
   }
-  DBuf<unsigned char> scratch_b;
-  if (legacy_b) {
-    t3b.start();
-    k3b_expand_kernel<<<nblocks_b, K3B_THREADS, 0, sc->stream>>>(sc->dev, b);
-    t3b.stop();
-  } else {
-    const int n_acc = (int)pac[0];
-    int grid_w = std::max(1, std::min(sc->num_sms * KW_CTAS_PER_SM, n_acc));
-    int nS = std::max(1, std::min(KW_MAX_SEEDS, (n_acc + grid_w - 1) / grid_w));
-    if (const char* e = getenv("EG3D_K3W_SEEDS")) nS = std::max(1, std::min(KW_MAX_SEEDS, atoi(e)));   // A/B runs
-    scratch.release();                                  // phase A's arenas are no longer needed
-    CK(scratch_b.alloc((size_t)grid_w * nS * spw));
-    b.scratch = scratch_b.p;
-    const size_t p64_bytes = (size_t)V * 12 * sizeof(double);
-    const int p64_in_smem = (p64_bytes * KW_CTAS_PER_SM <= 160 * 1024 && !getenv("EG3D_K3W_NO_SMEM")) ? 1 : 0;
-    const size_t dyn = p64_in_smem ? p64_bytes : 0;
-    static thread_local size_t dyn_set = 0;
-    if (dyn > 48 * 1024 && dyn > dyn_set) { CK(cudaFuncSetAttribute(k3w_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); dyn_set = dyn; }
-    static thread_local size_t dyn_set2 = 0;
-    if (dyn > 48 * 1024 && dyn > dyn_set2) { CK(cudaFuncSetAttribute(k3w_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)); dyn_set2 = dyn; }
-    t3b.start();
-    if (!getenv("EG3D_K3W_BARRIER")) k3w_async_kernel<<<grid_w, KW_THREADS, dyn, sc->stream>>>(sc->dev, b, nS, p64_in_smem);
-    else
-    k3w_expand_kernel<<<grid_w, KW_THREADS, dyn, sc->stream>>>(sc->dev, b, nS, p64_in_smem, getenv("EG3D_K3W_MERGE") ? 1 : 0, getenv("EG3D_K3W_NOFILL") ? 0 : 1);
-    t3b.stop();
-  }
+  t3b.start();
+  k3b_expand_kernel<<<nblocks_b, K3B_THREADS, 0, sc->stream>>>(sc->dev, b);
+  t3b.stop();
   unsigned long long cnt[4];
   CK(cudaMemcpyAsync(cnt, oc4.p, sizeof cnt, cudaMemcpyDeviceToHost, sc->stream));
   CK(cudaStreamSynchronize(sc->stream));
@@ -528,10 +501,6 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
                           "#epc_gn_calls", "#main_first_gn", "#avf_calls(main)", "#avf_ok(main)", "#walk_solve_calls", "#walk_solve_problems", "#main_points_visited", "#main_grid_unique_ok", "", "#follow_big", "#est_slot", "#combos_slot",
                           "#views_run", "#epc_matched", "#sum_len_at_view", "#walk_geo_calls", "#walk_geo_nwalk", "", "", ""};
     for (int k = 0; k < 32; k++) if (nm[k][0]) fprintf(stderr, "[k3prof] %-26s %14llu%s\n", nm[k], pr[k], k < 8 ? " warp-cycles" : "");
-    if (!legacy_b) fprintf(stderr, "[k3prof] wavefront phase B: region clocks (sum over CTAs) RG %llu R1 %llu R2 %llu R3 %llu; tasks RG %llu R1 %llu R2 %llu R3 %llu; cycles sum %llu max %llu; slowest CTA %llu clocks\n",
-                           pr[16], pr[17], pr[18], pr[19], pr[20], pr[21], pr[22], pr[23], pr[24], pr[25], pr[28]);
-    if (!legacy_b) fprintf(stderr, "[k3prof] wavefront tasks (clocks sum / count / max): R3 commit %llu / %llu / %llu; R3 main loop %llu / %llu / %llu; follow_big %llu / %llu / %llu; R2 %llu / %llu / %llu; R1 %llu / %llu / %llu\n",
-                           pr[30], pr[31], pr[32], pr[33], pr[34], pr[35], pr[36], pr[37], pr[38], pr[39], pr[40], pr[41], pr[42], pr[43], pr[44]);
     fprintf(stderr, "[k3prof] max seed cycles %llu (%.1f ms at 1.9 GHz); seeds > 50M cycles: %llu; > 200M cycles: %llu\n", pr[40], pr[40] / 1.9e6, pr[41], pr[42]);
 #ifdef EG3D_K3_PROFILE
     {

@@ -51,8 +51,6 @@ struct Pt3 {  // a 3-view point of the following phase (64 B)
   float cx[3], cy[3];
 };
 struct NTmp { float X[3]; uint32_t seg; float cx, cy; };  // a neighbour candidate (polyline id is implied)
-struct GnQ { int slot; float ex, ey; int pad; };   // wavefront phase B (eg3d_k3w.cuh): a queued warm-started solve = the observations of `slot` + (current view, ex, ey)
-struct GnR { float X[3]; int ok; };                // ... and its result
 
 struct PaRec;
 struct K3Args {
@@ -98,7 +96,6 @@ struct WS {  // per-warp scratch view
   unsigned char* selmask;                          // [oc]
   int* tq;                                         // [3*64] queue of triples that survived pruning
   int *fbs, *fbe, *fbm, *fbfs, *fbfe;                            // [oc], [oc], [4]: per-observation candidate counts of step_all_big at the chain's start / end slot + (slot, #observations evaluated) per side
-  GnQ* gq; GnR* gr; GnR* er; int* pe;              // [capc], [capc], [32], [32]: wavefront phase B problem queue, results, results of the epipolar-hit batch, hit index per problem
   int capf, capc, oc;
 };
 
@@ -113,7 +110,6 @@ inline __host__ __device__ size_t k3_scratch_bytes(int V, int capf, int capc, in
   b += k3_align(sizeof(int) * oc) + k3_align(oc);
   b += k3_align(sizeof(int) * 3 * 64);
   b += k3_align(sizeof(int) * oc) * 4 + k3_align(sizeof(int) * 4);
-  b += k3_align(sizeof(GnQ) * (size_t)(capc + 32)) + k3_align(sizeof(GnR) * (size_t)(capc + 32)) + k3_align(sizeof(GnR) * 32) + k3_align(sizeof(int) * 32);
   return b;
 }
 EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
@@ -138,10 +134,6 @@ EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
   w.tq = (int*)take(sizeof(int) * 3 * 64);
   w.fbs = (int*)take(sizeof(int) * oc); w.fbe = (int*)take(sizeof(int) * oc); w.fbm = (int*)take(sizeof(int) * 4);
   w.fbfs = (int*)take(sizeof(int) * oc); w.fbfe = (int*)take(sizeof(int) * oc);
-  w.gq = (GnQ*)take(sizeof(GnQ) * (size_t)(capc + 32));
-  w.gr = (GnR*)take(sizeof(GnR) * (size_t)(capc + 32));
-  w.er = (GnR*)take(sizeof(GnR) * 32);
-  w.pe = (int*)take(sizeof(int) * 32);
   w.capf = capf; w.capc = capc; w.oc = oc;
   return w;
 }
