@@ -29,6 +29,13 @@ namespace eg3d {
 #ifndef EG3D_K3A_FIRST_LOOKAHEAD
 #define EG3D_K3A_FIRST_LOOKAHEAD 2
 #endif
+// Epipolar hits of a view are solved EG3D_EPC_BATCH at a time, in order: the first hit whose solve AND neighbour search succeed
+// wins (triangulation.cpp:753-768), and on BASELINE configs[1] that is on average the third of ~9 survivors of the pruning, so
+// solving all survivors at once (2 lanes each) solved mostly hits nobody asked about.  Measured (k3b ms for 2 / 4 / 6 / 8 / 12 / 16 / all):
+// 183.5 / 185.9 / 180.2 / 176.2 / 183.0 / 180.2 / 186: smaller batches mean more trips through the non-loop code.
+#ifndef EG3D_EPC_BATCH
+#define EG3D_EPC_BATCH 8
+#endif
 #ifndef EG3D_K3B_THREADS
 #define EG3D_K3B_THREADS 128
 #endif
@@ -867,7 +874,7 @@ static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) 
       const size_t cb = (size_t)cslot * c.w.oc;
       const double Tp = prune_radius(S.prm, n + 1);
       const int probe[4] = {0, n / 3, (2 * n) / 3, n - 1};
-      while (nq < 32 && enext < nh) {
+      while (nq < EG3D_EPC_BATCH && enext < nh) {
         const int e = enext + c.lane;
         bool pass = false;
         if (e < nh) {
@@ -890,7 +897,7 @@ static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) 
     }
     K3P_END(c, 3, te0);
     if (nq == 0) break;
-    const int P = nq < 32 ? nq : 32;
+    const int P = nq < EG3D_EPC_BATCH ? nq : EG3D_EPC_BATCH;
     K3P_ADD(c, 11, P);
     const int G = gn_group_width(P);
     const bool active = (c.lane / G) < P;
@@ -914,9 +921,12 @@ static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) 
     K3P_END(c, 4, te1);
     float Xe[3] = {(float)X[0], (float)X[1], (float)X[2]};
     unsigned m = __ballot_sync(0xffffffffu, ok && ((c.lane & (G - 1)) == 0));
+    K3P_ADD(c, 29, __popc(m));                 // solves accepted in this batch
     while (m && !matched) {
       const int b = __ffs(m) - 1;
       m &= m - 1;
+      K3P_ADD(c, 30, 1);                       // add_view_finish attempts from epipolar hits
+      K3P_ADD(c, 31, b / G);                   // position of the attempted candidate within its batch
       eg3d_hit h = epcs[__shfl_sync(0xffffffffu, e, b)];
       float Xc[3] = {__shfl_sync(0xffffffffu, Xe[0], b), __shfl_sync(0xffffffffu, Xe[1], b), __shfl_sync(0xffffffffu, Xe[2], b)};
       Plg p; p.pl = h.polyline; p.seg = h.segment; p.c = make_float2(h.x, h.y);
