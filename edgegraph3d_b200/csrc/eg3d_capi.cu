@@ -443,6 +443,11 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
   a.hit_off_b = H.off_a.p; a.hits_b = H.hits_a.p; a.b_compact = 0;     // lazy form: replaced after phase A
   a.sel = H.sel.p; a.acc_seed = H.acc_seed.p;
   a.capf = capf; a.capc = capc; a.oc = oc;
+  // shared first Gauss-Newton iteration (k3b_expand_kernel<true>): on BASELINE configs[1] (200 views) the extra code costs more
+  // instruction fetches than the saved observation passes (k3b 177 -> 193 ms); with 1000 views (configs[2]) the observation loop
+  // dominates and it pays (1401 -> 1261 ms per 31 250-seed shard).  EG3D_GN_CACHE=0|1 overrides.
+  a.gn_cache = V >= 400 ? 1 : 0;
+  if (const char* e = getenv("EG3D_GN_CACHE")) a.gn_cache = atoi(e) ? 1 : 0;
   a.scratch = scratch.p; a.scratch_per_warp = spw; a.work_counter = counter.p;
   a.pt_cap = pt_cap; a.ob_cap = ob_cap; a.out_counters = oc4.p;
   a.o_X = uX.p; a.o_nobs = unobs.p; a.o_obase = uobase.p;
@@ -489,7 +494,8 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
     if (tm) tm->kernel_launches += 1;
   }
   t3b.start();
-  k3b_expand_kernel<<<nblocks_b, K3B_THREADS, 0, sc->stream>>>(sc->dev, b);
+  if (b.gn_cache) k3b_expand_kernel<true><<<nblocks_b, K3B_THREADS, 0, sc->stream>>>(sc->dev, b);
+  else k3b_expand_kernel<false><<<nblocks_b, K3B_THREADS, 0, sc->stream>>>(sc->dev, b);
   t3b.stop();
   unsigned long long cnt[4];
   CK(cudaMemcpyAsync(cnt, oc4.p, sizeof cnt, cudaMemcpyDeviceToHost, sc->stream));
@@ -1416,13 +1422,17 @@ void eg3d_points_free(eg3d_points* p) { if (p) { cudaSetDevice(p->device); delet
 // lanes per hypothesis of the warp-cooperative fp64 kernel: EG3D_GN_LANES=1|2|4|8|16|32 overrides (A/B runs)
 static int gn64_lanes(int typical_obs) {
   if (const char* e = getenv("EG3D_GN_LANES")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32) return g; }
-  return typical_obs >= 64 ? 8 : 4;
+  return typical_obs >= 64 ? 8 : (typical_obs >= 32 ? 4 : 2);     // BASELINE configs[4] (20 observations): 9.7 / 7.5 / 8.1 / 10.7 ms for 1 / 2 / 4 / 8 lanes
 }
 template <int G>
 static cudaError_t launch_gn64(eg3d_scene* sc, const GnProblem& pr, size_t smem) {
   cudaError_t e = cudaFuncSetAttribute(gn64_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const unsigned blocks = (unsigned)(((size_t)pr.n * G + GN_THREADS - 1) / GN_THREADS);
+  const int64_t want = ((int64_t)pr.n * G + GN_THREADS - 1) / GN_THREADS;
+  int per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn64_kernel<G>, GN_THREADS, smem);
+  if (e != cudaSuccess) return e;
+  const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sc->num_sms * std::max(per_sm, 1)));   // persistent grid
   gn64_kernel<G><<<blocks, GN_THREADS, smem, sc->stream>>>(sc->dev, pr);
   return cudaGetLastError();
 }

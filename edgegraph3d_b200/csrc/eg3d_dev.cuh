@@ -688,6 +688,9 @@ EG3D_D double prune_radius(const eg3d_params& prm, int n_obs) {  // T with T^2 =
 struct ObsSrc {
   const int* v; const float* x; const float* y; int n;
   int has_extra; int ev; float ex, ey;
+  // optional (gn_group only, null = off): the ten normal-equation sums of the n base observations at the slot's stored estimate,
+  // and the observation count they were taken at (valid iff *tag == n); left there by the first solve that needs them
+  double* cache; int* tag;
   EG3D_D int count() const { return n + has_extra; }
 };
 
@@ -735,15 +738,24 @@ EG3D_D void gn_accumulate_fast(const double* __restrict__ P, float px, float py,
 #ifdef EG3D_K3_PROFILE
 __device__ unsigned long long g_gnprof[8];   // [0] calls, [1] iterations, [2] observation-loop passes (max over lanes), [3] active lanes x iterations
 #endif
+// Shared first iteration (GC = true: the kernel variant used for rigs with many views, where the observation loop dominates; with
+// GC = false the code below folds to the plain loop — on BASELINE configs[1] merely carrying the extra code cost 6 %): every
+// problem "observations of slot s + one new observation", started from the slot's stored estimate, begins with the same sums
+// over the slot's n observations.  The first iteration takes them from the slot's cache (valid while the slot is unchanged:
+// *tag == n) or computes and leaves them there, then adds the new observation's terms — the same value up to the order of
+// summation.
+template <bool GC>
 static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o, bool active, int G, int lane, double X[3]) {
-  const int* __restrict__ ov = o.v;
-  const float* __restrict__ ox = o.x;
-  const float* __restrict__ oy = o.y;
+  const int* ov = o.v;
+  const float* ox = o.x;
+  const float* oy = o.y;
   const int n = o.n, ntot = o.n + o.has_extra;
   const int sub = lane & (G - 1);
   double X0 = X[0], X1 = X[1], X2 = X[2];
   double last_mse = 0;
   bool running = active, failed = false;
+  const bool use_cache = GC && active && o.has_extra;
+  const bool cached = use_cache && *o.tag == n;
 #ifdef EG3D_K3_PROFILE
   if (lane == 0) atomicAdd(&g_gnprof[0], 1ull);
 #endif
@@ -759,13 +771,19 @@ static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o,
     }
 #endif
     GnAcc a = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const bool first_shared = it == 0 && use_cache;
     if (running) {
       const double* __restrict__ P64 = S.P64;
+      if (first_shared && cached) {
+        if (sub == 0) { const double* q = o.cache; a.mse = q[0]; a.h00 = q[1]; a.h01 = q[2]; a.h02 = q[3]; a.h11 = q[4]; a.h12 = q[5]; a.h22 = q[6]; a.g0 = q[7]; a.g1 = q[8]; a.g2 = q[9]; }
+      } else {
+        const int nloop = first_shared ? n : ntot;
 #pragma unroll 1
-      for (int i = sub; i < ntot; i += G) {
-        int v; float px, py;
-        if (i < n) { v = ov[i]; px = ox[i]; py = oy[i]; } else { v = o.ev; px = o.ex; py = o.ey; }
-        gn_accumulate_fast(P64 + 12 * v, px, py, X0, X1, X2, a);
+        for (int i = sub; i < nloop; i += G) {
+          int v; float px, py;
+          if (i < n) { v = ov[i]; px = ox[i]; py = oy[i]; } else { v = o.ev; px = o.ex; py = o.ey; }
+          gn_accumulate_fast(P64 + 12 * v, px, py, X0, X1, X2, a);
+        }
       }
     }
 #pragma unroll 1
@@ -776,6 +794,13 @@ static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o,
       a.h12 += __shfl_xor_sync(0xffffffffu, a.h12, off); a.h22 += __shfl_xor_sync(0xffffffffu, a.h22, off);
       a.g0 += __shfl_xor_sync(0xffffffffu, a.g0, off); a.g1 += __shfl_xor_sync(0xffffffffu, a.g1, off);
       a.g2 += __shfl_xor_sync(0xffffffffu, a.g2, off);
+    }
+    if (first_shared && running) {
+      if (!cached && sub == 0) {
+        double* q = o.cache; q[0] = a.mse; q[1] = a.h00; q[2] = a.h01; q[3] = a.h02; q[4] = a.h11; q[5] = a.h12; q[6] = a.h22; q[7] = a.g0; q[8] = a.g1; q[9] = a.g2;
+        *o.tag = n;
+      }
+      gn_accumulate_fast(S.P64 + 12 * o.ev, o.ex, o.ey, X0, X1, X2, a);     // the new observation (every lane of the group: identical values)
     }
     if (running) {
       const double cur = a.mse / (ntot * 2);
@@ -795,6 +820,7 @@ static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o,
     }
   }
   X[0] = X0; X[1] = X1; X[2] = X2;
+  if (GC) __syncwarp();                           // cache rows written above are read by other lanes in later calls
   return active && !failed && last_mse < S.prm.gn_accept_mse;
 }
 

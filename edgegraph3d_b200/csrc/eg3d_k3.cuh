@@ -71,6 +71,7 @@ struct K3Args {
   const int* sel;           // [n_seeds][3] selected views (k3_select_views_kernel); sel[3*seed] < 0: fewer than 3 non-empty views
   int* acc_seed;            // [n_seeds] accepted seed of each phase-A record (rank order)
   int capf, capc, oc;       // capacities: follow points per list, chain points, observations per point
+  int gn_cache;             // phase B: share the first Gauss-Newton iteration of a chain point's solves (gn_group); pays on rigs with many views
   unsigned char* scratch; size_t scratch_per_warp;
   int* work_counter;
   // unordered outputs (a warp reserves a contiguous range per seed)
@@ -102,6 +103,7 @@ struct WS {  // per-warp scratch view
   int* idx;                                        // [oc] scratch index list (combination fallback)
   unsigned char* selmask;                          // [oc]
   int* tq;                                         // [3*64] queue of triples that survived pruning
+  double* gcache; int* gtag;                       // [capc+1][10], [capc+1]: per-slot base sums of gn_group's shared first iteration
   int *fbs, *fbe, *fbm, *fbfs, *fbfe;                            // [oc], [oc], [4]: per-observation candidate counts of step_all_big at the chain's start / end slot + (slot, #observations evaluated) per side
   int capf, capc, oc;
 };
@@ -117,6 +119,7 @@ inline __host__ __device__ size_t k3_scratch_bytes(int V, int capf, int capc, in
   b += k3_align(sizeof(int) * oc) + k3_align(oc);
   b += k3_align(sizeof(int) * 3 * 64);
   b += k3_align(sizeof(int) * oc) * 4 + k3_align(sizeof(int) * 4);
+  b += k3_align(sizeof(double) * 10 * (size_t)(capc + 1)) + k3_align(sizeof(int) * (size_t)(capc + 1));
   return b;
 }
 EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
@@ -141,6 +144,7 @@ EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
   w.tq = (int*)take(sizeof(int) * 3 * 64);
   w.fbs = (int*)take(sizeof(int) * oc); w.fbe = (int*)take(sizeof(int) * oc); w.fbm = (int*)take(sizeof(int) * 4);
   w.fbfs = (int*)take(sizeof(int) * oc); w.fbfe = (int*)take(sizeof(int) * oc);
+  w.gcache = (double*)take(sizeof(double) * 10 * (size_t)(capc + 1)); w.gtag = (int*)take(sizeof(int) * (size_t)(capc + 1));
   w.capf = capf; w.capc = capc; w.oc = oc;
   return w;
 }
@@ -436,10 +440,12 @@ static __device__ __noinline__ bool plg_compatible(Ctx& c, const Cur3& cand, int
 // expansion phase: chain of "big" points held in slots
 EG3D_D int slot_of(const Ctx& c, int pos) { return c.w.order[pos]; }
 
+template <bool GC = false>
 EG3D_D ObsSrc slot_obs(const Ctx& c, int slot, int n, bool extra, int ev, float ex, float ey) {
   ObsSrc o; size_t b = (size_t)slot * c.w.oc;
   o.v = c.w.ov + b; o.x = c.w.ox + b; o.y = c.w.oy + b; o.n = n;
   o.has_extra = extra ? 1 : 0; o.ev = ev; o.ex = ex; o.ey = ey;
+  if (GC) { o.cache = c.w.gcache + 10 * (size_t)slot; o.tag = c.w.gtag + slot; } else { o.cache = nullptr; o.tag = nullptr; }
   return o;
 }
 
@@ -536,7 +542,7 @@ static __device__ __noinline__ bool combos_slot(Ctx& c, int slot, int& n, float 
   int m = 3;
   for (int i = 0; i < n; i++) {
     if (c.w.selmask[i]) continue;
-    ObsSrc obs; obs.v = tv; obs.x = tx; obs.y = ty; obs.n = m; obs.has_extra = 1; obs.ev = ov[i]; obs.ex = ox[i]; obs.ey = oy[i];
+    ObsSrc obs; obs.v = tv; obs.x = tx; obs.y = ty; obs.n = m; obs.has_extra = 1; obs.ev = ov[i]; obs.ex = ox[i]; obs.ey = oy[i]; obs.cache = nullptr; obs.tag = nullptr;
     double Xd[3] = {X[0], X[1], X[2]};
     if (gn_seq_exact(S, obs, c.lane, Xd)) {
       X[0] = (float)Xd[0]; X[1] = (float)Xd[1]; X[2] = (float)Xd[2];
@@ -732,6 +738,7 @@ static __device__ __noinline__ int walk_geo(Ctx& c, int v, const Plg& p, uint32_
 // walk_solve: the warm-started GNs of the chain points reached by walk_geo are independent, so the cnt1 points towards
 // the start (tmp1) and the cnt2 points towards the end (tmp2) are solved together, up to 32 problems per gn_group call;
 // each side's list is cut at its first failure (keep1 / keep2 = accepted neighbours, their X written to tmp[].X).
+template <bool GC>
 static __device__ __noinline__ void walk_solve(Ctx& c, int v, int cur, NTmp* tmp1, int cnt1, NTmp* tmp2, int cnt2, int& keep1, int& keep2) {
   const DevScene& S = *c.S;
   keep1 = cnt1; keep2 = cnt2;
@@ -754,7 +761,7 @@ static __device__ __noinline__ void walk_solve(Ctx& c, int v, int cur, NTmp* tmp
       ex = tmp[k].cx; ey = tmp[k].cy;
     }
     K3P_ADD(c, 16, 1); K3P_ADD(c, 17, P);
-    const bool ok = gn_group(S, slot_obs(c, slot, n, true, v, ex, ey), active, G, c.lane, X);
+    const bool ok = gn_group<GC>(S, slot_obs<GC>(c, slot, n, true, v, ex, ey), active, G, c.lane, X);
     if (active) {
       if (ok) { if ((c.lane & (G - 1)) == 0) { tmp[k].X[0] = (float)X[0]; tmp[k].X[1] = (float)X[1]; tmp[k].X[2] = (float)X[2]; } }
       else fail = true;
@@ -770,17 +777,19 @@ static __device__ __noinline__ void walk_solve(Ctx& c, int v, int cur, NTmp* tmp
   __syncwarp();
 }
 
+template <bool GC>
 static __device__ __noinline__ int walk_dir(Ctx& c, int v, const Plg& p, uint32_t dir, bool towards_start, int lo, int cur, int hi, NTmp* tmp) {
   const int cnt = walk_geo(c, v, p, dir, towards_start, lo, cur, hi, tmp);
   if (cnt == 0) return 0;
   int k1 = 0, k2 = 0;
-  if (towards_start) walk_solve(c, v, cur, tmp, cnt, tmp, 0, k1, k2);
-  else walk_solve(c, v, cur, tmp, 0, tmp, cnt, k1, k2);
+  if (towards_start) walk_solve<GC>(c, v, cur, tmp, cnt, tmp, 0, k1, k2);
+  else walk_solve<GC>(c, v, cur, tmp, 0, tmp, cnt, k1, k2);
   return towards_start ? k1 : k2;
 }
 
 // add_view_to_3dpoint_and_sides_plgp_matches_vector after its first GN succeeded (plg_matching.cpp:1345-1412;
 // neighbour search = find_directions_on_plg_known_3D_point_no_update_vector :1011-1058)
+template <bool GC>
 static __device__ __noinline__ bool add_view_finish(Ctx& c, int v, const Plg& p, const float Xc[3], int lo, int cur, int hi, int& ns, int& ne) {
   const DevScene& S = *c.S;
   Pl pl = get_pl(S, v, p.pl);
@@ -793,21 +802,21 @@ static __device__ __noinline__ bool add_view_finish(Ctx& c, int v, const Plg& p,
     if (g1 > 0) {
       const int g2 = cur < hi ? walk_geo(c, v, p, pl.end, false, lo, cur, hi, c.w.tmp2) : 0;
       int k2 = 0;
-      walk_solve(c, v, cur, c.w.tmp1, g1, c.w.tmp2, g2, n1, k2);
+      walk_solve<GC>(c, v, cur, c.w.tmp1, g1, c.w.tmp2, g2, n1, k2);
       if (n1 > 0) n2 = k2;
     }
     if (n1 > 0) {
       nd1 = pl.start; nd2 = pl.end;
     } else {
-      n1 = walk_dir(c, v, p, pl.end, true, lo, cur, hi, c.w.tmp1);
+      n1 = walk_dir<GC>(c, v, p, pl.end, true, lo, cur, hi, c.w.tmp1);
       if (n1 > 0) {
         nd1 = pl.end; nd2 = pl.start;
-        if (cur < hi) n2 = walk_dir(c, v, p, pl.start, false, lo, cur, hi, c.w.tmp2);
+        if (cur < hi) n2 = walk_dir<GC>(c, v, p, pl.start, false, lo, cur, hi, c.w.tmp2);
       } else if (cur < hi) {
-        n2 = walk_dir(c, v, p, pl.end, false, lo, cur, hi, c.w.tmp2);
+        n2 = walk_dir<GC>(c, v, p, pl.end, false, lo, cur, hi, c.w.tmp2);
         if (n2 > 0) { nd2 = pl.end; nd1 = pl.start; }
         else {
-          n2 = walk_dir(c, v, p, pl.start, false, lo, cur, hi, c.w.tmp2);
+          n2 = walk_dir<GC>(c, v, p, pl.start, false, lo, cur, hi, c.w.tmp2);
           if (n2 > 0) { nd2 = pl.start; nd1 = pl.end; }
         }
       }
@@ -854,6 +863,7 @@ static __device__ __noinline__ bool add_view_finish(Ctx& c, int v, const Plg& p,
 // barrier in front of each): the epipolar hits on the central point (:753-768), then the projection loop over the chain
 // points the first half did not reach (:770-830).
 struct EvState { bool matched; int iv0, iv1; };
+template <bool GC>
 static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) {
   const DevScene& S = *c.S;
   const int64_t h0 = c.A->hit_off_b[c.hrow + v];
@@ -917,7 +927,7 @@ static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) 
     double X[3] = {c.w.sX[3 * cslot], c.w.sX[3 * cslot + 1], c.w.sX[3 * cslot + 2]};
     K3P_BEGIN(te1);
     K3P_ADD(c, 12, 1);
-    bool ok = gn_group(S, slot_obs(c, cslot, n, true, v, hx, hy), active, G, c.lane, X);
+    bool ok = gn_group<GC>(S, slot_obs<GC>(c, cslot, n, true, v, hx, hy), active, G, c.lane, X);
     K3P_END(c, 4, te1);
     float Xe[3] = {(float)X[0], (float)X[1], (float)X[2]};
     unsigned m = __ballot_sync(0xffffffffu, ok && ((c.lane & (G - 1)) == 0));
@@ -933,7 +943,7 @@ static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) 
       int ns = 0, ne = 0;
       const int cc = c.central;
       K3P_BEGIN(te2);
-      const bool avf = add_view_finish(c, v, p, Xc, 0, cc, c.len, ns, ne);
+      const bool avf = add_view_finish<GC>(c, v, p, Xc, 0, cc, c.len, ns, ne);
       K3P_END(c, 5, te2);
       if (avf) {
         matched = true;
@@ -946,6 +956,7 @@ static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) 
   }
   st.matched = matched; st.iv0 = iv0; st.iv1 = iv1;
 }
+template <bool GC>
 static __device__ __noinline__ void expand_view_main(Ctx& c, int v, const EvState& st) {
   const DevScene& S = *c.S;
   const bool matched = st.matched; const int iv0 = st.iv0, iv1 = st.iv1;
@@ -966,11 +977,11 @@ static __device__ __noinline__ void expand_view_main(Ctx& c, int v, const EvStat
     const int n = c.w.snobs[slot];
     double X[3] = {c.w.sX[3 * slot], c.w.sX[3 * slot + 1], c.w.sX[3 * slot + 2]};
     K3P_ADD(c, 13, 1);
-    if (!gn_group(S, slot_obs(c, slot, n, true, v, init.c.x, init.c.y), true, 32, c.lane, X)) continue;
+    if (!gn_group<GC>(S, slot_obs<GC>(c, slot, n, true, v, init.c.x, init.c.y), true, 32, c.lane, X)) continue;
     float Xc[3] = {(float)X[0], (float)X[1], (float)X[2]};
     int ns = 0, ne = 0;
     K3P_ADD(c, 14, 1);
-    if (add_view_finish(c, v, init, Xc, last + 1, cur, hi, ns, ne)) {
+    if (add_view_finish<GC>(c, v, init, Xc, last + 1, cur, hi, ns, ne)) {
       K3P_ADD(c, 15, 1);
       if (ns > cur) { c.central = ns; cur = ns + ne; }
       else cur = cur + ne;
@@ -1122,6 +1133,7 @@ static __device__ __noinline__ void seed_phase_b(Ctx& c, const PaRec& r, const P
   if (lane == 0) for (int k = 0; k < 3; k++) { c.w.sdirs[c.sel[k]] = r.fd1[k]; c.w.edirs[c.sel[k]] = r.fd2[k]; }
   __syncwarp();
   if (lane < 4) c.w.fbm[lane] = -1;
+  if (c.A->gn_cache) for (int i = lane; i <= c.w.capc; i += 32) c.w.gtag[i] = -1;
   __syncwarp();
   c.nslots = c.len;
   c.central = fn1;
@@ -1270,6 +1282,7 @@ __global__ void k3_order_keys_kernel(int n, const unsigned long long* __restrict
 // time and every line they pull in is used by batch x warps seeds, instead of each warp cycling through the whole
 // ~65 KB path on its own (profiles/r01_k3b_icache.md).
 struct SeedState { int seed, sv, sel0, sel1, sel2, len, nslots, central, overflow, live, ran, matched, iv0, iv1, has; long long hrow; };
+template <bool GC>
 __global__ void __launch_bounds__(K3B_THREADS, 1) k3b_expand_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
   constexpr int KB = EG3D_K3B_BATCH;
   __shared__ SeedState ss[K3B_THREADS / 32][KB];
@@ -1332,7 +1345,7 @@ __global__ void __launch_bounds__(K3B_THREADS, 1) k3b_expand_kernel(const __grid
         if (run) {
           load(j);
           EvState st; st.matched = false; st.iv0 = 0; st.iv1 = 0;
-          expand_view_epc(c, v, st);
+          expand_view_epc<false>(c, v, st);
           store(j);
           if (lane == 0) { SeedState& w = ss[wib][j]; w.matched = st.matched ? 1 : 0; w.iv0 = st.iv0; w.iv1 = st.iv1; }
         }
@@ -1346,7 +1359,7 @@ __global__ void __launch_bounds__(K3B_THREADS, 1) k3b_expand_kernel(const __grid
         if (q.ran && !q.overflow) {
           load(j);
           EvState st; st.matched = q.matched != 0; st.iv0 = q.iv0; st.iv1 = q.iv1;
-          expand_view_main(c, v, st);
+          expand_view_main<false>(c, v, st);
           store(j);
         }
       }
@@ -1360,6 +1373,8 @@ __global__ void __launch_bounds__(K3B_THREADS, 1) k3b_expand_kernel(const __grid
   }
 }
 #else
+// GC: the variant with the shared first Gauss-Newton iteration (gn_group); the host picks it for rigs with many views
+template <bool GC>
 __global__ void __launch_bounds__(K3B_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_kernel(const __grid_constant__ DevScene S, const __grid_constant__ K3Args A) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -1410,11 +1425,11 @@ __global__ void __launch_bounds__(K3B_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_k
 #if EG3D_K3B_SYNC
       __syncthreads();
 #endif
-      if (run) { K3P_ADD(c, 24, 1); expand_view_epc(c, v, st); if (st.matched) K3P_ADD(c, 25, 1); K3P_ADD(c, 26, c.len); }
+      if (run) { K3P_ADD(c, 24, 1); expand_view_epc<GC>(c, v, st); if (st.matched) K3P_ADD(c, 25, 1); K3P_ADD(c, 26, c.len); }
 #if EG3D_K3B_SYNC
       __syncthreads();
 #endif
-      if (run && !c.overflow) expand_view_main(c, v, st);
+      if (run && !c.overflow) expand_view_main<GC>(c, v, st);
     }
     K3P_END(c, 7, tall);
     if (!has) continue;
