@@ -36,6 +36,9 @@ namespace eg3d {
 #ifndef EG3D_EPC_BATCH
 #define EG3D_EPC_BATCH 8
 #endif
+#ifndef EG3D_EPC_BATCH_MIN_OBS
+#define EG3D_EPC_BATCH_MIN_OBS 48
+#endif
 #ifndef EG3D_K3B_THREADS
 #define EG3D_K3B_THREADS 128
 #endif
@@ -877,6 +880,9 @@ static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) 
   int* hq = c.w.tq;                           // bounded queue (<= 63) of surviving hit indices, ascending
   int nq = 0, enext = 0;
   while (!matched) {
+    // short observation lists (few views so far, or a rig with few views): one batch — a solve is cheap there and every extra
+    // gn_group call is a trip through non-loop code (the packaged 25-view example ran 3-8 % slower with batches of 8)
+    const int batch = c.w.snobs[slot_of(c, c.central)] >= EG3D_EPC_BATCH_MIN_OBS ? EG3D_EPC_BATCH : 32;
     K3P_BEGIN(te0);
     {
       const int cslot = slot_of(c, c.central);
@@ -884,7 +890,7 @@ static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) 
       const size_t cb = (size_t)cslot * c.w.oc;
       const double Tp = prune_radius(S.prm, n + 1);
       const int probe[4] = {0, n / 3, (2 * n) / 3, n - 1};
-      while (nq < EG3D_EPC_BATCH && enext < nh) {
+      while (nq < batch && enext < nh) {
         const int e = enext + c.lane;
         bool pass = false;
         if (e < nh) {
@@ -907,7 +913,7 @@ static __device__ __noinline__ void expand_view_epc(Ctx& c, int v, EvState& st) 
     }
     K3P_END(c, 3, te0);
     if (nq == 0) break;
-    const int P = nq < EG3D_EPC_BATCH ? nq : EG3D_EPC_BATCH;
+    const int P = nq < batch ? nq : batch;
     K3P_ADD(c, 11, P);
     const int G = gn_group_width(P);
     const bool active = (c.lane / G) < P;

@@ -366,3 +366,19 @@ def test_match_correspondences_is_the_consensus_step_alone(small):
     # empty batch
     e, _ = dev.match_correspondences(np.zeros(0, np.int32), np.zeros(1, np.int64), hits[:0])
     assert e.n_points == 0
+
+
+@pytest.mark.parametrize("seed,views,curves", [(7, 9, 20), (13, 12, 12)])
+def test_shared_first_iteration_kernel_variant_parity(seed, views, curves, monkeypatch):
+    """k3b_expand_kernel<true> (per-slot cache of the base normal-equation sums, the variant picked for rigs with >= 400 views):
+    forced on a small rig it must give the oracle's chains and observation lists, and the plain variant's points."""
+    sc = syn.make_scene(n_views=views, n_curves=curves, seed=seed, closed_frac=0.15, drop_view_frac=0.1)
+    dev, orc = E.DeviceScene(sc), O.OracleScene(sc)
+    seeds = syn.sample_seeds(E.sample_seeds, sc)
+    plain, _ = dev.match_seeds(seeds)
+    monkeypatch.setenv("EG3D_GN_CACHE", "1")
+    cached, _ = dev.match_seeds(seeds)
+    monkeypatch.delenv("EG3D_GN_CACHE")
+    assert cached.n_points > 50
+    assert_points_parity(sc, cached, orc.match_seeds(seeds))
+    assert_points_parity(sc, cached, plain)
