@@ -507,6 +507,8 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
                           "#epc_gn_calls", "#main_first_gn", "#avf_calls(main)", "#avf_ok(main)", "#walk_solve_calls", "#walk_solve_problems", "#main_points_visited", "#main_grid_unique_ok", "", "#follow_big", "#est_slot", "#combos_slot",
                           "#views_run", "#epc_matched", "#sum_len_at_view", "#walk_geo_calls", "#walk_geo_nwalk", "#epc_gn_accepted", "#epc_avf_attempts", "#epc_attempt_pos_sum"};
     for (int k = 0; k < 32; k++) if (nm[k][0]) fprintf(stderr, "[k3prof] %-26s %14llu%s\n", nm[k], pr[k], k < 8 ? " warp-cycles" : "");
+    if (pr[45]) fprintf(stderr, "[k3prof] phase B warps: %llu, mean busy %.2f ms, last one done after %.2f ms (tail = %.1f %% of the kernel)\n", pr[45], pr[43] / (double)pr[45] * 1e-6, pr[44] * 1e-6,
+                        100.0 * (1.0 - (pr[43] / (double)pr[45]) / (double)pr[44]));
     fprintf(stderr, "[k3prof] max seed cycles %llu (%.1f ms at 1.9 GHz); seeds > 50M cycles: %llu; > 200M cycles: %llu\n", pr[40], pr[40] / 1.9e6, pr[41], pr[42]);
 #ifdef EG3D_K3_PROFILE
     {

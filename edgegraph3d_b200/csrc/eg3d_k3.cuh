@@ -1389,11 +1389,21 @@ __global__ void __launch_bounds__(K3B_THREADS, EG3D_K3B_MIN_BLOCKS) k3b_expand_k
   c.w = make_ws(A.scratch + (size_t)warp * A.scratch_per_warp, S.V, A.capf, A.capc, A.oc);
   const int n_acc = (int)A.pa_counters[0];
   const int V = S.V;
+#ifdef EG3D_K3_PROFILE
+  unsigned long long t_warp0 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_warp0));
+#endif
   while (true) {
     int ri = 0;
     if (lane == 0) ri = atomicAdd(A.work_counter, 1);
     ri = __shfl_sync(0xffffffffu, ri, 0);
     const bool has = ri < n_acc;
+#ifdef EG3D_K3_PROFILE
+    if (!has && A.prof && lane == 0) {        // tail: when this warp ran out of seeds (ns since it started): sum / max over warps
+      unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      atomicAdd(&A.prof[43], t1 - t_warp0); atomicMax(&A.prof[44], t1 - t_warp0); atomicAdd(&A.prof[45], 1ull);
+    }
+#endif
 #if EG3D_K3B_SYNC
     if (!__syncthreads_or(has)) break;       // the CTA's warps take their seeds together and leave together
 #else

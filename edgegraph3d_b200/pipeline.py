@@ -139,7 +139,8 @@ def edge_matching(sfm_json, edges_folder, out_folder, params=None, _scene_factor
             # a per-seed capacity was too small for this input (the library reports it, it never truncates): double both and
             # run again on a fresh scene handle
             from . import _abi as A
-            if e.status != A.EG3D_ERR_CAPACITY or attempt == 3:
+            # (the device seeding's neighbourhood bound, A6_RAW / A6_IDS, is a different capacity: larger chain slots cannot help it)
+            if e.status != A.EG3D_ERR_CAPACITY or attempt == 3 or "A6_" in str(e):
                 raise
             prm.max_chain_points *= 2
             prm.max_follow_points *= 2
