@@ -420,7 +420,9 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
   if (nblocks > max_useful) nblocks = max_useful;
   // phase B: EG3D_K3B_MIN_BLOCKS CTAs of K3B_THREADS per SM (one CTA per SM in the lock-step form)
   const int warps_per_block_b = K3B_THREADS / 32;
-  int nblocks_b = sc->num_sms * EG3D_K3B_MIN_BLOCKS;
+  int blocks_per_sm_b = EG3D_K3B_MIN_BLOCKS;
+  if (const char* e = getenv("EG3D_K3B_BLOCKS_PER_SM")) blocks_per_sm_b = std::max(1, std::min(EG3D_K3B_MIN_BLOCKS, atoi(e)));   // A/B runs
+  int nblocks_b = sc->num_sms * blocks_per_sm_b;
   nblocks_b = std::max(1, std::min(nblocks_b, (n + warps_per_block_b - 1) / warps_per_block_b));
   const int batch_b = EG3D_K3B_BATCH > 0 ? EG3D_K3B_BATCH : 1;     // arenas per phase-B warp
   if (EG3D_K3B_BATCH > 0) nblocks_b = std::max(1, std::min(sc->num_sms, (n + warps_per_block_b * batch_b - 1) / (warps_per_block_b * batch_b)));

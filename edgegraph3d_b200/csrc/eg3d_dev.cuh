@@ -778,11 +778,18 @@ static __device__ __noinline__ bool gn_group(const DevScene& S, const ObsSrc& o,
         if (sub == 0) { const double* q = o.cache; a.mse = q[0]; a.h00 = q[1]; a.h01 = q[2]; a.h02 = q[3]; a.h11 = q[4]; a.h12 = q[5]; a.h22 = q[6]; a.g0 = q[7]; a.g1 = q[8]; a.g2 = q[9]; }
       } else {
         const int nloop = first_shared ? n : ntot;
+        // the next observation is fetched while the current one is accumulated: with ~1000 views a chain's observation lists no
+        // longer fit the L2 and the loop was bound by the latency of these loads (long-scoreboard stalls, profiles/r02_c3_k3b.txt)
+        int i = sub;
+        int v = 0; float px = 0.f, py = 0.f;
+        if (i < nloop) { if (i < n) { v = ov[i]; px = ox[i]; py = oy[i]; } else { v = o.ev; px = o.ex; py = o.ey; } }
 #pragma unroll 1
-        for (int i = sub; i < nloop; i += G) {
-          int v; float px, py;
-          if (i < n) { v = ov[i]; px = ox[i]; py = oy[i]; } else { v = o.ev; px = o.ex; py = o.ey; }
+        while (i < nloop) {
+          const int j = i + G;
+          int nv = 0; float npx = 0.f, npy = 0.f;
+          if (j < nloop) { if (j < n) { nv = ov[j]; npx = ox[j]; npy = oy[j]; } else { nv = o.ev; npx = o.ex; npy = o.ey; } }
           gn_accumulate_fast(P64 + 12 * v, px, py, X0, X1, X2, a);
+          v = nv; px = npx; py = npy; i = j;
         }
       }
     }
