@@ -40,6 +40,9 @@ def main():
     noi = [i for i, x in enumerate(H) if x.strip() in ("stall_no_inst", "stall_no_instruction")]
     base = None
     inst, samp = collections.Counter(), collections.Counter()
+    ilsb = H.index("stall_long_sb") if "stall_long_sb" in H else None
+    inoi = H.index("stall_no_inst") if "stall_no_inst" in H else None
+    lsb, nois = collections.Counter(), collections.Counter()
     for r in rows[h + 1:]:
         if len(r) <= max(ii, isamp) or not r[ia].startswith("0x"):
             if r and r[0] == "Kernel Name":
@@ -49,11 +52,14 @@ def main():
         base = a if base is None else base
         f = attr.get(a - base, "?")
         inst[f] += int(r[ii] or 0); samp[f] += int(r[isamp] or 0)
+        if ilsb is not None: lsb[f] += int(r[ilsb] or 0)
+        if inoi is not None: nois[f] += int(r[inoi] or 0)
     ti, ts = sum(inst.values()), sum(samp.values())
     print(f"# {kre} in {os.path.basename(rep)}: {ti:.4g} executed warp instructions, {ts} stall samples; per source function (inlined copies included)")
-    print(f"# {'function':44s} {'instructions':>14s} {'%':>6s} {'samples':>9s} {'% time':>7s} {'samples per 1e6 instr':>22s}")
+    print(f"# {'function':44s} {'instructions':>14s} {'%':>6s} {'samples':>9s} {'% time':>7s} {'samples per 1e6 instr':>22s} {'no_inst %':>10s} {'long_sb %':>10s}")
     for f, n in samp.most_common(45):
-        print(f"  {f:44s} {inst[f]:14d} {100.0 * inst[f] / ti:6.1f} {n:9d} {100.0 * n / ts:7.1f} {1e6 * n / max(1, inst[f]):22.1f}")
+        print(f"  {f:44s} {inst[f]:14d} {100.0 * inst[f] / ti:6.1f} {n:9d} {100.0 * n / ts:7.1f} {1e6 * n / max(1, inst[f]):22.1f} {100.0 * nois[f] / max(1, n):10.1f} {100.0 * lsb[f] / max(1, n):10.1f}")
+    print(f"# all: no_instruction {100.0 * sum(nois.values()) / ts:.1f} % of the samples, long_scoreboard {100.0 * sum(lsb.values()) / ts:.1f} %")
 
 
 if __name__ == "__main__":
