@@ -23,7 +23,7 @@ EXPORTS = [
     "eg3d_polyline_similarity_graph", "eg3d_similarity_graph_get", "eg3d_similarity_graph_communities", "eg3d_polyline_sets_from_communities",
     "eg3d_similarity_graph_free", "eg3d_triangulate_dlt_host", "eg3d_build_info", "eg3d_project_host",
     "eg3d_comm_unique_id", "eg3d_comm_create", "eg3d_comm_destroy", "eg3d_points_allgather",
-    "eg3d_match_correspondences", "eg3d_refpoint_correspondences", "eg3d_corr_get", "eg3d_corr_free",
+    "eg3d_match_correspondences", "eg3d_refpoint_correspondences", "eg3d_corr_get", "eg3d_corr_free", "eg3d_fundamental_from_tracks",
 ]
 
 
@@ -44,6 +44,7 @@ def load():
     L.eg3d_last_error.restype = C.c_char_p
     L.eg3d_device_count.restype = C.c_int
     L.eg3d_camera_fundamentals.argtypes = [A.c_f32p, C.c_int32, A.c_f64p]
+    L.eg3d_fundamental_from_tracks.argtypes = [C.POINTER(A.SceneDesc), C.c_int32, A.c_f64p, A.c_u8p]
     L.eg3d_params_default.argtypes = [C.POINTER(A.Params)]
     L.eg3d_scene_create.argtypes = [C.POINTER(A.SceneDesc), C.POINTER(A.Params), C.POINTER(C.c_void_p)]
     L.eg3d_scene_destroy.argtypes = [C.c_void_p]
@@ -118,6 +119,21 @@ def camera_fundamentals(cameras):
     out = np.zeros((V, V, 9), np.float64)
     load().eg3d_camera_fundamentals(A.ptr(cams, A.c_f32p), V, A.ptr(out, A.c_f64p))
     return out
+
+
+def fundamental_from_tracks(n_views, track_off, track_view, track_xy, min_common=10):
+    """f4 (host C++, no OpenCV): least-median-of-squares F[i][j] from the SfM tracks seen by both views
+    (generate_all_fundamental_matrices_from_Points, geometric_utilities.cpp:754-820).  -> (F [V][V][9] f64, valid [V][V] u8).
+    Same estimator family as cv2.findFundamentalMat(FM_LMEDS), not bit-identical to it (openmvg_io.fundamental_from_tracks is the
+    cv2 call that reproduces the committed dtu006 fixture)."""
+    d = A.SceneDesc()
+    off = np.ascontiguousarray(track_off, np.int64); tv = np.ascontiguousarray(track_view, np.int32)
+    xy = np.ascontiguousarray(track_xy, np.float32).reshape(-1, 2)
+    d.n_views = int(n_views); d.n_tracks = len(off) - 1
+    d.track_off = A.ptr(off, A.c_i64p); d.track_view = A.ptr(tv, A.c_i32p); d.track_xy = A.ptr(xy, A.c_f32p)
+    F = np.zeros((n_views, n_views, 9), np.float64); valid = np.zeros((n_views, n_views), np.uint8)
+    _check(load().eg3d_fundamental_from_tracks(C.byref(d), int(min_common), A.ptr(F, A.c_f64p), A.ptr(valid, A.c_u8p)))
+    return F, valid
 
 
 def polyline_sets_from_refpoints(scene, find_within_dist=10.0, mult=3.0):

@@ -70,10 +70,22 @@ def load_sfm_data(path_or_dict):
                 track_xy=np.array(txy, np.float32).reshape(-1, 2), view_keys=keys)
 
 
-def fundamental_from_tracks(n_views, track_off, track_view, track_xy, min_corr=10):
+def fundamental_from_tracks(n_views, track_off, track_view, track_xy, min_corr=10, engine="auto"):
     """F[i][j] = cv::findFundamentalMat(points_i, points_j, FM_LMEDS) over the tracks seen by both views in ascending
-    track id; pairs with < 10 common tracks are invalid (the reference's 1x1 dummy Mat).  Needs cv2 (host tool)."""
-    import cv2
+    track id; pairs with < 10 common tracks are invalid (the reference's 1x1 dummy Mat).
+    engine: "cv2" = the same third-party call the reference makes (reproduces the committed dtu006 fixture bit for bit);
+    "native" = libeg3d.so's own LMedS (eg3d_fundamental_from_tracks, host C++, no OpenCV: same estimator family, not
+    bit-identical); "auto" = cv2 when it can be imported, else native."""
+    if engine != "native":
+        try:
+            import cv2
+        except ImportError:
+            if engine == "cv2":
+                raise
+            engine = "native"
+    if engine == "native":
+        from . import lib as E
+        return E.fundamental_from_tracks(n_views, track_off, track_view, track_xy, min_corr)
     seen = [dict() for _ in range(n_views)]
     for p in range(len(track_off) - 1):
         for o in range(int(track_off[p]), int(track_off[p + 1])):

@@ -4,7 +4,7 @@ C-ABI.  Everything that computes lives in libeg3d.so; this file only orders the 
 
   read_sfm_data            -> openmvg_io.load_sfm_data                      (f3)
   edge images -> PLGs      -> eg3d_plg_from_edge_image                      (f1, host)
-  fundamental matrices     -> openmvg_io.fundamental_from_tracks           (f4, cv2 LMedS as in the reference)
+  fundamental matrices     -> openmvg_io.fundamental_from_tracks           (f4: cv2 LMedS as in the reference, or libeg3d.so's own LMedS without OpenCV)
   pipeline 1 candidates    -> eg3d_polyline_similarity_graph / _communities / eg3d_polyline_sets_from_communities (f2, host)
   pipeline 2 candidates    -> eg3d_polyline_sets_from_refpoints             (f2, host)
   pipelines 1, 2           -> eg3d_match_polyline_sets                      (device)

@@ -175,6 +175,15 @@ const char* eg3d_last_error(void);
  * the role of findFundamentalMatrixFromRt (geometric_utilities.cpp:683-710) for rigs with known poses.  Host code.
  * cameras [V][12], out [V][V][9] (row-major, unit Frobenius norm, zero on the diagonal). */
 void        eg3d_camera_fundamentals(const float* cameras, int32_t n_views, double* out);
+/* Row f4 without OpenCV: generate_all_fundamental_matrices_from_Points (geometric_utilities.cpp:754-820) — for every ordered view
+ * pair (i, j) with at least `min_common` (reference: MIN_CORRESPONDENCES_AMOUNT = 10) SfM tracks seen by both, a least-median-of-
+ * squares estimate of F[i][j] (x_j^T F x_i = 0) from the tracks' observations in ascending track id; other pairs stay invalid (the
+ * reference's 1x1 dummy Mat).  Host code, deterministic.  Same estimator family and constants as cv::findFundamentalMat(FM_LMEDS)
+ * (normalised 8-point on minimal samples, confidence 0.99, 2.5 * 1.4826 * (1 + 5/(n-8)) * sqrt(median) inlier band, refit on the
+ * inliers, rank 2, F[2][2] = 1) but NOT bit-identical to it: OpenCV's is driven by its own RNG, 7-point solver and SVD.  The path
+ * takes F as an input, as the reference's entry points do, so either source can be passed to eg3d_scene_create.
+ * Uses n_views and the track arrays of `desc` only.  out_F [V][V][9], out_valid [V][V]. */
+eg3d_status eg3d_fundamental_from_tracks(const eg3d_scene_desc* desc, int32_t min_common, double* out_F, uint8_t* out_valid);
 int         eg3d_device_count(void);
 /* Host evaluation of compute_projection (geometric_utilities.cpp:973-977) as the kernels compute it (tests). */
 void        eg3d_project_host(const float* cam12, const float* x3, float* out2);

@@ -11,6 +11,7 @@
 #include <string>
 #include <tuple>
 #include <utility>
+#include <cstring>
 #include <vector>
 #include "eg3d.h"
 
@@ -79,6 +80,26 @@ struct FundamentalSet {
   }
 #endif
 };
+
+// generate_all_fundamental_matrices (geometric_utilities.cpp:816-820 -> _from_Points :800-812): LMedS matrices from the SfM tracks,
+// host code of libeg3d.so (eg3d_fundamental_from_tracks: same estimator family as cv::findFundamentalMat(FM_LMEDS), not bit-identical;
+// a maintainer who keeps OpenCV's matrices uses the `cv::Mat**` constructor of FundamentalSet above instead).
+inline FundamentalSet generate_all_fundamental_matrices(const SfMData& sfmd) {
+  const int V = (int)sfmd.camerasList_.size();
+  std::vector<int64_t> off(1, 0); std::vector<int32_t> view; std::vector<float> xy;
+  for (size_t p = 0; p < sfmd.points_.size(); p++) {
+    for (size_t k = 0; k < sfmd.camViewingPointN_[p].size(); k++) {
+      view.push_back((int32_t)sfmd.camViewingPointN_[p][k]);
+      xy.push_back(sfmd.point2DoncamViewingPoint_[p][k][0]); xy.push_back(sfmd.point2DoncamViewingPoint_[p][k][1]);
+    }
+    off.push_back((int64_t)view.size());
+  }
+  eg3d_scene_desc d; std::memset(&d, 0, sizeof d);
+  d.n_views = V; d.n_tracks = (int64_t)sfmd.points_.size(); d.track_off = off.data(); d.track_view = view.data(); d.track_xy = xy.data();
+  FundamentalSet F(V);
+  check(eg3d_fundamental_from_tracks(&d, 10 /* MIN_CORRESPONDENCES_AMOUNT */, F.F.data(), F.valid.data()));
+  return F;
+}
 
 // Owns the device-resident scene: the role `plgs`, `plmaps`, `all_fundamental_matrices`, `em` play as long-lived
 // arguments of the reference's entry points (edge_matcher.cpp:83-115 builds them once).

@@ -1,5 +1,6 @@
 // Compile/link check of the header-only reference-API shim against libeg3d.so (stand-alone types).
 // With a CUDA device it runs pipelines 1-2 on a toy scene; without one it checks the loud EG3D_ERR_NO_DEVICE failure.
+#include <algorithm>
 #include <cstdio>
 #include <cmath>
 #include "eg3d_ref_api.hpp"
@@ -43,6 +44,31 @@ int main() {
     size_t live = 0; for (const auto& pl : g.polylines) live += pl.polyline_coords.size() > 1;
     std::printf("shim f1: %zu polyline ids, %zu live\n", g.polylines.size(), live);
     if (live == 0) return 4;
+  }
+  {   // f4 needs no device either: generate_all_fundamental_matrices from SfM tracks = the line's points seen by every view
+    for (int i = 0; i <= 30; i++) {
+      sfmd.points_.push_back(vec3(-0.5f + i / 30.0f, 0.2f * std::sin(i * 0.2f) + 0.05f * (i % 3), 0.1f * i / 30.0f + 0.03f * (i % 5)));
+      sfmd.camViewingPointN_.push_back(std::vector<int>()); sfmd.point2DoncamViewingPoint_.push_back(std::vector<vec2>());
+      for (int v = 0; v < V; v++) {
+        const mat4& P = sfmd.camerasList_[v].cameraMatrix; const vec3& X = sfmd.points_.back();
+        float h[3]; for (int r = 0; r < 3; r++) h[r] = P[r][0] * X[0] + P[r][1] * X[1] + P[r][2] * X[2] + P[r][3];
+        sfmd.camViewingPointN_.back().push_back(v); sfmd.point2DoncamViewingPoint_.back().push_back(vec2(h[0] / h[2], h[1] / h[2]));
+      }
+    }
+    FundamentalSet Ft = generate_all_fundamental_matrices(sfmd);
+    int nvalid = 0; double worst = 0;
+    for (int a = 0; a < V; a++) for (int b = 0; b < V; b++) if (Ft.valid[(size_t)a * V + b]) {
+      nvalid++;
+      const double* f = &Ft.F[((size_t)a * V + b) * 9];
+      for (size_t p = 0; p < sfmd.points_.size(); p++) {
+        const vec2 &x = sfmd.point2DoncamViewingPoint_[p][(size_t)a], &y = sfmd.point2DoncamViewingPoint_[p][(size_t)b];
+        const double l0 = f[0] * x[0] + f[1] * x[1] + f[2], l1 = f[3] * x[0] + f[4] * x[1] + f[5], l2 = f[6] * x[0] + f[7] * x[1] + f[8];
+        worst = std::max(worst, std::fabs(l0 * y[0] + l1 * y[1] + l2) / std::sqrt(l0 * l0 + l1 * l1));
+      }
+    }
+    std::printf("shim f4: %d valid pairs, worst epipolar distance %.4f px\n", nvalid, worst);
+    if (nvalid != V * (V - 1) || worst > 0.05) return 5;
+    sfmd.points_.clear(); sfmd.camViewingPointN_.clear(); sfmd.point2DoncamViewingPoint_.clear();     // the toy scene below has no tracks
   }
   try {
     Eg3dScene scene(sfmd, plgs, F);
