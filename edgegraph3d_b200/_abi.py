@@ -89,3 +89,9 @@ def ptr(arr, ctype_ptr):
     if arr is None:
         return C.cast(None, ctype_ptr)
     return arr.ctypes.data_as(ctype_ptr)
+
+
+class SfmView(C.Structure):
+    _fields_ = [("n_views", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("cameras", c_f32p), ("K", c_f32p), ("R", c_f32p), ("center", c_f32p), ("t", c_f32p), ("view_keys", c_i64p),
+                ("n_tracks", C.c_int64), ("track_xyz", c_f32p), ("track_off", c_i64p), ("track_view", c_i32p), ("track_xy", c_f32p)]

@@ -6,4 +6,4 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -prec-div=true -prec-sqrt=true \
-  -Xcompiler -fPIC -Xcompiler -O3 -Xcompiler -ffp-contract=off -shared -o "${OUT:-../libeg3d.so}" eg3d_capi.cu eg3d_plg_build.cpp eg3d_fundamental.cpp -ldl -lpthread "$@"
+  -Xcompiler -fPIC -Xcompiler -O3 -Xcompiler -ffp-contract=off -shared -o "${OUT:-../libeg3d.so}" eg3d_capi.cu eg3d_plg_build.cpp eg3d_fundamental.cpp eg3d_sfm_io.cpp -ldl -lpthread "$@"

@@ -24,6 +24,7 @@ EXPORTS = [
     "eg3d_similarity_graph_free", "eg3d_triangulate_dlt_host", "eg3d_build_info", "eg3d_project_host",
     "eg3d_comm_unique_id", "eg3d_comm_create", "eg3d_comm_destroy", "eg3d_points_allgather",
     "eg3d_match_correspondences", "eg3d_refpoint_correspondences", "eg3d_corr_get", "eg3d_corr_free", "eg3d_fundamental_from_tracks",
+    "eg3d_sfm_load", "eg3d_sfm_get", "eg3d_sfm_free", "eg3d_sfm_save", "eg3d_write_ply",
 ]
 
 
@@ -45,6 +46,12 @@ def load():
     L.eg3d_device_count.restype = C.c_int
     L.eg3d_camera_fundamentals.argtypes = [A.c_f32p, C.c_int32, A.c_f64p]
     L.eg3d_fundamental_from_tracks.argtypes = [C.POINTER(A.SceneDesc), C.c_int32, A.c_f64p, A.c_u8p]
+    L.eg3d_sfm_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    L.eg3d_sfm_get.argtypes = [C.c_void_p, C.POINTER(A.SfmView)]
+    L.eg3d_sfm_free.argtypes = [C.c_void_p]
+    L.eg3d_sfm_free.restype = None
+    L.eg3d_sfm_save.argtypes = [C.c_char_p, C.c_char_p, C.c_int64, A.c_f32p, A.c_i64p, A.c_i32p, A.c_f32p, A.c_u8p, A.c_i64p]
+    L.eg3d_write_ply.argtypes = [C.c_char_p, C.c_int64, A.c_f32p, A.c_u8p]
     L.eg3d_params_default.argtypes = [C.POINTER(A.Params)]
     L.eg3d_scene_create.argtypes = [C.POINTER(A.SceneDesc), C.POINTER(A.Params), C.POINTER(C.c_void_p)]
     L.eg3d_scene_destroy.argtypes = [C.c_void_p]
@@ -134,6 +141,43 @@ def fundamental_from_tracks(n_views, track_off, track_view, track_xy, min_common
     F = np.zeros((n_views, n_views, 9), np.float64); valid = np.zeros((n_views, n_views), np.uint8)
     _check(load().eg3d_fundamental_from_tracks(C.byref(d), int(min_common), A.ptr(F, A.c_f64p), A.ptr(valid, A.c_u8p)))
     return F, valid
+
+
+def sfm_load(path):
+    """f3 (host C++): OpenMVG sfm_data JSON -> the dict openmvg_io.load_sfm_data returns (same keys, same bits)."""
+    L = load()
+    h = C.c_void_p()
+    _check(L.eg3d_sfm_load(str(path).encode(), C.byref(h)))
+    try:
+        v = A.SfmView()
+        _check(L.eg3d_sfm_get(h, C.byref(v)))
+        V, NT = int(v.n_views), int(v.n_tracks)
+        arr = lambda p, shape, dt: (np.ctypeslib.as_array(p, shape=shape).astype(dt, copy=True) if int(np.prod(shape)) > 0 else np.zeros(shape, dt))
+        off = arr(v.track_off, (NT + 1,), np.int64)
+        nobs = int(off[-1])
+        return dict(width=int(v.width), height=int(v.height), cameras=arr(v.cameras, (V, 12), np.float32), K=arr(v.K, (V, 3, 3), np.float32),
+                    R=arr(v.R, (V, 3, 3), np.float32), center=arr(v.center, (V, 3), np.float32), t=arr(v.t, (V, 3), np.float32),
+                    track_xyz=arr(v.track_xyz, (NT, 3), np.float32), track_off=off, track_view=arr(v.track_view, (nobs,), np.int32),
+                    track_xy=arr(v.track_xy, (nobs, 2), np.float32), view_keys=[int(k) for k in arr(v.view_keys, (V,), np.int64)])
+    finally:
+        L.eg3d_sfm_free(h)
+
+
+def sfm_save(path, original_path, xyz, obs_off, obs_view, obs_xy, inliers=None):
+    """f3 (host C++): output_sfm_data — the original file's views / intrinsics / extrinsics + a rewritten `structure`.  -> points written."""
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3); off = np.ascontiguousarray(obs_off, np.int64)
+    ov = np.ascontiguousarray(obs_view, np.int32); xy = np.ascontiguousarray(obs_xy, np.float32).reshape(-1, 2)
+    keep = None if inliers is None else np.ascontiguousarray(np.asarray(inliers).astype(np.uint8))
+    n = C.c_int64()
+    _check(load().eg3d_sfm_save(str(path).encode(), str(original_path).encode(), len(off) - 1, A.ptr(xyz, A.c_f32p), A.ptr(off, A.c_i64p),
+                                A.ptr(ov, A.c_i32p), A.ptr(xy, A.c_f32p), A.ptr(keep, A.c_u8p) if keep is not None else None, C.byref(n)))
+    return int(n.value)
+
+
+def write_ply(path, xyz, rgb=None):
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    rgb = None if rgb is None else np.ascontiguousarray(rgb, np.uint8).reshape(-1, 3)
+    _check(load().eg3d_write_ply(str(path).encode(), len(xyz), A.ptr(xyz, A.c_f32p), A.ptr(rgb, A.c_u8p) if rgb is not None else None))
 
 
 def polyline_sets_from_refpoints(scene, find_within_dist=10.0, mult=3.0):

@@ -184,6 +184,37 @@ void        eg3d_camera_fundamentals(const float* cameras, int32_t n_views, doub
  * takes F as an input, as the reference's entry points do, so either source can be passed to eg3d_scene_create.
  * Uses n_views and the track arrays of `desc` only.  out_F [V][V][9], out_valid [V][V]. */
 eg3d_status eg3d_fundamental_from_tracks(const eg3d_scene_desc* desc, int32_t min_common, double* out_F, uint8_t* out_valid);
+
+/* Row f3 in C++ (host code, no device): the data formats either side of the path.
+ *   eg3d_sfm_load   OpenMVG sfm_data JSON -> what SfMData holds (OpenMvgParser.cpp:75-153, 241-301): view index = position
+ *                   in `extrinsics`; cameras = rows 0..2 of cameraMatrix = eMatrix * kMatrix with translation = -center * rotation,
+ *                   float arithmetic in the operation order of the reference's vendored glm (bit-identical camera matrices);
+ *                   radial distortion ignored as the reference does; tracks in file order.  The arrays feed eg3d_scene_desc directly.
+ *   eg3d_sfm_save   output_sfm_data (output_sfm_data.cpp:186-229): views / intrinsics / extrinsics of `original_path` kept verbatim,
+ *                   `structure` rewritten from the given points (key = running index, id_feat = 0), only those with keep[i] != 0 when
+ *                   `keep` is given; obs_view are view INDICES (mapped back to the file's pose keys).
+ *   eg3d_write_ply  output_point_cloud.cpp (ascii PLY, optional per-point colour).                                              */
+typedef struct eg3d_sfm eg3d_sfm;     /* opaque */
+typedef struct eg3d_sfm_view {
+  int32_t n_views, width, height;
+  const float*   cameras;     /* [V][12] */
+  const float*   K;           /* [V][9]  */
+  const float*   R;           /* [V][9]  */
+  const float*   center;      /* [V][3]  */
+  const float*   t;           /* [V][3]  */
+  const int64_t* view_keys;   /* [V] pose keys of the file, in view order */
+  int64_t        n_tracks;
+  const float*   track_xyz;   /* [NT][3] */
+  const int64_t* track_off;   /* [NT+1]  */
+  const int32_t* track_view;  /* [NOBS]  */
+  const float*   track_xy;    /* [NOBS][2] */
+} eg3d_sfm_view;
+eg3d_status eg3d_sfm_load(const char* path, eg3d_sfm** out);
+eg3d_status eg3d_sfm_get(const eg3d_sfm*, eg3d_sfm_view* view);   /* pointers valid until eg3d_sfm_free */
+void        eg3d_sfm_free(eg3d_sfm*);
+eg3d_status eg3d_sfm_save(const char* path, const char* original_path, int64_t n_points, const float* xyz, const int64_t* obs_off,
+                          const int32_t* obs_view, const float* obs_xy, const uint8_t* keep /* may be NULL */, int64_t* n_written /* may be NULL */);
+eg3d_status eg3d_write_ply(const char* path, int64_t n_points, const float* xyz, const uint8_t* rgb /* may be NULL */);
 int         eg3d_device_count(void);
 /* Host evaluation of compute_projection (geometric_utilities.cpp:973-977) as the kernels compute it (tests). */
 void        eg3d_project_host(const float* cam12, const float* x3, float* out2);

@@ -81,6 +81,50 @@ struct FundamentalSet {
 #endif
 };
 
+// OpenMvgParser::parse (OpenMvgParser.cpp:75-153, 241-301) without rapidjson: the C++ reader of libeg3d.so fills the SfMData fields
+// the path reads (cameras bit-identical to the reference's glm arithmetic; tracks in file order).
+inline SfMData load_sfm_data(const std::string& path) {
+  eg3d_sfm* h = nullptr;
+  check(eg3d_sfm_load(path.c_str(), &h));
+  eg3d_sfm_view v;
+  check(eg3d_sfm_get(h, &v));
+  SfMData s;
+  s.numCameras_ = v.n_views; s.imageWidth_ = v.width; s.imageHeight_ = v.height; s.numPoints_ = (int)v.n_tracks;
+  s.camerasList_.resize((size_t)v.n_views);
+  for (int i = 0; i < v.n_views; i++) {
+    CameraType& c = s.camerasList_[(size_t)i];
+    for (int r = 0; r < 4; r++) for (int k = 0; k < 4; k++) c.cameraMatrix[r][k] = r < 3 ? v.cameras[(size_t)i * 12 + r * 4 + k] : (k == 3 ? 1.f : 0.f);
+    c.imageWidth = v.width; c.imageHeight = v.height;
+  }
+  for (int64_t p = 0; p < v.n_tracks; p++) {
+    s.points_.push_back(vec3(v.track_xyz[3 * p], v.track_xyz[3 * p + 1], v.track_xyz[3 * p + 2]));
+    s.camViewingPointN_.push_back(std::vector<int>()); s.point2DoncamViewingPoint_.push_back(std::vector<vec2>());
+    for (int64_t o = v.track_off[p]; o < v.track_off[p + 1]; o++) {
+      s.camViewingPointN_.back().push_back(v.track_view[o]);
+      s.point2DoncamViewingPoint_.back().push_back(vec2(v.track_xy[2 * o], v.track_xy[2 * o + 1]));
+    }
+  }
+  eg3d_sfm_free(h);
+  return s;
+}
+// output_sfm_data (output_sfm_data.cpp:186-229): the original file's views / intrinsics / extrinsics + the points of `sfmd` as `structure`
+// (optionally only those flagged in `inliers`); returns the number of points written.
+inline int64_t output_sfm_data(const std::string& original_json, const SfMData& sfmd, const std::string& out_path, const std::vector<bool>* inliers = nullptr) {
+  std::vector<float> xyz, xy; std::vector<int64_t> off(1, 0); std::vector<int32_t> view; std::vector<uint8_t> keep;
+  for (size_t p = 0; p < sfmd.points_.size(); p++) {
+    xyz.push_back(sfmd.points_[p][0]); xyz.push_back(sfmd.points_[p][1]); xyz.push_back(sfmd.points_[p][2]);
+    for (size_t k = 0; k < sfmd.camViewingPointN_[p].size(); k++) {
+      view.push_back((int32_t)sfmd.camViewingPointN_[p][k]);
+      xy.push_back(sfmd.point2DoncamViewingPoint_[p][k][0]); xy.push_back(sfmd.point2DoncamViewingPoint_[p][k][1]);
+    }
+    off.push_back((int64_t)view.size());
+    if (inliers) keep.push_back((*inliers)[p] ? 1 : 0);
+  }
+  int64_t n = 0;
+  check(eg3d_sfm_save(out_path.c_str(), original_json.c_str(), (int64_t)sfmd.points_.size(), xyz.data(), off.data(), view.data(), xy.data(), inliers ? keep.data() : nullptr, &n));
+  return n;
+}
+
 // generate_all_fundamental_matrices (geometric_utilities.cpp:816-820 -> _from_Points :800-812): LMedS matrices from the SfM tracks,
 // host code of libeg3d.so (eg3d_fundamental_from_tracks: same estimator family as cv::findFundamentalMat(FM_LMEDS), not bit-identical;
 // a maintainer who keeps OpenCV's matrices uses the `cv::Mat**` constructor of FundamentalSet above instead).

@@ -55,6 +55,8 @@ int main() {
         sfmd.camViewingPointN_.back().push_back(v); sfmd.point2DoncamViewingPoint_.back().push_back(vec2(h[0] / h[2], h[1] / h[2]));
       }
     }
+    auto f3_load = load_sfm_data; auto f3_save = output_sfm_data;      // f3: file formats (exercised in tests/test_sfm_io.py through the C ABI; compile check here)
+    (void)f3_load; (void)f3_save;
     FundamentalSet Ft = generate_all_fundamental_matrices(sfmd);
     int nvalid = 0; double worst = 0;
     for (int a = 0; a < V; a++) for (int b = 0; b < V; b++) if (Ft.valid[(size_t)a * V + b]) {
