@@ -27,7 +27,7 @@ namespace eg3d {
 // CTA barrier in front of each half of a view's expansion so that the warps share the lines they pull in): 35 % fewer
 // instruction-cache requests but slower overall (barrier idling), kept for experiments.
 #ifndef EG3D_K3A_FIRST_LOOKAHEAD
-#define EG3D_K3A_FIRST_LOOKAHEAD 2
+#define EG3D_K3A_FIRST_LOOKAHEAD 1
 #endif
 // Epipolar hits of a view are solved EG3D_EPC_BATCH at a time, in order: the first hit whose solve AND neighbour search succeed
 // wins (triangulation.cpp:753-768), and on BASELINE configs[1] that is on average the third of ~9 survivors of the pruning, so
@@ -247,7 +247,8 @@ EG3D_D bool est_pt3(const DevScene& S, const int sel[3], Pt3* p) {
 static __device__ __noinline__ int first_extreme(Ctx& c, const Cur3& start, uint32_t first_dir, uint32_t dir_out[3], Pt3* dst) {
   const DevScene& S = *c.S;
   const int lane = c.lane;
-  // Look-ahead per batch: 2 steps in the first batch, 8 afterwards.  Almost every hypothesis handed to plg_compatible is a
+  // Look-ahead per batch: 1 step in the first batch, 8 afterwards (k3a on BASELINE configs[1]: 47.5 / 49.6 / 50.9 / 50.6 ms for a first
+  // batch of 1 / 2 / 4 / 8).  Almost every hypothesis handed to plg_compatible is a
   // wrong one whose four combos all die within the first step or two (1-2 % of the calls end in an accepted seed), so a
   // deep first batch mostly walks and solves points nobody asks for; the lifetimes, and with them the result, do not
   // depend on the batch size.
