@@ -114,7 +114,7 @@ struct WS {  // per-warp scratch view
 inline __host__ __device__ size_t k3_align(size_t x) { return (x + 15) & ~(size_t)15; }
 inline __host__ __device__ size_t k3_scratch_bytes(int V, int capf, int capc, int oc) {
   size_t b = 0;
-  b += k3_align(sizeof(Pt3) * (size_t)capf * 8);
+  b += k3_align(sizeof(Pt3) * (size_t)capf * 12);
   b += k3_align(sizeof(int) * (size_t)(capc + 1) * oc) * 5;
   b += k3_align(sizeof(float) * 3 * capc) + k3_align(sizeof(int) * capc) * 2;
   b += k3_align(sizeof(uint32_t) * V) * 2;
@@ -128,8 +128,8 @@ inline __host__ __device__ size_t k3_scratch_bytes(int V, int capf, int capc, in
 EG3D_D WS make_ws(unsigned char* base, int V, int capf, int capc, int oc) {
   WS w; size_t o = 0;
   auto take = [&](size_t bytes) { unsigned char* p = base + o; o += k3_align(bytes); return p; };
-  Pt3* p3 = (Pt3*)take(sizeof(Pt3) * (size_t)capf * 8);
-  w.tri = p3; w.D1 = p3 + 4 * capf; w.D2 = p3 + 5 * capf; w.fD1 = p3 + 6 * capf; w.fD2 = p3 + 7 * capf;
+  Pt3* p3 = (Pt3*)take(sizeof(Pt3) * (size_t)capf * 12);     // tri: 8 combo lists (first_extreme_dual), then D1, D2, fD1, fD2
+  w.tri = p3; w.D1 = p3 + 8 * capf; w.D2 = p3 + 9 * capf; w.fD1 = p3 + 10 * capf; w.fD2 = p3 + 11 * capf;
   w.ov = (int*)take(sizeof(int) * (size_t)(capc + 1) * oc);
   w.opl = (uint32_t*)take(sizeof(int) * (size_t)(capc + 1) * oc);
   w.oseg = (uint32_t*)take(sizeof(int) * (size_t)(capc + 1) * oc);
@@ -239,77 +239,98 @@ EG3D_D bool est_pt3(const DevScene& S, const int sel[3], Pt3* p) {
 
 // find_direction_given_first_extreme, plg_matching.cpp:142-203: the four (end_b, end_c) combos advance in lock-step and
 // the last survivor wins.  A combo's fate depends only on its own chain, and the triangulated X of a step only gates
-// validity (the next 2D step starts from the 2D points), so: lanes 0..3 walk their combo's geometry up to 8 steps
-// ahead, the up-to-32 DLT+GN solves of a batch run one per lane, and each combo's lifetime L_k is the number of
-// leading successes.  The lock-step loop `while (amount_of_valid > 1)` ends after round r* = L_(2) + 1 (second-largest
-// lifetime + 1); the survivor (if its lifetime is larger) keeps exactly its first r* points.  Returns the number of
-// points copied into `dst` (0 = fail).
-static __device__ __noinline__ int first_extreme(Ctx& c, const Cur3& start, uint32_t first_dir, uint32_t dir_out[3], Pt3* dst) {
+// validity (the next 2D step starts from the 2D points), so a combo's geometry can be walked ahead, the DLT+GN solves of a
+// batch run one per lane, and each combo's lifetime L_k is the number of leading successes.  The lock-step loop
+// `while (amount_of_valid > 1)` ends after round r* = L_(2) + 1 (second-largest lifetime + 1); the survivor (if its
+// lifetime is larger) keeps exactly its first r* points.
+//
+// The caller tries first extreme A (pla.start) and, only if that yields nothing, first extreme B (pla.end)
+// (plg_matching.cpp:325-370).  Almost every hypothesis that reaches this point is a wrong one whose combos all die in their
+// first step for BOTH extremes (1-2 % of the calls end in an accepted seed), so the first step of both extremes is taken at
+// once — lanes 0..3 the combos of A, lanes 4..7 those of B, one solve per lane — and only an extreme whose combos survive
+// goes on, 8 steps per batch, A before B as in the reference; B's speculative first step has no side effects.  Returns the
+// number of points copied into `dst` (0 = neither extreme works) and which extreme it was (`used`: 0 = A, 1 = B).
+static __device__ __noinline__ int first_extreme_dual(Ctx& c, const Cur3& start, uint32_t dirA, uint32_t dirB, int& used, uint32_t dir_out[3], Pt3* dst) {
   const DevScene& S = *c.S;
   const int lane = c.lane;
-  // Look-ahead per batch: 1 step in the first batch, 8 afterwards (k3a on BASELINE configs[1]: 47.5 / 49.6 / 50.9 / 50.6 ms for a first
-  // batch of 1 / 2 / 4 / 8).  Almost every hypothesis handed to plg_compatible is a
-  // wrong one whose four combos all die within the first step or two (1-2 % of the calls end in an accepted seed), so a
-  // deep first batch mostly walks and solves points nobody asks for; the lifetimes, and with them the result, do not
-  // depend on the batch size.
-  int R = EG3D_K3A_FIRST_LOOKAHEAD;
   Pl plb = get_pl(S, c.sel[1], start.pl[1]), plc = get_pl(S, c.sel[2], start.pl[2]);
-  uint32_t dir[3] = {first_dir, (lane & 2) ? plb.end : plb.start, (lane & 1) ? plc.end : plc.start};
-  bool alive = lane < 4;
+  uint32_t dir[3] = {(lane & 4) ? dirB : dirA, (lane & 2) ? plb.end : plb.start, (lane & 1) ? plc.end : plc.start};
+  bool alive = lane < 8;
   Cur3 cur = start;
-  int L = 0;                                  // successful steps so far (lanes 0..3)
-  Pt3* mine = c.w.tri + (size_t)(lane & 3) * c.w.capf;
-  while (true) {
-    int g = 0;                                // geometric steps of this batch
+  int L = 0;                                  // successful steps so far (lanes 0..7)
+  Pt3* mine = c.w.tri + (size_t)(lane & 7) * c.w.capf;
+  used = 0;
+  {   // first step of all eight combos
+    bool got = false;
     if (alive) {
-      if (L + R > c.w.capf) c.overflow = true;
-      else {
-        for (; g < R; g++) {
-          Cur3 nx;
-          if (!geo3(S, c.sel, cur, dir, nx)) break;
-          float X0[3] = {0.f, 0.f, 0.f};
-          store_pt3(mine + L + g, nx, X0);
-          cur = nx;
-        }
+      Cur3 nx;
+      if (geo3(S, c.sel, cur, dir, nx)) {
+        float X0[3] = {0.f, 0.f, 0.f};
+        store_pt3(mine, nx, X0);
+        cur = nx; got = true;
       }
     }
-    if (__any_sync(0xffffffffu, c.overflow)) { c.overflow = true; return 0; }
     __syncwarp();
-    // verification: lane (k*R + r) solves candidate r of combo k
-    const int kk = (lane / R) & 3, rr = lane % R;
-    const int gk = __shfl_sync(0xffffffffu, g, kk), Lk = __shfl_sync(0xffffffffu, L, kk);
     bool ok = false;
-    if (lane < 4 * R && rr < gk) ok = est_pt3(S, c.sel, c.w.tri + (size_t)kk * c.w.capf + Lk + rr);
-    unsigned okm = __ballot_sync(0xffffffffu, ok);
+    if (got) ok = est_pt3(S, c.sel, mine);
     __syncwarp();
-    if (alive) {
-      unsigned mine_ok = (okm >> (lane * R)) & ((1u << R) - 1u);
-      int lead = __ffs(~mine_ok) - 1;         // leading successes (R when all ok)
-      if (lead > g) lead = g;
-      L += lead;
-      if (lead < R) alive = false;            // geometry ended or a solve failed: lifetime is final
-    }
-    unsigned am = __ballot_sync(0xffffffffu, alive);
-    if (__popc(am) <= 1) break;
-    R = 8;
+    if (alive) { if (ok) L = 1; alive = ok; }   // a batch of one: the combo lives on iff its step exists and triangulates
   }
-  // lifetimes of the four combos
-  int L0 = __shfl_sync(0xffffffffu, L, 0), L1 = __shfl_sync(0xffffffffu, L, 1), L2 = __shfl_sync(0xffffffffu, L, 2), L3 = __shfl_sync(0xffffffffu, L, 3);
-  int Ls[4] = {L0, L1, L2, L3};
-  int win = 0;
-  for (int k = 1; k < 4; k++) if (Ls[k] > Ls[win]) win = k;
-  int second = -1;
-  for (int k = 0; k < 4; k++) if (k != win && Ls[k] > second) second = Ls[k];
-  if (Ls[win] <= second) return 0;            // the best two die in the same round: no survivor
-  const int n = second + 1;                   // rounds executed by the reference's loop
-  dir_out[0] = first_dir;
-  dir_out[1] = __shfl_sync(0xffffffffu, dir[1], win);
-  dir_out[2] = __shfl_sync(0xffffffffu, dir[2], win);
-  __syncwarp();
-  const Pt3* src = c.w.tri + (size_t)win * c.w.capf;
-  for (int i = lane; i < n; i += 32) dst[i] = src[i];
-  __syncwarp();
-  return n;
+  constexpr int R = 8;
+  for (int g = 0; g < 2; g++) {
+    const unsigned gmask = 0xfu << (4 * g);
+    const bool in_g = lane < 8 && (lane >> 2) == g;
+    while (__popc(__ballot_sync(0xffffffffu, alive) & gmask) > 1) {
+      int steps = 0;                            // geometric steps of this batch
+      if (alive && in_g) {
+        if (L + R > c.w.capf) c.overflow = true;
+        else {
+          for (; steps < R; steps++) {
+            Cur3 nx;
+            if (!geo3(S, c.sel, cur, dir, nx)) break;
+            float X0[3] = {0.f, 0.f, 0.f};
+            store_pt3(mine + L + steps, nx, X0);
+            cur = nx;
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, c.overflow)) { c.overflow = true; return 0; }
+      __syncwarp();
+      // verification: lane (k*8 + r) solves candidate r of combo k of this extreme
+      const int kk = lane >> 3, rr = lane & 7;
+      const int gk = __shfl_sync(0xffffffffu, steps, 4 * g + kk), Lk = __shfl_sync(0xffffffffu, L, 4 * g + kk);
+      bool ok = false;
+      if (rr < gk) ok = est_pt3(S, c.sel, c.w.tri + (size_t)(4 * g + kk) * c.w.capf + Lk + rr);
+      const unsigned okm = __ballot_sync(0xffffffffu, ok);
+      __syncwarp();
+      if (alive && in_g) {
+        const unsigned mine_ok = (okm >> ((lane & 3) * 8)) & 0xffu;
+        int lead = __ffs(~mine_ok) - 1;         // leading successes (8 when all ok)
+        if (lead > steps) lead = steps;
+        L += lead;
+        if (lead < R) alive = false;            // geometry ended or a solve failed: lifetime is final
+      }
+    }
+    // lifetimes of the four combos of this extreme
+    const int L0 = __shfl_sync(0xffffffffu, L, 4 * g), L1 = __shfl_sync(0xffffffffu, L, 4 * g + 1), L2 = __shfl_sync(0xffffffffu, L, 4 * g + 2), L3 = __shfl_sync(0xffffffffu, L, 4 * g + 3);
+    const int Ls[4] = {L0, L1, L2, L3};
+    int win = 0;
+    for (int k = 1; k < 4; k++) if (Ls[k] > Ls[win]) win = k;
+    int second = -1;
+    for (int k = 0; k < 4; k++) if (k != win && Ls[k] > second) second = Ls[k];
+    if (Ls[win] <= second) continue;            // the best two die in the same round: no survivor for this extreme
+    const int n = second + 1;                   // rounds executed by the reference's loop
+    dir_out[0] = g ? dirB : dirA;
+    dir_out[1] = __shfl_sync(0xffffffffu, dir[1], 4 * g + win);
+    dir_out[2] = __shfl_sync(0xffffffffu, dir[2], 4 * g + win);
+    __syncwarp();
+    const Pt3* src = c.w.tri + (size_t)(4 * g + win) * c.w.capf;
+    for (int i = lane; i < n; i += 32) dst[i] = src[i];
+    __syncwarp();
+    used = g;
+    return n;
+  }
+  return 0;
 }
 
 // Geometry of the all-view compatible (plg_matching.cpp:633-706) for a 3-view point and ONE driving view `si`:
@@ -409,27 +430,22 @@ static __device__ __noinline__ bool plg_compatible(Ctx& c, const Cur3& cand, int
     o[1] = plb.start == d[1] ? plb.end : plb.start;
     o[2] = plc.start == d[2] ? plc.end : plc.start;
   };
-  int n = first_extreme(c, cand, pla.start, dir1, c.w.D1);
+  int used = 0;
+  const int n = first_extreme_dual(c, cand, pla.start, pla.end, used, dir1, c.w.D1);
   if (c.overflow) return false;
   if (n > 0) {
     d1ok = true; n1 = n;
     d1[0] = dir1[0]; d1[1] = dir1[1]; d1[2] = dir1[2];
     opposite(dir1, d2);
-    Cur3 nx; float X[3];
-    if (step3(S, c.sel, cand, d2, nx, X)) {
-      d2ok = true;
-      __syncwarp();
-      if (c.lane == 0) store_pt3(c.w.D2, nx, X);
-      __syncwarp();
-      n2 = 1;
-    }
-  } else {
-    n = first_extreme(c, cand, pla.end, dir1, c.w.D1);
-    if (c.overflow) return false;
-    if (n > 0) {
-      d1ok = true; n1 = n;
-      d1[0] = dir1[0]; d1[1] = dir1[1]; d1[2] = dir1[2];
-      opposite(dir1, d2);
+    if (used == 0) {                            // the pla.start extreme worked: one step towards the opposite extremes (:345-356)
+      Cur3 nx; float X[3];
+      if (step3(S, c.sel, cand, d2, nx, X)) {
+        d2ok = true;
+        __syncwarp();
+        if (c.lane == 0) store_pt3(c.w.D2, nx, X);
+        __syncwarp();
+        n2 = 1;
+      }
     }
   }
   if (d1ok) follow3(c, d1, c.w.D1, n1);
