@@ -13,8 +13,13 @@
 namespace eg3d {
 
 constexpr int A6_THREADS = 128;
+// Per-observation capacities are run-time values (A6Args::raw_cap / ids_cap; dynamic shared memory): the host starts at
+// A6_RAW / A6_IDS and re-runs the seeding with four times as much when an observation's neighbourhood holds more (the
+// reference has no such bound), up to A6_RAW_MAX ids, where one warp per CTA still fits an SM's shared memory.
 constexpr int A6_RAW = 512;      // ids gathered from the nine cells, duplicates included
 constexpr int A6_IDS = 128;      // distinct polylines per observation
+constexpr int A6_RAW_MAX = 16384;
+inline __host__ __device__ size_t a6_smem_per_warp(int raw_cap, int ids_cap) { return (size_t)raw_cap * 9 + (size_t)ids_cap * 4; }   // raw + sorted (u32) + dup (u8) + uniq (u32)
 
 struct A6Rec { uint32_t id, seg; float px, py; int cls; };   // cls: 2 = seed + candidate (<= 10 px), 1 = candidate (<= 30 px), 0 = neither
 
@@ -22,7 +27,8 @@ struct A6Args {
   int64_t o_begin, o_end;          // observation range = track_off[tb] .. track_off[te]
   int64_t tb;
   const int* obs_track;            // [NO] track of every observation
-  A6Rec* recs;                     // [n_obs][A6_IDS]
+  int raw_cap, ids_cap;            // capacities per observation (multiples of 4)
+  A6Rec* recs;                     // [n_obs][ids_cap]
   int* n_ids; int* n_cand; int* n_seed; unsigned char* is_last;
   int* overflow;
   // fill
@@ -34,15 +40,15 @@ struct A6Args {
 };
 
 __global__ void __launch_bounds__(A6_THREADS) a6_classify_kernel(const __grid_constant__ DevScene S, const __grid_constant__ A6Args A) {
-  __shared__ uint32_t s_raw[A6_THREADS / 32][A6_RAW];
-  __shared__ uint32_t s_sorted[A6_THREADS / 32][A6_RAW];
-  __shared__ unsigned char s_dup[A6_THREADS / 32][A6_RAW];
-  __shared__ uint32_t s_uniq[A6_THREADS / 32][A6_IDS];
+  extern __shared__ __align__(16) unsigned char a6_smem[];
+  const int A6_RAW = A.raw_cap, A6_IDS = A.ids_cap;        // (shadow the defaults: this launch's capacities)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t ol = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // local observation index
   const int64_t o = A.o_begin + ol;
   if (o >= A.o_end) return;
-  uint32_t* raw = s_raw[wib]; uint32_t* sorted = s_sorted[wib]; unsigned char* dup = s_dup[wib]; uint32_t* uniq = s_uniq[wib];
+  unsigned char* mine = a6_smem + (size_t)wib * a6_smem_per_warp(A6_RAW, A6_IDS);
+  uint32_t* raw = reinterpret_cast<uint32_t*>(mine); uint32_t* sorted = raw + A6_RAW; uint32_t* uniq = sorted + A6_RAW;
+  unsigned char* dup = reinterpret_cast<unsigned char*>(uniq + A6_IDS);
   const int rp = A.obs_track[o];
   const int64_t t0 = S.track_off[rp], t1 = S.track_off[rp + 1];
   const int view = S.track_view[o];
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(A6_THREADS) a6_fill_kernel(const __grid_consta
   const int view = S.track_view[o];
   const int nu = A.n_ids[ol];
   const bool last = A.is_last[ol] != 0;
-  const A6Rec* in = A.recs + (size_t)ol * A6_IDS;
+  const A6Rec* in = A.recs + (size_t)ol * A.ids_cap;
   // the seed's reference point: the observation the lists were built around (last one of the view)
   const int64_t t0 = S.track_off[rp], t1 = S.track_off[rp + 1];
   int64_t jl = -1;

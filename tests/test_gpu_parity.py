@@ -196,6 +196,19 @@ def test_match_refpoints_parity(small):
     assert np.array_equal(np.concatenate([a.xyz, b.xyz]), gpu.xyz)
 
 
+def test_refpoint_seeding_capacities_grow_inside_the_call(small, monkeypatch):
+    """The device seeding of pipeline 3 holds a bounded number of polyline ids per 30 px neighbourhood; the reference has no
+    bound, so the bound grows inside the call (x4 per re-run).  Started from absurdly small capacities the result is unchanged."""
+    sc, dev, orc = small
+    full, _ = dev.match_refpoints()
+    monkeypatch.setenv("EG3D_TEST_A6_CAPS", "4,4")
+    tiny, tm = dev.match_refpoints()
+    monkeypatch.delenv("EG3D_TEST_A6_CAPS")
+    assert tm["n_capacity_retries"] >= 1
+    assert tiny.n_points == full.n_points and tiny.xyz.tobytes() == full.xyz.tobytes()
+    assert np.array_equal(tiny.obs_off, full.obs_off) and np.array_equal(tiny.obs_poly, full.obs_poly) and tiny.obs_xy.tobytes() == full.obs_xy.tobytes()
+
+
 def test_output_capacity_retry(small, monkeypatch):
     # the internal output buffers start tiny (test knob) and the call transparently re-runs K3 with larger ones
     sc, dev, orc = small
