@@ -58,6 +58,13 @@ struct DBuf {  // owning device buffer
   cudaError_t upload(const std::vector<T>& h, cudaStream_t st) { return upload(h.data(), h.size(), st); }
 };
 
+// grow-only reuse of a scene-owned buffer: (re)allocates with 25 % head-room only when the request exceeds what is there
+template <typename T>
+static cudaError_t ensure(DBuf<T>& b, size_t count) {
+  if (b.p && b.n >= count) return cudaSuccess;
+  return b.alloc(count + count / 4);
+}
+
 struct HostGrid { float cell; int w, h; std::vector<int> off; std::vector<uint32_t> ids; };
 
 // The library's stream is shared by a scene and by every result produced from it (their device buffers are freed on it):
@@ -87,6 +94,10 @@ struct eg3d_scene {
   HostGrid hg30;
   std::vector<int64_t> h_track_off; std::vector<int32_t> h_track_view; std::vector<float2> h_track_xy;
   int max_view_segs = 0;
+  // K3's large per-call temporaries (per-warp scratch arenas: GBs; unordered chain output) stay with the scene, grow-only.  Going
+  // through the stream-ordered pool per call made the pool re-grow by GBs whenever calls of different shapes alternate (the
+  // three pipelines of the reference's driver: 100+ ms of host stalls per call inside the timed region).
+  DBuf<unsigned char> k3_scratch; DBuf<float> k3_uX, k3_ux, k3_uy; DBuf<int> k3_unobs, k3_uv; DBuf<int64_t> k3_uobase; DBuf<uint32_t> k3_upl, k3_useg;
   // multi-GPU exchange (eg3d_comm_create): an NCCL communicator owned by the scene handle
   ncclComm_t comm = nullptr; int comm_rank = 0, comm_world = 1;
 };
@@ -427,17 +438,19 @@ static eg3d_status run_k3_once(eg3d_scene* sc, const DevSeeds& ds, HitLists& H, 
   const int batch_b = EG3D_K3B_BATCH > 0 ? EG3D_K3B_BATCH : 1;     // arenas per phase-B warp
   if (EG3D_K3B_BATCH > 0) nblocks_b = std::max(1, std::min(sc->num_sms, (n + warps_per_block_b * batch_b - 1) / (warps_per_block_b * batch_b)));
   const size_t nwarps = std::max((size_t)nblocks * warps_per_block, (size_t)nblocks_b * warps_per_block_b * batch_b);
-  DBuf<unsigned char> scratch; CK(scratch.alloc(nwarps * spw));
+  CK(ensure(sc->k3_scratch, nwarps * spw));
+  DBuf<unsigned char>& scratch = sc->k3_scratch;
   DBuf<int> counter; CK(counter.alloc(1)); CK(cudaMemsetAsync(counter.p, 0, sizeof(int), sc->stream));
   DBuf<unsigned long long> oc4; CK(oc4.alloc(4)); CK(cudaMemsetAsync(oc4.p, 0, 4 * sizeof(unsigned long long), sc->stream));
   // unordered output capacity: generous typical-case bound; exceeding it is reported, never silently truncated
   const bool tiny = getenv("EG3D_TEST_TINY_CAPS") != nullptr;   // test knob: start from absurdly small output buffers to exercise the retry
   int64_t pt_cap = std::min<int64_t>((int64_t)n * capc, (tiny ? (int64_t)64 : std::max<int64_t>((int64_t)n * 24, 1 << 16)) * cap_scale);
   int64_t ob_cap = pt_cap * std::min<int64_t>(oc, 64 + V / 2);
-  DBuf<float> uX; DBuf<int> unobs; DBuf<int64_t> uobase; DBuf<int> uv; DBuf<uint32_t> upl, useg; DBuf<float> ux, uy;
+  DBuf<float>& uX = sc->k3_uX; DBuf<int>& unobs = sc->k3_unobs; DBuf<int64_t>& uobase = sc->k3_uobase; DBuf<int>& uv = sc->k3_uv;
+  DBuf<uint32_t>&upl = sc->k3_upl, &useg = sc->k3_useg; DBuf<float>&ux = sc->k3_ux, &uy = sc->k3_uy;
   DBuf<int> snp; DBuf<int64_t> spb, sno;
-  CK(uX.alloc(3 * pt_cap)); CK(unobs.alloc(pt_cap)); CK(uobase.alloc(pt_cap));
-  CK(uv.alloc(ob_cap)); CK(upl.alloc(ob_cap)); CK(useg.alloc(ob_cap)); CK(ux.alloc(ob_cap)); CK(uy.alloc(ob_cap));
+  CK(ensure(uX, 3 * pt_cap)); CK(ensure(unobs, pt_cap)); CK(ensure(uobase, pt_cap));
+  CK(ensure(uv, ob_cap)); CK(ensure(upl, ob_cap)); CK(ensure(useg, ob_cap)); CK(ensure(ux, ob_cap)); CK(ensure(uy, ob_cap));
   CK(snp.alloc(n)); CK(spb.alloc(n)); CK(sno.alloc(n));
   K3Args a; memset(&a, 0, sizeof a);
   a.n_seeds = n; a.seed_view = ds.view.p; a.seed_pl = ds.pl.p; a.seed_seg = ds.seg.p; a.seed_xy = ds.xy.p;
