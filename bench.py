@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — triangulated 3D edge-points/sec on the BASELINE.json workload (see DESIGN.md "Measurement").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2strong|c3|c5|small|c1|c1real]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c2strong|c3|c4|c5|small|c1|c1real]
 
 A "step" is one pass of the hot path (K1 epipolar intersection -> K3 triple enumeration / PLG following / view expansion
 -> ordered packing [-> the library's NCCL exchange of the accepted points + device merge when N > 1]) over the whole seed
@@ -13,7 +13,7 @@ Workloads.  c2 (default) = BASELINE configs[1]: synthetic 200-view rig, 1920x108
 seeds; N > 1 is WEAK scaling on the same rig (every rank keeps 50 000 seeds: spacing 20/N px => 250*N seeds per view, starting
 views r, r+N, ... per rank).  c2strong = the same 50 000 seeds split over the N ranks (STRONG scaling).  c3 = BASELINE
 configs[2]: the 1000-view rig, 250 000 seeds, starting views sharded over the N ranks (strong scaling; 8 GPUs is the
-configuration BASELINE names).  c5 = BASELINE configs[4], the Gauss-Newton microbenchmark (10 M hypotheses x 20 observations).
+configuration BASELINE names).  c4 = BASELINE configs[3] (dtu006-shaped geometry, 10x seed density, candidate-set mode).  c5 = BASELINE configs[4], the Gauss-Newton microbenchmark (10 M hypotheses x 20 observations).
 small / c1 / c1real are documentation workloads.
 
 `value` = accepted (pre-dedup) 3D edge-points of all ranks / max-over-ranks device time of a step (CUDA events on the
@@ -381,6 +381,51 @@ def run_c5(args, E):
                               "observation and pass; the HBM fraction is therefore low by nature (the kernel is issue-bound), see DESIGN.md"}))
 
 
+def run_c4(args, E):
+    """BASELINE configs[3]: dtu006-shaped geometry at 10x seed density (SPLIT_INTERVAL_DISTANCE 20 -> 2 px), candidate-set mode
+    (pipelines 1-2 semantics): ~0.8 M seeds in one eg3d_match_polyline_sets call.  One JSON line; oracle check on the first
+    starting views."""
+    import torch
+    from tests import oracle_lib as O
+    cfg = dict(n_views=25, width=1600, height=1200, focal=2900.0, n_curves=600, segs_per_curve=20, curve_len=0.12, seed=1234, extent=0.55,
+               closed_frac=0.05, n_tracks=6268, track_cap=21, per_ring=25)
+    sc = syn.make_scene(**cfg)
+    cands = syn.curve_candidate_sets(sc, seed=cfg["seed"])
+    prm = E.default_params(split_interval_distance=2.0)
+    dev = E.DeviceScene(sc, prm)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    sampler = ClockSampler(0); sampler.start()
+    dev_ms, wall_ms, last = [], [], None
+    for i in range(args.warmup + args.steps):
+        flush.fill_(1); torch.cuda.synchronize()
+        t = time.perf_counter()
+        pts, tm = dev.match_polyline_sets(cands)                       # candidate CSR + seed sampling on the host, K1 (candidate form) + K3 + pack, D2H of the result
+        w = 1e3 * (time.perf_counter() - t)
+        if i >= args.warmup:
+            dev_ms.append(tm["total_ms"]); wall_ms.append(w); last = (pts, tm)
+    clocks = sampler.stop()
+    pts, tm = last
+    ve = 2
+    t = time.perf_counter()
+    ref = O.OracleScene(sc, prm).match_polyline_sets(cands, 0, ve, n_threads=os.cpu_count())
+    cpu_s = time.perf_counter() - t
+    got, _ = dev.match_polyline_sets(cands, 0, ve)
+    same = bool(got.n_points == ref.n_points and np.array_equal(got.obs_off, ref.obs_off) and np.array_equal(got.obs_view, ref.obs_view) and
+                np.array_equal(got.obs_poly, ref.obs_poly) and np.array_equal(got.obs_seg, ref.obs_seg) and got.obs_xy.tobytes() == ref.obs_xy.tobytes())
+    d, w = float(np.mean(dev_ms)), float(np.mean(wall_ms))
+    print(json.dumps({"metric": "triangulated 3D edge-points/sec (device-timed)", "unit": "points/s", "value": pts.n_points / (d * 1e-3), "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": d, "higher_is_better": True, "scaling": "weak", "dtype": "f64", "data": "synthetic", "vs_baseline": None,
+                      "config": {"workload": f"BASELINE configs[3]: dtu006-shaped geometry (25 views 1600x1200, {sc.n_segments(0)} segments/view), seeds every 2 px "
+                                             f"({tm['n_seeds']} seeds), candidate-set mode, pipelines 1-2, seed 1234", "l2": "flushed between iterations (256 MiB write)"},
+                      "measured": {"seeds": tm["n_seeds"], "points_per_step": pts.n_points, "observations": pts.n_obs},
+                      "e2e": {"value": pts.n_points / (w * 1e-3), "unit": "points/s", "ms_per_step": w, "h2d_bytes_per_step": int(cands.off.nbytes + cands.polyline.nbytes),
+                              "d2h_bytes_per_step": int(pts.n_points * 20 + 8 + pts.n_obs * 20),
+                              "note": "eg3d_match_polyline_sets with host buffers in and out (candidate sets H2D, host seed sampling, result D2H)"},
+                      "kernel_ms": {k: tm[k] for k in ("k1_count_ms", "k1_fill_ms", "scan_ms", "k3a_ms", "k3b_ms", "pack_ms")},
+                      "oracle_sample": {"starting_views": ve, "points": ref.n_points, "identical": same, "cpu_s": cpu_s, "cpu_threads": os.cpu_count(),
+                                        "cpu_points_per_s": ref.n_points / cpu_s}, "clocks": clocks}))
+
+
 def main():
     # Only the JSON line may reach stdout: library banners (NCCL prints its version there) are sent to stderr by
     # pointing fd 1 at fd 2 for the rest of the process and keeping the real stdout for the one line.
@@ -429,6 +474,8 @@ def main():
         return
     if args.workload == "c5":
         return run_c5(args, E)
+    if args.workload == "c4":
+        return run_c4(args, E)
     scene, cfg, per_view = build_workload(args.workload, n_gpus)
     if args.workload == "c1":
         return run_c1(args, scene, cfg, E)

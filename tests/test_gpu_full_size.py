@@ -112,3 +112,58 @@ def test_gn_microbench_device_resident(c2):
     # most clean hypotheses pass the filter threshold, most of the 10 % with a displaced observation do not
     assert 0.80 < res[0][2].mean() < 0.97
     print(f"GN microbench 500k x 20: fp32 {res[0][3]:.3f} ms, fp64 {res[1][3]:.3f} ms")
+
+
+
+def test_c4_density_full_size_oracle_sample():
+    """BASELINE configs[3] at its full size: dtu006-shaped geometry, seeds every 2 px (~0.8 M seeds, candidate-set mode) in ONE
+    call; size-independent properties over everything, identity with the oracle on the first starting view."""
+    cfg = dict(n_views=25, width=1600, height=1200, focal=2900.0, n_curves=600, segs_per_curve=20, curve_len=0.12, seed=1234, extent=0.55,
+               closed_frac=0.05, n_tracks=6268, track_cap=21, per_ring=25)
+    sc = syn.make_scene(**cfg)
+    cands = syn.curve_candidate_sets(sc, seed=cfg["seed"])
+    prm = E.default_params(split_interval_distance=2.0)
+    with E.DeviceScene(sc, prm) as dev:
+        pts, tm = dev.match_polyline_sets(cands)
+        first, _ = dev.match_polyline_sets(cands, 0, 1)
+    assert tm["n_seeds"] > 700_000 and pts.n_points > 3_000_000
+    assert np.all(np.diff(pts.seed.astype(np.int64)) >= 0)                               # ordered by seed, then chain position
+    lens = np.diff(pts.obs_off)
+    assert lens.min() >= 3 and lens.max() <= sc.n_views + 16      # (a followed point can carry a view twice, as in the reference: the per-point capacity is V + 16)
+    ref = O.OracleScene(sc, prm).match_polyline_sets(cands, 0, 1, n_threads=16)
+    assert first.n_points == ref.n_points and np.array_equal(first.obs_off, ref.obs_off) and np.array_equal(first.obs_view, ref.obs_view)
+    assert np.array_equal(first.obs_poly, ref.obs_poly) and np.array_equal(first.obs_seg, ref.obs_seg) and first.obs_xy.tobytes() == ref.obs_xy.tobytes()
+    assert np.abs(first.xyz - ref.xyz).max() < 1e-4
+
+
+def test_c5_gn_microbench_full_size_on_a_sample(c2):
+    """BASELINE configs[4] at its full size — 10 M hypotheses x 20 observations, device resident (1 M generated, repeated 10x on the
+    device as bench.py does) — both solvers; the oracle on a sample, and the ten repetitions must agree with each other bit for bit."""
+    import torch
+    sc, _, dev = c2
+    base_n, k, reps = 1_000_000, 20, 10
+    views, xy, init, _ = syn.gn_microbench_inputs(sc, base_n, k, seed=99)
+    n = base_n * reps
+    dv = torch.from_numpy(views).cuda().repeat(reps, 1).contiguous(); dxy = torch.from_numpy(xy).cuda().repeat(reps, 1, 1).contiguous()
+    di = torch.from_numpy(init).cuda().repeat(reps, 1).contiguous()
+    ox = torch.empty((n, 3), dtype=torch.float32, device="cuda"); om = torch.empty(n, dtype=torch.float32, device="cuda")
+    ok = torch.empty(n, dtype=torch.uint8, device="cuda")
+    sel = np.arange(0, base_n, 4999)
+    off = np.arange(len(sel) + 1, dtype=np.int64) * k
+    osc = O.OracleScene(sc)
+    for fp64 in (0, 1):
+        tm = dev.gn_triangulate_device(n, k, dv.data_ptr(), dxy.data_ptr(), di.data_ptr(), fp64, ox.data_ptr(), om.data_ptr(), ok.data_ptr())
+        torch.cuda.synchronize()
+        assert 0 < tm["gn_ms"] < 500
+        okc = ok.view(reps, base_n); oxc = ox.view(reps, base_n, 3)
+        assert bool((okc == okc[0]).all())                                               # identical problems, identical answers
+        good_all = okc[0] == 1
+        assert bool((oxc[:, good_all] == oxc[0, good_all]).all())
+        x, m, o = osc.gn_triangulate(off, views[sel].reshape(-1), xy[sel].reshape(-1, 2), init[sel], fp64, n_threads=16)
+        go = okc[0].cpu().numpy()[sel]; gx = oxc[0].cpu().numpy()[sel]
+        assert np.array_equal(go, o)
+        good = o == 1
+        if fp64:
+            assert np.abs(gx[good] - x[good]).max() < 2e-6
+        else:
+            assert np.array_equal(gx[good], x[good].astype(np.float32))
