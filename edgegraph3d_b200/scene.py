@@ -213,16 +213,26 @@ class PointSet:
                         arr(v.obs_xy, 2 * m, np.float32).reshape(m, 2))
 
     def view_struct(self):
+        """eg3d_points_view over this set's arrays.  Every field is coerced to the dtype / layout the C struct declares (a merged
+        `seed` can be int64: global ordinals; then it is narrowed, which is harmless — the C side never indexes by it) and the
+        coerced arrays are kept alive on the view object for as long as the caller holds it."""
         v = A.PointsView()
         v.n_points, v.n_obs = self.n_points, self.n_obs
-        v.xyz = A.ptr(np.ascontiguousarray(self.xyz), A.c_f32p)
-        v.seed = A.ptr(self.seed, A.c_i32p)
-        v.chain_pos = A.ptr(self.chain_pos, A.c_i32p)
-        v.obs_off = A.ptr(self.obs_off, A.c_i64p)
-        v.obs_view = A.ptr(self.obs_view, A.c_i32p)
-        v.obs_poly = A.ptr(self.obs_poly, A.c_u32p)
-        v.obs_seg = A.ptr(self.obs_seg, A.c_u32p)
-        v.obs_xy = A.ptr(np.ascontiguousarray(self.obs_xy), A.c_f32p)
+        keep = []
+
+        def arr(a, dt):
+            b = np.ascontiguousarray(a, dt)
+            keep.append(b)
+            return b
+        v.xyz = A.ptr(arr(self.xyz, np.float32), A.c_f32p)
+        v.seed = A.ptr(arr(self.seed, np.int32), A.c_i32p)
+        v.chain_pos = A.ptr(arr(self.chain_pos, np.int32), A.c_i32p)
+        v.obs_off = A.ptr(arr(self.obs_off, np.int64), A.c_i64p)
+        v.obs_view = A.ptr(arr(self.obs_view, np.int32), A.c_i32p)
+        v.obs_poly = A.ptr(arr(self.obs_poly, np.uint32), A.c_u32p)
+        v.obs_seg = A.ptr(arr(self.obs_seg, np.uint32), A.c_u32p)
+        v.obs_xy = A.ptr(arr(self.obs_xy, np.float32), A.c_f32p)
+        v._keep = keep
         return v
 
     def identity_keys(self):
