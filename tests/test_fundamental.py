@@ -5,6 +5,7 @@ rejected, and on the real tracks of the packaged example the matrices must expla
 committed fixture do."""
 import os
 import numpy as np
+import pytest
 from edgegraph3d_b200 import lib as E, synthetic as syn
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -93,6 +94,21 @@ def test_pairs_with_fewer_than_ten_common_tracks_stay_invalid():
     assert valid.sum() == 12
 
 
+def test_degenerate_inputs_do_not_break_the_call():
+    F, v = E.fundamental_from_tracks(3, np.array([0], np.int64), np.zeros(0, np.int32), np.zeros((0, 2), np.float32))
+    assert not v.any()
+    off = np.arange(0, 62, 2).astype(np.int64); view = np.tile([0, 1], 30).astype(np.int32)
+    same = np.tile([[100., 100.], [200., 200.]], (30, 1)).astype(np.float32)               # 30 copies of one correspondence
+    F, v = E.fundamental_from_tracks(2, off, view, same)
+    assert not v.any() and np.isfinite(F).all()
+    xs = np.linspace(0, 500, 30)
+    line = np.stack([np.stack([xs, xs], 1), np.stack([xs + 5, xs * 0.5], 1)], 1).reshape(-1, 2).astype(np.float32)   # collinear points: rank-deficient
+    F, v = E.fundamental_from_tracks(2, off, view, line)
+    assert np.isfinite(F).all()
+    with pytest.raises(E.Eg3dError):
+        E.fundamental_from_tracks(2, off, np.full_like(view, 5), line)                   # a view id outside the scene
+
+
 def test_real_dtu006_tracks_as_good_as_the_cv2_fixture():
     d = np.load(os.path.join(HERE, "golden", "dtu006_sfm.npz"))
     V = d["cameras"].shape[0]
@@ -109,9 +125,6 @@ def test_real_dtu006_tracks_as_good_as_the_cv2_fixture():
     assert np.median(own) <= 1.05 * np.median(cv)                           # measured: 0.74 px against 0.82 px
     assert np.percentile(own, 90) <= 1.1 * np.percentile(cv, 90)
     assert own.max() <= 2.5                                                 # cv2's worst pair: 1.65 px
-
-
-import pytest
 
 
 @pytest.mark.gpu
