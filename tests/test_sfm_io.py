@@ -77,6 +77,28 @@ def test_cpp_ply_equals_the_python_ply(tmp_path):
     assert (tmp_path / "c.ply").read_text() == (tmp_path / "d.ply").read_text()
 
 
+def test_cpp_reader_on_unusual_but_valid_json_text(tmp_path):
+    """Scientific notation, negative zero, integers where floats are expected, escaped strings, tabs / CRLF between tokens, unknown keys."""
+    doc = _doc(3, np.random.default_rng(11))
+    doc["root_path"] = 'C:\\data\\"dtu" A\n\ttab'                 # backslashes, quotes, control characters -> escapes in the file
+    doc["extra"] = {"a": [1, 2, {"b": None}], "t": True, "f": False}
+    doc["extrinsics"][1]["value"]["center"] = [-0.0, 1, 2.0]
+    doc["structure"][0]["value"]["X"] = [1, -2, 3]
+    text = json.dumps(doc)
+    assert '"focal_length": 520.25' in text and '"principal_point": [321.5, 239.25]' in text
+    text = text.replace('"focal_length": 520.25', '"focal_length": 5.2025E+2').replace('"principal_point": [321.5, 239.25]', '"principal_point": [3215e-1,\t239.25]')
+    text = text.replace('"center": [', '"center":\r\n [ ', 1).replace(", ", " ,\n\t", 40)
+    assert json.loads(text) == doc
+    p = tmp_path / "odd.json"
+    p.write_text(text)
+    _same(E.sfm_load(p), io.load_sfm_data(str(p)))
+    # the verbatim sections survive a save with their escapes intact
+    out = tmp_path / "out.json"
+    assert E.sfm_save(out, p, np.zeros((1, 3), np.float32), np.array([0, 1], np.int64), np.array([0], np.int32), np.array([[1.5, 2.5]], np.float32)) == 1
+    back = json.load(open(out))
+    assert back["root_path"] == doc["root_path"] and back["views"] == doc["views"] and back["extrinsics"] == doc["extrinsics"]
+
+
 def test_bad_files_are_refused(tmp_path):
     with pytest.raises(E.Eg3dError):
         E.sfm_load(tmp_path / "missing.json")
